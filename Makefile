@@ -1,0 +1,38 @@
+# Builds libb200pt.so (CUDA kernels + C ABI + headless host) and the b200pt CLI for sm_100a.
+# `python -c "import __graft_entry__ as g; g.build()"` drives this file.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+PKG       := rtx-pathtracer_b200
+BUILD     := $(PKG)/_build
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr
+CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall
+
+LIB       := $(PKG)/libb200pt.so
+CLI       := $(PKG)/b200pt
+CU_SRCS   := $(PKG)/csrc/api.cu $(PKG)/csrc/guiding_fit.cu
+HOST_SRCS := $(PKG)/host/scene.cpp $(PKG)/host/bvh.cpp $(PKG)/host/exr.cpp
+CU_OBJS   := $(patsubst $(PKG)/csrc/%.cu,$(BUILD)/%.o,$(CU_SRCS))
+HOST_OBJS := $(patsubst $(PKG)/host/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
+HEADERS   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/host/*.h) include/b200pt.h
+
+all: $(LIB) $(CLI)
+
+$(BUILD)/%.o: $(PKG)/csrc/%.cu $(HEADERS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
+
+$(BUILD)/%.o: $(PKG)/host/%.cpp $(HEADERS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(HOST_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lz -cudart static
+
+$(CLI): $(PKG)/host/main.cpp $(LIB) include/b200pt.h
+	$(CXX) $(CXXFLAGS) -o $@ $< -L$(PKG) -lb200pt -Wl,-rpath,'$$ORIGIN'
+
+clean:
+	rm -rf $(BUILD) $(LIB) $(CLI)
+
+.PHONY: all clean

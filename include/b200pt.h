@@ -1,0 +1,383 @@
+/*
+ * b200pt.h — C ABI of libb200pt.so, the B200-native path-tracing core.
+ *
+ * This is the drop-in boundary described in SURVEY.md §8(b).  The reference
+ * (FelixFifi/rtx-pathtracer) has no FFI layer; its de-facto boundary is "what
+ * the host binds to the Vulkan ray-tracing pipeline and what it reads back".
+ * Every entry point below names the reference call site it replaces.
+ *
+ * Conventions
+ *   - all functions return int: 0 = OK, negative = error (see B200PT_E_*);
+ *     b200pt_last_error() returns a human-readable message for the calling thread
+ *   - plain pointers and sizes only; the host keeps ownership of every input
+ *     array, the library copies what it needs to the device
+ *   - one context per GPU, not thread-safe per context
+ *   - all structs are byte-identical to the GLSL / C++ layouts of the reference
+ *     (little-endian float32 / int32), so buffers can be passed through unchanged
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_OK            0
+#define B200PT_E_INVALID    -1   /* bad argument */
+#define B200PT_E_CUDA       -2   /* CUDA runtime error */
+#define B200PT_E_IO         -3   /* file not found / parse error */
+#define B200PT_E_STATE      -4   /* call order violated (e.g. render before set_scene) */
+#define B200PT_E_NODEVICE   -5   /* no CUDA device: there is NO CPU fallback */
+
+/* shaders/limits.glsl:1-6 */
+#define B200PT_SIZE_LIGHT_RANDOM 10000
+#define B200PT_SIZE_TRI_RANDOM   10000
+#define B200PT_MAX_DISTRIBUTIONS 16
+#define B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL 16
+#define B200PT_INVALID_REGION 0xFFFFFFFFu      /* shaders/guiding.glsl:112 */
+
+/* material types, shaders/raytrace.rgen:21-27 / src/SceneLoader.h:31-39 */
+enum { B200PT_MAT_DIFFUSE = 0, B200PT_MAT_SPECULAR = 1, B200PT_MAT_DIELECTRIC = 2, B200PT_MAT_LIGHT = 3,
+       B200PT_MAT_PHONG = 4, B200PT_MAT_CONDUCTOR = 5, B200PT_MAT_ROUGH_CONDUCTOR = 6 };
+/* light types, shaders/raytrace.rgen:29-32 / src/SceneLoader.h:41-46 */
+enum { B200PT_LIGHT_AREA = 0, B200PT_LIGHT_POINT = 1, B200PT_LIGHT_SPHERE = 2, B200PT_LIGHT_ENV_MAP = 3 };
+
+/* ---- scene buffer layouts (SURVEY.md §8(a) layout table) ------------------------------- */
+
+/* shaders/wavefront.glsl:1-7 (std140 array) / src/Model.h:24-33 — 48 B */
+typedef struct b200pt_vertex {
+    float pos[3];      float _pad0;
+    float normal[3];   float _pad1;
+    float texCoord[2];
+    int32_t materialIndex;
+    int32_t _pad2;
+} b200pt_vertex;
+
+/* shaders/wavefront.glsl:9-23 (std430) / src/SceneLoader.h:48-62 — 96 B */
+typedef struct b200pt_material {
+    float lightColor[3]; float _pad0;
+    float diffuse[3];    float _pad1;
+    float specular[3];
+    float specularHighlight;
+    float transparency;
+    float refractionIndex;
+    float refractionIndexInv;
+    float eta;
+    float k;
+    float roughness;
+    int32_t textureIdDiffuse;   /* -1 = none */
+    int32_t textureIdSpecular;  /* -1 = none */
+    int32_t type;
+    int32_t _pad2[3];
+} b200pt_material;
+
+/* shaders/wavefront.glsl:25-30 (std140) / src/SceneLoader.h:64-69 — 144 B, matrices column-major */
+typedef struct b200pt_instance {
+    float transform[16];
+    float normalTransform[16];
+    int32_t modelIndex;
+    int32_t iLight;             /* -1 = not a light */
+    int32_t _pad[2];
+} b200pt_instance;
+
+/* shaders/wavefront.glsl:32-39 (scalar) / src/SceneLoader.h:71-78 — 40 B */
+typedef struct b200pt_light {
+    float color[3];
+    float pos[3];
+    uint32_t instanceIndex;     /* instance index (area) or sphere index (sphere light) */
+    float sampleProb;
+    float area;
+    int32_t type;
+} b200pt_light;
+
+/* shaders/wavefront.glsl:41-45 / src/SceneLoader.h:80-84 — 12 B */
+typedef struct b200pt_face_sample {
+    int32_t index;
+    float sampleProb;
+    float faceArea;
+} b200pt_face_sample;
+
+/* shaders/raycommon.glsl:71-76 (scalar) / src/Shapes.h:65-75 — 24 B */
+typedef struct b200pt_sphere {
+    float center[3];
+    float radius;
+    int32_t materialIndex;
+    int32_t iLight;             /* -1 = not a light */
+} b200pt_sphere;
+
+/* shaders/raycommon.glsl:78-81 / src/Shapes.h:19-22 — 24 B */
+typedef struct b200pt_aabb {
+    float min[3];
+    float max[3];
+} b200pt_aabb;
+
+/* shaders/raycommon.glsl:83-87 / src/IrradianceCache.h — 12 B */
+typedef struct b200pt_cache_header {
+    uint32_t nextCacheSlot;
+    uint32_t maxCaches;
+    uint32_t nextUpdateSlot;
+} b200pt_cache_header;
+
+/* shaders/raycommon.glsl:89-96 (scalar) / src/IrradianceCache.h:17-30 — 56 B */
+typedef struct b200pt_cache_data {
+    float color[3];
+    float normal[3];
+    float rotGrad[3];
+    float transGrad[3];
+    float harmonicR;
+    uint32_t numUpdates;
+} b200pt_cache_data;
+
+/* shaders/guiding.glsl:99-113 / external/lightpmm/include/pmm/DirectionalData.h:44-58 — 40 B */
+typedef struct b200pt_directional_data {
+    float position[3];
+    float direction[3];
+    float weight;
+    float pdf;
+    float distance;
+    uint32_t flags;             /* region id or B200PT_INVALID_REGION */
+} b200pt_directional_data;
+
+/* shaders/guiding.glsl:14-21 / src/PathGuiding.h:36-56 — 40 B */
+typedef struct b200pt_vmf_theta {
+    float mu[3];
+    float k;
+    float norm;
+    float eMin2K;
+    float distance;
+    float target[3];
+} b200pt_vmf_theta;
+
+/* shaders/guiding.glsl:46-51 / src/PathGuiding.h:58-75 — 720 B */
+typedef struct b200pt_vmm_theta {
+    b200pt_vmf_theta thetas[B200PT_MAX_DISTRIBUTIONS];
+    float pi[B200PT_MAX_DISTRIBUTIONS];
+    float meanPosition[3];
+    int32_t usedDistributions;
+} b200pt_vmm_theta;
+
+/* push constants: shaders/raycommon.glsl:19-69 / src/RayTracingApp.h:116-165 — 192 B, same field order,
+ * GLSL bools are 4-byte ints.  Defaults (b200pt_default_push_constants) are RayTracingApp.h's. */
+typedef struct b200pt_push_constants {
+    uint32_t randomUInt;
+    uint32_t previousFrames;
+    int32_t maxDepth;
+    int32_t maxFollowDiscrete;
+    int32_t samplesPerPixel;
+    int32_t enableRR;                 /* dead in the reference (never read by a shader) */
+    int32_t enableNEE;
+    int32_t numNEE;
+    int32_t enableAverageInsteadOfMix;
+    int32_t enableMIS;
+    int32_t usePowerHeuristic;
+    int32_t storeEstimate;
+    int32_t visualizeMode;
+    int32_t showIrradianceCacheOnly;
+    int32_t showIrradianceGradients;
+    int32_t useIrradianceCache;
+    int32_t highlightIrradianceCacheColor;
+    float irradianceA;
+    float irradianceUpdateProb;
+    float irradianceCreateProb;
+    float irradianceVisualizationScale;
+    int32_t useIrradianceGradients;
+    int32_t useIrradianceCacheOnGlossy;
+    float irradianceGradientsMaxLength;
+    int32_t isIrradiancePrepareFrame;
+    int32_t irradianceNumNEE;
+    float irradianceCacheMinRadius;
+    int32_t irradianceCachePerformVisibilityCheck;
+    int32_t useVisibleSphereSampling;
+    int32_t useADRRS;
+    float adrrsS;
+    int32_t adrrsSplit;
+    int32_t splitOnFirst;
+    int32_t useGuiding;
+    float guidingProb;
+    float guidingVisuScale;
+    float guidingVisuMax;
+    int32_t guidingVisuIgnoreOcclusioon;
+    int32_t updateGuiding;
+    int32_t useParallaxCompensation;
+    float time;
+    int32_t guidingVisuMove;
+    float guidingVisuPhiScale;
+    float guidingVisuThetaScale;
+    int32_t numGuidingRegions;
+    int32_t guidingPiPHighlightRegion;
+    int32_t guidingPiPShowSpheres;
+    float guidingPiPSize;
+} b200pt_push_constants;
+
+/* textures: binding 7 of set 1 (src/SceneLoader.cpp:184-236, :370-396). Index 0 is the environment map. */
+enum { B200PT_TEX_RGBA8_SRGB = 0, B200PT_TEX_RGBA32F = 1 };
+typedef struct b200pt_texture {
+    int32_t width, height;
+    int32_t format;           /* B200PT_TEX_* */
+    int32_t _pad;
+    const void *pixels;       /* width*height*4 bytes (RGBA8) or floats (RGBA32F), row 0 first */
+} b200pt_texture;
+
+/* everything the reference binds per scene: descriptor set 1 bindings 1..8 (src/RayTracingApp.cpp:396-557,
+ * src/SceneLoader.cpp:946-1099) */
+typedef struct b200pt_scene_desc {
+    int32_t num_models;
+    const b200pt_vertex *const *vertices;   /* [num_models] */
+    const int32_t *num_vertices;            /* [num_models] */
+    const uint32_t *const *indices;         /* [num_models], 3 per triangle */
+    const int32_t *num_indices;             /* [num_models] */
+    int32_t num_materials;
+    const b200pt_material *materials;
+    int32_t num_instances;
+    const b200pt_instance *instances;
+    int32_t num_lights;
+    const b200pt_light *lights;
+    const int32_t *random_light_index;      /* [B200PT_SIZE_LIGHT_RANDOM] */
+    int32_t num_face_tables;                /* one per mesh light, in light order (quirk 5) */
+    const b200pt_face_sample *random_tri_index; /* [num_face_tables][B200PT_SIZE_TRI_RANDOM] */
+    int32_t num_spheres;
+    const b200pt_sphere *spheres;
+    int32_t num_textures;
+    const b200pt_texture *textures;         /* [0] = env map (1x1 black RGBA8 when the scene has none) */
+    float scene_min[3], scene_max[3];       /* SceneLoader::calculateSceneSize, src/SceneLoader.cpp:350-368 */
+} b200pt_scene_desc;
+
+/* ray / hit records for the traversal-only parity hook (north_star level 1) */
+typedef struct b200pt_ray {
+    float origin[3]; float tmin;
+    float dir[3];    float tmax;
+} b200pt_ray;
+typedef struct b200pt_hit {
+    float t;            /* hit distance; undefined on miss */
+    uint32_t prim;      /* global primitive id (triangles of instance 0.., then spheres); 0xFFFFFFFF = miss */
+    float u, v;         /* barycentrics of vertices 1 and 2 (0,0 for spheres) */
+} b200pt_hit;
+#define B200PT_MISS 0xFFFFFFFFu
+
+/* counters filled by the kernels since the last b200pt_stats_reset */
+typedef struct b200pt_stats {
+    uint64_t extend_rays;      /* closest-hit path rays + MIS probe rays */
+    uint64_t shadow_rays;      /* any-hit visibility rays */
+    uint64_t path_vertices;    /* shade invocations on a surface hit */
+    uint64_t samples;          /* camera paths started */
+    uint64_t iterations;       /* wavefront iterations */
+    uint64_t kernel_launches;  /* CUDA kernels launched by this library */
+    float ms_trace;            /* device time in extend + shadow kernels (CUDA events) */
+    float ms_shade;            /* device time in generate/shade/resolve/accumulate kernels */
+    float ms_total;            /* device time of render_frame calls */
+    float _pad;
+} b200pt_stats;
+
+typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
+typedef struct b200pt_scene b200pt_scene;   /* opaque host-side scene (loader output) */
+
+enum { B200PT_IMAGE_OUTPUT = 0, B200PT_IMAGE_ACCUM = 1, B200PT_IMAGE_ESTIMATE = 2 };
+
+const char *b200pt_last_error(void);
+int b200pt_device_count(void);
+
+/* replaces RayTracingApp::RayTracingApp(width,height,icSize,guidingSplits,...) — src/RayTracingApp.cpp:11-53:
+ * allocates output / accumulate / estimate images (:55-73), IC buffers (src/IrradianceCache.cpp:46-79),
+ * the W*H*16 DirectionalData buffer (src/SampleCollector.cpp:29-51) and 2^splits guiding regions */
+int b200pt_create(int device_ordinal, int width, int height, int ic_size, int guiding_splits, b200pt_ctx **out);
+int b200pt_destroy(b200pt_ctx *ctx);        /* RayTracingApp::cleanup, src/RayTracingApp.cpp:1219-1241 */
+
+/* replaces SceneLoader::createVulkanObjects (src/SceneLoader.cpp:67-87): buffer uploads + BLAS/TLAS build
+ * (:1148-1193).  Builds a SAH BVH on the host, flattens it to compressed BVH8 nodes, uploads. Also rebuilds
+ * the guiding region tree from the scene AABB (src/PathGuiding.cpp:11-24,81-104) and resets the IC. */
+int b200pt_set_scene(b200pt_ctx *ctx, const b200pt_scene_desc *scene);
+
+/* replaces RayTracingApp::updateUniformBuffer (src/RayTracingApp.cpp:559-585); column-major mat4, inverses are
+ * computed inside like :578-579 */
+int b200pt_set_camera(b200pt_ctx *ctx, const float view[16], const float proj[16]);
+
+/* replaces pushConstants + traceRaysKHR(W,H,1) + waitIdle (src/RayTracingApp.cpp:1175-1201, :114).
+ * pc->randomUInt is the frame seed (the reference draws it from glm::linearRand, quirk 10). */
+int b200pt_render_frame(b200pt_ctx *ctx, const b200pt_push_constants *pc);
+
+/* replaces PostProcessing::saveOffscreenImage read-back (src/PostProcessing.cpp:310-338): W*H RGBA32F */
+int b200pt_read_image(b200pt_ctx *ctx, int which, float *rgba_host);
+int b200pt_write_image(b200pt_ctx *ctx, int which, const float *rgba_host);
+/* same, but into / from DEVICE memory owned by the caller (e.g. a torch tensor used for an NCCL all-reduce) */
+int b200pt_read_image_device(b200pt_ctx *ctx, int which, void *rgba_device);
+int b200pt_write_image_device(b200pt_ctx *ctx, int which, const void *rgba_device);
+
+/* level-1 parity hook: traversal only.  any_hit=0: closest hit (rgen:1011-1022 semantics);
+ * any_hit=1: visibility (rgen:626-637): hit[i].prim != MISS means occluded. Host buffers. */
+int b200pt_trace_rays(b200pt_ctx *ctx, const b200pt_ray *rays, int64_t n, b200pt_hit *hits, int any_hit);
+/* same with DEVICE buffers, no copies: used for kernel-only timing */
+int b200pt_trace_rays_device(b200pt_ctx *ctx, const void *rays_device, int64_t n, void *hits_device, int any_hit);
+
+int b200pt_stats_get(b200pt_ctx *ctx, b200pt_stats *out);
+int b200pt_stats_reset(b200pt_ctx *ctx);
+int b200pt_synchronize(b200pt_ctx *ctx);
+
+/* ---- guiding (PathGuiding / SampleCollector / lightpmm) ---------------------------------------- */
+
+/* knobs of PathGuiding.h:121-129 and VMMFactoryProperties (VMMFactory.h:45-61, PathGuiding.cpp:33-40) */
+typedef struct b200pt_guiding_params {
+    int32_t useParallaxCompensation;   /* enableParallaxCompensationForOptimization, RayTracingApp.h:208 */
+    int32_t splitAndMerge;             /* 1 */
+    int32_t minSamplesForMerging;      /* 8192 */
+    int32_t minSamplesForSplitting;    /* 4096 */
+    int32_t minSamplesForPostSplitFitting; /* 4096 */
+    float splitMinDivergence;          /* 0.5 */
+    float mergeMaxDivergence;          /* 0.025 */
+    int32_t numInitialComponents;      /* 8 */
+    int32_t minItr;                    /* 1 */
+    int32_t maxItr;                    /* 100 */
+    float relLogLikelihoodThreshold;   /* 0.005 */
+    float initKappa;                   /* 5 */
+    float maxKappa;                    /* 50000 */
+    float vPrior;                      /* 0.01 */
+    float rPrior;                      /* 0 */
+    float rPriorWeight;                /* 1 */
+} b200pt_guiding_params;
+void b200pt_default_guiding_params(b200pt_guiding_params *p);
+
+/* replaces PathGuiding::update(SampleCollector) (src/PathGuiding.cpp:276-312): sort by region, preFit,
+ * fit/updateFit, merge/split, distance update, pack VMM_Theta — all on the device. */
+int b200pt_guiding_update(b200pt_ctx *ctx, const b200pt_guiding_params *params);
+int b200pt_guiding_region_count(b200pt_ctx *ctx, int *count);
+int b200pt_guiding_get_aabbs(b200pt_ctx *ctx, b200pt_aabb *out, int n);
+int b200pt_guiding_get_vmms(b200pt_ctx *ctx, b200pt_vmm_theta *out, int n);
+int b200pt_guiding_put_vmms(b200pt_ctx *ctx, const b200pt_vmm_theta *in, int n);
+/* parity hooks for the W*H*16 DirectionalData buffer (binding 18): raw order, host memory */
+int b200pt_guiding_get_samples(b200pt_ctx *ctx, b200pt_directional_data *out, int64_t n);
+int b200pt_guiding_put_samples(b200pt_ctx *ctx, const b200pt_directional_data *in, int64_t n);
+int64_t b200pt_guiding_sample_capacity(b200pt_ctx *ctx);
+
+/* ---- irradiance cache parity hooks (bindings 10,12,13) ---------------------------------------- */
+int b200pt_ic_get(b200pt_ctx *ctx, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n);
+int b200pt_ic_put(b200pt_ctx *ctx, const b200pt_cache_header *hdr, const b200pt_cache_data *data,
+                  const b200pt_sphere *spheres, int n);
+
+/* ---- host side: the reference's scene surface (src/SceneLoader.*, src/MitsubaXML.h) ------------ */
+
+void b200pt_default_push_constants(b200pt_push_constants *pc);   /* RayTracingApp.h:116-165 defaults */
+
+/* SceneLoader(filepath): parses a Mitsuba-0.6 XML (or the reference's JSON) scene into the buffers above */
+int b200pt_scene_load(const char *path, b200pt_scene **out);
+int b200pt_scene_free(b200pt_scene *scene);
+int b200pt_scene_get_desc(const b200pt_scene *scene, b200pt_scene_desc *out);
+/* camera: origin, target, up, vfov as parsed (SceneLoader.h:147-150 defaults) */
+int b200pt_scene_get_camera(const b200pt_scene *scene, float origin[3], float target[3], float up[3], float *vfov);
+/* CameraController::lookAt + getViewMatrix + getProjMatrix (src/CameraController.cpp:76-107) */
+void b200pt_camera_matrices(const float origin[3], const float target[3], const float up[3], float vfov_deg,
+                            float aspect, float view[16], float proj[16]);
+/* glm::inverse as used for viewInverse / projInverse (src/RayTracingApp.cpp:578-579); returns 0 when singular.
+ * b200pt_set_camera applies exactly this function, so a checker can feed the same inverses to its own renderer. */
+int b200pt_mat4_inverse(const float m[16], float out[16]);
+/* CommonOps::writeEXR (src/CommonOps.cpp:12-38): 3 x FLOAT channels from RGBA32F */
+int b200pt_write_exr(const char *path, const float *rgba, int width, int height);
+/* CommonOps::readEXR (src/CommonOps.cpp:40-65): RGBA float (values pass through half like Imf::Rgba) */
+int b200pt_read_exr(const char *path, float **rgba_out, int *width, int *height);
+void b200pt_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,103 @@
+"""ORACLE — test infrastructure only.  ctypes wrapper of oracle/liboracle_tracer.so (tracer_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle_tracer.so")
+_lib = None
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("u", "<f4"), ("v", "<f4")])
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_set_scene.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_set_camera.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 4
+        L.oracle_render_region.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_image.restype = C.POINTER(C.c_float)
+        L.oracle_image.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_reset_counters.argtypes = [C.c_void_p]
+        L.oracle_set_guiding.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_samples.restype = C.c_void_p
+        L.oracle_samples.argtypes = [C.c_void_p]
+        L.oracle_ic_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_ic_put.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+class TracerOracle:
+    def __init__(self, width, height, ic_size=0, accel=True):
+        self.width, self.height, self.ic_size = width, height, ic_size
+        self._h = lib().oracle_create(width, height, ic_size, int(accel))
+
+    def set_scene(self, desc):
+        lib().oracle_set_scene(self._h, C.addressof(desc))
+
+    def set_camera(self, view, proj, view_inv, proj_inv):
+        arrs = [np.ascontiguousarray(x, dtype=np.float32) for x in (view, proj, view_inv, proj_inv)]
+        lib().oracle_set_camera(self._h, *[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+
+    def render_region(self, pc, x0=0, y0=0, x1=None, y1=None, threads=1):
+        x1 = self.width if x1 is None else x1
+        y1 = self.height if y1 is None else y1
+        lib().oracle_render_region(self._h, C.addressof(pc), x0, y0, x1, y1, threads)
+
+    def trace_rays(self, rays, any_hit=False, threads=1):
+        rays = np.ascontiguousarray(rays)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        lib().oracle_trace_rays(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, int(any_hit), threads)
+        return hits
+
+    def image(self, which=0):
+        p = lib().oracle_image(self._h, which)
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4)).copy()
+
+    def counters(self):
+        out = (C.c_uint64 * 3)()
+        lib().oracle_get_counters(self._h, out)
+        return {"extend_rays": out[0], "shadow_rays": out[1], "path_vertices": out[2]}
+
+    def reset_counters(self):
+        lib().oracle_reset_counters(self._h)
+
+    def set_guiding(self, aabbs, vmms):
+        a = np.ascontiguousarray(aabbs)
+        v = np.ascontiguousarray(vmms)
+        lib().oracle_set_guiding(self._h, a.ctypes.data, v.ctypes.data, a.shape[0])
+
+    def samples(self, dtype):
+        n = self.width * self.height * 16
+        p = lib().oracle_samples(self._h)
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    def close(self):
+        if self._h:
+            lib().oracle_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

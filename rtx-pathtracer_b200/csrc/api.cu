@@ -1,0 +1,635 @@
+// libb200pt.so — context management and the C ABI declared in include/b200pt.h.
+// There is NO CPU fallback: every compute entry point needs a CUDA device and fails loudly without one.
+#include "wavefront.cuh"
+#include "guiding_fit.cuh"
+#include "../host/scene.h"
+#include "../host/bvh.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+using namespace b200pt;
+
+static thread_local std::string g_lastError;
+static int setError(int code, const std::string &msg) { g_lastError = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return setError(B200PT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+namespace {
+template <typename T>
+struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        n = count;
+        return cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    }
+    cudaError_t upload(const T *src, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+}  // namespace
+
+struct b200pt_ctx {
+    int device = 0, width = 0, height = 0, icSize = 0, guidingSplits = 0;
+    int numPixels = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    bool hasScene = false, hasCamera = false;
+
+    // scene
+    DevBuf<float4> nodes, tris, sphereGeom, texels;
+    DevBuf<b200pt_vertex> vertices;
+    DevBuf<uint32_t> indices;
+    DevBuf<int32_t> modelVertexOffset, modelIndexOffset, randomLightIndex;
+    DevBuf<int4> primVerts;
+    DevBuf<b200pt_material> materials;
+    DevBuf<b200pt_instance> instances;
+    DevBuf<b200pt_light> lights;
+    DevBuf<b200pt_face_sample> randomTriIndex;
+    DevBuf<b200pt_sphere> spheres;
+    DevBuf<DeviceTexture> textures;
+    DeviceScene dscene{};
+    float sceneMin[3], sceneMax[3];
+    int bvhDepth = 0;
+
+    // camera
+    float view[16], proj[16], viewInv[16], projInv[16];
+
+    // images
+    DevBuf<float4> imgOutput, imgAccum, imgEstimate;
+
+    // wavefront
+    Wavefront wf{};
+    DevBuf<float4> pathRayO[2], pathRayD[2], pathHit, probeRayO, probeRayD, probeHit, probeA, probeB, shRayO, shRayD, shC, thr, pixelSum;
+    DevBuf<uint32_t> seed, state, sampleIdx, counters;
+    int queueNEE = 0;
+    uint32_t *hostCounters = nullptr;   // pinned
+
+    // guiding / IC state
+    GuidingState guiding;
+    DevBuf<b200pt_directional_data> samples;
+    DevBuf<b200pt_cache_data> icData;
+    DevBuf<b200pt_sphere> icSpheres;
+    DevBuf<b200pt_cache_header> icHeader;
+
+    // batch tracing scratch
+    DevBuf<float4> batchRays, batchHits;
+
+    b200pt_stats stats{};
+};
+
+static int ensureQueues(b200pt_ctx *c, int numNEE) {
+    if (numNEE < 1) numNEE = 1;
+    const size_t N = size_t(c->numPixels);
+    for (int i = 0; i < 2; i++) { CUDA_TRY(c->pathRayO[i].alloc(N)); CUDA_TRY(c->pathRayD[i].alloc(N)); }
+    CUDA_TRY(c->pathHit.alloc(N));
+    CUDA_TRY(c->thr.alloc(N)); CUDA_TRY(c->pixelSum.alloc(N));
+    CUDA_TRY(c->seed.alloc(N)); CUDA_TRY(c->state.alloc(N)); CUDA_TRY(c->sampleIdx.alloc(N));
+    CUDA_TRY(c->counters.alloc(CNT_NUM));
+    if (numNEE > c->queueNEE) {
+        const size_t M = N * size_t(numNEE);
+        CUDA_TRY(c->probeRayO.alloc(M)); CUDA_TRY(c->probeRayD.alloc(M)); CUDA_TRY(c->probeHit.alloc(M));
+        CUDA_TRY(c->probeA.alloc(M)); CUDA_TRY(c->probeB.alloc(M));
+        CUDA_TRY(c->shRayO.alloc(M)); CUDA_TRY(c->shRayD.alloc(M)); CUDA_TRY(c->shC.alloc(M));
+        c->queueNEE = numNEE;
+    }
+    Wavefront &w = c->wf;
+    for (int i = 0; i < 2; i++) { w.pathRayO[i] = c->pathRayO[i].p; w.pathRayD[i] = c->pathRayD[i].p; }
+    w.pathHit = c->pathHit.p;
+    w.probeRayO = c->probeRayO.p; w.probeRayD = c->probeRayD.p; w.probeHit = c->probeHit.p; w.probeA = c->probeA.p; w.probeB = c->probeB.p;
+    w.shRayO = c->shRayO.p; w.shRayD = c->shRayD.p; w.shC = c->shC.p;
+    w.seed = c->seed.p; w.thr = c->thr.p; w.state = c->state.p; w.sampleIdx = c->sampleIdx.p; w.pixelSum = c->pixelSum.p;
+    w.counters = c->counters.p;
+    return B200PT_OK;
+}
+
+extern "C" {
+
+const char *b200pt_last_error(void) { return g_lastError.c_str(); }
+
+int b200pt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200pt_create(int device_ordinal, int width, int height, int ic_size, int guiding_splits, b200pt_ctx **out) {
+    if (!out || width <= 0 || height <= 0 || ic_size < 0 || guiding_splits < 0 || guiding_splits > 16)
+        return setError(B200PT_E_INVALID, "b200pt_create: bad arguments");
+    int n = b200pt_device_count();
+    if (n <= 0) return setError(B200PT_E_NODEVICE, "b200pt_create: no CUDA device visible (libb200pt has no CPU fallback)");
+    if (device_ordinal < 0 || device_ordinal >= n) return setError(B200PT_E_INVALID, "b200pt_create: device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    b200pt_ctx *c = new b200pt_ctx();
+    c->device = device_ordinal; c->width = width; c->height = height; c->icSize = ic_size; c->guidingSplits = guiding_splits;
+    c->numPixels = width * height;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->evA)); CUDA_TRY(cudaEventCreate(&c->evB));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostCounters), CNT_NUM * sizeof(uint32_t)));
+    const size_t N = size_t(c->numPixels);
+    CUDA_TRY(c->imgOutput.alloc(N)); CUDA_TRY(c->imgAccum.alloc(N)); CUDA_TRY(c->imgEstimate.alloc(N));
+    CUDA_TRY(cudaMemsetAsync(c->imgOutput.p, 0, N * sizeof(float4), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->imgAccum.p, 0, N * sizeof(float4), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->imgEstimate.p, 0, N * sizeof(float4), c->stream));
+    // IC buffers: src/IrradianceCache.cpp:46-79 (header{0,maxCaches,0}, zeroed data, zero-radius spheres)
+    CUDA_TRY(c->icData.alloc(size_t(ic_size))); CUDA_TRY(c->icSpheres.alloc(size_t(ic_size))); CUDA_TRY(c->icHeader.alloc(1));
+    if (ic_size) {
+        CUDA_TRY(cudaMemsetAsync(c->icData.p, 0, size_t(ic_size) * sizeof(b200pt_cache_data), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->icSpheres.p, 0, size_t(ic_size) * sizeof(b200pt_sphere), c->stream));
+    }
+    b200pt_cache_header hdr{0u, uint32_t(ic_size), 0u};
+    CUDA_TRY(cudaMemcpyAsync(c->icHeader.p, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->stream));
+    // DirectionalData buffer: src/SampleCollector.cpp:29-51 (zero-initialised records)
+    CUDA_TRY(c->samples.alloc(N * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL));
+    CUDA_TRY(cudaMemsetAsync(c->samples.p, 0, N * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL * sizeof(b200pt_directional_data), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return B200PT_OK;
+}
+
+int b200pt_destroy(b200pt_ctx *c) {
+    if (!c) return B200PT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->nodes.release(); c->tris.release(); c->sphereGeom.release(); c->texels.release(); c->vertices.release(); c->indices.release();
+    c->modelVertexOffset.release(); c->modelIndexOffset.release(); c->randomLightIndex.release(); c->primVerts.release();
+    c->materials.release(); c->instances.release(); c->lights.release(); c->randomTriIndex.release(); c->spheres.release(); c->textures.release();
+    c->imgOutput.release(); c->imgAccum.release(); c->imgEstimate.release();
+    for (int i = 0; i < 2; i++) { c->pathRayO[i].release(); c->pathRayD[i].release(); }
+    c->pathHit.release(); c->probeRayO.release(); c->probeRayD.release(); c->probeHit.release(); c->probeA.release(); c->probeB.release();
+    c->shRayO.release(); c->shRayD.release(); c->shC.release(); c->thr.release(); c->pixelSum.release();
+    c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release();
+    c->samples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
+    c->batchRays.release(); c->batchHits.release();
+    c->guiding.release();
+    if (c->hostCounters) cudaFreeHost(c->hostCounters);
+    if (c->evA) cudaEventDestroy(c->evA);
+    if (c->evB) cudaEventDestroy(c->evB);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B200PT_OK;
+}
+
+static float srgbToLinear(uint8_t v) {
+    float c = float(v) / 255.0f;
+    return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+}
+
+int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
+    if (!c || !s) return setError(B200PT_E_INVALID, "b200pt_set_scene: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    try {
+        // concatenate per-model buffers
+        std::vector<int32_t> vOff(std::max(1, s->num_models)), iOff(std::max(1, s->num_models));
+        std::vector<b200pt_vertex> verts; std::vector<uint32_t> inds;
+        for (int m = 0; m < s->num_models; m++) {
+            vOff[m] = int32_t(verts.size()); iOff[m] = int32_t(inds.size());
+            if (s->num_indices[m] % 3) return setError(B200PT_E_INVALID, "b200pt_set_scene: index count not a multiple of 3");
+            verts.insert(verts.end(), s->vertices[m], s->vertices[m] + s->num_vertices[m]);
+            inds.insert(inds.end(), s->indices[m], s->indices[m] + s->num_indices[m]);
+            for (int k = 0; k < s->num_indices[m]; k++)
+                if (s->indices[m][k] >= uint32_t(s->num_vertices[m])) return setError(B200PT_E_INVALID, "b200pt_set_scene: vertex index out of range");
+        }
+        // flatten instances to world-space triangles; primitive ids follow instance order
+        std::vector<float> world; std::vector<int4> primVerts;
+        for (int i = 0; i < s->num_instances; i++) {
+            const b200pt_instance &inst = s->instances[i];
+            int m = inst.modelIndex;
+            if (m < 0 || m >= s->num_models) return setError(B200PT_E_INVALID, "b200pt_set_scene: instance model index out of range");
+            int nt = s->num_indices[m] / 3;
+            for (int t = 0; t < nt; t++) {
+                int4 pv;
+                int *pvp = &pv.x;
+                for (int k = 0; k < 3; k++) {
+                    uint32_t li = s->indices[m][3 * t + k];
+                    float w[3];
+                    mat4TransformPoint(inst.transform, s->vertices[m][li].pos, w);
+                    world.insert(world.end(), w, w + 3);
+                    pvp[k] = vOff[m] + int(li);
+                }
+                pv.w = i;
+                primVerts.push_back(pv);
+            }
+        }
+        for (int i = 0; i < s->num_materials; i++)
+            if ((s->materials[i].textureIdDiffuse >= s->num_textures) || (s->materials[i].textureIdSpecular >= s->num_textures))
+                return setError(B200PT_E_INVALID, "b200pt_set_scene: texture id out of range");
+        if (s->num_textures < 1) return setError(B200PT_E_INVALID, "b200pt_set_scene: texture 0 (env map slot) is required");
+        uint32_t numTris = uint32_t(primVerts.size());
+        Bvh8 bvh;
+        buildBvh8(world.data(), numTris, bvh);
+        if (bvh.maxDepth > PT_STACK_LOCAL) return setError(B200PT_E_INVALID, "b200pt_set_scene: BVH too deep for the traversal stack");
+        c->bvhDepth = bvh.maxDepth;
+
+        cudaStream_t st = c->stream;
+        CUDA_TRY(c->nodes.upload(reinterpret_cast<const float4 *>(bvh.nodes.data()), bvh.nodes.size() * 5, st));
+        CUDA_TRY(c->tris.upload(reinterpret_cast<const float4 *>(bvh.tris.data()), bvh.tris.size() * 3, st));
+        std::vector<float4> sg(size_t(s->num_spheres));
+        for (int i = 0; i < s->num_spheres; i++) sg[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
+        CUDA_TRY(c->sphereGeom.upload(sg.data(), sg.size(), st));
+        CUDA_TRY(c->vertices.upload(verts.data(), verts.size(), st));
+        CUDA_TRY(c->indices.upload(inds.data(), inds.size(), st));
+        CUDA_TRY(c->modelVertexOffset.upload(vOff.data(), vOff.size(), st));
+        CUDA_TRY(c->modelIndexOffset.upload(iOff.data(), iOff.size(), st));
+        CUDA_TRY(c->primVerts.upload(primVerts.data(), primVerts.size(), st));
+        CUDA_TRY(c->materials.upload(s->materials, size_t(s->num_materials), st));
+        CUDA_TRY(c->instances.upload(s->instances, size_t(s->num_instances), st));
+        CUDA_TRY(c->lights.upload(s->lights, size_t(s->num_lights), st));
+        CUDA_TRY(c->randomLightIndex.upload(s->random_light_index, B200PT_SIZE_LIGHT_RANDOM, st));
+        CUDA_TRY(c->randomTriIndex.upload(s->random_tri_index, size_t(std::max(1, s->num_face_tables)) * B200PT_SIZE_TRI_RANDOM, st));
+        CUDA_TRY(c->spheres.upload(s->spheres, size_t(s->num_spheres), st));
+        // textures → linear float4 texels (R8G8B8A8_SRGB decodes to linear before filtering)
+        std::vector<float4> texels; std::vector<size_t> texOff;
+        for (int t = 0; t < s->num_textures; t++) {
+            const b200pt_texture &tx = s->textures[t];
+            if (tx.width <= 0 || tx.height <= 0 || !tx.pixels) return setError(B200PT_E_INVALID, "b200pt_set_scene: bad texture");
+            texOff.push_back(texels.size());
+            size_t np = size_t(tx.width) * tx.height;
+            if (tx.format == B200PT_TEX_RGBA32F) {
+                const float *px = static_cast<const float *>(tx.pixels);
+                for (size_t p = 0; p < np; p++) texels.push_back(make_float4(px[4 * p], px[4 * p + 1], px[4 * p + 2], px[4 * p + 3]));
+            } else {
+                const uint8_t *px = static_cast<const uint8_t *>(tx.pixels);
+                for (size_t p = 0; p < np; p++)
+                    texels.push_back(make_float4(srgbToLinear(px[4 * p]), srgbToLinear(px[4 * p + 1]), srgbToLinear(px[4 * p + 2]), float(px[4 * p + 3]) / 255.0f));
+            }
+        }
+        CUDA_TRY(c->texels.upload(texels.data(), texels.size(), st));
+        std::vector<DeviceTexture> dts(size_t(s->num_textures));
+        for (int t = 0; t < s->num_textures; t++) { dts[t].texels = c->texels.p + texOff[t]; dts[t].width = s->textures[t].width; dts[t].height = s->textures[t].height; }
+        CUDA_TRY(c->textures.upload(dts.data(), dts.size(), st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+
+        DeviceScene &d = c->dscene;
+        d.trace.nodes = c->nodes.p; d.trace.tris = c->tris.p; d.trace.spheres = c->sphereGeom.p;
+        d.trace.numTris = numTris; d.trace.numSpheres = uint32_t(s->num_spheres);
+        d.vertices = c->vertices.p; d.indices = c->indices.p; d.modelVertexOffset = c->modelVertexOffset.p; d.modelIndexOffset = c->modelIndexOffset.p;
+        d.primVerts = c->primVerts.p; d.materials = c->materials.p; d.instances = c->instances.p; d.lights = c->lights.p;
+        d.randomLightIndex = c->randomLightIndex.p; d.randomTriIndex = c->randomTriIndex.p; d.spheres = c->spheres.p; d.textures = c->textures.p;
+        d.numLights = s->num_lights; d.numFaceTables = s->num_face_tables; d.numTextures = s->num_textures; d.numInstances = s->num_instances;
+        memcpy(c->sceneMin, s->scene_min, 12); memcpy(c->sceneMax, s->scene_max, 12);
+        c->hasScene = true;
+
+        // guiding regions are rebuilt from the scene AABB (RayTracingApp::sceneSwitcher, src/RayTracingApp.cpp:327-367)
+        int rc = c->guiding.init(c->guidingSplits, c->sceneMin, c->sceneMax, c->stream);
+        if (rc != B200PT_OK) return setError(rc, "b200pt_set_scene: guiding init failed: " + c->guiding.error);
+        // and the irradiance cache starts empty
+        b200pt_cache_header hdr{0u, uint32_t(c->icSize), 0u};
+        CUDA_TRY(cudaMemcpyAsync(c->icHeader.p, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } catch (const std::exception &e) {
+        return setError(B200PT_E_INVALID, std::string("b200pt_set_scene: ") + e.what());
+    }
+    return B200PT_OK;
+}
+
+int b200pt_set_camera(b200pt_ctx *c, const float view[16], const float proj[16]) {
+    if (!c || !view || !proj) return setError(B200PT_E_INVALID, "b200pt_set_camera: null argument");
+    memcpy(c->view, view, 64); memcpy(c->proj, proj, 64);
+    if (!mat4Inverse(view, c->viewInv) || !mat4Inverse(proj, c->projInv)) return setError(B200PT_E_INVALID, "b200pt_set_camera: singular matrix");
+    c->hasCamera = true;
+    return B200PT_OK;
+}
+
+static inline unsigned gridFor(uint64_t n, unsigned block) { return unsigned((n + block - 1) / block); }
+
+int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
+    if (!c || !pc) return setError(B200PT_E_INVALID, "b200pt_render_frame: null argument");
+    if (!c->hasScene || !c->hasCamera) return setError(B200PT_E_STATE, "b200pt_render_frame: set_scene and set_camera must be called first");
+    if (pc->useIrradianceCache || pc->useADRRS || pc->useGuiding || pc->updateGuiding || pc->splitOnFirst || pc->showIrradianceCacheOnly)
+        return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS / guiding render modes are not implemented in this build");
+    if (pc->numNEE < 1 || pc->samplesPerPixel < 1 || pc->maxDepth < 0 || pc->maxDepth > 60000)
+        return setError(B200PT_E_INVALID, "b200pt_render_frame: numNEE, samplesPerPixel must be >= 1 and maxDepth in [0, 60000]");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensureQueues(c, pc->enableNEE ? pc->numNEE : 1);
+    if (rc != B200PT_OK) return rc;
+
+    FrameParams fp;
+    fp.pc = *pc;
+    memcpy(fp.view, c->view, 64); memcpy(fp.proj, c->proj, 64); memcpy(fp.viewInv, c->viewInv, 64); memcpy(fp.projInv, c->projInv, 64);
+    fp.width = c->width; fp.height = c->height; fp.numPixels = c->numPixels;
+    fp.samplesPerPixel = pc->isIrradiancePrepareFrame ? 1 : pc->samplesPerPixel;
+
+    cudaStream_t st = c->stream;
+    const uint32_t N = uint32_t(c->numPixels);
+    CUDA_TRY(cudaEventRecord(c->evA, st));
+    k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf);
+    c->stats.kernel_launches++;
+    c->stats.samples += N;
+    uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    uint32_t nPath = N, nProbe = 0, nShadow = 0;
+    int cur = 0;
+    const uint64_t maxIter = uint64_t(fp.samplesPerPixel) * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4;
+    uint64_t iter = 0;
+    while (nPath + nProbe + nShadow > 0) {
+        if (++iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
+        if (nPath + nProbe > 0) {
+            k_extend<<<gridFor(uint64_t(nPath) + nProbe, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(
+                c->dscene.trace, c->wf.pathRayO[cur], c->wf.pathRayD[cur], c->wf.pathHit, nPath, c->wf.probeRayO, c->wf.probeRayD, c->wf.probeHit, nProbe);
+            c->stats.kernel_launches++;
+        }
+        if (nShadow > 0) {
+            k_shadow<<<gridFor(nShadow, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf.shRayO, c->wf.shRayD, c->wf.shC, c->wf.pixelSum, nShadow);
+            c->stats.kernel_launches++;
+        }
+        if (nProbe > 0) {
+            k_probe_resolve<<<gridFor(nProbe, 256), 256, 0, st>>>(fp, c->dscene, c->wf, nProbe);
+            c->stats.kernel_launches++;
+        }
+        c->stats.extend_rays += uint64_t(nPath) + nProbe;
+        c->stats.shadow_rays += nShadow;
+        c->stats.path_vertices += nPath;
+        c->stats.iterations++;
+        // reset the output counters, shade, read the new queue sizes back
+        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PATH0 + (1 - cur), 0, sizeof(uint32_t), st));
+        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PROBE, 0, 2 * sizeof(uint32_t), st));
+        if (nPath > 0) {
+            k_shade<<<gridFor(nPath, 128), 128, 0, st>>>(fp, c->dscene, c->wf, cur, nPath);
+            c->stats.kernel_launches++;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cur = 1 - cur;
+        nPath = c->hostCounters[CNT_PATH0 + cur];
+        nProbe = c->hostCounters[CNT_PROBE];
+        nShadow = c->hostCounters[CNT_SHADOW];
+        if (nPath > N || nProbe > N * uint32_t(c->queueNEE) || nShadow > N * uint32_t(c->queueNEE))
+            return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
+    }
+    k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p);
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaEventRecord(c->evB, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
+    c->stats.ms_total += ms;
+    return B200PT_OK;
+}
+
+static float4 *imagePtr(b200pt_ctx *c, int which) {
+    switch (which) {
+        case B200PT_IMAGE_OUTPUT: return c->imgOutput.p;
+        case B200PT_IMAGE_ACCUM: return c->imgAccum.p;
+        case B200PT_IMAGE_ESTIMATE: return c->imgEstimate.p;
+        default: return nullptr;
+    }
+}
+
+int b200pt_read_image(b200pt_ctx *c, int which, float *rgba) {
+    if (!c || !rgba || !imagePtr(c, which)) return setError(B200PT_E_INVALID, "b200pt_read_image: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(rgba, imagePtr(c, which), size_t(c->numPixels) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_write_image(b200pt_ctx *c, int which, const float *rgba) {
+    if (!c || !rgba || !imagePtr(c, which)) return setError(B200PT_E_INVALID, "b200pt_write_image: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(imagePtr(c, which), rgba, size_t(c->numPixels) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_read_image_device(b200pt_ctx *c, int which, void *dst) {
+    if (!c || !dst || !imagePtr(c, which)) return setError(B200PT_E_INVALID, "b200pt_read_image_device: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, imagePtr(c, which), size_t(c->numPixels) * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_write_image_device(b200pt_ctx *c, int which, const void *src) {
+    if (!c || !src || !imagePtr(c, which)) return setError(B200PT_E_INVALID, "b200pt_write_image_device: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(imagePtr(c, which), src, size_t(c->numPixels) * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_trace_rays_device(b200pt_ctx *c, const void *rays, int64_t n, void *hits, int any_hit) {
+    if (!c || (n > 0 && (!rays || !hits)) || n < 0) return setError(B200PT_E_INVALID, "b200pt_trace_rays_device: bad argument");
+    if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_trace_rays: set_scene must be called first");
+    if (n == 0) return B200PT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (any_hit) k_trace_batch<true><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
+    else k_trace_batch<false><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
+    c->stats.kernel_launches++;
+    if (any_hit) c->stats.shadow_rays += uint64_t(n); else c->stats.extend_rays += uint64_t(n);
+    CUDA_TRY(cudaGetLastError());
+    return B200PT_OK;
+}
+
+int b200pt_trace_rays(b200pt_ctx *c, const b200pt_ray *rays, int64_t n, b200pt_hit *hits, int any_hit) {
+    if (!c || (n > 0 && (!rays || !hits)) || n < 0) return setError(B200PT_E_INVALID, "b200pt_trace_rays: bad argument");
+    if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_trace_rays: set_scene must be called first");
+    if (n == 0) return B200PT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->batchRays.alloc(size_t(n) * 2)); CUDA_TRY(c->batchHits.alloc(size_t(n)));
+    CUDA_TRY(cudaMemcpyAsync(c->batchRays.p, rays, size_t(n) * sizeof(b200pt_ray), cudaMemcpyHostToDevice, c->stream));
+    int rc = b200pt_trace_rays_device(c, c->batchRays.p, n, c->batchHits.p, any_hit);
+    if (rc != B200PT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hits, c->batchHits.p, size_t(n) * sizeof(b200pt_hit), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_stats_get(b200pt_ctx *c, b200pt_stats *out) {
+    if (!c || !out) return setError(B200PT_E_INVALID, "b200pt_stats_get: null argument");
+    *out = c->stats;
+    return B200PT_OK;
+}
+int b200pt_stats_reset(b200pt_ctx *c) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_stats_reset: null argument");
+    memset(&c->stats, 0, sizeof(c->stats));
+    return B200PT_OK;
+}
+int b200pt_synchronize(b200pt_ctx *c) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_synchronize: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+// ---- guiding ---------------------------------------------------------------------------------------------------
+void b200pt_default_guiding_params(b200pt_guiding_params *p) {
+    if (!p) return;
+    p->useParallaxCompensation = 1; p->splitAndMerge = 1;
+    p->minSamplesForMerging = 8192; p->minSamplesForSplitting = 4096; p->minSamplesForPostSplitFitting = 4096;
+    p->splitMinDivergence = 0.5f; p->mergeMaxDivergence = 0.025f;
+    p->numInitialComponents = 8; p->minItr = 1; p->maxItr = 100; p->relLogLikelihoodThreshold = 0.005f;
+    p->initKappa = 5.0f; p->maxKappa = 50000.0f; p->vPrior = 0.01f; p->rPrior = 0.0f; p->rPriorWeight = 1.0f;
+}
+
+int b200pt_guiding_update(b200pt_ctx *c, const b200pt_guiding_params *params) {
+    if (!c || !params) return setError(B200PT_E_INVALID, "b200pt_guiding_update: null argument");
+    if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update: set_scene must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.update(c->samples.p, int64_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL, *params, c->stream, &c->stats);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_region_count(b200pt_ctx *c, int *count) {
+    if (!c || !count) return setError(B200PT_E_INVALID, "b200pt_guiding_region_count: null argument");
+    *count = c->guiding.regionCount;
+    return B200PT_OK;
+}
+int b200pt_guiding_get_aabbs(b200pt_ctx *c, b200pt_aabb *out, int n) {
+    if (!c || !out || n < 0 || n > c->guiding.regionCount) return setError(B200PT_E_INVALID, "b200pt_guiding_get_aabbs: bad argument");
+    memcpy(out, c->guiding.hostAabbs.data(), size_t(n) * sizeof(b200pt_aabb));
+    return B200PT_OK;
+}
+int b200pt_guiding_get_vmms(b200pt_ctx *c, b200pt_vmm_theta *out, int n) {
+    if (!c || !out || n < 0 || n > c->guiding.regionCount) return setError(B200PT_E_INVALID, "b200pt_guiding_get_vmms: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, c->guiding.vmms, size_t(n) * sizeof(b200pt_vmm_theta), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_guiding_put_vmms(b200pt_ctx *c, const b200pt_vmm_theta *in, int n) {
+    if (!c || !in || n < 0 || n > c->guiding.regionCount) return setError(B200PT_E_INVALID, "b200pt_guiding_put_vmms: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->guiding.vmms, in, size_t(n) * sizeof(b200pt_vmm_theta), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int64_t b200pt_guiding_sample_capacity(b200pt_ctx *c) { return c ? int64_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL : 0; }
+int b200pt_guiding_get_samples(b200pt_ctx *c, b200pt_directional_data *out, int64_t n) {
+    if (!c || !out || n < 0 || n > b200pt_guiding_sample_capacity(c)) return setError(B200PT_E_INVALID, "b200pt_guiding_get_samples: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, c->samples.p, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_guiding_put_samples(b200pt_ctx *c, const b200pt_directional_data *in, int64_t n) {
+    if (!c || !in || n < 0 || n > b200pt_guiding_sample_capacity(c)) return setError(B200PT_E_INVALID, "b200pt_guiding_put_samples: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->samples.p, in, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+// ---- irradiance cache parity hooks -------------------------------------------------------------------------------
+int b200pt_ic_get(b200pt_ctx *c, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n) {
+    if (!c || n < 0 || n > c->icSize) return setError(B200PT_E_INVALID, "b200pt_ic_get: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (hdr) CUDA_TRY(cudaMemcpyAsync(hdr, c->icHeader.p, sizeof(*hdr), cudaMemcpyDeviceToHost, c->stream));
+    if (data && n) CUDA_TRY(cudaMemcpyAsync(data, c->icData.p, size_t(n) * sizeof(*data), cudaMemcpyDeviceToHost, c->stream));
+    if (spheres && n) CUDA_TRY(cudaMemcpyAsync(spheres, c->icSpheres.p, size_t(n) * sizeof(*spheres), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+int b200pt_ic_put(b200pt_ctx *c, const b200pt_cache_header *hdr, const b200pt_cache_data *data, const b200pt_sphere *spheres, int n) {
+    if (!c || n < 0 || n > c->icSize) return setError(B200PT_E_INVALID, "b200pt_ic_put: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (hdr) CUDA_TRY(cudaMemcpyAsync(c->icHeader.p, hdr, sizeof(*hdr), cudaMemcpyHostToDevice, c->stream));
+    if (data && n) CUDA_TRY(cudaMemcpyAsync(c->icData.p, data, size_t(n) * sizeof(*data), cudaMemcpyHostToDevice, c->stream));
+    if (spheres && n) CUDA_TRY(cudaMemcpyAsync(c->icSpheres.p, spheres, size_t(n) * sizeof(*spheres), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+void b200pt_default_push_constants(b200pt_push_constants *pc) {   // src/RayTracingApp.h:116-165
+    if (!pc) return;
+    memset(pc, 0, sizeof(*pc));
+    pc->previousFrames = 0xFFFFFFFFu;
+    pc->maxDepth = 30; pc->maxFollowDiscrete = 3; pc->samplesPerPixel = 1; pc->enableNEE = 1; pc->numNEE = 1;
+    pc->usePowerHeuristic = 1;
+    pc->irradianceA = 0.2f; pc->irradianceUpdateProb = 0.00001f; pc->irradianceCreateProb = 0.0005f; pc->irradianceVisualizationScale = 1.0f;
+    pc->irradianceGradientsMaxLength = 5; pc->irradianceNumNEE = 1; pc->irradianceCacheMinRadius = 0.1f;
+    pc->adrrsS = 5; pc->adrrsSplit = 1; pc->guidingProb = 0.5f; pc->guidingVisuScale = 0.5f; pc->guidingVisuMax = 1.0f;
+    pc->useParallaxCompensation = 1; pc->guidingVisuPhiScale = 0.004f; pc->guidingVisuThetaScale = 0.01f;
+    pc->guidingPiPShowSpheres = 1; pc->guidingPiPSize = 0.3f;
+}
+
+struct b200pt_scene { Scene scene; };
+
+int b200pt_scene_load(const char *path, b200pt_scene **out) {
+    if (!path || !out) return setError(B200PT_E_INVALID, "b200pt_scene_load: null argument");
+    b200pt_scene *s = new b200pt_scene();
+    try { s->scene.loadFile(path); }
+    catch (const std::exception &e) { delete s; return setError(B200PT_E_IO, std::string("b200pt_scene_load: ") + e.what()); }
+    *out = s;
+    return B200PT_OK;
+}
+int b200pt_scene_free(b200pt_scene *s) { delete s; return B200PT_OK; }
+int b200pt_scene_get_desc(const b200pt_scene *s, b200pt_scene_desc *out) {
+    if (!s || !out) return setError(B200PT_E_INVALID, "b200pt_scene_get_desc: null argument");
+    s->scene.fillDesc(out);
+    return B200PT_OK;
+}
+int b200pt_scene_get_camera(const b200pt_scene *s, float origin[3], float target[3], float up[3], float *vfov) {
+    if (!s) return setError(B200PT_E_INVALID, "b200pt_scene_get_camera: null argument");
+    if (origin) memcpy(origin, s->scene.origin, 12);
+    if (target) memcpy(target, s->scene.target, 12);
+    if (up) memcpy(up, s->scene.upDir, 12);
+    if (vfov) *vfov = s->scene.vfov;
+    return B200PT_OK;
+}
+
+// CameraController::lookAt → quatLookAt(viewDirection, up) (conjugated) → getViewMatrix = translate(mat4_cast(q), -pos);
+// getProjMatrix = glm::perspective(radians(vfov), aspect, 0.1, 1000) with [1][1] *= -1   (src/CameraController.cpp:76-107).
+// The rotation is built directly as the matrix quatLookAtRH forms (no quaternion round trip).
+void b200pt_camera_matrices(const float origin[3], const float target[3], const float up[3], float vfov_deg, float aspect, float view[16], float proj[16]) {
+    float dir[3] = {target[0] - origin[0], target[1] - origin[1], target[2] - origin[2]};
+    float l = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    for (float &v : dir) v /= l;
+    float c2[3] = {-dir[0], -dir[1], -dir[2]};                               // Result[2] = -direction
+    float right[3] = {up[1] * c2[2] - c2[1] * up[2], up[2] * c2[0] - c2[2] * up[0], up[0] * c2[1] - c2[0] * up[1]};   // cross(up, Result[2])
+    float rl = 1.0f / sqrtf(fmaxf(0.00001f, right[0] * right[0] + right[1] * right[1] + right[2] * right[2]));
+    float c0[3] = {right[0] * rl, right[1] * rl, right[2] * rl};
+    float c1[3] = {c2[1] * c0[2] - c0[1] * c2[2], c2[2] * c0[0] - c0[2] * c2[0], c2[0] * c0[1] - c0[0] * c2[1]};       // cross(Result[2], Result[0])
+    // view rotation = transpose of [c0 c1 c2]; column-major storage
+    float R[16];
+    mat4Identity(R);
+    for (int a = 0; a < 3; a++) { R[a * 4 + 0] = c0[a]; R[a * 4 + 1] = c1[a]; R[a * 4 + 2] = c2[a]; }
+    for (int r = 0; r < 4; r++) R[12 + r] = R[0 + r] * -origin[0] + R[4 + r] * -origin[1] + R[8 + r] * -origin[2] + R[12 + r];
+    memcpy(view, R, 64);
+    float fovy = vfov_deg * 0.01745329251994329576923690768489f;
+    float tanHalf = tanf(fovy / 2.0f);
+    const float zn = 0.1f, zf = 1000.0f;
+    float P[16];
+    memset(P, 0, sizeof(P));
+    P[0] = 1.0f / (aspect * tanHalf);
+    P[5] = -(1.0f / tanHalf);
+    P[10] = zf / (zn - zf);              // GLM_FORCE_DEPTH_ZERO_TO_ONE (src/Model.h:13); irrelevant for ray directions
+    P[11] = -1.0f;
+    P[14] = -(zf * zn) / (zf - zn);
+    memcpy(proj, P, 64);
+}
+
+int b200pt_mat4_inverse(const float m[16], float out[16]) { return (m && out && mat4Inverse(m, out)) ? 1 : 0; }
+
+int b200pt_write_exr(const char *path, const float *rgba, int width, int height) {
+    if (!path || !rgba || width <= 0 || height <= 0) return setError(B200PT_E_INVALID, "b200pt_write_exr: bad argument");
+    try { writeExrRGB(path, rgba, width, height); }
+    catch (const std::exception &e) { return setError(B200PT_E_IO, std::string("b200pt_write_exr: ") + e.what()); }
+    return B200PT_OK;
+}
+int b200pt_read_exr(const char *path, float **rgba_out, int *width, int *height) {
+    if (!path || !rgba_out || !width || !height) return setError(B200PT_E_INVALID, "b200pt_read_exr: bad argument");
+    try {
+        std::vector<float> px;
+        readExrRGBA(path, px, *width, *height, true);
+        *rgba_out = static_cast<float *>(malloc(px.size() * sizeof(float)));
+        memcpy(*rgba_out, px.data(), px.size() * sizeof(float));
+    } catch (const std::exception &e) { return setError(B200PT_E_IO, std::string("b200pt_read_exr: ") + e.what()); }
+    return B200PT_OK;
+}
+void b200pt_free(void *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// Software ray traversal of the compressed BVH8 (host/bvh.h) — replaces the RT-core traceRayEXT calls of the
+// reference (shaders/raytrace.rgen:1011-1022 closest hit, :626-637 shadow) and the analytic sphere intersection
+// shader (shaders/raytrace.sphere.rint:11-29).
+//
+// Semantics (ours; the reference leaves them to the driver, SURVEY.md §7 "hard parts"):
+//   - triangles: Möller–Trumbore with every product/sum individually rounded (no FMA contraction) so the CPU oracle
+//     reproduces t,u,v bit for bit; a hit needs tmin < t < tmax (exclusive, Vulkan triangle rule)
+//   - spheres: both roots reported far-then-near like the .rint shader; accepted when tmin <= t <= tmax
+//   - closest hit = lexicographic minimum of (t, primitive id); primitive ids: triangles of instance 0,1,.. then spheres
+//   - node boxes are dilated on the host (Bvh8::pad) so culling can compare against the current best t exactly
+#pragma once
+#include "device_math.cuh"
+
+namespace b200pt {
+
+struct TraceScene {
+    const float4 *nodes;      // 5 float4 per Bvh8Node
+    const float4 *tris;       // 3 float4 per PackedTri
+    const float4 *spheres;    // center.xyz, radius
+    uint32_t numTris;
+    uint32_t numSpheres;
+};
+
+struct HitRec { float t; uint32_t prim; float u, v; };
+#define PT_MISS 0xFFFFFFFFu
+
+#define PT_STACK_SMEM 8       // entries per thread kept in shared memory
+#define PT_STACK_LOCAL 24     // overflow entries in local memory
+#define PT_TRACE_BLOCK 128
+
+// exact (non-contracted) Möller–Trumbore; returns true and t,u,v when the ray hits the triangle's plane inside it
+__device__ __forceinline__ bool intersectTriExact(const float4 a, const float4 b, const float4 c, const vec3 o, const vec3 d,
+                                                  float &t, float &u, float &v) {
+    // a = v0 (w = prim), b = e1, c = e2
+    const float px = __fsub_rn(__fmul_rn(d.y, c.z), __fmul_rn(d.z, c.y));
+    const float py = __fsub_rn(__fmul_rn(d.z, c.x), __fmul_rn(d.x, c.z));
+    const float pz = __fsub_rn(__fmul_rn(d.x, c.y), __fmul_rn(d.y, c.x));
+    const float det = __fadd_rn(__fadd_rn(__fmul_rn(b.x, px), __fmul_rn(b.y, py)), __fmul_rn(b.z, pz));
+    if (det == 0.0f) return false;
+    const float inv = __fdiv_rn(1.0f, det);
+    const float tx = __fsub_rn(o.x, a.x), ty = __fsub_rn(o.y, a.y), tz = __fsub_rn(o.z, a.z);
+    u = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, px), __fmul_rn(ty, py)), __fmul_rn(tz, pz)), inv);
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const float qx = __fsub_rn(__fmul_rn(ty, b.z), __fmul_rn(tz, b.y));
+    const float qy = __fsub_rn(__fmul_rn(tz, b.x), __fmul_rn(tx, b.z));
+    const float qz = __fsub_rn(__fmul_rn(tx, b.y), __fmul_rn(ty, b.x));
+    v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(d.x, qx), __fmul_rn(d.y, qy)), __fmul_rn(d.z, qz)), inv);
+    if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+    t = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.x, qx), __fmul_rn(c.y, qy)), __fmul_rn(c.z, qz)), inv);
+    return true;
+}
+
+// raytrace.sphere.rint:13-28 with individually rounded operations; returns the two roots (far first)
+__device__ __forceinline__ bool intersectSphereExact(const float4 s, const vec3 o, const vec3 d, float &t1, float &t2) {
+    const float ox = __fsub_rn(o.x, s.x), oy = __fsub_rn(o.y, s.y), oz = __fsub_rn(o.z, s.z);
+    const float dotDOC = __fadd_rn(__fadd_rn(__fmul_rn(d.x, ox), __fmul_rn(d.y, oy)), __fmul_rn(d.z, oz));
+    const float ococ = __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
+    const float rootTerm = __fadd_rn(__fsub_rn(__fmul_rn(dotDOC, dotDOC), ococ), __fmul_rn(s.w, s.w));
+    if (rootTerm < 0.0f) return false;
+    const float root = __fsqrt_rn(rootTerm);
+    t1 = __fadd_rn(-dotDOC, root);
+    t2 = __fsub_rn(-dotDOC, root);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t byteOf(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
+
+// ANY: stop at the first accepted hit.  SMEM: stack base points into shared memory with stride blockDim.x
+template <bool ANY, bool SMEM>
+__device__ __forceinline__ void traceRay(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, float tmax,
+                                         HitRec &hit, uint2 *smemStack) {
+    hit.prim = PT_MISS;
+    hit.t = tmax;
+    hit.u = 0.0f; hit.v = 0.0f;
+    float best = tmax;            // triangles need t < best  (or == best with a lower id once something was hit)
+
+    // analytic spheres first (few per scene; kept out of the BVH)
+    for (uint32_t i = 0; i < sc.numSpheres; i++) {
+        float t1, t2;
+        if (!intersectSphereExact(__ldg(&sc.spheres[i]), o, d, t1, t2)) continue;
+        // reportIntersectionEXT(t1) then (t2): each accepted if inside [tmin, current tmax]
+        const uint32_t id = sc.numTris + i;
+        if (t1 >= tmin && (t1 < best || (t1 == best && (hit.prim == PT_MISS || id < hit.prim)))) { best = t1; hit.t = t1; hit.prim = id; }
+        if (t2 >= tmin && (t2 < best || (t2 == best && (hit.prim == PT_MISS || id < hit.prim)))) { best = t2; hit.t = t2; hit.prim = id; }
+        if (ANY && hit.prim != PT_MISS) return;
+    }
+    if (sc.numTris == 0) return;
+
+    const float eps = 1e-20f;
+    const float idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+    const float idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+    const float idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    const uint32_t octInv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+    const uint32_t octInv4 = octInv * 0x01010101u;
+
+    uint2 localStack[PT_STACK_LOCAL];
+    int sp = 0;
+    uint2 cur = make_uint2(0u, 0x80000000u);   // node group: (base index, hit bits | imask)
+    const int stride = SMEM ? blockDim.x : 1;
+
+    for (;;) {
+        uint2 triGroup;
+        if (cur.y & 0xff000000u) {
+            const uint32_t hits = cur.y;
+            const int bit = 31 - __clz(hits);
+            cur.y &= ~(1u << bit);
+            if (cur.y & 0xff000000u) {   // push the rest of the group
+                if (SMEM && sp < PT_STACK_SMEM) smemStack[sp * stride] = cur;
+                else localStack[SMEM ? sp - PT_STACK_SMEM : sp] = cur;
+                sp++;
+            }
+            const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
+            const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));   // low byte of hits = imask
+            const uint32_t nodeIdx = cur.x + rel;
+
+            const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
+            const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
+            const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
+            const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
+            const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
+            const uint32_t e = __float_as_uint(n0.w);
+            const float ax = __uint_as_float((e & 0xffu) << 23) * idx;
+            const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * idy;
+            const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * idz;
+            const float ox = (n0.x - o.x) * idx, oy = (n0.y - o.y) * idy, oz = (n0.z - o.z) * idz;
+            uint32_t hitmask = 0;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+                const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
+                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+                const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+                const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+                const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
+                const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
+                const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
+                    const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
+                    const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
+                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
+                    if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
+                }
+            }
+            cur.x = __float_as_uint(n1.x);
+            cur.y = (hitmask & 0xff000000u) | (e >> 24);
+            triGroup.x = __float_as_uint(n1.y);
+            triGroup.y = hitmask & 0x00ffffffu;
+        } else {
+            triGroup = cur;
+            cur = make_uint2(0u, 0u);
+        }
+
+        while (triGroup.y) {
+            const int ti = __ffs(triGroup.y) - 1;
+            triGroup.y &= triGroup.y - 1;
+            const uint32_t base = (triGroup.x + uint32_t(ti)) * 3u;
+            const float4 a = __ldg(&sc.tris[base + 0]);
+            const float4 b = __ldg(&sc.tris[base + 1]);
+            const float4 c = __ldg(&sc.tris[base + 2]);
+            float t, u, v;
+            if (intersectTriExact(a, b, c, o, d, t, u, v)) {
+                const uint32_t id = __float_as_uint(a.w);
+                if (t > tmin && t < tmax && (t < best || (t == best && id < hit.prim))) {
+                    best = t; hit.t = t; hit.prim = id; hit.u = u; hit.v = v;
+                    if (ANY) return;
+                }
+            }
+        }
+
+        if ((cur.y & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            sp--;
+            if (SMEM && sp < PT_STACK_SMEM) cur = smemStack[sp * stride];
+            else cur = localStack[SMEM ? sp - PT_STACK_SMEM : sp];
+        }
+    }
+}
+
+}  // namespace b200pt

@@ -1,0 +1,337 @@
+// Wavefront path-tracing kernels: generate -> extend -> shade -> shadow-connect, with per-stage ray queues.
+// The reference is a per-pixel megakernel (shaders/raytrace.rgen:1623-1827); here every pixel owns ONE path at a
+// time (its samples are serialised exactly like the megakernel's spp loop, so the per-pixel RNG stream is consumed in
+// the same order — SURVEY.md Appendix A) and the bounce loop is turned inside out into queue-driven kernels.
+#pragma once
+#include "shading.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace b200pt {
+
+struct FrameParams {
+    b200pt_push_constants pc;
+    float view[16], proj[16], viewInv[16], projInv[16];   // CameraMatrices UBO, rgen:128-134
+    int width, height;
+    int numPixels;
+    int samplesPerPixel;     // pc.isIrradiancePrepareFrame ? 1 : pc.samplesPerPixel (rgen:1661)
+};
+
+// queue counters (device)
+enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_NUM = 8 };
+
+struct Wavefront {
+    float4 *pathRayO[2];     // xyz origin, w = path id bits
+    float4 *pathRayD[2];     // xyz direction
+    float4 *pathHit;         // t, prim bits, u, v — indexed like the current path queue
+    float4 *probeRayO;       // MIS probe rays (rgen:665-728): xyz origin
+    float4 *probeRayD;       // xyz direction
+    float4 *probeHit;
+    float4 *probeA;          // bsdf value (f*cos) xyz, w = pdfMat
+    float4 *probeB;          // path throughput xyz, w = pixel id bits
+    float4 *shRayO;          // shadow rays: xyz origin, w = pixel id bits
+    float4 *shRayD;          // xyz direction, w = tmax
+    float4 *shC;             // contribution to add when unoccluded
+    uint32_t *seed;          // per-pixel LCG state
+    float4 *thr;             // per-path throughput
+    uint32_t *state;         // depth (0..15) | followCount (16..23) | flags (24..)
+    uint32_t *sampleIdx;     // index of the sample the path is working on
+    float4 *pixelSum;        // sum of the frame's sample radiances per pixel
+    uint32_t *counters;      // CNT_*
+};
+
+#define ST_ADDNEXT (1u << 24)
+#define ST_FOLLOW  (1u << 25)
+
+// warp-aggregated queue append: the lanes that are converged at the call share ONE atomic and get consecutive slots
+// (keeps the queues roughly path-ordered and the counter traffic 32x lower than per-thread atomics)
+__device__ __forceinline__ uint32_t queuePush(uint32_t *counter) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    return base + g.thread_rank();
+}
+
+// rgen:1487-1494
+__device__ __forceinline__ void cameraRay(const FrameParams &fp, uint32_t &seed, int px, int py, vec3 &origin, vec3 &direction) {
+    float r1 = rndNegPos(seed), r2 = rndNegPos(seed);
+    float ux = ((float(px) + 0.5f) + r1 / 2.0f) / float(fp.width);
+    float uy = ((float(py) + 0.5f) + r2 / 2.0f) / float(fp.height);
+    float dx = ux * 2.0f - 1.0f, dy = uy * 2.0f - 1.0f;
+    origin = mat4MulPoint(fp.viewInv, V3(0.0f), 1.0f);
+    vec3 target = mat4MulPoint(fp.projInv, V3(dx, dy, 1.0f), 1.0f);
+    direction = normalize(mat4MulPoint(fp.viewInv, normalize(target), 0.0f));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generate: rgen main() :1625 (seed) and the first getCameraRay of the spp loop (:1668-1670)
+__global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.numPixels) return;
+    uint32_t seed = tea(uint32_t(p), fp.pc.randomUInt);
+    const int px = p % fp.width, py = p / fp.width;
+    vec3 o, d;
+    cameraRay(fp, seed, px, py, o, d);
+    wf.pathRayO[0][p] = make_f4(o, __int_as_float(p));
+    wf.pathRayD[0][p] = make_f4(d, 0.0f);
+    wf.seed[p] = seed;
+    wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    wf.state[p] = ST_ADDNEXT;     // depth 0, addNextDirectLights = addFirstHitLight = true (rgen:995,1676)
+    wf.sampleIdx[p] = 0;
+    wf.pixelSum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// extend: closest hit for the path queue and the MIS probe queue in one launch
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_extend(TraceScene sc, const float4 *__restrict__ rayO0, const float4 *__restrict__ rayD0,
+                                                           float4 *__restrict__ hit0, uint32_t n0, const float4 *__restrict__ rayO1,
+                                                           const float4 *__restrict__ rayD1, float4 *__restrict__ hit1, uint32_t n1) {
+    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + n1) return;
+    const bool second = i >= n0;
+    const uint32_t k = second ? i - n0 : i;
+    const float4 ro = second ? rayO1[k] : rayO0[k];
+    const float4 rd = second ? rayD1[k] : rayD0[k];
+    HitRec h;
+    traceRay<false, true>(sc, make_vec3(ro), make_vec3(rd), PT_TMIN, PT_TMAX, h, stack + threadIdx.x);
+    const float4 out = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+    if (second) hit1[k] = out; else hit0[k] = out;
+}
+
+// shadow-connect: any-hit visibility, fused with the contribution splat (rgen:622-663, shadow.rmiss)
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_shadow(TraceScene sc, const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
+                                                           const float4 *__restrict__ contrib, float4 *pixelSum, uint32_t n) {
+    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = rayO[i], rd = rayD[i];
+    HitRec h;
+    traceRay<true, true>(sc, make_vec3(ro), make_vec3(rd), PT_TMIN, rd.w, h, stack + threadIdx.x);
+    if (h.prim == PT_MISS) {
+        const float4 c = contrib[i];
+        float *dst = reinterpret_cast<float *>(&pixelSum[__float_as_int(ro.w)]);
+        atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+    }
+}
+
+// generic ray batch for the traversal-only parity hook (b200pt_trace_rays)
+template <bool ANY>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, int64_t n) {
+    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+    HitRec h;
+    traceRay<ANY, true>(sc, make_vec3(ro), make_vec3(rd), ro.w, rd.w, h, stack + threadIdx.x);
+    hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// probe resolve: the BSDF-sampled direct-light check of MIS (rgen:684-727), run on the probe hits
+__global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceScene sc, Wavefront wf, uint32_t n) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 hr = wf.probeHit[k];
+    const float4 A = wf.probeA[k], B = wf.probeB[k];
+    const vec3 bsdf = make_vec3(A), T = make_vec3(B);
+    const float pdfMat = A.w;
+    const int pix = __float_as_int(B.w);
+    const vec3 o = make_vec3(wf.probeRayO[k]), d = make_vec3(wf.probeRayD[k]);
+    HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
+    vec3 lightColor; float pdfLights;
+    if (h.prim == PT_MISS) {
+        lightColor = envColor(sc, d);
+        pdfLights = 1.0f / (2.0f * PT_PI) / float(sc.numLights);
+    } else {
+        HitInfo info;
+        computeHitInfo(sc, h, o, d, info);
+        const b200pt_material *m = &sc.materials[info.matIndex];
+        if (m->type != B200PT_MAT_LIGHT) return;
+        int iLight = info.isSphere ? sc.spheres[info.instanceIndex].iLight : sc.instances[info.instanceIndex].iLight;
+        if (iLight < 0) return;
+        lightColor = V3(m->lightColor[0], m->lightColor[1], m->lightColor[2]);
+        pdfLights = pdfLight(sc.lights[iLight], d, info.normal, info.t);
+    }
+    const float heuristic = fp.pc.usePowerHeuristic ? powerHeuristic(pdfMat, pdfLights) : balanceHeuristic(pdfMat, pdfLights);
+    if (h.prim != PT_MISS && isnan(heuristic)) return;
+    const vec3 c = T * ((bsdf * lightColor * heuristic / pdfMat) / float(fp.pc.numNEE));
+    float *dst = reinterpret_cast<float *>(&wf.pixelSum[pix]);
+    atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
+__global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur, uint32_t n) {
+    __shared__ uint2 stack[PT_STACK_SMEM * 128];
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = qi < n;
+    bool pushPath = false;
+    vec3 outO = V3(0.0f), outD = V3(0.0f);
+    int pid = 0;
+
+    if (active) {
+        const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
+        const float4 hr = wf.pathHit[qi];
+        pid = __float_as_int(ro.w);
+        vec3 origin = make_vec3(ro), direction = make_vec3(rd);
+        uint32_t seed = wf.seed[pid];
+        vec3 T = make_vec3(wf.thr[pid]);
+        uint32_t st = wf.state[pid];
+        uint32_t depth = st & 0xffffu, followCount = (st >> 16) & 0xffu;
+        bool addNext = (st & ST_ADDNEXT) != 0, follow = (st & ST_FOLLOW) != 0;
+        vec3 add = V3(0.0f);
+
+        const b200pt_push_constants &pc = fp.pc;
+        const bool useNEE = pc.enableNEE != 0;
+        const bool addDirectLights = !useNEE;
+        bool terminated = false;
+        depth++;
+
+        HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
+        if (h.prim == PT_MISS) {                       // rgen:1025-1040
+            if (addDirectLights || addNext) add += T * envColor(sc, direction);
+            terminated = true;
+        } else {
+            HitInfo info;
+            computeHitInfo(sc, h, origin, direction, info);
+            const b200pt_material mat = sc.materials[info.matIndex];
+            origin = info.worldPos;
+            const vec3 normal = info.normal;
+            const vec3 wi = -direction;
+
+            if (mat.type == B200PT_MAT_LIGHT && (addDirectLights || addNext))       // rgen:1054-1060
+                add += T * V3(mat.lightColor[0], mat.lightColor[1], mat.lightColor[2]);
+
+            if (hasDiscreteDirection(mat.type)) {      // rgen:1062-1075
+                addNext = true;
+                follow = true;
+                if (int(depth) >= pc.maxDepth) followCount++;
+            } else {
+                addNext = false;
+                follow = false;
+                if (useNEE && neeSupported(mat.type)) {   // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
+                    for (int iNee = 0; iNee < pc.numNEE; iNee++) {
+                        vec3 lightDir, lightColor; float lightDistance;
+                        const float pdfLights = sampleLights(sc, seed, pc.useVisibleSphereSampling != 0, origin, normal, lightDir, lightColor, lightDistance);
+                        const float cosThetaLight = dot(normal, lightDir);
+                        const bool traceShadow = cosThetaLight > 0 && pdfLights > 0;
+                        bool pushShadow = false, skipProbe = false;
+                        vec3 C = V3(0.0f);
+                        if (traceShadow) {
+                            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, lightDir, true);
+                            if (pc.enableMIS) {
+                                const float pdfMatL = pdfBSDF(mat, normal, wi, lightDir);
+                                const float heuristic = pc.usePowerHeuristic ? powerHeuristic(pdfLights, pdfMatL) : balanceHeuristic(pdfLights, pdfMatL);
+                                if (isnan(heuristic)) {
+                                    // rgen:653-655 returns before the BSDF probe, but only when the light is visible:
+                                    // resolve the visibility here so the RNG stream stays identical (rare)
+                                    HitRec sh;
+                                    traceRay<true, true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack + threadIdx.x);
+                                    if (sh.prim == PT_MISS) skipProbe = true;
+                                } else {
+                                    C = f * lightColor * heuristic / pdfLights;
+                                    pushShadow = true;
+                                }
+                            } else {
+                                C = f * lightColor / pdfLights;
+                                pushShadow = true;
+                            }
+                        }
+                        if (pushShadow) {
+                            const uint32_t slotS = queuePush(&wf.counters[CNT_SHADOW]);
+                            wf.shRayO[slotS] = make_f4(origin, __int_as_float(pid));
+                            wf.shRayD[slotS] = make_f4(lightDir, lightDistance * (1 - 0.0001f));
+                            wf.shC[slotS] = make_f4(T * (C / float(pc.numNEE)), 0.0f);
+                        }
+                        bool pushProbe = false;
+                        vec3 bsdfDir = V3(0.0f); float pdfMat = 0.0f;
+                        if (pc.enableMIS && !skipProbe) {         // rgen:665-728
+                            pdfMat = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, bsdfDir);
+                            pushProbe = pdfMat > 0;
+                        }
+                        if (pushProbe) {
+                            const uint32_t slotP = queuePush(&wf.counters[CNT_PROBE]);
+                            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, bsdfDir, true);
+                            wf.probeRayO[slotP] = make_f4(origin, 0.0f);
+                            wf.probeRayD[slotP] = make_f4(bsdfDir, 0.0f);
+                            wf.probeA[slotP] = make_f4(f, pdfMat);
+                            wf.probeB[slotP] = make_f4(T, __int_as_float(pid));
+                        }
+                    }
+                }
+            }
+
+            // getNewDirection (rgen:923-960, unguided branch) + throughput update (:1169-1177)
+            if (!terminated) {
+                vec3 newDirection = V3(0.0f);
+                const float pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
+                if (pdf <= 0.0f) terminated = true;
+                else {
+                    const vec3 change = evalBsdf(sc, mat, info.u, info.v, normal, wi, newDirection, info.isFrontFace) / pdf;
+                    T *= change;
+                    direction = newDirection;
+                }
+            }
+        }
+        // do { ... } while (depth <= maxDepth || (follow && followCount <= maxFollowDiscrete))   rgen:1215
+        if (!terminated && !(int(depth) <= pc.maxDepth || (follow && int(followCount) <= pc.maxFollowDiscrete))) terminated = true;
+
+        if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f || isnan(add.x + add.y + add.z)) {
+            float4 ps = wf.pixelSum[pid];
+            ps.x += add.x; ps.y += add.y; ps.z += add.z;
+            wf.pixelSum[pid] = ps;
+        }
+
+        if (terminated) {
+            // next sample of this pixel (rgen:1668-1681): same RNG stream, fresh path state
+            const uint32_t s = wf.sampleIdx[pid] + 1;
+            wf.sampleIdx[pid] = s;
+            if (int(s) < fp.samplesPerPixel) {
+                cameraRay(fp, seed, pid % fp.width, pid / fp.width, outO, outD);
+                T = V3(1.0f);
+                depth = 0; followCount = 0; addNext = true; follow = false;
+                pushPath = true;
+            }
+        } else {
+            outO = origin; outD = direction;
+            pushPath = true;
+        }
+        wf.seed[pid] = seed;
+        wf.thr[pid] = make_f4(T, 0.0f);
+        wf.state[pid] = (depth & 0xffffu) | ((followCount & 0xffu) << 16) | (addNext ? ST_ADDNEXT : 0u) | (follow ? ST_FOLLOW : 0u);
+    }
+    if (pushPath) {
+        const uint32_t slot = queuePush(&wf.counters[CNT_PATH0 + (1 - cur)]);
+        wf.pathRayO[1 - cur][slot] = make_f4(outO, __int_as_float(pid));
+        wf.pathRayD[1 - cur][slot] = make_f4(outD, 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// accumulate: result /= spp, saveEstimate, saveResult (rgen:1710-1720, 1459-1485, 1602-1605)
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams fp, const float4 *__restrict__ pixelSum, float4 *image, float4 *accum, float4 *estimate) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.numPixels) return;
+    const float4 s = pixelSum[p];
+    vec3 result = V3(s.x, s.y, s.z) / float(fp.samplesPerPixel);
+    if (fp.pc.storeEstimate) estimate[p] = make_f4(result, 1.0f);
+    if (fp.pc.visualizeMode != 0) return;   // debug views are out of scope
+    const uint32_t prev = fp.pc.previousFrames;
+    if (fp.pc.enableAverageInsteadOfMix) {
+        if (prev > 0) {
+            vec3 a = make_vec3(accum[p]) + result;
+            image[p] = make_f4(a / float(prev + 1u), 1.0f);
+            accum[p] = make_f4(a, 1.0f);
+        } else {
+            accum[p] = make_f4(result, 1.0f);
+            image[p] = make_f4(result, 1.0f);
+        }
+    } else {
+        if (prev > 0) result = mix(make_vec3(image[p]), result, 1.0f / float(prev + 1u));
+        image[p] = make_f4(result, 1.0f);
+    }
+}
+
+}  // namespace b200pt

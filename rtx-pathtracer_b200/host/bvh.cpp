@@ -1,0 +1,225 @@
+#include "bvh.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace b200pt {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
+    void grow(const float p[3]) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float halfArea() const {
+        float d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        if (d[0] < 0) return 0;
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+    }
+};
+
+struct Node2 {
+    Box box;
+    int left = -1, right = -1;   // children (inner) or -1
+    uint32_t first = 0, count = 0;
+};
+
+struct Builder {
+    const float *verts;
+    std::vector<Box> triBox;
+    std::vector<float> centroid;   // 3 per tri
+    std::vector<uint32_t> order;
+    std::vector<Node2> nodes;
+
+    int build(uint32_t first, uint32_t count) {
+        int idx = int(nodes.size());
+        nodes.emplace_back();
+        Box box, cbox;
+        box.reset(); cbox.reset();
+        for (uint32_t i = first; i < first + count; i++) { box.grow(triBox[order[i]]); cbox.grow(&centroid[3 * order[i]]); }
+        nodes[idx].box = box;
+        nodes[idx].first = first; nodes[idx].count = count;
+        if (count <= 1) return idx;
+
+        const int NB = 16;
+        float bestCost = std::numeric_limits<float>::infinity();
+        int bestAxis = -1, bestBin = -1;
+        for (int axis = 0; axis < 3; axis++) {
+            float ext = cbox.hi[axis] - cbox.lo[axis];
+            if (!(ext > 0)) continue;
+            Box bb[NB]; uint32_t bc[NB];
+            for (int b = 0; b < NB; b++) { bb[b].reset(); bc[b] = 0; }
+            float scale = NB / ext;
+            for (uint32_t i = first; i < first + count; i++) {
+                uint32_t t = order[i];
+                int b = std::min(NB - 1, std::max(0, int((centroid[3 * t + axis] - cbox.lo[axis]) * scale)));
+                bb[b].grow(triBox[t]); bc[b]++;
+            }
+            float rightArea[NB]; uint32_t rightCount[NB];
+            Box acc; acc.reset(); uint32_t n = 0;
+            for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); n += bc[b]; rightArea[b] = acc.halfArea(); rightCount[b] = n; }
+            acc.reset(); n = 0;
+            for (int b = 0; b < NB - 1; b++) {
+                acc.grow(bb[b]); n += bc[b];
+                if (n == 0 || rightCount[b + 1] == 0) continue;
+                float cost = acc.halfArea() * n + rightArea[b + 1] * rightCount[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+            }
+        }
+        // leaves hold at most 3 triangles (unary count in 3 bits of the node meta byte)
+        if (count <= 3) {
+            float leafCost = box.halfArea() * count;
+            if (bestAxis < 0 || bestCost + box.halfArea() * 0.5f >= leafCost) return idx;
+        }
+        uint32_t mid;
+        if (bestAxis >= 0) {
+            float ext = cbox.hi[bestAxis] - cbox.lo[bestAxis];
+            float scale = NB / ext;
+            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t t) {
+                int b = std::min(NB - 1, std::max(0, int((centroid[3 * t + bestAxis] - cbox.lo[bestAxis]) * scale)));
+                return b <= bestBin;
+            });
+            mid = uint32_t(it - order.begin());
+        } else {
+            mid = first + count / 2;   // all centroids coincide: split by index
+        }
+        if (mid == first || mid == first + count) mid = first + count / 2;
+        int l = build(first, mid - first);
+        int r = build(mid, first + count - mid);
+        nodes[idx].left = l; nodes[idx].right = r;
+        return idx;
+    }
+};
+
+}  // namespace
+
+void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
+    out.nodes.clear(); out.tris.clear(); out.maxDepth = 0;
+    // world-space dilation: ~100 ulp of the largest coordinate, so that float rounding in the slab test can never
+    // cull a box whose triangle the (exactly specified) triangle test would accept
+    float maxAbs = 0;
+    for (size_t i = 0; i < size_t(numTris) * 9; i++) maxAbs = std::max(maxAbs, std::fabs(verts[i]));
+    float pad = std::max(maxAbs, 1e-3f) * 1.2e-5f;
+    out.pad = pad;
+
+    Builder b;
+    b.verts = verts;
+    b.triBox.resize(numTris); b.centroid.resize(size_t(numTris) * 3); b.order.resize(numTris);
+    std::iota(b.order.begin(), b.order.end(), 0u);
+    for (uint32_t t = 0; t < numTris; t++) {
+        Box bx; bx.reset();
+        for (int k = 0; k < 3; k++) bx.grow(verts + size_t(t) * 9 + k * 3);
+        for (int a = 0; a < 3; a++) { b.centroid[3 * t + a] = 0.5f * (bx.lo[a] + bx.hi[a]); bx.lo[a] -= pad; bx.hi[a] += pad; }
+        b.triBox[t] = bx;
+    }
+    if (numTris == 0) {
+        Bvh8Node n; memset(&n, 0, sizeof(n));
+        n.e[0] = n.e[1] = n.e[2] = 1;
+        out.nodes.push_back(n);
+        return;
+    }
+    b.nodes.reserve(size_t(numTris) * 2);
+    int root2 = b.build(0, numTris);
+
+    struct Work { int node2; uint32_t node8; int depth; };
+    std::vector<Work> queue;
+    out.nodes.emplace_back();
+    queue.push_back({root2, 0, 1});
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        Work w = queue[qi];
+        out.maxDepth = std::max(out.maxDepth, w.depth);
+        const Node2 &n2 = b.nodes[w.node2];
+        // gather up to 8 children by repeatedly opening the inner child with the largest area
+        int kids[8]; int nk = 0;
+        if (n2.left < 0) kids[nk++] = w.node2;   // the whole (sub)tree is a single leaf
+        else { kids[nk++] = n2.left; kids[nk++] = n2.right; }
+        for (;;) {
+            if (nk == 8) break;
+            int best = -1; float bestArea = -1;
+            for (int k = 0; k < nk; k++) {
+                const Node2 &c = b.nodes[kids[k]];
+                if (c.left < 0) continue;
+                float a = c.box.halfArea();
+                if (a > bestArea) { bestArea = a; best = k; }
+            }
+            if (best < 0) break;
+            const Node2 &c = b.nodes[kids[best]];
+            kids[best] = c.left; kids[nk++] = c.right;
+        }
+        // slot assignment: greedy matching of children to octant directions (slot bit set = high side of the axis)
+        float nc[3];
+        for (int a = 0; a < 3; a++) nc[a] = 0.5f * (n2.box.lo[a] + n2.box.hi[a]);
+        int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false};
+        bool kidDone[8] = {false, false, false, false, false, false, false, false};
+        float cost[8][8];
+        for (int k = 0; k < nk; k++) {
+            const Box &cb = b.nodes[kids[k]].box;
+            for (int s = 0; s < 8; s++) {
+                float c = 0;
+                for (int a = 0; a < 3; a++) {
+                    float d = 0.5f * (cb.lo[a] + cb.hi[a]) - nc[a];
+                    c += ((s >> (2 - a)) & 1) ? d : -d;
+                }
+                cost[k][s] = c;
+            }
+        }
+        for (int it = 0; it < nk; it++) {
+            int bk = -1, bs = -1; float bc = -std::numeric_limits<float>::infinity();
+            for (int k = 0; k < nk; k++) if (!kidDone[k])
+                for (int s = 0; s < 8; s++) if (!slotUsed[s] && cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
+            kidDone[bk] = true; slotUsed[bs] = true; slotOf[bk] = bs;
+        }
+        int kidInSlot[8];
+        for (int s = 0; s < 8; s++) kidInSlot[s] = -1;
+        for (int k = 0; k < nk; k++) kidInSlot[slotOf[k]] = kids[k];
+
+        Bvh8Node n; memset(&n, 0, sizeof(n));
+        for (int a = 0; a < 3; a++) {
+            n.p[a] = n2.box.lo[a];
+            double ext = double(n2.box.hi[a]) - double(n2.box.lo[a]);
+            int e = (ext > 0) ? int(std::ceil(std::log2(ext / 255.0))) : -126;
+            // make sure 255 * 2^e really covers the extent (log2 rounding)
+            while (e < 127 && std::ldexp(255.0, e) < ext) e++;
+            e = std::max(-126, std::min(127, e));
+            n.e[a] = uint8_t(e + 127);
+        }
+        n.childBase = uint32_t(out.nodes.size());
+        n.triBase = uint32_t(out.tris.size());
+        uint32_t triOffset = 0;
+        for (int s = 0; s < 8; s++) {
+            int k2 = kidInSlot[s];
+            if (k2 < 0) continue;
+            const Node2 &c = b.nodes[k2];
+            for (int a = 0; a < 3; a++) {
+                double scale = std::ldexp(1.0, int(n.e[a]) - 127);
+                double lo = std::floor((double(c.box.lo[a]) - double(n.p[a])) / scale);
+                double hi = std::ceil((double(c.box.hi[a]) - double(n.p[a])) / scale);
+                n.qlo[a][s] = uint8_t(std::max(0.0, std::min(255.0, lo)));
+                n.qhi[a][s] = uint8_t(std::max(0.0, std::min(255.0, hi)));
+            }
+            if (c.left >= 0) {
+                n.imask |= uint8_t(1u << s);
+                n.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
+                out.nodes.emplace_back();
+                queue.push_back({k2, uint32_t(out.nodes.size() - 1), w.depth + 1});
+            } else {
+                uint32_t unary = c.count == 1 ? 1u : c.count == 2 ? 3u : 7u;
+                n.meta[s] = uint8_t((unary << 5) | triOffset);
+                for (uint32_t i = c.first; i < c.first + c.count; i++) {
+                    uint32_t t = b.order[i];
+                    const float *v = verts + size_t(t) * 9;
+                    PackedTri pt;
+                    for (int a = 0; a < 3; a++) { pt.v0[a] = v[a]; pt.e1[a] = v[3 + a] - v[a]; pt.e2[a] = v[6 + a] - v[a]; }
+                    pt.prim = t; pt.pad0 = 0; pt.pad1 = 0;
+                    out.tris.push_back(pt);
+                }
+                triOffset += c.count;
+            }
+        }
+        out.nodes[w.node8] = n;
+    }
+}
+
+}  // namespace b200pt

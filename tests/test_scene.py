@@ -1,0 +1,95 @@
+"""CPU: the headless scene front-end against facts about the reference's scenes recorded in SURVEY.md."""
+import numpy as np
+import pytest
+
+import helpers
+
+
+def test_cornell_dielectric_counts_and_aabb():
+    P = helpers.pt()
+    s = P.Scene(helpers.scene_path("cornell-dielectric"))
+    d = s.desc
+    assert d.num_models == 8 and d.num_instances == 8 and d.num_spheres == 0
+    # 3950 triangles without the glass shell (5 walls x 2 + ball 3936 + emitter 4) + stand-in shell 3936
+    assert s.num_triangles == 3950 + 3936
+    # materials: 4 top-level bsdfs + the emitter copy (src/SceneLoader.cpp:437-453)
+    assert d.num_materials == 5
+    assert [d.materials[i].type for i in range(5)] == [0, 0, 0, 2, 3]
+    assert d.materials[3].refractionIndex == pytest.approx(1.5) and d.materials[3].refractionIndexInv == pytest.approx(1 / 1.5)
+    assert list(d.materials[4].lightColor) == [15, 15, 15] and list(d.materials[4].diffuse) == pytest.approx([0.3, 0.3, 0.3])
+    # one area light on the emitter instance, uniform selection probability
+    assert d.num_lights == 1 and d.lights[0].type == 0 and d.lights[0].instanceIndex == 7 and d.lights[0].sampleProb == 1.0
+    assert d.instances[7].iLight == 0 and all(d.instances[i].iLight == -1 for i in range(7))
+    # emitter: two quads of 1.51779^2 each
+    assert d.lights[0].area == pytest.approx(2 * 1.51779 ** 2, rel=1e-4)
+    # scene AABB as SURVEY §8(d) config 1 states it (the stand-in shell does not enlarge x/z; ymin of the ball mesh)
+    assert list(d.scene_min)[0] == pytest.approx(-1.686433) and list(d.scene_max) == pytest.approx([1.686433, 3.386433, 1.686433])
+    assert list(d.scene_min)[2] == pytest.approx(-1.686433)
+    o, t, u, f = s.camera()
+    assert o == [0, 2, 5] and t == [0, 1.5, 0] and u == [0, 1, 0] and f == 45
+    assert d.num_textures == 1 and d.textures[0].width == 1   # 1x1 default env texture
+
+
+def test_light_tables_follow_weighted_sampler():
+    P = helpers.pt()
+    s = P.Scene(helpers.scene_path("cornell-dielectric"))
+    d = s.desc
+    rl = np.ctypeslib.as_array(d.random_light_index, shape=(P.SIZE_LIGHT_RANDOM,))
+    assert np.all(rl == 0)
+    assert d.num_face_tables == 1
+    ft = np.ctypeslib.as_array(C_cast(d.random_tri_index, P), shape=(P.SIZE_TRI_RANDOM, 3))
+    idx = ft[:, 0].view(np.int32)
+    # 4 emissive triangles (two quads), equal areas -> roughly uniform; the stream is std::mt19937(5489)
+    assert set(np.unique(idx)) == {0, 1, 2, 3}
+    counts = np.bincount(idx, minlength=4)
+    assert counts.min() > 2300 and counts.max() < 2700
+    assert np.allclose(ft[:, 1], 0.25, atol=1e-6)
+    # first draws of libstdc++'s mt19937 + uniform_real_distribution<float>: u0 = 0.8147237 -> last quarter
+    assert idx[0] == 3
+
+
+def C_cast(ptr, P):
+    import ctypes as C
+    return C.cast(ptr, C.POINTER(C.c_float))
+
+
+def test_veach_mis_scene():
+    P = helpers.pt()
+    s = P.Scene(helpers.scene_path("veachMIS"))
+    d = s.desc
+    assert d.num_spheres == 4 and d.num_instances == 5 and s.num_triangles == 12
+    assert d.num_lights == 4 and all(d.lights[i].type == 2 for i in range(4))
+    assert [round(d.spheres[i].radius, 5) for i in range(4)] == [0.1, 0.03333, 0.3, 0.9]
+    assert d.lights[3].area == pytest.approx(4 * np.pi * 0.81, rel=1e-6)
+    rough = [d.materials[i].roughness for i in range(d.num_materials) if d.materials[i].type == 6]
+    assert rough == pytest.approx([0.02, 0.06, 0.1, 0.2])
+    # OBJ files without normals get per-face normals (src/SceneLoader.cpp:299-308)
+    v = d.vertices[4][0]
+    assert np.linalg.norm(list(v.normal)) == pytest.approx(1.0, rel=1e-6)
+    rl = np.ctypeslib.as_array(d.random_light_index, shape=(P.SIZE_LIGHT_RANDOM,))
+    assert set(np.unique(rl)) == {0, 1, 2, 3}
+
+
+def test_missing_obj_is_an_error(tmp_path):
+    P = helpers.pt()
+    xml = tmp_path / "s.xml"
+    xml.write_text('<scene version="0.6.0"><bsdf type="diffuse" id="a"><rgb name="reflectance" value="0.5"/></bsdf>'
+                   '<shape type="obj"><string name="filename" value="nope.obj"/><ref id="a"/></shape></scene>')
+    with pytest.raises(P.B200ptError, match="nope.obj"):   # SceneLoader::readObjFile throws, src/SceneLoader.cpp:128-137
+        P.Scene(str(xml))
+
+
+def test_camera_matrices():
+    P = helpers.pt()
+    view, proj = P.camera_matrices([0, 2, 5], [0, 1.5, 0], [0, 1, 0], 45.0, 16 / 9)
+    V = view.reshape(4, 4).T
+    # rotation part orthonormal, camera origin maps to 0, view direction maps to -z
+    assert np.allclose(V[:3, :3] @ V[:3, :3].T, np.eye(3), atol=1e-6)
+    assert np.allclose(V @ np.array([0, 2, 5, 1]), [0, 0, 0, 1], atol=1e-5)
+    fwd = np.array([0, -0.5, -5]); fwd /= np.linalg.norm(fwd)
+    assert np.allclose(V[:3, :3] @ fwd, [0, 0, -1], atol=1e-6)
+    Pm = proj.reshape(4, 4).T
+    assert Pm[1, 1] == pytest.approx(-1 / np.tan(np.radians(45) / 2), rel=1e-6)   # proj[1][1] *= -1
+    assert Pm[0, 0] == pytest.approx(1 / (16 / 9 * np.tan(np.radians(45) / 2)), rel=1e-6)
+    inv = P.mat4_inverse(view).reshape(4, 4).T
+    assert np.allclose(inv @ V, np.eye(4), atol=1e-5)

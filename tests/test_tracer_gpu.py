@@ -1,0 +1,141 @@
+"""GPU parity tests (call through the C ABI):
+   level 1 — hit primitive ids bit-exact against the brute-force oracle on identical rays (north_star);
+   level 2 — per-pixel radiance of identical RNG streams within 1e-4 relative of the oracle's shader restatement."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+MISS = 0xFFFFFFFF
+NT = os.cpu_count() or 1
+
+
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong"])
+def test_closest_hit_bit_exact(scene_name):
+    w, h = 256, 144
+    scene, r, o = helpers.make_pair(scene_name, w, h, accel=True)
+    prim = helpers.camera_rays(scene, w, h)
+    sec = helpers.secondary_rays(o, prim)
+    for name, rays in (("primary", prim), ("secondary", sec)):
+        g = r.trace_rays(rays)
+        c = o.trace_rays(rays, threads=NT)
+        assert np.array_equal(g["prim"], c["prim"]), "%s: %d primitive ids differ" % (name, np.sum(g["prim"] != c["prim"]))
+        hit = c["prim"] != MISS
+        assert hit.mean() > 0.3
+        # t, u, v are computed with identical individually-rounded operations: bit-exact
+        for f in ("t", "u", "v"):
+            assert np.array_equal(g[f][hit].view(np.uint32), c[f][hit].view(np.uint32)), f
+
+
+def test_closest_hit_vs_pure_brute_force_subset():
+    """Same check against the O(N) brute force (no oracle BVH at all) on a subset."""
+    w, h = 96, 54
+    scene, r, o = helpers.make_pair("cornell-dielectric", w, h, accel=False)
+    prim = helpers.camera_rays(scene, w, h, seed=5)
+    rays = np.concatenate([prim[::3], helpers.secondary_rays(o, prim, seed=6)[:2500]])
+    g = r.trace_rays(rays)
+    c = o.trace_rays(rays, threads=NT)
+    assert np.array_equal(g["prim"], c["prim"])
+    hit = c["prim"] != MISS
+    assert np.array_equal(g["t"][hit], c["t"][hit])
+
+
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS"])
+def test_any_hit_matches_oracle(scene_name):
+    w, h = 256, 144
+    scene, r, o = helpers.make_pair(scene_name, w, h)
+    prim = helpers.camera_rays(scene, w, h, seed=3)
+    sh = helpers.secondary_rays(o, prim, seed=4, shadow=True)
+    g = r.trace_rays(sh, any_hit=True)
+    c = o.trace_rays(sh, any_hit=True, threads=NT)
+    assert np.array_equal(g["prim"] != MISS, c["prim"] != MISS)
+    assert 0.02 < np.mean(c["prim"] != MISS) < 0.98
+
+
+def test_edge_cases_empty_and_degenerate_rays():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair("veachMIS", 16, 16)
+    assert r.trace_rays(np.zeros(0, dtype=P.RAY_DTYPE)).shape == (0,)
+    rays = np.zeros(6, dtype=P.RAY_DTYPE)
+    rays["origin"] = [[0, 2, 15]] * 6
+    rays["dir"] = [[0, 0, -1], [0, -1, 0], [1, 0, 0], [0, 0, 1], [0, -0.3, -1], [0, -0.3, -1]]
+    rays["tmin"] = 1e-3
+    rays["tmax"] = [1e6, 1e6, 1e6, 1e6, 1e6, 0.5]      # last one: interval too short to reach anything
+    rays["dir"][4:] /= np.linalg.norm(rays["dir"][4:], axis=1, keepdims=True)
+    g = r.trace_rays(rays)
+    c = o.trace_rays(rays)
+    assert np.array_equal(g["prim"], c["prim"])
+    assert g["prim"][5] == MISS
+
+
+def _render_both(scene_name, w, h, frames=1, **pc_over):
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(scene_name, w, h)
+    imgs = []
+    for f in range(frames):
+        pc = P.default_push_constants(randomUInt=P.tea(f, 0xC0FFEE), previousFrames=f, **pc_over)
+        r.render_frame(pc)
+        o.render_region(pc, threads=NT)
+    return r, o, r.read_image()[..., :3].astype(np.float64), o.image()[..., :3].astype(np.float64)
+
+
+def _assert_radiance_parity(g, c, min_frac):
+    assert np.isfinite(g).all()
+    den = np.maximum(np.abs(c), 1e-3)           # 1e-4 relative, with an absolute floor of 1e-7 for black pixels
+    rel = np.abs(g - c) / den
+    ok = (rel <= 1e-4).all(axis=-1)
+    frac = ok.mean()
+    # a handful of pixels legitimately differ: a 1-ulp difference between CUDA's and glibc's sin/cos/pow/log flips a
+    # stochastic decision (rejection loop, Fresnel coin, hit vs. miss at an edge) and the two paths then diverge.
+    assert frac >= min_frac, "only %.4f of pixels within 1e-4 (worst rel %.3g)" % (frac, rel.max())
+    # and the images agree in the mean far tighter than any visible difference
+    assert abs(g.mean() - c.mean()) <= 2e-3 * c.mean() + 1e-6
+
+
+@pytest.mark.parametrize("mode", ["nee_mis", "nee", "bsdf"])
+def test_radiance_parity_cornell(mode):
+    over = dict(nee_mis=dict(enableNEE=1, enableMIS=1), nee=dict(enableNEE=1, enableMIS=0), bsdf=dict(enableNEE=0))[mode]
+    r, o, g, c = _render_both("cornell-dielectric", 160, 90, samplesPerPixel=2, **over)
+    _assert_radiance_parity(g, c, 0.995)
+    # identical paths => identical ray counts (the shade kernel's rare in-line visibility test is not queued)
+    s, oc = r.stats(), o.counters()
+    assert abs(int(s.extend_rays) - oc["extend_rays"]) <= 2e-4 * oc["extend_rays"]
+    assert abs(int(s.shadow_rays) - oc["shadow_rays"]) <= 2e-4 * oc["shadow_rays"] + 2
+
+
+@pytest.mark.parametrize("scene_name,mode", [("veachMIS", "nee_mis"), ("veachMIS", "nee"), ("veachMIS", "bsdf"), ("miPhong", "nee_mis")])
+def test_radiance_parity_glossy(scene_name, mode):
+    over = dict(nee_mis=dict(enableNEE=1, enableMIS=1), nee=dict(enableNEE=1, enableMIS=0), bsdf=dict(enableNEE=0))[mode]
+    r, o, g, c = _render_both(scene_name, 160, 90, samplesPerPixel=2, **over)
+    _assert_radiance_parity(g, c, 0.99)
+
+
+def test_accumulation_over_frames_matches_oracle():
+    """previousFrames > 0: running mean mix(prev, x, 1/(n+1)) (rgen:1476-1483), and the sum/divide variant."""
+    r, o, g, c = _render_both("veachMIS", 96, 54, frames=3, samplesPerPixel=1, enableMIS=1)
+    _assert_radiance_parity(g, c, 0.99)
+    r, o, g, c = _render_both("veachMIS", 96, 54, frames=3, samplesPerPixel=1, enableMIS=1, enableAverageInsteadOfMix=1)
+    _assert_radiance_parity(g, c, 0.99)
+
+
+def test_numNEE_balance_heuristic_and_depth_limits():
+    r, o, g, c = _render_both("cornell-dielectric", 96, 54, samplesPerPixel=1, enableMIS=1, numNEE=3, usePowerHeuristic=0, maxDepth=4, maxFollowDiscrete=1)
+    _assert_radiance_parity(g, c, 0.99)
+
+
+def test_converges_to_reference_image():
+    """Level 3 at test scale: a 256-spp 160x90 render against the box-filtered golden (Mitsuba) image of the reference.
+    veachMIS has no missing asset; its rough-conductor plates use the reference's own (quirky) BSDF, so the tolerance is
+    loose here and the strict relMSE < 1e-3 check is oracle-vs-kernel at equal spp (test_radiance_parity_*)."""
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair("veachMIS", 160, 90)
+    for f in range(16):
+        r.render_frame(P.default_push_constants(randomUInt=P.tea(f, 1), previousFrames=f, samplesPerPixel=16, enableMIS=1))
+    img = r.read_image()[..., :3].astype(np.float64)
+    gold = np.load(os.path.join(helpers.ROOT, "tests", "golden", "veachMIS_160x90.npy")).astype(np.float64)
+    assert abs(img.mean() - gold.mean()) < 0.05 * gold.mean()
+    rel = ((img - gold) ** 2 / (gold ** 2 + 1e-2)).mean()
+    assert rel < 0.05
