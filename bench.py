@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native path-tracing core.
+
+Workload (BASELINE.json configs[1]): cornell-dielectric 1280x720, plain path tracing + NEE/MIS, power heuristic,
+maxDepth 30, 16 spp per frame (the glass shell is the documented stand-in of
+scenes/make_standins.py because the reference's shell.obj is a missing blob).  One "step" = one frame = 16 spp over the
+whole image.  Metric: Mrays/s = (closest-hit extend rays + MIS probe rays + shadow rays) per second, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun, one rank per GPU: ranks render disjoint frames (frame_seed = tea(step*N + rank, seed)),
+the accumulation image is all-reduced over NCCL inside the timed region ("weak" scaling: per-GPU work is fixed).
+--impl reference times the CPU restatement of the reference's tracer (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+WIDTH, HEIGHT, SPP = 1280, 720, 16
+SCENE = os.path.join(ROOT, "scenes", "cornell-dielectric", "cornell-dielectric.xml")
+SEED = 0xC0FFEE
+BYTES_PER_RAY = 152          # algorithmic wavefront-state bytes per extend/shadow ray
+METRIC, UNIT = "Mrays/s (extend+shadow) cornell-dielectric 1280x720 NEE+MIS", "Mrays/s"
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def push_constants(P, frame_seed, previous_frames, spp=SPP):
+    return P.default_push_constants(randomUInt=frame_seed, previousFrames=previous_frames, samplesPerPixel=spp, enableNEE=1,
+                                    enableMIS=1, usePowerHeuristic=1, numNEE=1, maxDepth=30, maxFollowDiscrete=3)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(P, width, height, spp, frames, threads):
+    """The oracle (CPU port of the reference's shader megakernel) on a bounded sample of the workload: a centred
+    width x height crop of the 1280x720 frame is not available through the camera model, so the sample is the full
+    view rendered at width x height (same scene, camera, push constants), `frames` frames of `spp` spp."""
+    O = _load("b200pt_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    scene = P.Scene(SCENE)
+    view, proj = scene.camera_matrices(WIDTH / HEIGHT)
+    o = O.TracerOracle(width, height, 0, accel=True)
+    o.set_scene(scene.desc)
+    o.set_camera(view, proj, P.mat4_inverse(view), P.mat4_inverse(proj))
+    times, rays = [], []
+    for f in range(frames):
+        o.reset_counters()
+        pc = push_constants(P, P.tea(f, SEED), 0, spp)
+        t0 = time.perf_counter()
+        o.render_region(pc, threads=threads)
+        times.append(time.perf_counter() - t0)
+        c = o.counters()
+        rays.append(c["extend_rays"] + c["shadow_rays"])
+    return times, rays
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's tracer has no CPU implementation (GLSL + RT cores), so this times the CPU port
+    (oracle/) with every host thread, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    P = _load("b200pt_binding", os.path.join(ROOT, "rtx-pathtracer_b200", "b200pt.py"))
+    threads = os.cpu_count() or 1
+    w, h, spp = 320, 180, 4
+    times, rays = cpu_oracle_run(P, w, h, spp, args.warmup + args.steps, threads)
+    t = sum(times[args.warmup:])
+    r = sum(rays[args.warmup:])
+    value = r / t / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "cornell-dielectric 1280x720 NEE+MIS 16 spp/frame (stand-in shell)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%dx%d view of the same scene/camera, %d spp per step, oracle/tracer_oracle.cpp with its own BVH" % (w, h, spp)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    P = _load("b200pt_binding", os.path.join(ROOT, "rtx-pathtracer_b200", "b200pt.py"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = P.Scene(SCENE)
+    view, proj = scene.camera_matrices(WIDTH / HEIGHT)
+    r = P.Renderer(WIDTH, HEIGHT, 0, 0, device=local_rank)
+    r.set_scene(scene)
+    r.set_camera(view, proj)
+    r.set_stage_timing(True)
+    accum = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda:%d" % local_rank)
+    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        r.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        # device-resident step: frame i of this rank; running mean over this rank's frames
+        r.render_frame(push_constants(P, P.tea(i * world + rank, SEED), i))
+
+    for i in range(args.warmup):
+        step(i)
+    if world > 1:   # warm the collective
+        r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
+        dist.all_reduce(accum)
+
+    # ---- timed region 1: `value` (inputs resident, K frames + the image reduction) --------------------------------
+    barrier()
+    r.stats_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
+    if world > 1:
+        dist.all_reduce(accum)       # sum of per-rank means; divided by world below (outside the hot path: one scale)
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.summary()
+    st = r.stats()
+    rays = int(st.extend_rays) + int(st.shadow_rays)
+    stats = {k: getattr(st, k) for k in ("extend_rays", "shadow_rays", "iterations", "kernel_launches", "launches_extend", "launches_shadow",
+                                         "launches_shade", "ms_extend", "ms_shadow", "ms_shade", "ms_total")}
+
+    # ---- timed region 2: `e2e` through the C ABI with HOST buffers (camera + push constants in, image out) ---------
+    barrier()
+    r.stats_reset()
+    t1 = time.perf_counter()
+    for i in range(args.steps):
+        r.set_camera(view, proj)                                  # host -> device: 2 x mat4 (the reference's UBO update)
+        r.render_frame(push_constants(P, P.tea(i * world + rank, SEED), i))   # 192 B of push constants
+        P._check(P.lib().b200pt_read_image(r._h, P.IMAGE_OUTPUT, host_img.data_ptr()))   # device -> pinned host, 16 B/px
+    barrier()
+    e2e_elapsed = time.perf_counter() - t1
+    st2 = r.stats()
+    e2e_rays = int(st2.extend_rays) + int(st2.shadow_rays)
+
+    # max over ranks, totals over ranks
+    if world > 1:
+        tt = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed, e2e_elapsed = float(tt[0]), float(tt[1])
+        rr = torch.tensor([rays, e2e_rays, int(st.kernel_launches)], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(rr)
+        total_rays, total_e2e_rays, launches = float(rr[0]), float(rr[1]), int(rr[2])
+    else:
+        total_rays, total_e2e_rays, launches = float(rays), float(e2e_rays), int(st.kernel_launches)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # dominant kernel = k_extend: algorithmic bytes per launch = rays per launch x 152 B; duration = CUDA events
+        ext_launches = max(1, stats["launches_extend"])
+        ext_ms = stats["ms_extend"] / ext_launches
+        ext_bytes = stats["extend_rays"] / ext_launches * BYTES_PER_RAY
+        achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        value = total_rays / elapsed / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cornell-dielectric 1280x720 NEE+MIS (power heuristic), maxDepth 30, 16 spp per step, stand-in shell.obj",
+                       "spp_per_step": SPP, "frames_per_rank": args.steps, "parallelism": "spp-sharded x%d" % world,
+                       "l2": "no flush: the wavefront queues touched per iteration (~230 MB at 921600 paths) exceed the 126 MB L2"},
+            "spp_per_s": SPP * args.steps * world / elapsed,
+            "e2e": {"value": total_e2e_rays / e2e_elapsed / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 + 192, "d2h_bytes_per_step": WIDTH * HEIGHT * 16},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_extend (BVH8 closest hit)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "152 algorithmic bytes/ray of wavefront state (SURVEY 8d); the kernel is latency/issue bound, see profiles/"},
+            "stage_ms": {"extend": stats["ms_extend"], "shadow": stats["ms_shadow"], "shade": stats["ms_shade"], "frame_total": stats["ms_total"],
+                         "wall": 1e3 * elapsed},
+            "rays": {"extend": stats["extend_rays"], "shadow": stats["shadow_rays"], "iterations": stats["iterations"]},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            w, h, spp = 320, 180, 4
+            times, crays = cpu_oracle_run(P, w, h, spp, 2, threads)
+            line["cpu_baseline"] = {"value": crays[-1] / times[-1] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%dx%d view of the same scene/camera, %d spp, 1 warm-up + 1 timed frame of oracle/tracer_oracle.cpp (own BVH)" % (w, h, spp)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

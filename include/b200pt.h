@@ -257,18 +257,21 @@ typedef struct b200pt_hit {
 } b200pt_hit;
 #define B200PT_MISS 0xFFFFFFFFu
 
-/* counters filled by the kernels since the last b200pt_stats_reset */
+/* counters since the last b200pt_stats_reset */
 typedef struct b200pt_stats {
     uint64_t extend_rays;      /* closest-hit path rays + MIS probe rays */
     uint64_t shadow_rays;      /* any-hit visibility rays */
-    uint64_t path_vertices;    /* shade invocations on a surface hit */
+    uint64_t path_vertices;    /* entries processed by the shade kernel */
     uint64_t samples;          /* camera paths started */
     uint64_t iterations;       /* wavefront iterations */
     uint64_t kernel_launches;  /* CUDA kernels launched by this library */
-    float ms_trace;            /* device time in extend + shadow kernels (CUDA events) */
-    float ms_shade;            /* device time in generate/shade/resolve/accumulate kernels */
-    float ms_total;            /* device time of render_frame calls */
-    float _pad;
+    uint64_t launches_extend;  /* launches of the closest-hit kernel */
+    uint64_t launches_shadow;  /* launches of the any-hit kernel */
+    uint64_t launches_shade;   /* launches of generate / shade / probe-resolve / accumulate */
+    float ms_extend;           /* device time in the closest-hit kernel (CUDA events; only with stage timing on) */
+    float ms_shadow;           /* device time in the any-hit kernel */
+    float ms_shade;            /* device time in generate / shade / probe-resolve / accumulate */
+    float ms_total;            /* device time of render_frame calls, first to last kernel (always measured) */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
@@ -312,6 +315,8 @@ int b200pt_trace_rays(b200pt_ctx *ctx, const b200pt_ray *rays, int64_t n, b200pt
 int b200pt_trace_rays_device(b200pt_ctx *ctx, const void *rays_device, int64_t n, void *hits_device, int any_hit);
 
 int b200pt_stats_get(b200pt_ctx *ctx, b200pt_stats *out);
+/* per-kernel CUDA-event timing of the wavefront stages (replaces the reference's std::chrono prints) */
+int b200pt_set_stage_timing(b200pt_ctx *ctx, int enabled);
 int b200pt_stats_reset(b200pt_ctx *ctx);
 int b200pt_synchronize(b200pt_ctx *ctx);
 

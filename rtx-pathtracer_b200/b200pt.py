@@ -115,8 +115,9 @@ class GuidingParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("path_vertices", C.c_uint64), ("samples", C.c_uint64),
-                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_trace", C.c_float), ("ms_shade", C.c_float),
-                ("ms_total", C.c_float), ("_pad", C.c_float)]
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("launches_extend", C.c_uint64),
+                ("launches_shadow", C.c_uint64), ("launches_shade", C.c_uint64), ("ms_extend", C.c_float), ("ms_shadow", C.c_float),
+                ("ms_shade", C.c_float), ("ms_total", C.c_float)]
 
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
@@ -139,7 +140,7 @@ assert C.sizeof(Vertex) == 48 and C.sizeof(Material) == 96 and C.sizeof(Instance
 EXPORTS = [
     "b200pt_last_error", "b200pt_device_count", "b200pt_create", "b200pt_destroy", "b200pt_set_scene", "b200pt_set_camera",
     "b200pt_render_frame", "b200pt_read_image", "b200pt_write_image", "b200pt_read_image_device", "b200pt_write_image_device",
-    "b200pt_trace_rays", "b200pt_trace_rays_device", "b200pt_stats_get", "b200pt_stats_reset", "b200pt_synchronize",
+    "b200pt_trace_rays", "b200pt_trace_rays_device", "b200pt_stats_get", "b200pt_set_stage_timing", "b200pt_stats_reset", "b200pt_synchronize",
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
     "b200pt_guiding_sample_capacity", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
@@ -176,6 +177,7 @@ def lib():
         L.b200pt_trace_rays_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.b200pt_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.b200pt_stats_reset.argtypes = [C.c_void_p]
+        L.b200pt_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
         L.b200pt_synchronize.argtypes = [C.c_void_p]
         L.b200pt_guiding_update.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_guiding_region_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
@@ -337,6 +339,9 @@ class Renderer:
         s = Stats()
         _check(lib().b200pt_stats_get(self._h, C.byref(s)))
         return s
+
+    def set_stage_timing(self, enabled):
+        _check(lib().b200pt_set_stage_timing(self._h, int(enabled)))
 
     def stats_reset(self):
         _check(lib().b200pt_stats_reset(self._h))

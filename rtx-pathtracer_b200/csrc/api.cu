@@ -90,7 +90,40 @@ struct b200pt_ctx {
     DevBuf<float4> batchRays, batchHits;
 
     b200pt_stats stats{};
+
+    // optional per-kernel timing: (kind, start event, stop event) triples resolved at the end of a frame
+    bool stageTiming = false;
+    std::vector<cudaEvent_t> eventPool;
+    size_t eventsUsed = 0;
+    struct Span { int kind; size_t a, b; };
+    std::vector<Span> spans;
+    cudaEvent_t nextEvent() {
+        if (eventsUsed == eventPool.size()) { cudaEvent_t e; cudaEventCreate(&e); eventPool.push_back(e); }
+        return eventPool[eventsUsed++];
+    }
 };
+
+enum { KIND_EXTEND = 0, KIND_SHADOW = 1, KIND_SHADE = 2 };
+struct StageTimer {   // records start/stop events around one launch when stage timing is on
+    b200pt_ctx *c; int kind; size_t a = 0;
+    StageTimer(b200pt_ctx *ctx, int k) : c(ctx), kind(k) {
+        if (c->stageTiming) { a = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); }
+    }
+    ~StageTimer() {
+        if (c->stageTiming) { size_t b = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); c->spans.push_back({kind, a, b}); }
+        c->stats.kernel_launches++;
+        if (kind == KIND_EXTEND) c->stats.launches_extend++; else if (kind == KIND_SHADOW) c->stats.launches_shadow++; else c->stats.launches_shade++;
+    }
+};
+static void resolveStageTimes(b200pt_ctx *c) {
+    for (const auto &sp : c->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->eventPool[sp.a], c->eventPool[sp.b]) != cudaSuccess) continue;
+        if (sp.kind == KIND_EXTEND) c->stats.ms_extend += ms; else if (sp.kind == KIND_SHADOW) c->stats.ms_shadow += ms; else c->stats.ms_shade += ms;
+    }
+    c->spans.clear();
+    c->eventsUsed = 0;
+}
 
 static int ensureQueues(b200pt_ctx *c, int numNEE) {
     if (numNEE < 1) numNEE = 1;
@@ -176,6 +209,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->samples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
     c->guiding.release();
+    for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
@@ -327,8 +361,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     cudaStream_t st = c->stream;
     const uint32_t N = uint32_t(c->numPixels);
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf);
-    c->stats.kernel_launches++;
+    { StageTimer t(c, KIND_SHADE); k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf); }
     c->stats.samples += N;
     uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -339,17 +372,17 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     while (nPath + nProbe + nShadow > 0) {
         if (++iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
         if (nPath + nProbe > 0) {
+            StageTimer t(c, KIND_EXTEND);
             k_extend<<<gridFor(uint64_t(nPath) + nProbe, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(
                 c->dscene.trace, c->wf.pathRayO[cur], c->wf.pathRayD[cur], c->wf.pathHit, nPath, c->wf.probeRayO, c->wf.probeRayD, c->wf.probeHit, nProbe);
-            c->stats.kernel_launches++;
         }
         if (nShadow > 0) {
+            StageTimer t(c, KIND_SHADOW);
             k_shadow<<<gridFor(nShadow, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf.shRayO, c->wf.shRayD, c->wf.shC, c->wf.pixelSum, nShadow);
-            c->stats.kernel_launches++;
         }
         if (nProbe > 0) {
+            StageTimer t(c, KIND_SHADE);
             k_probe_resolve<<<gridFor(nProbe, 256), 256, 0, st>>>(fp, c->dscene, c->wf, nProbe);
-            c->stats.kernel_launches++;
         }
         c->stats.extend_rays += uint64_t(nPath) + nProbe;
         c->stats.shadow_rays += nShadow;
@@ -357,10 +390,10 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         c->stats.iterations++;
         // reset the output counters, shade, read the new queue sizes back
         CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PATH0 + (1 - cur), 0, sizeof(uint32_t), st));
-        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PROBE, 0, 2 * sizeof(uint32_t), st));
+        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PROBE, 0, 3 * sizeof(uint32_t), st));
         if (nPath > 0) {
+            StageTimer t(c, KIND_SHADE);
             k_shade<<<gridFor(nPath, 128), 128, 0, st>>>(fp, c->dscene, c->wf, cur, nPath);
-            c->stats.kernel_launches++;
         }
         CUDA_TRY(cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -368,17 +401,18 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         nPath = c->hostCounters[CNT_PATH0 + cur];
         nProbe = c->hostCounters[CNT_PROBE];
         nShadow = c->hostCounters[CNT_SHADOW];
+        c->stats.shadow_rays += c->hostCounters[CNT_INLINE_SHADOW];   // visibility rays traced in-line by the shade kernel
         if (nPath > N || nProbe > N * uint32_t(c->queueNEE) || nShadow > N * uint32_t(c->queueNEE))
             return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
     }
-    k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p);
-    c->stats.kernel_launches++;
+    { StageTimer t(c, KIND_SHADE); k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p); }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.ms_total += ms;
+    resolveStageTimes(c);
     return B200PT_OK;
 }
 
@@ -428,7 +462,7 @@ int b200pt_trace_rays_device(b200pt_ctx *c, const void *rays, int64_t n, void *h
     if (any_hit) k_trace_batch<true><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
     else k_trace_batch<false><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
     c->stats.kernel_launches++;
-    if (any_hit) c->stats.shadow_rays += uint64_t(n); else c->stats.extend_rays += uint64_t(n);
+    if (any_hit) { c->stats.shadow_rays += uint64_t(n); c->stats.launches_shadow++; } else { c->stats.extend_rays += uint64_t(n); c->stats.launches_extend++; }
     CUDA_TRY(cudaGetLastError());
     return B200PT_OK;
 }
@@ -455,6 +489,11 @@ int b200pt_stats_get(b200pt_ctx *c, b200pt_stats *out) {
 int b200pt_stats_reset(b200pt_ctx *c) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_stats_reset: null argument");
     memset(&c->stats, 0, sizeof(c->stats));
+    return B200PT_OK;
+}
+int b200pt_set_stage_timing(b200pt_ctx *c, int enabled) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_set_stage_timing: null argument");
+    c->stageTiming = enabled != 0;
     return B200PT_OK;
 }
 int b200pt_synchronize(b200pt_ctx *c) {

@@ -18,7 +18,7 @@ struct FrameParams {
 };
 
 // queue counters (device)
-enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_NUM = 8 };
+enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_INLINE_SHADOW = 4, CNT_NUM = 8 };
 
 struct Wavefront {
     float4 *pathRayO[2];     // xyz origin, w = path id bits
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                                     // rgen:653-655 returns before the BSDF probe, but only when the light is visible:
                                     // resolve the visibility here so the RNG stream stays identical (rare)
                                     HitRec sh;
+                                    atomicAdd(&wf.counters[CNT_INLINE_SHADOW], 1u);
                                     traceRay<true, true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack + threadIdx.x);
                                     if (sh.prim == PT_MISS) skipProbe = true;
                                 } else {
