@@ -5,7 +5,7 @@ CXX       ?= g++
 PKG       := rtx-pathtracer_b200
 BUILD     := $(PKG)/_build
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall
 
 LIB       := $(PKG)/libb200pt.so

@@ -178,13 +178,18 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
+    r.timer_start()                  # CUDA event on the library's stream (the one every kernel is launched on)
     for i in range(args.steps):
         step(i)
     r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
+    dev_ms = r.timer_stop()
     if world > 1:
         dist.all_reduce(accum)       # sum of per-rank means; divided by world below (outside the hot path: one scale)
     barrier()
-    elapsed = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    # single GPU: device time between the two events; multi GPU: the collective runs on torch's stream, so the region
+    # is closed by the barrier and timed by the host clock around it (max over ranks below)
+    elapsed = dev_ms * 1e-3 if world == 1 else wall
     clocks = sampler.summary()
     st = r.stats()
     rays = int(st.extend_rays) + int(st.shadow_rays)
@@ -195,12 +200,14 @@ def main():
     barrier()
     r.stats_reset()
     t1 = time.perf_counter()
+    r.timer_start()
     for i in range(args.steps):
         r.set_camera(view, proj)                                  # host -> device: 2 x mat4 (the reference's UBO update)
         r.render_frame(push_constants(P, P.tea(i * world + rank, SEED), i))   # 192 B of push constants
         P._check(P.lib().b200pt_read_image(r._h, P.IMAGE_OUTPUT, host_img.data_ptr()))   # device -> pinned host, 16 B/px
+    e2e_dev_ms = r.timer_stop()
     barrier()
-    e2e_elapsed = time.perf_counter() - t1
+    e2e_elapsed = e2e_dev_ms * 1e-3 if world == 1 else time.perf_counter() - t1
     st2 = r.stats()
     e2e_rays = int(st2.extend_rays) + int(st2.shadow_rays)
 
@@ -223,10 +230,11 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel = k_extend: algorithmic bytes per launch = rays per launch x 152 B; duration = CUDA events
+        # dominant kernel = k_trace (persistent BVH8 traversal of the path, probe and shadow queues): algorithmic bytes
+        # per launch = rays per launch x 152 B; duration = CUDA events around every launch on the launching stream
         ext_launches = max(1, stats["launches_extend"])
         ext_ms = stats["ms_extend"] / ext_launches
-        ext_bytes = stats["extend_rays"] / ext_launches * BYTES_PER_RAY
+        ext_bytes = (stats["extend_rays"] + stats["shadow_rays"]) / ext_launches * BYTES_PER_RAY
         achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         value = total_rays / elapsed / 1e6
         line = {
@@ -240,11 +248,12 @@ def main():
             "e2e": {"value": total_e2e_rays / e2e_elapsed / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 + 192, "d2h_bytes_per_step": WIDTH * HEIGHT * 16},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_extend (BVH8 closest hit)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_trace (persistent BVH8 traversal: closest hit + any hit)", "launches": stats["launches_extend"], "avg_launch_us": 1e3 * ext_ms,
+                         "trace_Mrays_per_s": (stats["extend_rays"] + stats["shadow_rays"]) / max(stats["ms_extend"], 1e-9) / 1e3, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "note": "152 algorithmic bytes/ray of wavefront state (SURVEY 8d); the kernel is latency/issue bound, see profiles/"},
-            "stage_ms": {"extend": stats["ms_extend"], "shadow": stats["ms_shadow"], "shade": stats["ms_shade"], "frame_total": stats["ms_total"],
-                         "wall": 1e3 * elapsed},
+            "stage_ms": {"trace": stats["ms_extend"], "shade": stats["ms_shade"], "frame_total": stats["ms_total"],
+                         "device": dev_ms, "wall": 1e3 * wall},
             "rays": {"extend": stats["extend_rays"], "shadow": stats["shadow_rays"], "iterations": stats["iterations"]},
         }
         if not args.no_cpu_baseline:

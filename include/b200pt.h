@@ -319,6 +319,10 @@ int b200pt_stats_get(b200pt_ctx *ctx, b200pt_stats *out);
 int b200pt_set_stage_timing(b200pt_ctx *ctx, int enabled);
 int b200pt_stats_reset(b200pt_ctx *ctx);
 int b200pt_synchronize(b200pt_ctx *ctx);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library is launched on):
+ * start records an event, stop records a second one, waits for it and returns the device time between them */
+int b200pt_timer_start(b200pt_ctx *ctx);
+int b200pt_timer_stop(b200pt_ctx *ctx, float *ms);
 
 /* ---- guiding (PathGuiding / SampleCollector / lightpmm) ---------------------------------------- */
 

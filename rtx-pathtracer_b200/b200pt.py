@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+LIB_PATH = os.environ.get("B200PT_LIB") or os.path.join(_HERE, "libb200pt.so")   # B200PT_LIB: A/B a second build of the same library
 
 SIZE_LIGHT_RANDOM = 10000
 SIZE_TRI_RANDOM = 10000
@@ -141,6 +141,7 @@ EXPORTS = [
     "b200pt_last_error", "b200pt_device_count", "b200pt_create", "b200pt_destroy", "b200pt_set_scene", "b200pt_set_camera",
     "b200pt_render_frame", "b200pt_read_image", "b200pt_write_image", "b200pt_read_image_device", "b200pt_write_image_device",
     "b200pt_trace_rays", "b200pt_trace_rays_device", "b200pt_stats_get", "b200pt_set_stage_timing", "b200pt_stats_reset", "b200pt_synchronize",
+    "b200pt_timer_start", "b200pt_timer_stop",
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
     "b200pt_guiding_sample_capacity", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
@@ -179,6 +180,8 @@ def lib():
         L.b200pt_stats_reset.argtypes = [C.c_void_p]
         L.b200pt_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
         L.b200pt_synchronize.argtypes = [C.c_void_p]
+        L.b200pt_timer_start.argtypes = [C.c_void_p]
+        L.b200pt_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.b200pt_guiding_update.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_guiding_region_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.b200pt_guiding_get_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -334,6 +337,15 @@ class Renderer:
 
     def synchronize(self):
         _check(lib().b200pt_synchronize(self._h))
+
+    def timer_start(self):
+        _check(lib().b200pt_timer_start(self._h))
+
+    def timer_stop(self):
+        """Device milliseconds since timer_start, measured with CUDA events on the library's stream."""
+        ms = C.c_float()
+        _check(lib().b200pt_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def stats(self):
         s = Stats()

@@ -47,7 +47,7 @@ struct b200pt_ctx {
     int device = 0, width = 0, height = 0, icSize = 0, guidingSplits = 0;
     int numPixels = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evTimer0 = nullptr, evTimer1 = nullptr;
     bool hasScene = false, hasCamera = false;
 
     // scene
@@ -77,7 +77,15 @@ struct b200pt_ctx {
     DevBuf<float4> pathRayO[2], pathRayD[2], pathHit, probeRayO, probeRayD, probeHit, probeA, probeB, shRayO, shRayD, shC, thr, pixelSum;
     DevBuf<uint32_t> seed, state, sampleIdx, counters;
     int queueNEE = 0;
-    uint32_t *hostCounters = nullptr;   // pinned
+    // pinned ring of queue-counter snapshots: the host looks at iteration i-LAG while iteration i is being issued
+    enum { RING = 4, LAG = 2 };
+    uint32_t *hostCounters = nullptr;   // pinned, RING x CNT_NUM
+    unsigned long long *hostDstats = nullptr;   // pinned, DST_NUM
+    cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf<unsigned long long> dstats;
+    DevBuf<uint32_t> batchCounter;
+    int numSMs = 0, traceGrid = 0, shadeGrid = 0, resolveGrid = 0;
+    TraceTuning tune{64u, 8};
 
     // guiding / IC state
     GuidingState guiding;
@@ -132,7 +140,7 @@ static int ensureQueues(b200pt_ctx *c, int numNEE) {
     CUDA_TRY(c->pathHit.alloc(N));
     CUDA_TRY(c->thr.alloc(N)); CUDA_TRY(c->pixelSum.alloc(N));
     CUDA_TRY(c->seed.alloc(N)); CUDA_TRY(c->state.alloc(N)); CUDA_TRY(c->sampleIdx.alloc(N));
-    CUDA_TRY(c->counters.alloc(CNT_NUM));
+    CUDA_TRY(c->counters.alloc(CNT_NUM)); CUDA_TRY(c->dstats.alloc(DST_NUM));
     if (numNEE > c->queueNEE) {
         const size_t M = N * size_t(numNEE);
         CUDA_TRY(c->probeRayO.alloc(M)); CUDA_TRY(c->probeRayD.alloc(M)); CUDA_TRY(c->probeHit.alloc(M));
@@ -146,7 +154,7 @@ static int ensureQueues(b200pt_ctx *c, int numNEE) {
     w.probeRayO = c->probeRayO.p; w.probeRayD = c->probeRayD.p; w.probeHit = c->probeHit.p; w.probeA = c->probeA.p; w.probeB = c->probeB.p;
     w.shRayO = c->shRayO.p; w.shRayD = c->shRayD.p; w.shC = c->shC.p;
     w.seed = c->seed.p; w.thr = c->thr.p; w.state = c->state.p; w.sampleIdx = c->sampleIdx.p; w.pixelSum = c->pixelSum.p;
-    w.counters = c->counters.p;
+    w.counters = c->counters.p; w.dstats = c->dstats.p;
     return B200PT_OK;
 }
 
@@ -172,7 +180,25 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->numPixels = width * height;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->evA)); CUDA_TRY(cudaEventCreate(&c->evB));
-    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostCounters), CNT_NUM * sizeof(uint32_t)));
+    CUDA_TRY(cudaEventCreate(&c->evTimer0)); CUDA_TRY(cudaEventCreate(&c->evTimer1));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostCounters), b200pt_ctx::RING * CNT_NUM * sizeof(uint32_t)));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostDstats), DST_NUM * sizeof(unsigned long long)));
+    for (auto &e : c->ringEvent) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(c->batchCounter.alloc(1));
+    // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+    c->numSMs = prop.multiProcessorCount;
+    int occTrace = 0, occShade = 0, occResolve = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace, PT_TRACE_BLOCK, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
+    c->traceGrid = c->numSMs * std::max(1, occTrace);
+    c->shadeGrid = c->numSMs * std::max(1, occShade);
+    c->resolveGrid = c->numSMs * std::max(1, occResolve);
+    if (const char *e = getenv("B200PT_TRACE_CHUNK")) c->tune.chunk = uint32_t(std::max(32, atoi(e)));
+    if (const char *e = getenv("B200PT_TRACE_REFILL")) c->tune.refillMin = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("B200PT_TRACE_GRID_PER_SM")) c->traceGrid = c->numSMs * std::max(1, atoi(e));
     const size_t N = size_t(c->numPixels);
     CUDA_TRY(c->imgOutput.alloc(N)); CUDA_TRY(c->imgAccum.alloc(N)); CUDA_TRY(c->imgEstimate.alloc(N));
     CUDA_TRY(cudaMemsetAsync(c->imgOutput.p, 0, N * sizeof(float4), c->stream));
@@ -205,7 +231,9 @@ int b200pt_destroy(b200pt_ctx *c) {
     for (int i = 0; i < 2; i++) { c->pathRayO[i].release(); c->pathRayD[i].release(); }
     c->pathHit.release(); c->probeRayO.release(); c->probeRayD.release(); c->probeHit.release(); c->probeA.release(); c->probeB.release();
     c->shRayO.release(); c->shRayD.release(); c->shC.release(); c->thr.release(); c->pixelSum.release();
-    c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release();
+    c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release(); c->dstats.release(); c->batchCounter.release();
+    for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
+    if (c->hostDstats) cudaFreeHost(c->hostDstats);
     c->samples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
     c->guiding.release();
@@ -213,6 +241,8 @@ int b200pt_destroy(b200pt_ctx *c) {
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
+    if (c->evTimer0) cudaEventDestroy(c->evTimer0);
+    if (c->evTimer1) cudaEventDestroy(c->evTimer1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B200PT_OK;
@@ -365,46 +395,35 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     c->stats.samples += N;
     uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    uint32_t nPath = N, nProbe = 0, nShadow = 0;
+    CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, DST_NUM * sizeof(unsigned long long), st));
+    // Wavefront loop.  Every kernel reads its queue sizes from device memory, so iterations are issued back-to-back;
+    // the host only peeks at the counters of iteration i-LAG to learn when the queues have drained.
     int cur = 0;
-    const uint64_t maxIter = uint64_t(fp.samplesPerPixel) * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4;
-    uint64_t iter = 0;
-    while (nPath + nProbe + nShadow > 0) {
-        if (++iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
-        if (nPath + nProbe > 0) {
-            StageTimer t(c, KIND_EXTEND);
-            k_extend<<<gridFor(uint64_t(nPath) + nProbe, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(
-                c->dscene.trace, c->wf.pathRayO[cur], c->wf.pathRayD[cur], c->wf.pathHit, nPath, c->wf.probeRayO, c->wf.probeRayD, c->wf.probeHit, nProbe);
-        }
-        if (nShadow > 0) {
-            StageTimer t(c, KIND_SHADOW);
-            k_shadow<<<gridFor(nShadow, PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf.shRayO, c->wf.shRayD, c->wf.shC, c->wf.pixelSum, nShadow);
-        }
-        if (nProbe > 0) {
-            StageTimer t(c, KIND_SHADE);
-            k_probe_resolve<<<gridFor(nProbe, 256), 256, 0, st>>>(fp, c->dscene, c->wf, nProbe);
-        }
-        c->stats.extend_rays += uint64_t(nPath) + nProbe;
-        c->stats.shadow_rays += nShadow;
-        c->stats.path_vertices += nPath;
-        c->stats.iterations++;
-        // reset the output counters, shade, read the new queue sizes back
-        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PATH0 + (1 - cur), 0, sizeof(uint32_t), st));
-        CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_PROBE, 0, 3 * sizeof(uint32_t), st));
-        if (nPath > 0) {
-            StageTimer t(c, KIND_SHADE);
-            k_shade<<<gridFor(nPath, 128), 128, 0, st>>>(fp, c->dscene, c->wf, cur, nPath);
-        }
-        CUDA_TRY(cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t maxIter = uint64_t(fp.samplesPerPixel) * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
+    bool drained = false;
+    for (uint64_t iter = 0; !drained; iter++) {
+        if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
+        { StageTimer t(c, KIND_EXTEND); k_trace<<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune); }
+        if (pc->enableNEE && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
+        k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
+        c->stats.kernel_launches++;
+        { StageTimer t(c, KIND_SHADE); k_shade<<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur); }
         cur = 1 - cur;
-        nPath = c->hostCounters[CNT_PATH0 + cur];
-        nProbe = c->hostCounters[CNT_PROBE];
-        nShadow = c->hostCounters[CNT_SHADOW];
-        c->stats.shadow_rays += c->hostCounters[CNT_INLINE_SHADOW];   // visibility rays traced in-line by the shade kernel
-        if (nPath > N || nProbe > N * uint32_t(c->queueNEE) || nShadow > N * uint32_t(c->queueNEE))
-            return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
+        const int slot = int(iter % b200pt_ctx::RING);
+        CUDA_TRY(cudaMemcpyAsync(c->hostCounters + slot * CNT_NUM, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(c->ringEvent[slot], st));
+        if (iter >= b200pt_ctx::LAG) {
+            const int old = int((iter - b200pt_ctx::LAG) % b200pt_ctx::RING);
+            CUDA_TRY(cudaEventSynchronize(c->ringEvent[old]));
+            const uint32_t *hc = c->hostCounters + old * CNT_NUM;
+            // after iteration j the live path queue is PATH[(j+1)&1]; all three empty => every later iteration is a no-op
+            const int liveQ = int((iter - b200pt_ctx::LAG + 1) & 1);
+            if (hc[CNT_PATH0 + liveQ] > N || hc[CNT_PROBE] > N * uint32_t(c->queueNEE) || hc[CNT_SHADOW] > N * uint32_t(c->queueNEE))
+                return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
+            drained = hc[CNT_PATH0 + liveQ] == 0 && hc[CNT_PROBE] == 0 && hc[CNT_SHADOW] == 0;
+        }
     }
+    CUDA_TRY(cudaMemcpyAsync(c->hostDstats, c->dstats.p, DST_NUM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     { StageTimer t(c, KIND_SHADE); k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p); }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -412,6 +431,10 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.ms_total += ms;
+    c->stats.extend_rays += c->hostDstats[DST_EXTEND];
+    c->stats.shadow_rays += c->hostDstats[DST_SHADOW];
+    c->stats.path_vertices += c->hostDstats[DST_VERTICES];
+    c->stats.iterations += c->hostDstats[DST_ITERATIONS];
     resolveStageTimes(c);
     return B200PT_OK;
 }
@@ -459,8 +482,10 @@ int b200pt_trace_rays_device(b200pt_ctx *c, const void *rays, int64_t n, void *h
     if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_trace_rays: set_scene must be called first");
     if (n == 0) return B200PT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (any_hit) k_trace_batch<true><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
-    else k_trace_batch<false><<<gridFor(uint64_t(n), PT_TRACE_BLOCK), PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), n);
+    if (n > int64_t(0x7fffffff)) return setError(B200PT_E_INVALID, "b200pt_trace_rays_device: at most 2^31-1 rays per call");
+    CUDA_TRY(cudaMemsetAsync(c->batchCounter.p, 0, sizeof(uint32_t), c->stream));
+    k_trace_batch<<<c->traceGrid, PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), uint32_t(n),
+                                                                 any_hit, c->batchCounter.p, c->tune);
     c->stats.kernel_launches++;
     if (any_hit) { c->stats.shadow_rays += uint64_t(n); c->stats.launches_shadow++; } else { c->stats.extend_rays += uint64_t(n); c->stats.launches_extend++; }
     CUDA_TRY(cudaGetLastError());
@@ -494,6 +519,20 @@ int b200pt_stats_reset(b200pt_ctx *c) {
 int b200pt_set_stage_timing(b200pt_ctx *c, int enabled) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_set_stage_timing: null argument");
     c->stageTiming = enabled != 0;
+    return B200PT_OK;
+}
+int b200pt_timer_start(b200pt_ctx *c) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_timer_start: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->evTimer0, c->stream));
+    return B200PT_OK;
+}
+int b200pt_timer_stop(b200pt_ctx *c, float *ms) {
+    if (!c || !ms) return setError(B200PT_E_INVALID, "b200pt_timer_stop: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->evTimer1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->evTimer1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->evTimer0, c->evTimer1));
     return B200PT_OK;
 }
 int b200pt_synchronize(b200pt_ctx *c) {

@@ -65,119 +65,192 @@ __device__ __forceinline__ bool intersectSphereExact(const float4 s, const vec3 
 
 __device__ __forceinline__ uint32_t byteOf(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
 
-// ANY: stop at the first accepted hit.  SMEM: stack base points into shared memory with stride blockDim.x
-template <bool ANY, bool SMEM>
-__device__ __forceinline__ void traceRay(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, float tmax,
-                                         HitRec &hit, uint2 *smemStack) {
-    hit.prim = PT_MISS;
-    hit.t = tmax;
-    hit.u = 0.0f; hit.v = 0.0f;
-    float best = tmax;            // triangles need t < best  (or == best with a lower id once something was hit)
+// Traversal is written as an explicit per-lane state machine (init / step) so that the persistent trace kernel can
+// hand a lane a NEW ray as soon as its current one is finished (dynamic ray fetch), instead of idling until the slowest
+// ray of the warp is done.  One step = pop one entry: visit a BVH8 node (5 x 128-bit loads, 8 slab tests) or test one
+// group of leaf triangles (3 x 128-bit loads each).
+struct Trav {
+    vec3 o, d;
+    float idx, idy, idz;
+    float tmin, tmax, best;       // triangles need t < best  (or == best with a lower id once something was hit)
+    uint32_t octInv;
+    HitRec hit;
+    uint2 cur;                    // node group: (base index, hit bits | imask) or triangle group (base, bits)
+    int sp;
+};
 
+// returns true when the ray is already finished (no triangles, or ANY and a sphere was hit)
+__device__ __forceinline__ bool travInit(Trav &s, const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax, const bool ANY) {
+    s.o = o; s.d = d; s.tmin = tmin; s.tmax = tmax;
+    s.hit.prim = PT_MISS; s.hit.t = tmax; s.hit.u = 0.0f; s.hit.v = 0.0f;
+    s.best = tmax;
     // analytic spheres first (few per scene; kept out of the BVH)
     for (uint32_t i = 0; i < sc.numSpheres; i++) {
         float t1, t2;
         if (!intersectSphereExact(__ldg(&sc.spheres[i]), o, d, t1, t2)) continue;
         // reportIntersectionEXT(t1) then (t2): each accepted if inside [tmin, current tmax]
         const uint32_t id = sc.numTris + i;
-        if (t1 >= tmin && (t1 < best || (t1 == best && (hit.prim == PT_MISS || id < hit.prim)))) { best = t1; hit.t = t1; hit.prim = id; }
-        if (t2 >= tmin && (t2 < best || (t2 == best && (hit.prim == PT_MISS || id < hit.prim)))) { best = t2; hit.t = t2; hit.prim = id; }
-        if (ANY && hit.prim != PT_MISS) return;
+        if (t1 >= tmin && (t1 < s.best || (t1 == s.best && (s.hit.prim == PT_MISS || id < s.hit.prim)))) { s.best = t1; s.hit.t = t1; s.hit.prim = id; }
+        if (t2 >= tmin && (t2 < s.best || (t2 == s.best && (s.hit.prim == PT_MISS || id < s.hit.prim)))) { s.best = t2; s.hit.t = t2; s.hit.prim = id; }
+        if (ANY && s.hit.prim != PT_MISS) return true;
     }
-    if (sc.numTris == 0) return;
-
+    if (sc.numTris == 0) return true;
     const float eps = 1e-20f;
-    const float idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
-    const uint32_t octInv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
-    const uint32_t octInv4 = octInv * 0x01010101u;
+    s.idx = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+    s.idy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+    s.idz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    s.octInv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+    s.cur = make_uint2(0u, 0x80000000u);
+    s.sp = 0;
+    return false;
+}
 
+// one traversal step; returns true when the ray is finished.  The stack is split: the first PT_STACK_SMEM entries
+// live in shared memory (stride = blockDim.x, conflict-free), the overflow in a per-thread local array.
+__device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *smemStack, uint2 *localStack, const int stride, const bool ANY) {
+    const vec3 o = s.o, d = s.d;
+    uint2 cur = s.cur;
+    uint2 triGroup;
+    if (cur.y & 0xff000000u) {
+        const uint32_t hits = cur.y;
+        const int bit = 31 - __clz(hits);
+        cur.y &= ~(1u << bit);
+        if (cur.y & 0xff000000u) {   // push the rest of the group
+            if (s.sp < PT_STACK_SMEM) smemStack[s.sp * stride] = cur;
+            else localStack[s.sp - PT_STACK_SMEM] = cur;
+            s.sp++;
+        }
+        const uint32_t octInv = s.octInv;
+        const uint32_t octInv4 = octInv * 0x01010101u;
+        const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
+        const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));   // low byte of hits = imask
+        const uint32_t nodeIdx = cur.x + rel;
+
+        const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
+        const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
+        const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
+        const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
+        const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
+        const uint32_t e = __float_as_uint(n0.w);
+        const float ax = __uint_as_float((e & 0xffu) << 23) * s.idx;
+        const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * s.idy;
+        const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
+        const float ox = (n0.x - o.x) * s.idx, oy = (n0.y - o.y) * s.idy, oz = (n0.z - o.z) * s.idz;
+        const float best = s.best;
+        uint32_t hitmask = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+            const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+            const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
+            const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+            const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+            const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+            const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
+            const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
+            const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
+                const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
+                const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
+                const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
+                if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
+            }
+        }
+        cur.x = __float_as_uint(n1.x);
+        cur.y = (hitmask & 0xff000000u) | (e >> 24);
+        triGroup.x = __float_as_uint(n1.y);
+        triGroup.y = hitmask & 0x00ffffffu;
+    } else {
+        triGroup = cur;
+        cur = make_uint2(0u, 0u);
+    }
+
+    while (triGroup.y) {
+        const int ti = __ffs(triGroup.y) - 1;
+        triGroup.y &= triGroup.y - 1;
+        const uint32_t base = (triGroup.x + uint32_t(ti)) * 3u;
+        const float4 a = __ldg(&sc.tris[base + 0]);
+        const float4 b = __ldg(&sc.tris[base + 1]);
+        const float4 c = __ldg(&sc.tris[base + 2]);
+        float t, u, v;
+        if (intersectTriExact(a, b, c, o, d, t, u, v)) {
+            const uint32_t id = __float_as_uint(a.w);
+            if (t > s.tmin && t < s.tmax && (t < s.best || (t == s.best && id < s.hit.prim))) {
+                s.best = t; s.hit.t = t; s.hit.prim = id; s.hit.u = u; s.hit.v = v;
+                if (ANY) return true;
+            }
+        }
+    }
+
+    if ((cur.y & 0xff000000u) == 0) {
+        if (s.sp == 0) return true;
+        s.sp--;
+        if (s.sp < PT_STACK_SMEM) cur = smemStack[s.sp * stride];
+        else cur = localStack[s.sp - PT_STACK_SMEM];
+    }
+    s.cur = cur;
+    return false;
+}
+
+// whole-ray convenience wrapper (used for the rare in-line visibility rays of the shade kernel)
+template <bool ANY>
+__device__ __forceinline__ void traceRay(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                         HitRec &hit, uint2 *smemStack, const int stride) {
+    Trav s;
     uint2 localStack[PT_STACK_LOCAL];
-    int sp = 0;
-    uint2 cur = make_uint2(0u, 0x80000000u);   // node group: (base index, hit bits | imask)
-    const int stride = SMEM ? blockDim.x : 1;
+    bool done = travInit(s, sc, o, d, tmin, tmax, ANY);
+    while (!done) done = travStep(s, sc, smemStack, localStack, stride, ANY);
+    hit = s.hit;
+}
 
+// Persistent-warp ray loop with dynamic fetch.  `total` rays are numbered 0..total-1; warps take chunks of `chunk`
+// consecutive rays from the global work counter (one atomic per chunk) and hand them to lanes as lanes fall idle: a
+// lane whose ray is finished gets the warp's next ray once at least `refillMin` lanes are idle (or the whole warp is).
+// IO::load(idx, o, d, tmin, tmax, any) reads ray idx, IO::store(idx, hit, any) consumes the result; results are keyed
+// by ray index, so the output does not depend on which lane traced which ray.
+template <typename IO>
+__device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &io, const uint32_t total, uint32_t *workCounter,
+                                                const uint32_t chunk, const int refillMin, uint2 *smemStack) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int stride = blockDim.x;
+    uint2 localStack[PT_STACK_LOCAL];
+    Trav s;
+    uint32_t rayIdx = 0, wBase = 0, wEnd = 0;
+    bool active = false, any = false, exhausted = false;
     for (;;) {
-        uint2 triGroup;
-        if (cur.y & 0xff000000u) {
-            const uint32_t hits = cur.y;
-            const int bit = 31 - __clz(hits);
-            cur.y &= ~(1u << bit);
-            if (cur.y & 0xff000000u) {   // push the rest of the group
-                if (SMEM && sp < PT_STACK_SMEM) smemStack[sp * stride] = cur;
-                else localStack[SMEM ? sp - PT_STACK_SMEM : sp] = cur;
-                sp++;
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refillMin)) {
+            if (wBase >= wEnd) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(workCounter, chunk);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= total) { exhausted = true; wBase = wEnd = 0; }
+                else { wBase = b; wEnd = min(b + chunk, total); }
             }
-            const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
-            const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));   // low byte of hits = imask
-            const uint32_t nodeIdx = cur.x + rel;
-
-            const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
-            const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
-            const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
-            const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
-            const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
-            const uint32_t e = __float_as_uint(n0.w);
-            const float ax = __uint_as_float((e & 0xffu) << 23) * idx;
-            const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * idy;
-            const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * idz;
-            const float ox = (n0.x - o.x) * idx, oy = (n0.y - o.y) * idy, oz = (n0.z - o.z) * idz;
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-                const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
-                const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
-                const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
-                const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
-                const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
-                const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
-                    const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
-                    const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
-                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
-                    if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
+            if (!active) {
+                const uint32_t idx = wBase + __popc(idle & ltMask);
+                if (idx < wEnd) {
+                    vec3 o, d; float tmin, tmax;
+                    io.load(idx, o, d, tmin, tmax, any);
+                    rayIdx = idx;
+                    active = !travInit(s, sc, o, d, tmin, tmax, any);
+                    if (!active) io.store(idx, s.hit, any);
                 }
             }
-            cur.x = __float_as_uint(n1.x);
-            cur.y = (hitmask & 0xff000000u) | (e >> 24);
-            triGroup.x = __float_as_uint(n1.y);
-            triGroup.y = hitmask & 0x00ffffffu;
-        } else {
-            triGroup = cur;
-            cur = make_uint2(0u, 0u);
+            wBase = min(wEnd, wBase + uint32_t(__popc(idle)));
         }
-
-        while (triGroup.y) {
-            const int ti = __ffs(triGroup.y) - 1;
-            triGroup.y &= triGroup.y - 1;
-            const uint32_t base = (triGroup.x + uint32_t(ti)) * 3u;
-            const float4 a = __ldg(&sc.tris[base + 0]);
-            const float4 b = __ldg(&sc.tris[base + 1]);
-            const float4 c = __ldg(&sc.tris[base + 2]);
-            float t, u, v;
-            if (intersectTriExact(a, b, c, o, d, t, u, v)) {
-                const uint32_t id = __float_as_uint(a.w);
-                if (t > tmin && t < tmax && (t < best || (t == best && id < hit.prim))) {
-                    best = t; hit.t = t; hit.prim = id; hit.u = u; hit.v = v;
-                    if (ANY) return;
-                }
+        if (active) {
+            if (travStep(s, sc, smemStack, localStack, stride, any)) {
+                io.store(rayIdx, s.hit, any);
+                active = false;
             }
-        }
-
-        if ((cur.y & 0xff000000u) == 0) {
-            if (sp == 0) break;
-            sp--;
-            if (SMEM && sp < PT_STACK_SMEM) cur = smemStack[sp * stride];
-            else cur = localStack[SMEM ? sp - PT_STACK_SMEM : sp];
         }
     }
 }

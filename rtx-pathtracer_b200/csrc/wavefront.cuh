@@ -17,8 +17,14 @@ struct FrameParams {
     int samplesPerPixel;     // pc.isIrradiancePrepareFrame ? 1 : pc.samplesPerPixel (rgen:1661)
 };
 
-// queue counters (device)
-enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_INLINE_SHADOW = 4, CNT_NUM = 8 };
+// queue counters (device).  The host never needs them to size a launch: every stage kernel is persistent / grid-stride
+// and reads its own element count from here, so a frame's iterations are issued back-to-back without host round trips.
+enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_INLINE_SHADOW = 4, CNT_WORK_TRACE = 5, CNT_SHADE_N = 6,
+       CNT_NUM = 8 };
+// 64-bit statistics accumulated on the device by k_iter_prep
+enum { DST_EXTEND = 0, DST_SHADOW = 1, DST_VERTICES = 2, DST_ITERATIONS = 3, DST_NUM = 4 };
+
+struct TraceTuning { uint32_t chunk; int refillMin; };
 
 struct Wavefront {
     float4 *pathRayO[2];     // xyz origin, w = path id bits
@@ -38,6 +44,7 @@ struct Wavefront {
     uint32_t *sampleIdx;     // index of the sample the path is working on
     float4 *pixelSum;        // sum of the frame's sample radiances per pixel
     uint32_t *counters;      // CNT_*
+    unsigned long long *dstats;   // DST_*
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -83,56 +90,87 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// extend: closest hit for the path queue and the MIS probe queue in one launch
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_extend(TraceScene sc, const float4 *__restrict__ rayO0, const float4 *__restrict__ rayD0,
-                                                           float4 *__restrict__ hit0, uint32_t n0, const float4 *__restrict__ rayO1,
-                                                           const float4 *__restrict__ rayD1, float4 *__restrict__ hit1, uint32_t n1) {
-    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n0 + n1) return;
-    const bool second = i >= n0;
-    const uint32_t k = second ? i - n0 : i;
-    const float4 ro = second ? rayO1[k] : rayO0[k];
-    const float4 rd = second ? rayD1[k] : rayD0[k];
-    HitRec h;
-    traceRay<false, true>(sc, make_vec3(ro), make_vec3(rd), PT_TMIN, PT_TMAX, h, stack + threadIdx.x);
-    const float4 out = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
-    if (second) hit1[k] = out; else hit0[k] = out;
-}
-
-// shadow-connect: any-hit visibility, fused with the contribution splat (rgen:622-663, shadow.rmiss)
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_shadow(TraceScene sc, const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
-                                                           const float4 *__restrict__ contrib, float4 *pixelSum, uint32_t n) {
-    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = rayO[i], rd = rayD[i];
-    HitRec h;
-    traceRay<true, true>(sc, make_vec3(ro), make_vec3(rd), PT_TMIN, rd.w, h, stack + threadIdx.x);
-    if (h.prim == PT_MISS) {
-        const float4 c = contrib[i];
-        float *dst = reinterpret_cast<float *>(&pixelSum[__float_as_int(ro.w)]);
-        atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+// trace: ONE persistent launch per wavefront iteration traces all three ray queues — path rays and MIS probe rays
+// (closest hit, rgen:1011-1022 / :671-682) and NEE shadow rays (any hit, rgen:622-638 + shadow.rmiss) whose
+// contribution is splatted when unoccluded (rgen:657-663).  Ray index space: [path | probe | shadow].
+struct WavefrontRayIO {
+    const float4 *pathO, *pathD; float4 *pathHit;
+    const float4 *probeO, *probeD; float4 *probeHit;
+    const float4 *shO, *shD, *shC; float4 *pixelSum;
+    uint32_t nPath, nProbe;
+    __device__ __forceinline__ void load(uint32_t idx, vec3 &o, vec3 &d, float &tmin, float &tmax, bool &any) const {
+        float4 ro, rd;
+        tmin = PT_TMIN;
+        if (idx < nPath) { ro = pathO[idx]; rd = pathD[idx]; tmax = PT_TMAX; any = false; }
+        else if (idx < nPath + nProbe) { ro = probeO[idx - nPath]; rd = probeD[idx - nPath]; tmax = PT_TMAX; any = false; }
+        else { ro = shO[idx - nPath - nProbe]; rd = shD[idx - nPath - nProbe]; tmax = rd.w; any = true; }
+        o = make_vec3(ro); d = make_vec3(rd);
     }
+    __device__ __forceinline__ void store(uint32_t idx, const HitRec &h, bool any) const {
+        if (!any) {
+            const float4 out = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+            if (idx < nPath) pathHit[idx] = out; else probeHit[idx - nPath] = out;
+        } else if (h.prim == PT_MISS) {
+            const uint32_t k = idx - nPath - nProbe;
+            const float4 c = shC[k];
+            float *dst = reinterpret_cast<float *>(&pixelSum[__float_as_int(shO[k].w)]);
+            atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+        }
+    }
+};
+
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefront wf, int cur, TraceTuning tune) {
+    __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
+    WavefrontRayIO io;
+    io.nPath = wf.counters[CNT_PATH0 + cur]; io.nProbe = wf.counters[CNT_PROBE];
+    const uint32_t total = io.nPath + io.nProbe + wf.counters[CNT_SHADOW];
+    if (total == 0) return;
+    io.pathO = wf.pathRayO[cur]; io.pathD = wf.pathRayD[cur]; io.pathHit = wf.pathHit;
+    io.probeO = wf.probeRayO; io.probeD = wf.probeRayD; io.probeHit = wf.probeHit;
+    io.shO = wf.shRayO; io.shD = wf.shRayD; io.shC = wf.shC; io.pixelSum = wf.pixelSum;
+    // small queues (the tail of a frame): shrink the chunk so the rays spread over all SMs
+    const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
+    uint32_t chunk = tune.chunk;
+    while (chunk > 32 && total / chunk < warps) chunk >>= 1;
+    tracePersistent(sc, io, total, &wf.counters[CNT_WORK_TRACE], chunk, tune.refillMin, stack + threadIdx.x);
 }
 
-// generic ray batch for the traversal-only parity hook (b200pt_trace_rays)
-template <bool ANY>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, int64_t n) {
+// generic ray batch for the traversal-only parity hook (b200pt_trace_rays): same persistent loop
+struct BatchRayIO {
+    const float4 *rays; float4 *hits; bool any;
+    __device__ __forceinline__ void load(uint32_t idx, vec3 &o, vec3 &d, float &tmin, float &tmax, bool &a) const {
+        const float4 ro = rays[2 * size_t(idx)], rd = rays[2 * size_t(idx) + 1];
+        o = make_vec3(ro); d = make_vec3(rd); tmin = ro.w; tmax = rd.w; a = any;
+    }
+    __device__ __forceinline__ void store(uint32_t idx, const HitRec &h, bool) const { hits[idx] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v); }
+};
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, uint32_t n,
+                                                                int any, uint32_t *workCounter, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
-    HitRec h;
-    traceRay<ANY, true>(sc, make_vec3(ro), make_vec3(rd), ro.w, rd.w, h, stack + threadIdx.x);
-    hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+    BatchRayIO io; io.rays = rays; io.hits = hits; io.any = any != 0;
+    const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
+    uint32_t chunk = tune.chunk;
+    while (chunk > 32 && n / chunk < warps) chunk >>= 1;
+    tracePersistent(sc, io, n, workCounter, chunk, tune.refillMin, stack + threadIdx.x);
+}
+
+// between trace and shade of one iteration: fold the queue sizes into the 64-bit statistics, publish the shade count
+// and reset the counters the shade kernel is about to fill
+__global__ void k_iter_prep(Wavefront wf, int cur) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t *c = wf.counters;
+    const uint32_t nPath = c[CNT_PATH0 + cur], nProbe = c[CNT_PROBE], nShadow = c[CNT_SHADOW];
+    wf.dstats[DST_EXTEND] += (unsigned long long)nPath + nProbe;
+    wf.dstats[DST_SHADOW] += (unsigned long long)nShadow + c[CNT_INLINE_SHADOW];
+    wf.dstats[DST_VERTICES] += nPath;
+    if (nPath + nProbe + nShadow) wf.dstats[DST_ITERATIONS] += 1;
+    c[CNT_SHADE_N] = nPath;
+    c[CNT_PATH0 + (1 - cur)] = 0; c[CNT_PROBE] = 0; c[CNT_SHADOW] = 0; c[CNT_INLINE_SHADOW] = 0; c[CNT_WORK_TRACE] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // probe resolve: the BSDF-sampled direct-light check of MIS (rgen:684-727), run on the probe hits
-__global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceScene sc, Wavefront wf, uint32_t n) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+__device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const DeviceScene &sc, const Wavefront &wf, const uint32_t k) {
     const float4 hr = wf.probeHit[k];
     const float4 A = wf.probeA[k], B = wf.probeB[k];
     const vec3 bsdf = make_vec3(A), T = make_vec3(B);
@@ -160,13 +198,18 @@ __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceSce
     float *dst = reinterpret_cast<float *>(&wf.pixelSum[pix]);
     atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
 }
+__global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceScene sc, Wavefront wf) {
+    const uint32_t n = wf.counters[CNT_PROBE];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) probeResolveOne(fp, sc, wf, k);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
-__global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur, uint32_t n) {
+__global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
-    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = qi < n;
+    const uint32_t n = wf.counters[CNT_SHADE_N];
+  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+    const bool active = true;
     bool pushPath = false;
     vec3 outO = V3(0.0f), outD = V3(0.0f);
     int pid = 0;
@@ -229,7 +272,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                                     // resolve the visibility here so the RNG stream stays identical (rare)
                                     HitRec sh;
                                     atomicAdd(&wf.counters[CNT_INLINE_SHADOW], 1u);
-                                    traceRay<true, true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack + threadIdx.x);
+                                    traceRay<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack + threadIdx.x, blockDim.x);
                                     if (sh.prim == PT_MISS) skipProbe = true;
                                 } else {
                                     C = f * lightColor * heuristic / pdfLights;
@@ -308,6 +351,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
         wf.pathRayO[1 - cur][slot] = make_f4(outO, __int_as_float(pid));
         wf.pathRayD[1 - cur][slot] = make_f4(outD, 0.0f);
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
