@@ -272,6 +272,13 @@ typedef struct b200pt_stats {
     float ms_shadow;           /* device time in the any-hit kernel */
     float ms_shade;            /* device time in generate / shade / probe-resolve / accumulate */
     float ms_total;            /* device time of render_frame calls, first to last kernel (always measured) */
+    /* guiding update (b200pt_guiding_update) */
+    uint64_t guiding_samples;               /* valid DirectionalData records consumed */
+    uint64_t guiding_em_sample_iterations;  /* sum over regions of N_r x EM iterations of fit / updateFit */
+    uint64_t guiding_regions_fit;           /* non-empty regions processed */
+    uint64_t launches_guiding;              /* sort + fit kernels launched */
+    float ms_guiding_sort;                  /* device time: sort by region + preFit + SoA conversion */
+    float ms_guiding_fit;                   /* device time: per-region EM / merge / split / statistics / pack */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
@@ -358,6 +365,25 @@ int b200pt_guiding_put_vmms(b200pt_ctx *ctx, const b200pt_vmm_theta *in, int n);
 int b200pt_guiding_get_samples(b200pt_ctx *ctx, b200pt_directional_data *out, int64_t n);
 int b200pt_guiding_put_samples(b200pt_ctx *ctx, const b200pt_directional_data *in, int64_t n);
 int64_t b200pt_guiding_sample_capacity(b200pt_ctx *ctx);
+/* PathGuiding is rebuilt (regions kept, mixtures re-initialised with VMMFactory::initialize, firstFit = true) — what
+ * RayTracingApp::sceneSwitcher does by constructing a new PathGuiding (src/RayTracingApp.cpp:327-367) */
+int b200pt_guiding_reset(b200pt_ctx *ctx, const b200pt_guiding_params *params);
+/* like b200pt_guiding_update, but on `n` caller-provided records in HOST memory instead of the context's own W*H*16
+ * buffer (copied to a device staging buffer first): the reference-facing call for a host that keeps its own
+ * SampleCollector, and the e2e leg of the EM benchmark */
+int b200pt_guiding_update_host(b200pt_ctx *ctx, const b200pt_guiding_params *params, const b200pt_directional_data *samples, int64_t n);
+/* same with `n` records already resident in DEVICE memory (no copy) */
+int b200pt_guiding_update_device(b200pt_ctx *ctx, const b200pt_guiding_params *params, const void *samples_device, int64_t n);
+/* parity hooks: the sorted + pre-fitted samples of the last update (what SampleCollector::getSortedData + preFit
+ * produce; positions are the region's parallax mean) with region offsets [regions + 1]; either pointer may be NULL */
+int64_t b200pt_guiding_sorted_count(b200pt_ctx *ctx);
+int b200pt_guiding_get_sorted(b200pt_ctx *ctx, b200pt_directional_data *out, uint32_t *region_offsets);
+/* full per-region fit state: scalars5 = K, sampleWeight, numSamples, totalNumSamples, numEMIterations; per_component =
+ * 14 rows of 16: weight, kappa, r, mu x/y/z, distance, distance sumWeights, chi2 value, chi2 numSamples, cov xx/yy/xy,
+ * cov sumWeights (lightpmm PMM + PMM_ExtraData, src/PathGuiding.h:77-85) */
+int b200pt_guiding_get_state(b200pt_ctx *ctx, int region, float scalars5[5], float per_component[224]);
+/* known-answer hook: lightpmm::exp (PMM_APPROX_EXP fastexp, pmm-vcl.h:157-184) as evaluated by the device code */
+int b200pt_guiding_fastexp(b200pt_ctx *ctx, const float *in_host, float *out_host, int n);
 
 /* ---- irradiance cache parity hooks (bindings 10,12,13) ---------------------------------------- */
 int b200pt_ic_get(b200pt_ctx *ctx, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n);

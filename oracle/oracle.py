@@ -101,3 +101,110 @@ class TracerOracle:
             self.close()
         except Exception:
             pass
+
+
+# ---- guiding fit: the reference's own lightpmm / guiding headers compiled into oracle/_ref/libguiding_ref.so ----------
+REF_GUIDING_PATH = os.path.join(_HERE, "_ref", "libguiding_ref.so")
+_glib = None
+
+DIRECTIONAL_DATA_DTYPE = np.dtype([("position", "<f4", 3), ("direction", "<f4", 3), ("weight", "<f4"), ("pdf", "<f4"),
+                                   ("distance", "<f4"), ("flags", "<u4")])
+VMF_THETA_DTYPE = np.dtype([("mu", "<f4", 3), ("k", "<f4"), ("norm", "<f4"), ("eMin2K", "<f4"), ("distance", "<f4"),
+                            ("target", "<f4", 3)])
+VMM_THETA_DTYPE = np.dtype([("thetas", VMF_THETA_DTYPE, 16), ("pi", "<f4", 16), ("meanPosition", "<f4", 3),
+                            ("usedDistributions", "<i4")])
+AABB_DTYPE = np.dtype([("min", "<f4", 3), ("max", "<f4", 3)])
+STATE_FIELDS = ("weight", "kappa", "r", "mux", "muy", "muz", "distance", "distSumW", "chi", "chiN", "covxx", "covyy", "covxy", "covSumW")
+
+
+def ref_guiding_available():
+    return os.path.exists(REF_GUIDING_PATH)
+
+
+def glib():
+    """oracle/_ref/libguiding_ref.so — built by oracle/Makefile only where /root/reference exists; the prebuilt file travels."""
+    global _glib
+    if _glib is None:
+        if not os.path.exists(REF_GUIDING_PATH):
+            build()
+        if not os.path.exists(REF_GUIDING_PATH):
+            raise RuntimeError("oracle/_ref/libguiding_ref.so is missing and /root/reference is not here to build it")
+        L = C.CDLL(REF_GUIDING_PATH)
+        L.refguiding_create.restype = C.c_void_p
+        L.refguiding_create.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
+        L.refguiding_destroy.argtypes = [C.c_void_p]
+        L.refguiding_region_count.argtypes = [C.c_void_p]
+        L.refguiding_get_aabbs.argtypes = [C.c_void_p, C.c_void_p]
+        L.refguiding_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.refguiding_get_vmms.argtypes = [C.c_void_p, C.c_void_p]
+        L.refguiding_em_sample_iterations.restype = C.c_uint64
+        L.refguiding_em_sample_iterations.argtypes = [C.c_void_p]
+        L.refguiding_sorted_count.restype = C.c_int64
+        L.refguiding_sorted_count.argtypes = [C.c_void_p]
+        L.refguiding_get_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refguiding_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.refguiding_fastexp.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _glib = L
+    return _glib
+
+
+class GuidingRef:
+    """PathGuiding (region tree + per-region lightpmm mixtures) on the CPU: the reference's headers + restated glue."""
+
+    def __init__(self, splits, scene_min, scene_max, params):
+        self._params = params      # ctypes b200pt_guiding_params (same layout as include/b200pt.h)
+        mn = (C.c_float * 3)(*scene_min)
+        mx = (C.c_float * 3)(*scene_max)
+        self._h = glib().refguiding_create(splits, mn, mx, C.addressof(params))
+        self.region_count = glib().refguiding_region_count(self._h)
+
+    def aabbs(self):
+        out = np.empty(self.region_count, dtype=AABB_DTYPE)
+        glib().refguiding_get_aabbs(self._h, out.ctypes.data)
+        return out
+
+    def update(self, samples, threads=1):
+        a = np.ascontiguousarray(samples, dtype=DIRECTIONAL_DATA_DTYPE)
+        glib().refguiding_update(self._h, a.ctypes.data, a.shape[0], threads)
+
+    def vmms(self):
+        out = np.empty(self.region_count, dtype=VMM_THETA_DTYPE)
+        glib().refguiding_get_vmms(self._h, out.ctypes.data)
+        return out
+
+    def em_sample_iterations(self):
+        return int(glib().refguiding_em_sample_iterations(self._h))
+
+    def sorted_samples(self):
+        n = glib().refguiding_sorted_count(self._h)
+        out = np.empty(n, dtype=DIRECTIONAL_DATA_DTYPE)
+        off = np.empty(self.region_count + 1, dtype=np.uint32)
+        glib().refguiding_get_sorted(self._h, out.ctypes.data, off.ctypes.data)
+        return out, off
+
+    def state(self, region):
+        sc = np.empty(5, dtype=np.float32)
+        pc = np.empty((14, 16), dtype=np.float32)
+        glib().refguiding_get_state(self._h, region, sc.ctypes.data, pc.ctypes.data)
+        d = {"K": int(sc[0]), "sampleWeight": float(sc[1]), "numSamples": float(sc[2]), "totalNumSamples": int(sc[3]), "numEMIterations": int(sc[4])}
+        for i, f in enumerate(STATE_FIELDS):
+            d[f] = pc[i].copy()
+        return d
+
+    def close(self):
+        if self._h:
+            glib().refguiding_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_fastexp(x):
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(a)
+    glib().refguiding_fastexp(a.ctypes.data, out.ctypes.data, a.size)
+    return out

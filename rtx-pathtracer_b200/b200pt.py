@@ -117,7 +117,9 @@ class Stats(C.Structure):
     _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("path_vertices", C.c_uint64), ("samples", C.c_uint64),
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("launches_extend", C.c_uint64),
                 ("launches_shadow", C.c_uint64), ("launches_shade", C.c_uint64), ("ms_extend", C.c_float), ("ms_shadow", C.c_float),
-                ("ms_shade", C.c_float), ("ms_total", C.c_float)]
+                ("ms_shade", C.c_float), ("ms_total", C.c_float),
+                ("guiding_samples", C.c_uint64), ("guiding_em_sample_iterations", C.c_uint64), ("guiding_regions_fit", C.c_uint64),
+                ("launches_guiding", C.c_uint64), ("ms_guiding_sort", C.c_float), ("ms_guiding_fit", C.c_float)]
 
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
@@ -144,7 +146,8 @@ EXPORTS = [
     "b200pt_timer_start", "b200pt_timer_stop",
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
-    "b200pt_guiding_sample_capacity", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
+    "b200pt_guiding_sample_capacity", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
+    "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_free"]
 
@@ -189,6 +192,14 @@ def lib():
         L.b200pt_guiding_put_vmms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_guiding_get_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.b200pt_guiding_put_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.b200pt_guiding_reset.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
+        L.b200pt_guiding_update_host.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
+        L.b200pt_guiding_update_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
+        L.b200pt_guiding_sorted_count.restype = C.c_int64
+        L.b200pt_guiding_sorted_count.argtypes = [C.c_void_p]
+        L.b200pt_guiding_get_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200pt_guiding_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b200pt_guiding_fastexp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_ic_get.argtypes = [C.c_void_p, C.POINTER(CacheHeader), C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_ic_put.argtypes = [C.c_void_p, C.POINTER(CacheHeader), C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -394,6 +405,44 @@ class Renderer:
     def guiding_update(self, params=None):
         params = params or default_guiding_params()
         _check(lib().b200pt_guiding_update(self._h, C.byref(params)))
+
+    def guiding_reset(self, params=None):
+        params = params or default_guiding_params()
+        _check(lib().b200pt_guiding_reset(self._h, C.byref(params)))
+
+    def guiding_update_host(self, samples, params=None):
+        """PathGuiding::update on caller-provided host records (copied to the device inside the call)."""
+        params = params or default_guiding_params()
+        a = np.ascontiguousarray(samples, dtype=DIRECTIONAL_DATA_DTYPE)
+        _check(lib().b200pt_guiding_update_host(self._h, C.byref(params), a.ctypes.data, a.shape[0]))
+
+    def guiding_update_device(self, device_ptr, n, params=None):
+        params = params or default_guiding_params()
+        _check(lib().b200pt_guiding_update_device(self._h, C.byref(params), C.c_void_p(device_ptr), n))
+
+    def guiding_sorted(self):
+        n = lib().b200pt_guiding_sorted_count(self._h)
+        out = np.empty(n, dtype=DIRECTIONAL_DATA_DTYPE)
+        off = np.empty(self.guiding_region_count() + 1, dtype=np.uint32)
+        _check(lib().b200pt_guiding_get_sorted(self._h, out.ctypes.data, off.ctypes.data))
+        return out, off
+
+    GUIDING_STATE_FIELDS = ("weight", "kappa", "r", "mux", "muy", "muz", "distance", "distSumW", "chi", "chiN", "covxx", "covyy", "covxy", "covSumW")
+
+    def guiding_state(self, region):
+        sc = np.empty(5, dtype=np.float32)
+        pc = np.empty((14, 16), dtype=np.float32)
+        _check(lib().b200pt_guiding_get_state(self._h, region, sc.ctypes.data, pc.ctypes.data))
+        d = {"K": int(sc[0]), "sampleWeight": float(sc[1]), "numSamples": float(sc[2]), "totalNumSamples": int(sc[3]), "numEMIterations": int(sc[4])}
+        for i, f in enumerate(self.GUIDING_STATE_FIELDS):
+            d[f] = pc[i].copy()
+        return d
+
+    def guiding_fastexp(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(a)
+        _check(lib().b200pt_guiding_fastexp(self._h, a.ctypes.data, out.ctypes.data, a.size))
+        return out
 
     # irradiance cache
     def ic_get(self):

@@ -89,7 +89,7 @@ struct b200pt_ctx {
 
     // guiding / IC state
     GuidingState guiding;
-    DevBuf<b200pt_directional_data> samples;
+    DevBuf<b200pt_directional_data> samples, hostSamples;
     DevBuf<b200pt_cache_data> icData;
     DevBuf<b200pt_sphere> icSpheres;
     DevBuf<b200pt_cache_header> icHeader;
@@ -234,7 +234,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release(); c->dstats.release(); c->batchCounter.release();
     for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
-    c->samples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
+    c->samples.release(); c->hostSamples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
     c->guiding.release();
     for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
@@ -558,6 +558,54 @@ int b200pt_guiding_update(b200pt_ctx *c, const b200pt_guiding_params *params) {
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = c->guiding.update(c->samples.p, int64_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL, *params, c->stream, &c->stats);
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_reset(b200pt_ctx *c, const b200pt_guiding_params *params) {
+    if (!c || !params) return setError(B200PT_E_INVALID, "b200pt_guiding_reset: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.reset(*params, c->stream);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_reset: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_update_device(b200pt_ctx *c, const b200pt_guiding_params *params, const void *samples_device, int64_t n) {
+    if (!c || !params || n < 0 || (n > 0 && !samples_device)) return setError(B200PT_E_INVALID, "b200pt_guiding_update_device: bad argument");
+    if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update_device: set_scene must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.update(static_cast<b200pt_directional_data *>(const_cast<void *>(samples_device)), n, *params, c->stream, &c->stats);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_device: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_update_host(b200pt_ctx *c, const b200pt_guiding_params *params, const b200pt_directional_data *samples, int64_t n) {
+    if (!c || !params || n < 0 || (n > 0 && !samples)) return setError(B200PT_E_INVALID, "b200pt_guiding_update_host: bad argument");
+    if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update_host: set_scene must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->hostSamples.alloc(size_t(n)));
+    if (n) CUDA_TRY(cudaMemcpyAsync(c->hostSamples.p, samples, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyHostToDevice, c->stream));
+    int rc = c->guiding.update(c->hostSamples.p, n, *params, c->stream, &c->stats);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_host: " + c->guiding.error);
+    return B200PT_OK;
+}
+int64_t b200pt_guiding_sorted_count(b200pt_ctx *c) { return c ? int64_t(c->guiding.lastValidSamples) : 0; }
+int b200pt_guiding_get_sorted(b200pt_ctx *c, b200pt_directional_data *out, uint32_t *region_offsets) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_guiding_get_sorted: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.getSorted(out, region_offsets, nullptr, c->stream);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_get_sorted: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_get_state(b200pt_ctx *c, int region, float scalars5[5], float per_component[224]) {
+    if (!c || !scalars5 || !per_component) return setError(B200PT_E_INVALID, "b200pt_guiding_get_state: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.getState(region, scalars5, per_component, c->stream);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_get_state: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_guiding_fastexp(b200pt_ctx *c, const float *in, float *out, int n) {
+    if (!c || n < 0 || (n > 0 && (!in || !out))) return setError(B200PT_E_INVALID, "b200pt_guiding_fastexp: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::string err;
+    int rc = guidingFastExp(in, out, n, c->stream, err);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_fastexp: " + err);
     return B200PT_OK;
 }
 int b200pt_guiding_region_count(b200pt_ctx *c, int *count) {

@@ -1,10 +1,29 @@
-// Guiding region tree and mixture fit (device).  Region creation follows PathGuiding::createRegions
-// (src/PathGuiding.cpp:81-104) with Aabb::addEpsilon / splitAabb (src/Shapes.h:32-53).
+// Guiding update on the device: PathGuiding::update(SampleCollector) (src/PathGuiding.cpp:276-312) without the
+// 0.6-5.3 GB read-back and the CPU sort/fit of the reference.
+//
+//   1. sort      SampleCollector::getSortedData (src/SampleCollector.cpp:76-131): stable counting sort of the W*H*16
+//                DirectionalData records by region id — k_sort_count (per-warp histograms with __match_any_sync),
+//                k_sort_scan_tiles / k_sort_scan_regions (offsets), k_sort_scatter.  The scatter also applies the
+//                sample part of PathGuiding::preFit (:386-402, re-anchoring at the region centre) and writes the
+//                samples as SoA (float4 dir+weight | float2 pdf+distance): the EM passes then stream 16 B per sample.
+//   2. fit       k_guiding_update: ONE thread block per non-empty region runs the whole updateRegion sequence
+//                (fit | updateFit, mergeAll, chi^2 / covariance statistics, splitAll with masked fits, distance update)
+//                on a shared-memory copy of the mixture; every pass over the samples is a block-wide loop with a
+//                warp-shuffle + shared-memory reduction, the per-component logic runs on one thread (guiding_math.cuh).
+//   3. pack      the region's VMM_Theta (binding 16) is rewritten in place — no host round trip.
+// Region creation follows PathGuiding::createRegions (src/PathGuiding.cpp:81-104) with Aabb::addEpsilon / splitAabb
+// (src/Shapes.h:32-53).
 #include "guiding_fit.cuh"
+#include "guiding_math.cuh"
 #include <cstring>
-#include <tuple>
+#include <algorithm>
 
 namespace b200pt {
+
+#define G_BLOCK 512                 // threads of the per-region block
+#define G_WARPS (G_BLOCK / 32)
+#define SORT_TILE 2048              // records per warp in the counting sort
+#define SORT_WARPS 8                // warps per block in the counting sort
 
 static void splitAabb(const b200pt_aabb &b, b200pt_aabb &l, b200pt_aabb &r) {   // src/Shapes.h:32-46, axis = largest
     float size[3] = {b.max[0] - b.min[0], b.max[1] - b.min[1], b.max[2] - b.min[2]};
@@ -13,6 +32,352 @@ static void splitAabb(const b200pt_aabb &b, b200pt_aabb &l, b200pt_aabb &r) {   
     l.max[axis] -= 0.5f * size[axis];
     r.min[axis] += 0.5f * size[axis];
 }
+
+// ---- sort ------------------------------------------------------------------------------------------------------------
+// warp-level stable ranking: lanes holding the same key get consecutive ranks in lane order; `hist` is the warp's
+// running histogram in shared memory (R + 1 bins, bin R = INVALID)
+__device__ __forceinline__ uint32_t warpRank(uint32_t *hist, uint32_t key, bool valid, unsigned lane) {
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+    uint32_t base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (valid && int(lane) == leader) { base = hist[key]; hist[key] = base + __popc(peers); }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_count(const b200pt_directional_data *__restrict__ recs, uint64_t n, uint32_t R,
+                                                                uint32_t *__restrict__ tileCounts /* [tiles][R] */, uint32_t numTiles) {
+    extern __shared__ uint32_t hist[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * SORT_WARPS + warp;
+    uint32_t *h = hist + warp * R;
+    for (uint32_t i = lane; i < R; i += 32) h[i] = 0;
+    __syncwarp();
+    if (tile < numTiles) {
+        const uint64_t begin = uint64_t(tile) * SORT_TILE;
+        for (uint32_t k = 0; k < SORT_TILE; k += 32) {
+            const uint64_t i = begin + k + lane;
+            const uint32_t key = i < n ? recs[i].flags : 0xffffffffu;
+            warpRank(h, key, key < R, lane);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < R; i += 32) tileCounts[uint64_t(tile) * R + i] = h[i];
+    }
+}
+
+// per region: exclusive scan of its counts over the tiles (in place) and the region total
+__global__ void __launch_bounds__(256) k_sort_scan_tiles(uint32_t *tileCounts, uint32_t numTiles, uint32_t R, uint32_t *regionTotal) {
+    __shared__ uint32_t warpSum[8];
+    __shared__ uint32_t running;
+    const uint32_t r = blockIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < numTiles; base += 256) {
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t v = t < numTiles ? tileCounts[uint64_t(t) * R + r] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += u; }
+        if (lane == 31) warpSum[warp] = incl;
+        __syncthreads();
+        uint32_t before = running;
+        for (unsigned w = 0; w < warp; w++) before += warpSum[w];
+        if (t < numTiles) tileCounts[uint64_t(t) * R + r] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) running = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) regionTotal[r] = running;
+}
+
+// exclusive scan of the region totals -> regionOffset[R + 1]; also the list of non-empty regions for the fit launch
+__global__ void __launch_bounds__(1024) k_sort_scan_regions(const uint32_t *__restrict__ regionTotal, uint32_t R, uint32_t *regionOffset,
+                                                            uint32_t *activeRegions, uint32_t *numActive) {
+    __shared__ uint32_t warpSum[32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t v = threadIdx.x < R ? regionTotal[threadIdx.x] : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += u; }
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (unsigned w = 0; w < warp; w++) before += warpSum[w];
+    if (threadIdx.x < R) regionOffset[threadIdx.x] = before + incl - v;
+    if (threadIdx.x == R - 1) regionOffset[R] = before + incl;
+    // compact the non-empty regions (ascending region id)
+    const unsigned has = __ballot_sync(0xffffffffu, v > 0);
+    __syncthreads();
+    if (lane == 0) warpSum[warp] = __popc(has);
+    __syncthreads();
+    uint32_t pos = 0;
+    for (unsigned w = 0; w < warp; w++) pos += warpSum[w];
+    if (v > 0) activeRegions[pos + __popc(has & ((1u << lane) - 1u))] = threadIdx.x;
+    if (threadIdx.x == 1023) { uint32_t tot = 0; for (int w = 0; w < 32; w++) tot += warpSum[w]; *numActive = tot; }
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_scatter(const b200pt_directional_data *__restrict__ recs, uint64_t n, uint32_t R,
+                                                                  const uint32_t *__restrict__ tileOffsets, uint32_t numTiles,
+                                                                  const uint32_t *__restrict__ regionOffset, const b200pt_aabb *__restrict__ aabbs,
+                                                                  int parallax, float4 *__restrict__ dirw, float2 *__restrict__ pdfDist,
+                                                                  uint32_t *__restrict__ srcIndex) {
+    extern __shared__ uint32_t hist[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * SORT_WARPS + warp;
+    uint32_t *h = hist + warp * R;
+    if (tile < numTiles) for (uint32_t i = lane; i < R; i += 32) h[i] = regionOffset[i] + tileOffsets[uint64_t(tile) * R + i];
+    __syncwarp();
+    if (tile >= numTiles) return;
+    const uint64_t begin = uint64_t(tile) * SORT_TILE;
+    for (uint32_t k = 0; k < SORT_TILE; k += 32) {
+        const uint64_t i = begin + k + lane;
+        b200pt_directional_data d;
+        d.flags = 0xffffffffu;
+        if (i < n) d = recs[i];
+        const bool valid = d.flags < R;
+        const uint32_t dst = warpRank(h, d.flags, valid, lane);
+        if (valid) {
+            if (parallax) {     // PathGuiding::preFit: parallaxMean = aabb.min + 0.5 * (aabb.max - aabb.min)
+                const b200pt_aabb bb = aabbs[d.flags];
+                float mean[3];
+                for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
+                gPrefitSample(d.position, d.direction, d.distance, mean);
+            }
+            dirw[dst] = make_float4(d.direction[0], d.direction[1], d.direction[2], d.weight);
+            pdfDist[dst] = make_float2(d.pdf, d.distance);
+            srcIndex[dst] = uint32_t(i);
+        }
+    }
+}
+
+// ---- per-region fit ----------------------------------------------------------------------------------------------------
+struct BlockShared {
+    GMix mix;
+    GPacked packed;
+    GFrames frames;
+    GFitState fitState;
+    union { EmAcc em; StatAcc stat; DistAcc dist; float raw[G_STATACC_FLOATS]; } acc;
+    float metric[G_MAXK * (G_MAXK - 1) / 2];
+    float red[G_WARPS][G_STATACC_FLOATS];
+    float staged[G_STATACC_FLOATS];
+    int bc;
+};
+
+// block-wide sum of NV per-thread values (registers) -> out[0..NV), deterministic order
+template <int NV>
+__device__ __forceinline__ void blockReduce(const float (&v)[NV], float (*red)[G_STATACC_FLOATS], float *out) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        float x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[warp][i] = x;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < G_WARPS; w++) s += red[w][i];
+        out[i] = s;
+    }
+    __syncthreads();
+}
+
+struct BlockExec {
+    BlockShared &sh;
+    const float4 *dirw;
+    const float2 *pdfDist;
+    uint32_t N;
+
+    __device__ bool leader() const { return threadIdx.x == 0; }
+    __device__ int bcast(int v) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.bc = v;
+        __syncthreads();
+        return sh.bc;
+    }
+    __device__ EmAcc &em() { return sh.acc.em; }
+    __device__ StatAcc &stat() { return sh.acc.stat; }
+    __device__ DistAcc &dst() { return sh.acc.dist; }
+    __device__ GFrames &frames() { return sh.frames; }
+    __device__ float *metric() { return sh.metric; }
+    __device__ GFitState &fit() { return sh.fitState; }
+
+    __device__ void publish(const GMix &m) {     // leader's mixture -> packed broadcast copy, visible to the block
+        __syncthreads();
+        if (threadIdx.x < G_MAXK) {
+            const int c = threadIdx.x;
+            sh.packed.a[c].mx = m.mux[c]; sh.packed.a[c].my = m.muy[c]; sh.packed.a[c].mz = m.muz[c]; sh.packed.a[c].kappa = m.kappa[c];
+            sh.packed.b[c].norm = m.norm[c]; sh.packed.b[c].w = m.w[c];
+        }
+        __syncthreads();
+    }
+
+    template <int KPAD> __device__ void emPassT(EmAcc &out) {
+        EmAcc a;   // register view: only the first KPAD slots of each array are touched
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { a.W[c] = 0.0f; a.Rx[c] = 0.0f; a.Ry[c] = 0.0f; a.Rz[c] = 0.0f; }
+        a.sumWeight = 0.0f; a.logLikelihood = 0.0f;
+        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+            const float4 s = dirw[i];
+            gEmSample<KPAD>(sh.packed, s.x, s.y, s.z, s.w, a);
+        }
+        float v[4 * KPAD + 2];
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { v[c] = a.W[c]; v[KPAD + c] = a.Rx[c]; v[2 * KPAD + c] = a.Ry[c]; v[3 * KPAD + c] = a.Rz[c]; }
+        v[4 * KPAD] = a.sumWeight; v[4 * KPAD + 1] = a.logLikelihood;
+        float *staged = sh.staged;   // reduce into a staging row, then unpack into the EmAcc layout
+        blockReduce<4 * KPAD + 2>(v, sh.red, staged);
+        if (threadIdx.x < KPAD) {
+            const int c = threadIdx.x;
+            out.W[c] = staged[c]; out.Rx[c] = staged[KPAD + c]; out.Ry[c] = staged[2 * KPAD + c]; out.Rz[c] = staged[3 * KPAD + c];
+        }
+        if (threadIdx.x == 0) { out.sumWeight = staged[4 * KPAD]; out.logLikelihood = staged[4 * KPAD + 1]; }
+        __syncthreads();
+    }
+    __device__ void emPass(const GMix &m, EmAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: emPassT<4>(out); break;
+            case 8: emPassT<8>(out); break;
+            case 12: emPassT<12>(out); break;
+            default: emPassT<16>(out); break;
+        }
+    }
+
+    template <int KPAD> __device__ void statPassT(const GFrames &f, StatAcc &out) {
+        StatAcc a;
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { a.chi[c] = 0.0f; a.covW[c] = 0.0f; a.covXX[c] = 0.0f; a.covYY[c] = 0.0f; a.covXY[c] = 0.0f; }
+        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+            const float4 s = dirw[i];
+            const float2 pd = pdfDist[i];
+            gStatSample<KPAD>(sh.packed, f, s.x, s.y, s.z, s.w, pd.x, a);
+        }
+        float v[5 * KPAD];
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { v[c] = a.chi[c]; v[KPAD + c] = a.covW[c]; v[2 * KPAD + c] = a.covXX[c]; v[3 * KPAD + c] = a.covYY[c]; v[4 * KPAD + c] = a.covXY[c]; }
+        float *staged = sh.staged;
+        blockReduce<5 * KPAD>(v, sh.red, staged);
+        if (threadIdx.x < KPAD) {
+            const int c = threadIdx.x;
+            out.chi[c] = staged[c]; out.covW[c] = staged[KPAD + c]; out.covXX[c] = staged[2 * KPAD + c]; out.covYY[c] = staged[3 * KPAD + c]; out.covXY[c] = staged[4 * KPAD + c];
+        }
+        __syncthreads();
+    }
+    __device__ void statPass(const GMix &m, const GFrames &f, StatAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: statPassT<4>(f, out); break;
+            case 8: statPassT<8>(f, out); break;
+            case 12: statPassT<12>(f, out); break;
+            default: statPassT<16>(f, out); break;
+        }
+    }
+
+    template <int KPAD> __device__ void distPassT(DistAcc &out) {
+        DistAcc a;
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { a.w[c] = 0.0f; a.wd[c] = 0.0f; }
+        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+            const float4 s = dirw[i];
+            const float2 pd = pdfDist[i];
+            gDistSample<KPAD>(sh.packed, s.x, s.y, s.z, s.w, pd.y, a);
+        }
+        float v[2 * KPAD];
+#pragma unroll
+        for (int c = 0; c < KPAD; c++) { v[c] = a.w[c]; v[KPAD + c] = a.wd[c]; }
+        float *staged = sh.staged;
+        blockReduce<2 * KPAD>(v, sh.red, staged);
+        if (threadIdx.x < KPAD) { const int c = threadIdx.x; out.w[c] = staged[c]; out.wd[c] = staged[KPAD + c]; }
+        __syncthreads();
+    }
+    __device__ void distPass(const GMix &m, DistAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: distPassT<4>(out); break;
+            case 8: distPassT<8>(out); break;
+            case 12: distPassT<12>(out); break;
+            default: distPassT<16>(out); break;
+        }
+    }
+
+    __device__ void metricPass(const GMix &m, float *metric) {
+        __syncthreads();
+        const int K = m.K, numPairs = K * (K - 1) / 2;
+        for (int p = threadIdx.x; p < numPairs; p += G_BLOCK) {
+            int idx = p, a = 0;
+            while (idx >= K - 1 - a) { idx -= K - 1 - a; a++; }
+            metric[p] = gMergeMetricPair(m, a, a + 1 + idx);
+        }
+        __syncthreads();
+    }
+};
+
+__global__ void __launch_bounds__(G_BLOCK, 1) k_guiding_update(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
+                                                              const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ regionOffset,
+                                                              const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist,
+                                                              b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
+    __shared__ BlockShared sh;
+    const uint32_t region = activeRegions[blockIdx.x];
+    const uint32_t begin = regionOffset[region], end = regionOffset[region + 1];
+    {   // mixture -> shared
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&mixes[region]);
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(&sh.mix);
+        for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += G_BLOCK) dstw[i] = src[i];
+    }
+    __syncthreads();
+    BlockExec x{sh, dirw + begin, pdfDist + begin, end - begin};
+    const b200pt_aabb bb = aabbs[region];
+    float mean[3];
+    for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
+    uint64_t iters = 0;
+    gUpdateRegion(x, sh.mix, gp, end - begin, firstFit != 0, mean, &iters);
+    __syncthreads();
+    {
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(&mixes[region]);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&sh.mix);
+        for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += G_BLOCK) dstw[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        gPackTheta(sh.mix, gp.useParallaxCompensation != 0, vmms[region]);
+        atomicAdd(emSampleIterations, (unsigned long long)iters);
+    }
+}
+
+// PathGuiding::createPMMs + syncPMMsToVMM_Thetas at construction (src/PathGuiding.cpp:42-51, 101-103)
+__global__ void k_guiding_init(GMix *mixes, b200pt_vmm_theta *vmms, uint32_t R, b200pt_guiding_params gp) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    GMix m;
+    gInitialize(m, gp);
+    mixes[r] = m;
+    gPackTheta(m, gp.useParallaxCompensation != 0, vmms[r]);
+}
+
+// known-answer hook: the device build of lightpmm's approximate exp on an array
+__global__ void k_fastexp(const float *__restrict__ in, float *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gFastExp(in[i]);
+}
+int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stream, std::string &error) {
+    if (n <= 0) return B200PT_OK;
+    float *d = nullptr;
+    if (cudaMalloc(reinterpret_cast<void **>(&d), size_t(n) * 2 * sizeof(float)) != cudaSuccess) { error = "cudaMalloc failed"; return B200PT_E_CUDA; }
+    cudaMemcpyAsync(d, hostIn, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, stream);
+    k_fastexp<<<(n + 255) / 256, 256, 0, stream>>>(d, d + n, n);
+    cudaMemcpyAsync(hostOut, d + n, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { error = cudaGetErrorString(e); return B200PT_E_CUDA; }
+    return B200PT_OK;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+#define G_TRY(expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) { error = std::string(#expr) + ": " + cudaGetErrorString(_e); return B200PT_E_CUDA; } \
+    } while (0)
 
 int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream) {
     release();
@@ -31,27 +396,168 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
         for (const auto &b : hostAabbs) { b200pt_aabb l, r; splitAabb(b, l, r); next.push_back(l); next.push_back(r); }
         hostAabbs.swap(next);
     }
-    if (cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(regionCount) * sizeof(b200pt_aabb)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(regionCount) * sizeof(b200pt_vmm_theta)) != cudaSuccess) {
-        error = "cudaMalloc failed";
-        return B200PT_E_CUDA;
-    }
-    cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream);
-    cudaMemsetAsync(vmms, 0, size_t(regionCount) * sizeof(b200pt_vmm_theta), stream);
-    if (cudaStreamSynchronize(stream) != cudaSuccess) { error = "upload failed"; return B200PT_E_CUDA; }
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(regionCount) * sizeof(b200pt_aabb)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(regionCount) * sizeof(b200pt_vmm_theta)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&mixes), size_t(regionCount) * sizeof(GMix)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionTotal), size_t(regionCount) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionOffset), size_t(regionCount + 1) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&activeRegions), size_t(regionCount) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&devScalars), 4 * sizeof(unsigned long long)));
+    G_TRY(cudaMallocHost(reinterpret_cast<void **>(&hostScalars), 4 * sizeof(unsigned long long)));
+    G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemsetAsync(devScalars, 0, 4 * sizeof(unsigned long long), stream));
+    b200pt_default_guiding_params(&lastParams);
+    k_guiding_init<<<(regionCount + 127) / 128, 128, 0, stream>>>(mixes, vmms, uint32_t(regionCount), lastParams);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaStreamSynchronize(stream));
+    firstFit = true;
     ready = true;
     return B200PT_OK;
 }
 
-int GuidingState::update(b200pt_directional_data *, int64_t, const b200pt_guiding_params &, cudaStream_t, b200pt_stats *) {
-    error = "guiding fit kernel not built yet";
-    return B200PT_E_STATE;
+int GuidingState::reset(const b200pt_guiding_params &params, cudaStream_t stream) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    lastParams = params;
+    k_guiding_init<<<(regionCount + 127) / 128, 128, 0, stream>>>(mixes, vmms, uint32_t(regionCount), params);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaStreamSynchronize(stream));
+    firstFit = true;
+    return B200PT_OK;
+}
+
+int GuidingState::ensureCapacity(int64_t numSamples) {
+    if (numSamples <= capacity) return B200PT_OK;
+    if (dirw) cudaFree(dirw);
+    if (pdfDist) cudaFree(pdfDist);
+    if (srcIndex) cudaFree(srcIndex);
+    if (tileCounts) cudaFree(tileCounts);
+    dirw = nullptr; pdfDist = nullptr; srcIndex = nullptr; tileCounts = nullptr; capacity = 0;
+    const size_t n = size_t(std::max<int64_t>(numSamples, 1));
+    const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&dirw), n * sizeof(float4)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&pdfDist), n * sizeof(float2)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&srcIndex), n * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&tileCounts), tiles * size_t(regionCount) * sizeof(uint32_t)));
+    capacity = numSamples;
+    return B200PT_OK;
+}
+
+int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream,
+                         b200pt_stats *stats) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    if (regionCount > 1024) { error = "the device sort supports at most 1024 guiding regions (GUIDING_SPLITS <= 10)"; return B200PT_E_INVALID; }
+    if (numSamples < 0 || numSamples > int64_t(0xfffffff0u)) { error = "bad sample count"; return B200PT_E_INVALID; }
+    if (params.numInitialComponents < 1 || params.numInitialComponents > G_MAXK || params.maxItr < 0 || params.minItr < 0) {
+        error = "bad guiding parameters"; return B200PT_E_INVALID;
+    }
+    if (firstFit && memcmp(&params, &lastParams, sizeof(params)) != 0) {   // factory properties changed before the first fit: re-initialise
+        int rc = reset(params, stream);
+        if (rc != B200PT_OK) return rc;
+    }
+    lastParams = params;
+    int rc = ensureCapacity(numSamples);
+    if (rc != B200PT_OK) return rc;
+    const uint32_t R = uint32_t(regionCount);
+    const uint32_t numTiles = uint32_t((uint64_t(numSamples) + SORT_TILE - 1) / SORT_TILE);
+    const uint32_t sortBlocks = (numTiles + SORT_WARPS - 1) / SORT_WARPS;
+    const size_t sortSmem = size_t(SORT_WARPS) * R * sizeof(uint32_t);
+    cudaEvent_t e0, e1, e2;
+    G_TRY(cudaEventCreate(&e0)); G_TRY(cudaEventCreate(&e1)); G_TRY(cudaEventCreate(&e2));
+    G_TRY(cudaEventRecord(e0, stream));
+    G_TRY(cudaMemsetAsync(devScalars, 0, 2 * sizeof(unsigned long long), stream));
+    if (numTiles) {
+        k_sort_count<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles);
+        k_sort_scan_tiles<<<R, 256, 0, stream>>>(tileCounts, numTiles, R, regionTotal);
+    } else {
+        G_TRY(cudaMemsetAsync(regionTotal, 0, R * sizeof(uint32_t), stream));
+    }
+    uint32_t *numActiveDev = reinterpret_cast<uint32_t *>(devScalars + 1);
+    k_sort_scan_regions<<<1, 1024, 0, stream>>>(regionTotal, R, regionOffset, activeRegions, numActiveDev);
+    if (numTiles)
+        k_sort_scatter<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles, regionOffset, aabbs,
+                                                                          params.useParallaxCompensation, dirw, pdfDist, srcIndex);
+    G_TRY(cudaEventRecord(e1, stream));
+    G_TRY(cudaMemcpyAsync(hostScalars + 1, devScalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    const uint32_t numActive = uint32_t(hostScalars[1] & 0xffffffffu);
+    if (numActive)
+        k_guiding_update<<<numActive, G_BLOCK, 0, stream>>>(mixes, vmms, aabbs, activeRegions, regionOffset, dirw, pdfDist, params, firstFit ? 1 : 0, devScalars);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaEventRecord(e2, stream));
+    G_TRY(cudaMemcpyAsync(hostScalars, devScalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    uint32_t validCount = 0;
+    G_TRY(cudaMemcpyAsync(&validCount, regionOffset + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    float msSort = 0, msFit = 0;
+    cudaEventElapsedTime(&msSort, e0, e1);
+    cudaEventElapsedTime(&msFit, e1, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    firstFit = false;
+    lastValidSamples = validCount;
+    if (stats) {
+        stats->guiding_samples += validCount;
+        stats->guiding_em_sample_iterations += hostScalars[0];
+        stats->guiding_regions_fit += numActive;
+        stats->ms_guiding_sort += msSort;
+        stats->ms_guiding_fit += msFit;
+        stats->kernel_launches += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
+        stats->launches_guiding += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
+    }
+    return B200PT_OK;
+}
+
+int GuidingState::getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream) {
+    if (!ready || region < 0 || region >= regionCount) { error = "bad region"; return B200PT_E_INVALID; }
+    GMix m;
+    G_TRY(cudaMemcpyAsync(&m, mixes + region, sizeof(GMix), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    scalars5[0] = float(m.K); scalars5[1] = m.sampleWeight; scalars5[2] = m.numSamples; scalars5[3] = float(m.totalNumSamples); scalars5[4] = float(m.numEMIterations);
+    const float *src[14] = {m.w, m.kappa, m.r, m.mux, m.muy, m.muz, m.dist, m.distSumW, m.chi, m.chiN, m.covxx, m.covyy, m.covxy, m.covSumW};
+    for (int f = 0; f < 14; f++) memcpy(perComponent + f * 16, src[f], 16 * sizeof(float));
+    return B200PT_OK;
+}
+
+int GuidingState::getSorted(b200pt_directional_data *out, uint32_t *offsets, const b200pt_directional_data *rawDevice, cudaStream_t stream) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    const uint32_t n = lastValidSamples;
+    if (offsets) G_TRY(cudaMemcpyAsync(offsets, regionOffset, size_t(regionCount + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    if (out && n) {
+        std::vector<float4> dw(n); std::vector<float2> pd(n); std::vector<uint32_t> off(size_t(regionCount) + 1);
+        G_TRY(cudaMemcpyAsync(dw.data(), dirw, n * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        G_TRY(cudaMemcpyAsync(pd.data(), pdfDist, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        G_TRY(cudaMemcpyAsync(off.data(), regionOffset, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        G_TRY(cudaStreamSynchronize(stream));
+        uint32_t r = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            while (r + 1 < uint32_t(regionCount) && i >= off[r + 1]) r++;
+            b200pt_directional_data &d = out[i];
+            const b200pt_aabb &bb = hostAabbs[r];
+            for (int a = 0; a < 3; a++) d.position[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
+            d.direction[0] = dw[i].x; d.direction[1] = dw[i].y; d.direction[2] = dw[i].z; d.weight = dw[i].w;
+            d.pdf = pd[i].x; d.distance = pd[i].y; d.flags = r;
+        }
+    }
+    G_TRY(cudaStreamSynchronize(stream));
+    (void)rawDevice;
+    return B200PT_OK;
 }
 
 void GuidingState::release() {
     if (aabbs) cudaFree(aabbs);
     if (vmms) cudaFree(vmms);
-    aabbs = nullptr; vmms = nullptr; ready = false; regionCount = 0;
+    if (mixes) cudaFree(mixes);
+    if (regionTotal) cudaFree(regionTotal);
+    if (regionOffset) cudaFree(regionOffset);
+    if (activeRegions) cudaFree(activeRegions);
+    if (devScalars) cudaFree(devScalars);
+    if (hostScalars) cudaFreeHost(hostScalars);
+    if (dirw) cudaFree(dirw);
+    if (pdfDist) cudaFree(pdfDist);
+    if (srcIndex) cudaFree(srcIndex);
+    if (tileCounts) cudaFree(tileCounts);
+    aabbs = nullptr; vmms = nullptr; mixes = nullptr; regionTotal = nullptr; regionOffset = nullptr; activeRegions = nullptr;
+    devScalars = nullptr; hostScalars = nullptr; dirw = nullptr; pdfDist = nullptr; srcIndex = nullptr; tileCounts = nullptr;
+    capacity = 0; ready = false; regionCount = 0; firstFit = true; lastValidSamples = 0;
     hostAabbs.clear();
 }
 

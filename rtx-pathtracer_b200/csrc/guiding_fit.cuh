@@ -1,4 +1,5 @@
-// Guiding state on the device: region tree + per-region vMF mixtures (PathGuiding, src/PathGuiding.{h,cpp}).
+// Guiding state on the device: region tree + per-region vMF mixtures (PathGuiding, src/PathGuiding.{h,cpp}) and the
+// scratch buffers of the on-device sample sort (SampleCollector::getSortedData, src/SampleCollector.cpp:76-131).
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
@@ -7,17 +8,35 @@
 
 namespace b200pt {
 
+struct GMix;
+
 struct GuidingState {
     bool ready = false;
+    bool firstFit = true;                  // PathGuiding::firstFit (global: cleared by the first update)
     int regionCount = 0;
     std::vector<b200pt_aabb> hostAabbs;
     b200pt_aabb *aabbs = nullptr;          // device, binding 15
     b200pt_vmm_theta *vmms = nullptr;      // device, binding 16
+    GMix *mixes = nullptr;                 // device: lightpmm PMM + PMM_ExtraData per region
+    // sort scratch
+    uint32_t *regionTotal = nullptr, *regionOffset = nullptr, *activeRegions = nullptr, *tileCounts = nullptr, *srcIndex = nullptr;
+    float4 *dirw = nullptr;                // sorted samples: direction (after preFit) + weight
+    float2 *pdfDist = nullptr;             // sorted samples: pdf, distance (after preFit)
+    int64_t capacity = 0;
+    uint32_t lastValidSamples = 0;
+    unsigned long long *devScalars = nullptr, *hostScalars = nullptr;   // [0] EM sample-iterations, [1] active regions
+    b200pt_guiding_params lastParams{};
     std::string error;
 
     int init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream);
+    int reset(const b200pt_guiding_params &params, cudaStream_t stream);
+    int ensureCapacity(int64_t numSamples);
     int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats);
+    int getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream);
+    int getSorted(b200pt_directional_data *out, uint32_t *offsets, const b200pt_directional_data *rawDevice, cudaStream_t stream);
     void release();
 };
+
+int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stream, std::string &error);
 
 }  // namespace b200pt
