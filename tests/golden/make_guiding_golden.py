@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import guiding_data
 import helpers
 
-SCENE_MIN, SCENE_MAX = [-1.686433, -0.0356, -1.686433], [1.686433, 3.386433, 1.686433]
+SCENE_MIN, SCENE_MAX = helpers.scene_box("cornell-dielectric")   # (-1.686433, -0.0356, -1.686433) .. (1.686433, 3.386433, 1.686433)
 SPLITS, PER_REGION, SEEDS = 2, 3000, (11, 12, 13)
 
 

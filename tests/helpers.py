@@ -105,3 +105,9 @@ def secondary_rays(scene_oracle, primary, seed=2, shadow=False):
     rays["tmin"] = 1e-3
     rays["tmax"] = rng.uniform(0.2, 3.0, o.shape[0]).astype(np.float32) if shadow else 1e6
     return rays
+
+
+def scene_box(scene_name="cornell-dielectric"):
+    """SceneLoader::calculateSceneSize box of a scene exactly as the loader computes it (float32)."""
+    scene = pt().Scene(scene_path(scene_name))
+    return [float(x) for x in scene.desc.scene_min[:]], [float(x) for x in scene.desc.scene_max[:]]
