@@ -18,9 +18,13 @@ HEADERS   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/host/*.h) include/b
 
 all: $(LIB) $(CLI)
 
+# per-file extras (GUIDING_FLAGS: tuning overrides for guiding_fit.cu, e.g. -DG_BLOCK=256 -DG_BLOCKS_PER_SM=2)
+GUIDING_FLAGS ?=
+EXTRA_guiding_fit := $(GUIDING_FLAGS)
+
 $(BUILD)/%.o: $(PKG)/csrc/%.cu $(HEADERS)
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
+	$(NVCC) $(NVFLAGS) $(EXTRA_$*) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
 
 $(BUILD)/%.o: $(PKG)/host/%.cpp $(HEADERS)
 	@mkdir -p $(BUILD)

@@ -16,12 +16,23 @@
 #include "guiding_fit.cuh"
 #include "guiding_math.cuh"
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 
 namespace b200pt {
 
+#ifndef G_BLOCK
 #define G_BLOCK 512                 // threads of the per-region block
+#endif
+#ifndef G_BLOCKS_PER_SM
+#define G_BLOCKS_PER_SM 1
+#endif
 #define G_WARPS (G_BLOCK / 32)
+// The lobe parameters live in shared memory (GPacked) and are re-read for every sample with 128-/64-bit broadcast
+// loads.  Without this compiler barrier nvcc hoists all 96 loop-invariant loads into registers and spills the
+// accumulators to local memory instead.
+#define G_NO_HOIST() asm volatile("" ::: "memory")
 #define SORT_TILE 2048              // records per warp in the counting sort
 #define SORT_WARPS 8                // warps per block in the counting sort
 
@@ -218,6 +229,7 @@ struct BlockExec {
         for (int c = 0; c < KPAD; c++) { a.W[c] = 0.0f; a.Rx[c] = 0.0f; a.Ry[c] = 0.0f; a.Rz[c] = 0.0f; }
         a.sumWeight = 0.0f; a.logLikelihood = 0.0f;
         for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+            G_NO_HOIST();
             const float4 s = dirw[i];
             gEmSample<KPAD>(sh.packed, s.x, s.y, s.z, s.w, a);
         }
@@ -251,6 +263,7 @@ struct BlockExec {
         for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
             const float4 s = dirw[i];
             const float2 pd = pdfDist[i];
+            G_NO_HOIST();
             gStatSample<KPAD>(sh.packed, f, s.x, s.y, s.z, s.w, pd.x, a);
         }
         float v[5 * KPAD];
@@ -281,6 +294,7 @@ struct BlockExec {
         for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
             const float4 s = dirw[i];
             const float2 pd = pdfDist[i];
+            G_NO_HOIST();
             gDistSample<KPAD>(sh.packed, s.x, s.y, s.z, s.w, pd.y, a);
         }
         float v[2 * KPAD];
@@ -313,11 +327,12 @@ struct BlockExec {
     }
 };
 
-__global__ void __launch_bounds__(G_BLOCK, 1) k_guiding_update(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
+__global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
                                                               const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ regionOffset,
                                                               const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist,
                                                               b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
     __shared__ BlockShared sh;
+    const long long t0 = clock64();
     const uint32_t region = activeRegions[blockIdx.x];
     const uint32_t begin = regionOffset[region], end = regionOffset[region + 1];
     {   // mixture -> shared
@@ -332,6 +347,7 @@ __global__ void __launch_bounds__(G_BLOCK, 1) k_guiding_update(GMix *mixes, b200
     for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
     uint64_t iters = 0;
     gUpdateRegion(x, sh.mix, gp, end - begin, firstFit != 0, mean, &iters);
+    if (threadIdx.x == 0) sh.mix.lastUpdateKCycles = uint32_t((clock64() - t0) >> 10);
     __syncthreads();
     {
         uint32_t *dstw = reinterpret_cast<uint32_t *>(&mixes[region]);
@@ -494,6 +510,18 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     firstFit = false;
     lastValidSamples = validCount;
+    if (getenv("B200PT_GUIDING_PROFILE")) {   // per-region cost distribution (development aid)
+        std::vector<GMix> hm;
+        hm.resize(size_t(regionCount));
+        cudaMemcpy(hm.data(), mixes, hm.size() * sizeof(GMix), cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> kc, it;
+        for (const GMix &m : hm) { kc.push_back(m.lastUpdateKCycles); it.push_back(m.numEMIterations); }
+        std::sort(kc.begin(), kc.end()); std::sort(it.begin(), it.end());
+        double sum = 0; for (uint32_t v : kc) sum += v;
+        fprintf(stderr, "[guiding profile] regions %d fit %.2f ms | per-region Mcycles: min %.2f median %.2f p90 %.2f max %.2f sum %.1f | EM iterations (cumulative): min %u median %u max %u\n",
+                regionCount, msFit, kc.front() / 1024.0, kc[kc.size() / 2] / 1024.0, kc[kc.size() * 9 / 10] / 1024.0, kc.back() / 1024.0, sum / 1024.0,
+                it.front(), it[it.size() / 2], it.back());
+    }
     if (stats) {
         stats->guiding_samples += validCount;
         stats->guiding_em_sample_iterations += hostScalars[0];
