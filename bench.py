@@ -99,6 +99,59 @@ def cpu_oracle_run(P, width, height, spp, frames, threads):
     return times, rays
 
 
+EM_SPLITS, EM_PER_REGION = 8, 57600     # BASELINE configs[0]: 2^8 regions x (1280*720*16 / 256) records = the full sample buffer
+EM_BYTES_PER_SAMPLE_ITER = 16           # direction + weight per sample per EM iteration
+
+
+def em_batches(P, aabbs):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import guiding_data                      # synthetic sample generator (numpy only; not part of oracle/)
+    return [guiding_data.make_batch(aabbs, EM_PER_REGION, seed, invalid_fraction=0.0) for seed in (0x5EED0001, 0x5EED0002)]
+
+
+def em_cpu_reference(P, batches, threads):
+    """The reference's own lightpmm + guiding headers (oracle/_ref, compiled from /root/reference in the build container)
+    driven by the restated PathGuiding::update: first update = fit, second = updateFit; all regions on `threads` cores."""
+    O = _load("b200pt_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    if not O.ref_guiding_available():
+        return None
+    scene = P.Scene(SCENE)
+    g = O.GuidingRef(EM_SPLITS, [float(x) for x in scene.desc.scene_min[:]], [float(x) for x in scene.desc.scene_max[:]], P.default_guiding_params())
+    times = []
+    for b in batches:
+        t0 = time.perf_counter()
+        g.update(b, threads=threads)
+        times.append(time.perf_counter() - t0)
+    n = sum(len(b) for b in batches)
+    return {"value": n / sum(times), "unit": "samples/s", "cores": threads, "kind": "reference",
+            "sample": "full workload: 2 updates (fit, updateFit) of %d records each, lightpmm SSE build, region loop on %d threads" % (len(batches[0]), threads),
+            "seconds": times, "em_sample_iterations": g.em_sample_iterations()}
+
+
+def em_gpu(P, r, batches, torch, device):
+    """Guiding update on the GPU: `value` with the records resident in HBM, `e2e` from pinned host memory through
+    b200pt_guiding_update_host (H2D copy inside the timed region).  CUDA events on the library's stream."""
+    gp = P.default_guiding_params()
+    dev = [torch.from_numpy(b.view("u1").reshape(len(b), 40)).to(device) for b in batches]
+    pinned = [torch.from_numpy(b.view("u1").reshape(len(b), 40)).pin_memory() for b in batches]
+    res = {}
+    for mode in ("warmup", "device", "host"):
+        r.guiding_reset(gp)
+        r.stats_reset()
+        ms = []
+        for i in range(len(batches)):
+            r.timer_start()
+            if mode == "host":
+                P._check(P.lib().b200pt_guiding_update_host(r._h, gp, pinned[i].data_ptr(), len(batches[i])))
+            else:
+                r.guiding_update_device(dev[i].data_ptr(), len(batches[i]), gp)
+            ms.append(r.timer_stop())
+        st = r.stats()
+        res[mode] = {"ms": ms, "ms_sort": st.ms_guiding_sort, "ms_fit": st.ms_guiding_fit, "sample_iters": int(st.guiding_em_sample_iterations),
+                     "samples": int(st.guiding_samples), "launches": int(st.launches_guiding)}
+    return res
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's tracer has no CPU implementation (GLSL + RT cores), so this times the CPU port
     (oracle/) with every host thread, each step a bounded sample of the workload."""
@@ -117,6 +170,14 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%dx%d view of the same scene/camera, %d spp per step, oracle/tracer_oracle.cpp with its own BVH" % (w, h, spp)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if world == 1 and not args.no_em:
+        # second headline: the reference's CPU guiding fit (its own lightpmm code), all host threads
+        O = _load("b200pt_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+        if O.ref_guiding_available():
+            scene = P.Scene(SCENE)
+            g = O.GuidingRef(EM_SPLITS, [float(x) for x in scene.desc.scene_min[:]], [float(x) for x in scene.desc.scene_max[:]], P.default_guiding_params())
+            em = em_cpu_reference(P, em_batches(P, g.aabbs()), threads)
+            line["em"] = {"metric": "guiding EM samples/s, 256 regions x 57600 records, fit + updateFit", "value": em["value"], "unit": "samples/s", "cpu_baseline": em}
     print(json.dumps(line), flush=True)
 
 
@@ -127,6 +188,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-em", action="store_true", help="skip the guiding-EM leg (second headline metric)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -236,6 +298,20 @@ def main():
         ext_ms = stats["ms_extend"] / ext_launches
         ext_bytes = (stats["extend_rays"] + stats["shadow_rays"]) / ext_launches * BYTES_PER_RAY
         achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        # DRAM traffic of one k_trace launch from the committed ncu --set full capture (profiles/), if present
+        traffic = None
+        try:
+            rd = wr = None
+            for l in open(os.path.join(ROOT, "profiles", "r01b_ncu_trace.txt")):
+                f = l.split()
+                if l.startswith("dram__bytes_read.sum") and rd is None:
+                    rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+                if l.startswith("dram__bytes_write.sum") and wr is None:
+                    wr = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if rd is not None and wr is not None:
+                traffic = rd + wr
+        except Exception:
+            pass
         value = total_rays / elapsed / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -250,12 +326,37 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_trace (persistent BVH8 traversal: closest hit + any hit)", "launches": stats["launches_extend"], "avg_launch_us": 1e3 * ext_ms,
                          "trace_Mrays_per_s": (stats["extend_rays"] + stats["shadow_rays"]) / max(stats["ms_extend"], 1e-9) / 1e3, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": ext_bytes, "peak_source": peak_src,
                          "note": "152 algorithmic bytes/ray of wavefront state (SURVEY 8d); the kernel is latency/issue bound, see profiles/"},
             "stage_ms": {"trace": stats["ms_extend"], "shade": stats["ms_shade"], "frame_total": stats["ms_total"],
                          "device": dev_ms, "wall": 1e3 * wall},
             "rays": {"extend": stats["extend_rays"], "shadow": stats["shadow_rays"], "iterations": stats["iterations"]},
         }
+        if world == 1 and not args.no_em:
+            # ---- second headline metric: guiding EM samples/s (BASELINE configs[0]) ------------------------------------
+            rg = P.Renderer(64, 64, 0, EM_SPLITS, device=local_rank)
+            rg.set_scene(scene)
+            batches = em_batches(P, rg.guiding_aabbs())
+            g = em_gpu(P, rg, batches, torch, "cuda:%d" % local_rank)
+            n = sum(len(b) for b in batches)
+            dev_s, host_s = sum(g["device"]["ms"]) * 1e-3, sum(g["host"]["ms"]) * 1e-3
+            fit_s = g["device"]["ms_fit"] * 1e-3
+            em = {"metric": "guiding EM samples/s: PathGuiding::update (sort + preFit + fit|updateFit + merge/split + statistics + pack), "
+                            "256 regions x 57600 records, 2 updates",
+                  "value": n / dev_s, "unit": "samples/s", "ms_per_update": g["device"]["ms"], "ms_sort_total": g["device"]["ms_sort"], "ms_fit_total": g["device"]["ms_fit"],
+                  "em_sample_iterations": g["device"]["sample_iters"], "gpu_launches": g["device"]["launches"],
+                  "e2e": {"value": n / host_s, "unit": "samples/s", "h2d_bytes_per_step": len(batches[0]) * 40, "d2h_bytes_per_step": 0, "ms_per_update": g["host"]["ms"]},
+                  "roofline": {"bound": "hbm", "kernel": "k_guiding_update (one block per region)", "achieved": g["device"]["sample_iters"] * EM_BYTES_PER_SAMPLE_ITER / fit_s / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": g["device"]["sample_iters"] * EM_BYTES_PER_SAMPLE_ITER / fit_s / 1e9 / hbm_peak, "traffic": None,
+                               "sample_iterations_per_s": g["device"]["sample_iters"] / fit_s,
+                               "note": "16 B per sample per EM iteration of fit/updateFit (masked post-split fits and the statistics passes are extra work "
+                                       "not counted here); the kernel is bounded by per-region serial depth, not HBM — see DESIGN.md"}}
+            if not args.no_cpu_baseline:
+                cpu = em_cpu_reference(P, batches, os.cpu_count() or 1)
+                if cpu:
+                    em["cpu_baseline"] = cpu
+                    em["speedup_vs_cpu_all_cores"] = em["value"] / cpu["value"]
+            line["em"] = em
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             w, h, spp = 320, 180, 4
