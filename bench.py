@@ -203,6 +203,7 @@ def main():
     import torch
     import torch.distributed as dist
     P = _load("b200pt_binding", os.path.join(ROOT, "rtx-pathtracer_b200", "b200pt.py"))
+    S = _load("b200pt_sharding", os.path.join(ROOT, "rtx-pathtracer_b200", "sharding.py"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -226,13 +227,13 @@ def main():
 
     def step(i):
         # device-resident step: frame i of this rank; running mean over this rank's frames
-        r.render_frame(push_constants(P, P.tea(i * world + rank, SEED), i))
+        r.render_frame(push_constants(P, S.frame_seed(i, rank, world, SEED), i))
 
     for i in range(args.warmup):
         step(i)
     if world > 1:   # warm the collective
         r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
-        dist.all_reduce(accum)
+        S.combine_images(accum, args.warmup)
 
     # ---- timed region 1: `value` (inputs resident, K frames + the image reduction) --------------------------------
     barrier()
@@ -245,8 +246,7 @@ def main():
         step(i)
     r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
     dev_ms = r.timer_stop()
-    if world > 1:
-        dist.all_reduce(accum)       # sum of per-rank means; divided by world below (outside the hot path: one scale)
+    final = S.combine_images(accum, args.steps)      # N > 1: one NCCL all-reduce of the image (+ a scalar); N = 1: no-op
     barrier()
     wall = time.perf_counter() - t0
     # single GPU: device time between the two events; multi GPU: the collective runs on torch's stream, so the region
@@ -265,7 +265,7 @@ def main():
     r.timer_start()
     for i in range(args.steps):
         r.set_camera(view, proj)                                  # host -> device: 2 x mat4 (the reference's UBO update)
-        r.render_frame(push_constants(P, P.tea(i * world + rank, SEED), i))   # 192 B of push constants
+        r.render_frame(push_constants(P, S.frame_seed(i, rank, world, SEED), i))   # 192 B of push constants
         P._check(P.lib().b200pt_read_image(r._h, P.IMAGE_OUTPUT, host_img.data_ptr()))   # device -> pinned host, 16 B/px
     e2e_dev_ms = r.timer_stop()
     barrier()
