@@ -76,6 +76,9 @@ struct b200pt_ctx {
     Wavefront wf{};
     DevBuf<float4> pathRayO[2], pathRayD[2], pathHit, probeRayO, probeRayD, probeHit, probeA, probeB, shRayO, shRayD, shC, thr, pixelSum;
     DevBuf<uint32_t> seed, state, sampleIdx, counters;
+    DevBuf<float4> shG, recLightSums, recSampleThr, recPathSum;
+    DevBuf<int4> recState;
+    DevBuf<float> recDistanceFactor;
     int queueNEE = 0;
     // pinned ring of queue-counter snapshots: the host looks at iteration i-LAG while iteration i is being issued
     enum { RING = 4, LAG = 2 };
@@ -84,7 +87,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
-    int numSMs = 0, traceGrid = 0, shadeGrid = 0, resolveGrid = 0;
+    int numSMs = 0, traceGrid = 0, shadeGrid = 0, shadeGridGuided = 0, resolveGrid = 0;
     TraceTuning tune{64u, 8};
 
     // guiding / IC state
@@ -191,7 +194,10 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->numSMs = prop.multiProcessorCount;
     int occTrace = 0, occShade = 0, occResolve = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace, PT_TRACE_BLOCK, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade<false>, 128, 0));
+    int occShadeGuided = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeGuided, k_shade<true>, 128, 0));
+    c->shadeGridGuided = c->numSMs * std::max(1, occShadeGuided);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
     c->traceGrid = c->numSMs * std::max(1, occTrace);
     c->shadeGrid = c->numSMs * std::max(1, occShade);
@@ -231,6 +237,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     for (int i = 0; i < 2; i++) { c->pathRayO[i].release(); c->pathRayD[i].release(); }
     c->pathHit.release(); c->probeRayO.release(); c->probeRayD.release(); c->probeHit.release(); c->probeA.release(); c->probeB.release();
     c->shRayO.release(); c->shRayD.release(); c->shC.release(); c->thr.release(); c->pixelSum.release();
+    c->shG.release(); c->recLightSums.release(); c->recSampleThr.release(); c->recPathSum.release(); c->recState.release(); c->recDistanceFactor.release();
     c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release(); c->dstats.release(); c->batchCounter.release();
     for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
@@ -374,14 +381,31 @@ static inline unsigned gridFor(uint64_t n, unsigned block) { return unsigned((n 
 int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     if (!c || !pc) return setError(B200PT_E_INVALID, "b200pt_render_frame: null argument");
     if (!c->hasScene || !c->hasCamera) return setError(B200PT_E_STATE, "b200pt_render_frame: set_scene and set_camera must be called first");
-    if (pc->useIrradianceCache || pc->useADRRS || pc->useGuiding || pc->updateGuiding || pc->splitOnFirst || pc->showIrradianceCacheOnly)
-        return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS / guiding render modes are not implemented in this build");
+    if (pc->useIrradianceCache || pc->useADRRS || pc->splitOnFirst || pc->showIrradianceCacheOnly)
+        return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS / splitOnFirst render modes are not implemented in this build");
+    const bool guided = pc->useGuiding || pc->updateGuiding;
+    if (guided && !c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_render_frame: guiding needs a scene (region tree)");
     if (pc->numNEE < 1 || pc->samplesPerPixel < 1 || pc->maxDepth < 0 || pc->maxDepth > 60000)
         return setError(B200PT_E_INVALID, "b200pt_render_frame: numNEE, samplesPerPixel must be >= 1 and maxDepth in [0, 60000]");
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ensureQueues(c, pc->enableNEE ? pc->numNEE : 1);
     if (rc != B200PT_OK) return rc;
 
+    {   // guiding views: region tree + mixtures, and (training frames) the sample-recording state
+        Wavefront &w = c->wf;
+        w.guide.levels = c->guiding.levelAabbs; w.guide.vmms = c->guiding.vmms; w.guide.splits = c->guiding.splits;
+        w.rec = GuidingRecord{};
+        if (pc->updateGuiding) {
+            const size_t N16 = size_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL;
+            CUDA_TRY(c->recLightSums.alloc(N16)); CUDA_TRY(c->recSampleThr.alloc(N16));
+            CUDA_TRY(c->recState.alloc(size_t(c->numPixels))); CUDA_TRY(c->recDistanceFactor.alloc(size_t(c->numPixels)));
+            CUDA_TRY(c->recPathSum.alloc(size_t(c->numPixels)));
+            CUDA_TRY(c->shG.alloc(size_t(c->numPixels) * size_t(c->queueNEE)));
+            w.rec.samples = c->samples.p; w.rec.lightSums = c->recLightSums.p; w.rec.sampleThr = c->recSampleThr.p;
+            w.rec.state = c->recState.p; w.rec.distanceFactor = c->recDistanceFactor.p; w.rec.pathSum = c->recPathSum.p;
+            w.shG = c->shG.p;
+        }
+    }
     FrameParams fp;
     fp.pc = *pc;
     memcpy(fp.view, c->view, 64); memcpy(fp.proj, c->proj, 64); memcpy(fp.viewInv, c->viewInv, 64); memcpy(fp.projInv, c->projInv, 64);
@@ -407,7 +431,11 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         if (pc->enableNEE && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
         k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
         c->stats.kernel_launches++;
-        { StageTimer t(c, KIND_SHADE); k_shade<<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur); }
+        {
+            StageTimer t(c, KIND_SHADE);
+            if (guided) k_shade<true><<<c->shadeGridGuided, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            else k_shade<false><<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+        }
         cur = 1 - cur;
         const int slot = int(iter % b200pt_ctx::RING);
         CUDA_TRY(cudaMemcpyAsync(c->hostCounters + slot * CNT_NUM, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -424,7 +452,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         }
     }
     CUDA_TRY(cudaMemcpyAsync(c->hostDstats, c->dstats.p, DST_NUM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    { StageTimer t(c, KIND_SHADE); k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p); }
+    { StageTimer t(c, KIND_SHADE); k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec); }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,132 @@
+// Guiding inside the tracer: region lookup, vMF-mixture pdf / sampling and the per-pixel sample-recording state.
+// Restates shaders/guiding.glsl:32-96 (vMF, VMM, sampleVMF, sampleVMM), shaders/raytrace.guiding.rint:12-19 +
+// raytrace.rgen:904-921 (getGuidingRegion: point-in-AABB query on the guiding acceleration structure) and the sample
+// bookkeeping of raytrace.rgen:966-990 (updateSamples / commitSamples).
+#pragma once
+#include "device_math.cuh"
+#include "../../include/b200pt.h"
+
+namespace b200pt {
+
+// The reference finds the region with a TerminateOnFirstHit query against one AABB per region.  The regions come
+// from recursive halving (PathGuiding::createRegions), so the lookup here walks that tree: level L holds 2^L boxes,
+// node i has the children 2i and 2i+1.  Sibling boxes are computed independently (l.max -= h, r.min += h,
+// src/Shapes.h:32-46) and may overlap or leave a gap of one ulp, so a plain descent could disagree with an exhaustive
+// scan; the walk backtracks, which makes it return exactly the LOWEST-index leaf that contains the point (the rule the
+// oracle's linear scan defines; the reference leaves the choice among overlapping boxes to the driver).
+struct GuidingView {
+    const b200pt_aabb *levels;        // all levels concatenated: level L starts at (2^L - 1)
+    const b200pt_vmm_theta *vmms;     // binding 16
+    int splits;
+};
+
+__device__ __forceinline__ bool aabbContains(const b200pt_aabb &b, vec3 p) {   // raytrace.guiding.rint:15-17: min(aabb.min, p) == aabb.min && max(aabb.max, p) == aabb.max
+    return fminf(b.min[0], p.x) == b.min[0] && fminf(b.min[1], p.y) == b.min[1] && fminf(b.min[2], p.z) == b.min[2] &&
+           fmaxf(b.max[0], p.x) == b.max[0] && fmaxf(b.max[1], p.y) == b.max[1] && fmaxf(b.max[2], p.z) == b.max[2];
+}
+
+__device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 p) {
+    if (!aabbContains(g.levels[0], p)) return B200PT_INVALID_REGION;
+    if (g.splits == 0) return 0u;
+    int level = 0;
+    uint32_t node = 0;
+    uint32_t triedRight = 0;          // bit L: the right child of the node on the current path at level L was entered
+    for (;;) {
+        // descend: prefer the left child
+        const b200pt_aabb *next = g.levels + ((1u << (level + 1)) - 1u);
+        const uint32_t l = 2u * node, r = l + 1u;
+        if (!((triedRight >> level) & 1u) && aabbContains(next[l], p)) {
+            node = l; level++;
+        } else if (!((triedRight >> level) & 1u) && aabbContains(next[r], p)) {
+            triedRight |= 1u << level;
+            node = r; level++;
+        } else {
+            // dead end (or both children exhausted): back up to the nearest ancestor whose right child is untried
+            for (;;) {
+                if (level == 0) return B200PT_INVALID_REGION;
+                const bool cameFromLeft = (node & 1u) == 0u;
+                triedRight &= ~(1u << level);
+                level--; node >>= 1;
+                if (cameFromLeft && !((triedRight >> level) & 1u)) {
+                    const b200pt_aabb *nx = g.levels + ((1u << (level + 1)) - 1u);
+                    if (aabbContains(nx[2u * node + 1u], p)) { triedRight |= 1u << level; node = 2u * node + 1u; level++; break; }
+                    triedRight |= 1u << level;      // right child does not contain p either: keep backing up
+                }
+            }
+        }
+        if (level == g.splits) return node;
+    }
+}
+
+__device__ __forceinline__ float vmfPdf(vec3 wo, const b200pt_vmf_theta &th, vec3 worldPos, bool parallax) {   // guiding.glsl:32-44
+    if (th.k == 0.0f) return 0.07957747155f;
+    vec3 mu = V3(th.mu[0], th.mu[1], th.mu[2]);
+    if (parallax && th.distance > 0.0f) mu = normalize(V3(th.target[0], th.target[1], th.target[2]) - worldPos);
+    return th.norm * expf(th.k * (dot(mu, wo) - 1.0f));
+}
+__device__ __forceinline__ float vmmPdf(vec3 wo, const b200pt_vmm_theta &vmm, vec3 worldPos, bool parallax) {   // guiding.glsl:53-60
+    float res = 0.0f;
+    for (int i = 0; i < vmm.usedDistributions; i++) res += vmm.pi[i] * vmfPdf(wo, vmm.thetas[i], worldPos, parallax);
+    return res;
+}
+__device__ __forceinline__ vec3 sampleVmf(uint32_t &seed, const b200pt_vmf_theta &th, vec3 worldPos, bool parallax) {   // guiding.glsl:62-82
+    if (th.k > 0.0f) {
+        const float r1 = rnd(seed);
+        const float r2 = rnd(seed);
+        const float cosTheta = 1.0f + logf(1.0f + th.eMin2K * r1 - r1) / th.k;
+        const float sinTheta = 1.0f - cosTheta * cosTheta <= 0.0f ? 0.0f : sqrtf(1.0f - cosTheta * cosTheta);
+        const float phi = 2.f * PT_PI * r2;
+        const float cosPhi = cosf(phi), sinPhi = sinf(phi);
+        vec3 mu = V3(th.mu[0], th.mu[1], th.mu[2]);
+        if (parallax && th.distance > 0.0f) mu = normalize(V3(th.target[0], th.target[1], th.target[2]) - worldPos);
+        return toWorld(V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta), mu);
+    }
+    return randomOnUnitSphere(seed);
+}
+__device__ __forceinline__ vec3 sampleVmm(uint32_t &seed, const b200pt_vmm_theta &vmm, vec3 worldPos, bool parallax) {   // guiding.glsl:84-96
+    const float rndDist = rnd(seed);
+    int i = 0;
+    const int maxDistribution = vmm.usedDistributions - 1;
+    float piSum = vmm.pi[0];
+    while (piSum < rndDist && i < maxDistribution) { i++; piSum += vmm.pi[i]; }
+    return sampleVmf(seed, vmm.thetas[i], worldPos, parallax);
+}
+
+// per-pixel sample-recording state of the megakernel (rgen: sampleOffset, lightSums[], sampleThroughputs[] and the
+// raytrace() locals currentSampleOffset / iUpdateDistance / distanceFactor), kept in global memory between the
+// wavefront stages
+struct GuidingRecord {
+    b200pt_directional_data *samples;   // binding 18: W*H*16 records
+    float4 *lightSums;                  // [pixel * 16 + i]
+    float4 *sampleThr;                  // [pixel * 16 + i]
+    int4 *state;                        // x sampleOffset, y currentSampleOffset, z iUpdateDistance, w pending commit (cso of the finished path, -1 none)
+    float *distanceFactor;
+    float4 *pathSum;                    // radiance of the pixel's current path (for `length(result) > 0`, rgen:1219-1222)
+};
+
+// updateSamples (rgen:973-978) on data in global memory.  ATOMIC: used by the shadow / probe resolvers, where several
+// NEE results of one pixel may arrive concurrently.
+template <bool ATOMIC>
+__device__ __forceinline__ void updateSamples(const GuidingRecord &g, int pix, int sampleOffset, int currentSampleOffset, vec3 light) {
+    for (int i = currentSampleOffset - 1; i >= sampleOffset; i--) {
+        float *ls = reinterpret_cast<float *>(&g.lightSums[pix * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i]);
+        if (ATOMIC) { atomicAdd(ls + 0, light.x); atomicAdd(ls + 1, light.y); atomicAdd(ls + 2, light.z); }
+        else { ls[0] += light.x; ls[1] += light.y; ls[2] += light.z; }
+        light *= make_vec3(g.sampleThr[pix * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i]);
+    }
+}
+
+// commitSamples (rgen:980-990) followed by `if (length(result) > 0) sampleOffset += currentSampleOffset` (rgen:1219-1222, sic)
+__device__ __forceinline__ void commitSamples(const GuidingRecord &g, int pix, int4 &st) {
+    const int cso = st.w;
+    for (int i = st.x; i < cso; i++) {
+        b200pt_directional_data &dd = g.samples[pix * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i];
+        const float weight = length(make_vec3(g.lightSums[pix * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i])) / dd.pdf;
+        if (weight <= 0.0f) dd.flags = B200PT_INVALID_REGION;
+        else dd.weight = weight;
+    }
+    if (length(make_vec3(g.pathSum[pix])) > 0.0f) st.x += cso;
+    st.w = -1;
+}
+
+}  // namespace b200pt

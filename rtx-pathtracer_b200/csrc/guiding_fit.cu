@@ -406,12 +406,18 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
         scene.max[a] = center + 0.50001f * extent;
     }
     hostAabbs.assign(1, scene);
+    std::vector<b200pt_aabb> allLevels(1, scene);      // every level of the halving tree, for the tracer's region lookup
     for (int i = 0; i < splits; i++) {
         std::vector<b200pt_aabb> next;
         next.reserve(hostAabbs.size() * 2);
         for (const auto &b : hostAabbs) { b200pt_aabb l, r; splitAabb(b, l, r); next.push_back(l); next.push_back(r); }
         hostAabbs.swap(next);
+        allLevels.insert(allLevels.end(), hostAabbs.begin(), hostAabbs.end());
     }
+    this->splits = splits;
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&levelAabbs), allLevels.size() * sizeof(b200pt_aabb)));
+    G_TRY(cudaMemcpyAsync(levelAabbs, allLevels.data(), allLevels.size() * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaStreamSynchronize(stream));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(regionCount) * sizeof(b200pt_aabb)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(regionCount) * sizeof(b200pt_vmm_theta)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&mixes), size_t(regionCount) * sizeof(GMix)));
@@ -572,6 +578,8 @@ int GuidingState::getSorted(b200pt_directional_data *out, uint32_t *offsets, con
 
 void GuidingState::release() {
     if (aabbs) cudaFree(aabbs);
+    if (levelAabbs) cudaFree(levelAabbs);
+    levelAabbs = nullptr;
     if (vmms) cudaFree(vmms);
     if (mixes) cudaFree(mixes);
     if (regionTotal) cudaFree(regionTotal);

@@ -15,7 +15,9 @@ struct GuidingState {
     bool firstFit = true;                  // PathGuiding::firstFit (global: cleared by the first update)
     int regionCount = 0;
     std::vector<b200pt_aabb> hostAabbs;
+    int splits = 0;
     b200pt_aabb *aabbs = nullptr;          // device, binding 15
+    b200pt_aabb *levelAabbs = nullptr;     // device: all 2^(splits+1)-1 boxes of the halving tree, level by level
     b200pt_vmm_theta *vmms = nullptr;      // device, binding 16
     GMix *mixes = nullptr;                 // device: lightpmm PMM + PMM_ExtraData per region
     // sort scratch

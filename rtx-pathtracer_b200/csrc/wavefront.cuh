@@ -4,6 +4,7 @@
 // the same order — SURVEY.md Appendix A) and the bounce loop is turned inside out into queue-driven kernels.
 #pragma once
 #include "shading.cuh"
+#include "guiding_device.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -37,7 +38,8 @@ struct Wavefront {
     float4 *probeB;          // path throughput xyz, w = pixel id bits
     float4 *shRayO;          // shadow rays: xyz origin, w = pixel id bits
     float4 *shRayD;          // xyz direction, w = tmax
-    float4 *shC;             // contribution to add when unoccluded
+    float4 *shC;             // contribution to add when unoccluded (path throughput applied)
+    float4 *shG;             // guiding training only: the NEE value without the path throughput (xyz), w = currentSampleOffset bits
     uint32_t *seed;          // per-pixel LCG state
     float4 *thr;             // per-path throughput
     uint32_t *state;         // depth (0..15) | followCount (16..23) | flags (24..)
@@ -45,6 +47,8 @@ struct Wavefront {
     float4 *pixelSum;        // sum of the frame's sample radiances per pixel
     uint32_t *counters;      // CNT_*
     unsigned long long *dstats;   // DST_*
+    GuidingView guide;       // region tree + mixtures (useGuiding / updateGuiding)
+    GuidingRecord rec;       // sample-recording state (updateGuiding); rec.samples == nullptr when not recording
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -87,6 +91,12 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
     wf.state[p] = ST_ADDNEXT;     // depth 0, addNextDirectLights = addFirstHitLight = true (rgen:995,1676)
     wf.sampleIdx[p] = 0;
     wf.pixelSum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (fp.pc.updateGuiding) {           // resetSamplesToInvalid (rgen:1615-1621, :1642-1643) + fresh recording state
+        for (int i = 0; i < B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL; i++) wf.rec.samples[p * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i].flags = B200PT_INVALID_REGION;
+        wf.rec.state[p] = make_int4(0, 0, -1, -1);
+        wf.rec.distanceFactor[p] = 1.0f;
+        wf.rec.pathSum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -96,7 +106,8 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
 struct WavefrontRayIO {
     const float4 *pathO, *pathD; float4 *pathHit;
     const float4 *probeO, *probeD; float4 *probeHit;
-    const float4 *shO, *shD, *shC; float4 *pixelSum;
+    const float4 *shO, *shD, *shC, *shG; float4 *pixelSum;
+    GuidingRecord rec;
     uint32_t nPath, nProbe;
     __device__ __forceinline__ void load(uint32_t idx, vec3 &o, vec3 &d, float &tmin, float &tmax, bool &any) const {
         float4 ro, rd;
@@ -113,8 +124,15 @@ struct WavefrontRayIO {
         } else if (h.prim == PT_MISS) {
             const uint32_t k = idx - nPath - nProbe;
             const float4 c = shC[k];
-            float *dst = reinterpret_cast<float *>(&pixelSum[__float_as_int(shO[k].w)]);
+            const int pix = __float_as_int(shO[k].w);
+            float *dst = reinterpret_cast<float *>(&pixelSum[pix]);
             atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+            if (rec.samples) {       // the deferred half of `updateSamples(currentSampleOffset, neeLight)` (rgen:1164-1165)
+                float *ps = reinterpret_cast<float *>(&rec.pathSum[pix]);
+                atomicAdd(ps + 0, c.x); atomicAdd(ps + 1, c.y); atomicAdd(ps + 2, c.z);
+                const float4 g = shG[k];
+                updateSamples<true>(rec, pix, rec.state[pix].x, __float_as_int(g.w), make_vec3(g));
+            }
         }
     }
 };
@@ -127,7 +145,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefro
     if (total == 0) return;
     io.pathO = wf.pathRayO[cur]; io.pathD = wf.pathRayD[cur]; io.pathHit = wf.pathHit;
     io.probeO = wf.probeRayO; io.probeD = wf.probeRayD; io.probeHit = wf.probeHit;
-    io.shO = wf.shRayO; io.shD = wf.shRayD; io.shC = wf.shC; io.pixelSum = wf.pixelSum;
+    io.shO = wf.shRayO; io.shD = wf.shRayD; io.shC = wf.shC; io.shG = wf.shG; io.pixelSum = wf.pixelSum; io.rec = wf.rec;
     // small queues (the tail of a frame): shrink the chunk so the rays spread over all SMs
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
@@ -194,9 +212,15 @@ __device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const Dev
     }
     const float heuristic = fp.pc.usePowerHeuristic ? powerHeuristic(pdfMat, pdfLights) : balanceHeuristic(pdfMat, pdfLights);
     if (h.prim != PT_MISS && isnan(heuristic)) return;
-    const vec3 c = T * ((bsdf * lightColor * heuristic / pdfMat) / float(fp.pc.numNEE));
+    const vec3 nee = (bsdf * lightColor * heuristic / pdfMat) / float(fp.pc.numNEE);
+    const vec3 c = T * nee;
     float *dst = reinterpret_cast<float *>(&wf.pixelSum[pix]);
     atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
+    if (wf.rec.samples) {
+        float *ps = reinterpret_cast<float *>(&wf.rec.pathSum[pix]);
+        atomicAdd(ps + 0, c.x); atomicAdd(ps + 1, c.y); atomicAdd(ps + 2, c.z);
+        updateSamples<true>(wf.rec, pix, wf.rec.state[pix].x, __float_as_int(wf.probeRayO[k].w), nee);
+    }
 }
 __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceScene sc, Wavefront wf) {
     const uint32_t n = wf.counters[CNT_PROBE];
@@ -205,6 +229,8 @@ __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceSce
 
 // ---------------------------------------------------------------------------------------------------------------
 // shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
+// GUIDE compiles in guided sampling (pc.useGuiding) and sample recording (pc.updateGuiding)
+template <bool GUIDE>
 __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = wf.counters[CNT_SHADE_N];
@@ -230,11 +256,32 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
         const bool useNEE = pc.enableNEE != 0;
         const bool addDirectLights = !useNEE;
         bool terminated = false;
+        const bool saveSamples = GUIDE && pc.updateGuiding != 0;
+        const int sbase = pid * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL;
+        int4 gst = make_int4(0, 0, -1, -1);      // sampleOffset, currentSampleOffset, iUpdateDistance, pending commit
+        float distanceFactor = 1.0f;
+        if (saveSamples) {
+            gst = wf.rec.state[pid];
+            distanceFactor = wf.rec.distanceFactor[pid];
+            if (depth == 0) {        // first vertex of a new path: finish the previous path of this pixel (its last NEE
+                                     // results have been resolved by now), then start the raytrace() locals afresh
+                if (gst.w >= 0) commitSamples(wf.rec, pid, gst);
+                gst.y = gst.x; gst.z = -1; distanceFactor = 1.0f;
+                wf.rec.pathSum[pid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
         depth++;
 
         HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
         if (h.prim == PT_MISS) {                       // rgen:1025-1040
-            if (addDirectLights || addNext) add += T * envColor(sc, direction);
+            if (addDirectLights || addNext) {
+                const vec3 miss = envColor(sc, direction);
+                add += T * miss;
+                if (saveSamples) {                                    // rgen:1031-1037
+                    updateSamples<false>(wf.rec, pid, gst.x, gst.y, miss);
+                    if (gst.z != -1) wf.rec.samples[sbase + gst.z].distance = 0.0f;
+                }
+            }
             terminated = true;
         } else {
             HitInfo info;
@@ -244,16 +291,24 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
             const vec3 normal = info.normal;
             const vec3 wi = -direction;
 
-            if (mat.type == B200PT_MAT_LIGHT && (addDirectLights || addNext))       // rgen:1054-1060
-                add += T * V3(mat.lightColor[0], mat.lightColor[1], mat.lightColor[2]);
+            if (mat.type == B200PT_MAT_LIGHT && (addDirectLights || addNext)) {     // rgen:1054-1060
+                const vec3 Le = V3(mat.lightColor[0], mat.lightColor[1], mat.lightColor[2]);
+                add += T * Le;
+                if (saveSamples) updateSamples<false>(wf.rec, pid, gst.x, gst.y, Le);
+            }
 
             if (hasDiscreteDirection(mat.type)) {      // rgen:1062-1075
                 addNext = true;
                 follow = true;
                 if (int(depth) >= pc.maxDepth) followCount++;
+                if (saveSamples && gst.z != -1) wf.rec.samples[sbase + gst.z].distance += info.t * distanceFactor;   // rgen:1073-1075
             } else {
                 addNext = false;
                 follow = false;
+                if (saveSamples && gst.z != -1) {                     // rgen:1149-1156
+                    wf.rec.samples[sbase + gst.z].distance += info.t * distanceFactor;
+                    if (!isMatAlmostDiscrete(mat)) gst.z = -1;
+                }
                 if (useNEE && neeSupported(mat.type)) {   // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
                     for (int iNee = 0; iNee < pc.numNEE; iNee++) {
                         vec3 lightDir, lightColor; float lightDistance;
@@ -288,6 +343,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                             wf.shRayO[slotS] = make_f4(origin, __int_as_float(pid));
                             wf.shRayD[slotS] = make_f4(lightDir, lightDistance * (1 - 0.0001f));
                             wf.shC[slotS] = make_f4(T * (C / float(pc.numNEE)), 0.0f);
+                            if (saveSamples) wf.shG[slotS] = make_f4(C / float(pc.numNEE), __int_as_float(gst.y));
                         }
                         bool pushProbe = false;
                         vec3 bsdfDir = V3(0.0f); float pdfMat = 0.0f;
@@ -298,7 +354,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                         if (pushProbe) {
                             const uint32_t slotP = queuePush(&wf.counters[CNT_PROBE]);
                             const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, bsdfDir, true);
-                            wf.probeRayO[slotP] = make_f4(origin, 0.0f);
+                            wf.probeRayO[slotP] = make_f4(origin, __int_as_float(gst.y));
                             wf.probeRayD[slotP] = make_f4(bsdfDir, 0.0f);
                             wf.probeA[slotP] = make_f4(f, pdfMat);
                             wf.probeB[slotP] = make_f4(T, __int_as_float(pid));
@@ -307,14 +363,52 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                 }
             }
 
-            // getNewDirection (rgen:923-960, unguided branch) + throughput update (:1169-1177)
+            // getNewDirection (rgen:923-960) + throughput update (:1169-1177) + sample recording (:1179-1212)
             if (!terminated) {
                 vec3 newDirection = V3(0.0f);
-                const float pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
+                float pdf;
+                if (GUIDE && pc.useGuiding && !hasDiscreteDirection(mat.type)) {
+                    const bool parallax = pc.useParallaxCompensation != 0;
+                    const uint32_t iRegion = getGuidingRegion(wf.guide, origin);
+                    if (iRegion == B200PT_INVALID_REGION) pdf = 0.0f;
+                    else {
+                        const b200pt_vmm_theta &vmm = wf.guide.vmms[iRegion];
+                        float pdfMat;
+                        if (rnd(seed) < pc.guidingProb) {
+                            newDirection = sampleVmm(seed, vmm, origin, parallax);
+                            pdfMat = pdfBSDF(mat, normal, wi, newDirection);
+                        } else pdfMat = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
+                        if (dot(newDirection, normal) < 0.0f || pdfMat <= 0.0f) pdf = 0.0f;
+                        else {
+                            const float pdfGuiding = vmmPdf(newDirection, vmm, origin, parallax);
+                            if (isnan(pdfGuiding)) pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
+                            else pdf = mixf(pdfMat, pdfGuiding, pc.guidingProb);
+                        }
+                    }
+                } else pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
                 if (pdf <= 0.0f) terminated = true;
                 else {
                     const vec3 change = evalBsdf(sc, mat, info.u, info.v, normal, wi, newDirection, info.isFrontFace) / pdf;
                     T *= change;
+                    if (saveSamples && gst.y < B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL) {
+                        b200pt_directional_data &sd = wf.rec.samples[sbase + gst.y];
+                        if (hasDiscreteDirection(mat.type) || isMatAlmostDiscrete(mat)) sd.flags = B200PT_INVALID_REGION;
+                        else {
+                            sd.position[0] = origin.x; sd.position[1] = origin.y; sd.position[2] = origin.z;
+                            sd.direction[0] = newDirection.x; sd.direction[1] = newDirection.y; sd.direction[2] = newDirection.z;
+                            sd.weight = 0.0f; sd.pdf = pdf; sd.distance = 0.0f;
+                            sd.flags = getGuidingRegion(wf.guide, origin);
+                            gst.z = gst.y;
+                            distanceFactor = 1.0f;
+                        }
+                        wf.rec.lightSums[sbase + gst.y] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        wf.rec.sampleThr[sbase + gst.y] = make_f4(change, 0.0f);
+                        gst.y++;
+                    } else if (gst.z != -1 && mat.type == B200PT_MAT_DIELECTRIC && dot(newDirection, normal) < 0.0f) {
+                        float eta = mat.refractionIndex;
+                        if (!info.isFrontFace) eta = mat.refractionIndexInv;
+                        distanceFactor = fabsf(dot(normal, direction) / dot(normal, newDirection)) * eta;
+                    }
                     direction = newDirection;
                 }
             }
@@ -326,6 +420,16 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
             float4 ps = wf.pixelSum[pid];
             ps.x += add.x; ps.y += add.y; ps.z += add.z;
             wf.pixelSum[pid] = ps;
+            if (saveSamples) {
+                float4 pp = wf.rec.pathSum[pid];
+                pp.x += add.x; pp.y += add.y; pp.z += add.z;
+                wf.rec.pathSum[pid] = pp;
+            }
+        }
+        if (saveSamples) {
+            if (terminated) gst.w = gst.y;       // commitSamples + the sampleOffset update wait for this path's last NEE results
+            wf.rec.state[pid] = gst;
+            wf.rec.distanceFactor[pid] = distanceFactor;
         }
 
         if (terminated) {
@@ -356,9 +460,14 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
 
 // ---------------------------------------------------------------------------------------------------------------
 // accumulate: result /= spp, saveEstimate, saveResult (rgen:1710-1720, 1459-1485, 1602-1605)
-__global__ void __launch_bounds__(256) k_accumulate(FrameParams fp, const float4 *__restrict__ pixelSum, float4 *image, float4 *accum, float4 *estimate) {
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams fp, const float4 *__restrict__ pixelSum, float4 *image, float4 *accum, float4 *estimate,
+                                                    GuidingRecord rec) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= fp.numPixels) return;
+    if (fp.pc.updateGuiding && rec.samples) {     // the frame's last path of this pixel
+        int4 gst = rec.state[p];
+        if (gst.w >= 0) { commitSamples(rec, p, gst); rec.state[p] = gst; }
+    }
     const float4 s = pixelSum[p];
     vec3 result = V3(s.x, s.y, s.z) / float(fp.samplesPerPixel);
     if (fp.pc.storeEstimate) estimate[p] = make_f4(result, 1.0f);
