@@ -21,6 +21,8 @@ all: $(LIB) $(CLI)
 # per-file extras (GUIDING_FLAGS: tuning overrides for guiding_fit.cu, e.g. -DG_BLOCK=256 -DG_BLOCKS_PER_SM=2)
 GUIDING_FLAGS ?=
 EXTRA_guiding_fit := $(GUIDING_FLAGS)
+TRACER_FLAGS ?=
+EXTRA_api := $(TRACER_FLAGS)
 
 $(BUILD)/%.o: $(PKG)/csrc/%.cu $(HEADERS)
 	@mkdir -p $(BUILD)

@@ -87,7 +87,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
-    int numSMs = 0, traceGrid = 0, shadeGrid = 0, shadeGridGuided = 0, resolveGrid = 0;
+    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, resolveGrid = 0;
     TraceTuning tune{64u, 8};
 
     // guiding / IC state
@@ -193,7 +193,10 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
     c->numSMs = prop.multiProcessorCount;
     int occTrace = 0, occShade = 0, occResolve = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace, PT_TRACE_BLOCK, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace<false>, PT_TRACE_BLOCK, 0));
+    int occTraceRec = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTraceRec, k_trace<true>, PT_TRACE_BLOCK, 0));
+    c->traceGridRec = c->numSMs * std::max(1, occTraceRec);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade<false>, 128, 0));
     int occShadeGuided = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeGuided, k_shade<true>, 128, 0));
@@ -427,7 +430,11 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     bool drained = false;
     for (uint64_t iter = 0; !drained; iter++) {
         if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
-        { StageTimer t(c, KIND_EXTEND); k_trace<<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune); }
+        {
+            StageTimer t(c, KIND_EXTEND);
+            if (pc->updateGuiding) k_trace<true><<<c->traceGridRec, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+            else k_trace<false><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+        }
         if (pc->enableNEE && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
         k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
         c->stats.kernel_launches++;

@@ -107,6 +107,11 @@ __device__ __forceinline__ bool travInit(Trav &s, const TraceScene &sc, const ve
 
 // one traversal step; returns true when the ray is finished.  The stack is split: the first PT_STACK_SMEM entries
 // live in shared memory (stride = blockDim.x, conflict-free), the overflow in a per-thread local array.
+// triCap bounds the triangle tests of one step: a node can hand a lane up to 24 leaf triangles while its neighbours get
+// none, and the whole warp would sit through that lane's loop; the surplus goes back on the stack as a triangle group.
+#ifndef PT_TRI_CAP
+#define PT_TRI_CAP 0          // compile-time: 0 = no cap (test every triangle of the group in this step)
+#endif
 __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *smemStack, uint2 *localStack, const int stride, const bool ANY) {
     const vec3 o = s.o, d = s.d;
     uint2 cur = s.cur;
@@ -170,7 +175,13 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
         cur = make_uint2(0u, 0u);
     }
 
+#if PT_TRI_CAP > 0
+#pragma unroll
+    for (int it = 0; it < PT_TRI_CAP; it++) {
+        if (!triGroup.y) break;
+#else
     while (triGroup.y) {
+#endif
         const int ti = __ffs(triGroup.y) - 1;
         triGroup.y &= triGroup.y - 1;
         const uint32_t base = (triGroup.x + uint32_t(ti)) * 3u;
@@ -187,6 +198,17 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
         }
     }
 
+#if PT_TRI_CAP > 0
+    if (triGroup.y) {            // budget exhausted: continue with these triangles in the next step
+        if (cur.y & 0xff000000u) {
+            if (s.sp < PT_STACK_SMEM) smemStack[s.sp * stride] = cur;
+            else localStack[s.sp - PT_STACK_SMEM] = cur;
+            s.sp++;
+        }
+        s.cur = triGroup;
+        return false;
+    }
+#endif
     if ((cur.y & 0xff000000u) == 0) {
         if (s.sp == 0) return true;
         s.sp--;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
 // trace: ONE persistent launch per wavefront iteration traces all three ray queues — path rays and MIS probe rays
 // (closest hit, rgen:1011-1022 / :671-682) and NEE shadow rays (any hit, rgen:622-638 + shadow.rmiss) whose
 // contribution is splatted when unoccluded (rgen:657-663).  Ray index space: [path | probe | shadow].
+template <bool REC>       // REC: guiding training frame — shadow hits also feed the recorded samples (kept out of the plain kernel: +7 registers)
 struct WavefrontRayIO {
     const float4 *pathO, *pathD; float4 *pathHit;
     const float4 *probeO, *probeD; float4 *probeHit;
@@ -127,7 +128,7 @@ struct WavefrontRayIO {
             const int pix = __float_as_int(shO[k].w);
             float *dst = reinterpret_cast<float *>(&pixelSum[pix]);
             atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
-            if (rec.samples) {       // the deferred half of `updateSamples(currentSampleOffset, neeLight)` (rgen:1164-1165)
+            if (REC) {               // the deferred half of `updateSamples(currentSampleOffset, neeLight)` (rgen:1164-1165)
                 float *ps = reinterpret_cast<float *>(&rec.pathSum[pix]);
                 atomicAdd(ps + 0, c.x); atomicAdd(ps + 1, c.y); atomicAdd(ps + 2, c.z);
                 const float4 g = shG[k];
@@ -137,15 +138,17 @@ struct WavefrontRayIO {
     }
 };
 
+template <bool REC>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefront wf, int cur, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
-    WavefrontRayIO io;
+    WavefrontRayIO<REC> io;
     io.nPath = wf.counters[CNT_PATH0 + cur]; io.nProbe = wf.counters[CNT_PROBE];
     const uint32_t total = io.nPath + io.nProbe + wf.counters[CNT_SHADOW];
     if (total == 0) return;
     io.pathO = wf.pathRayO[cur]; io.pathD = wf.pathRayD[cur]; io.pathHit = wf.pathHit;
     io.probeO = wf.probeRayO; io.probeD = wf.probeRayD; io.probeHit = wf.probeHit;
-    io.shO = wf.shRayO; io.shD = wf.shRayD; io.shC = wf.shC; io.shG = wf.shG; io.pixelSum = wf.pixelSum; io.rec = wf.rec;
+    io.shO = wf.shRayO; io.shD = wf.shRayD; io.shC = wf.shC; io.shG = wf.shG; io.pixelSum = wf.pixelSum;
+    if (REC) io.rec = wf.rec;
     // small queues (the tail of a frame): shrink the chunk so the rays spread over all SMs
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
