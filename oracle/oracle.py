@@ -80,6 +80,22 @@ class TracerOracle:
     def reset_counters(self):
         lib().oracle_reset_counters(self._h)
 
+    def set_image(self, which, rgba):
+        p = lib().oracle_image(self._h, which)
+        np.ctypeslib.as_array(p, shape=(self.height, self.width, 4))[...] = np.asarray(rgba, dtype=np.float32).reshape(self.height, self.width, 4)
+
+    def ic_get(self, P):
+        hdr = P.CacheHeader()
+        data = np.zeros(self.ic_size, dtype=P.CACHE_DATA_DTYPE)
+        spheres = np.zeros(self.ic_size, dtype=P.SPHERE_DTYPE)
+        lib().oracle_ic_get(self._h, C.addressof(hdr), data.ctypes.data, spheres.ctypes.data, self.ic_size)
+        return hdr, data, spheres
+
+    def ic_put(self, hdr, data, spheres):
+        d = np.ascontiguousarray(data)
+        s = np.ascontiguousarray(spheres)
+        lib().oracle_ic_put(self._h, C.addressof(hdr), d.ctypes.data, s.ctypes.data, d.shape[0])
+
     def set_guiding(self, aabbs, vmms):
         a = np.ascontiguousarray(aabbs)
         v = np.ascontiguousarray(vmms)

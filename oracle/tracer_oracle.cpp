@@ -16,6 +16,13 @@
 //   spheres  : raytrace.sphere.rint:13-28, both roots, accepted when tmin <= t <= tmax
 //   closest hit = lexicographic minimum of (t, primitive id); ids = triangles in instance order, then spheres.
 // A median-split BVH (ORACLE_ACCEL) gives the same answers faster; tests check it against the brute force.
+//
+// Irradiance cache, frame semantic (ours — the reference races here): inside one frame every lookup
+// sees the cache as it was when the frame started (in the reference new entries are not in the lookup acceleration
+// structure before the host refits it for the next frame either; only the ~10 entries per frame that
+// updateIrradianceCache rewrites can be observed half-way there).  Update slots (header.nextUpdateSlot++) and new cache
+// slots (header.nextCacheSlot++) are handed out in pixel order, and the results are committed in that order after the
+// last pixel: that is what the reference does when its invocations happen to run one after the other.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -152,6 +159,15 @@ struct oracle_ctx {
     b200pt_cache_header header{0, 0, 0};
     std::vector<b200pt_cache_data> cache;
     std::vector<b200pt_sphere> cacheSpheres;
+    // frame-start snapshot (what every lookup of the frame reads) and the frame's deferred writes
+    b200pt_cache_header snapHeader{0, 0, 0};
+    std::vector<b200pt_cache_data> snapCache;
+    std::vector<b200pt_sphere> snapSpheres;
+    struct PendingEntry { bool valid; float harmonicR; float origin[3], normal[3], color[3], rotGrad[3], transGrad[3]; };
+    std::vector<int32_t> updateSlotOfPixel;                 // per pixel of the region: cache index to update, -1 none
+    std::vector<PendingEntry> pendingUpdate;                // per pixel of the region
+    std::vector<std::vector<PendingEntry>> pendingCreate;   // per pixel of the region, in creation order
+    int regionX0 = 0, regionY0 = 0, regionNX = 0;
     // guiding (bindings 15,16,18)
     std::vector<b200pt_aabb> guidingAabbs;
     std::vector<b200pt_vmm_theta> guidingVMM;
@@ -691,10 +707,10 @@ struct Pixel {
     bool queryIrradianceCache(v3 origin, v3 normal, v3 &color) const {
         v3 cacheValueSum(0.0f);
         float totalWeight = 0;
-        uint32_t n = std::min<uint32_t>(uint32_t(C.cacheSpheres.size()), C.header.maxCaches);
-        for (uint32_t i = 0; i < n; i++) {
-            const b200pt_sphere &cs = C.cacheSpheres[i];
-            const b200pt_cache_data &cd = C.cache[i];
+        uint32_t n = std::min<uint32_t>(std::min<uint32_t>(uint32_t(C.snapSpheres.size()), C.snapHeader.maxCaches), C.snapHeader.nextCacheSlot);
+        for (uint32_t i = 0; i < n; i++) {       // any-hit order is the driver's; ours: ascending cache index
+            const b200pt_sphere &cs = C.snapSpheres[i];
+            const b200pt_cache_data &cd = C.snapCache[i];
             v3 oc = origin - v3(cs.center);
             if (!(length(oc) <= cs.radius)) continue;          // .rint
             float weight = 1.0f / (length(origin - v3(cs.center)) / cd.harmonicR + sqrtf(1 - dot(normal, v3(cd.normal))));
@@ -997,52 +1013,32 @@ struct Pixel {
         if (invDistanceSum == 0 || numDistances == 0) return -1;
         return 1.0f / (invDistanceSum / numDistances);
     }
-    void clampGradients(v3 &rotGrad, v3 &transGrad) const {              // rgen:1318-1329
+    static void clampGradients(float maxLength, v3 &rotGrad, v3 &transGrad) {   // rgen:1318-1329
         float lr = length(rotGrad);
-        if (lr > pushC.irradianceGradientsMaxLength) rotGrad *= pushC.irradianceGradientsMaxLength / lr;
+        if (lr > maxLength) rotGrad *= maxLength / lr;
         float lt = length(transGrad);
-        if (lt > pushC.irradianceGradientsMaxLength) transGrad *= pushC.irradianceGradientsMaxLength / lt;
+        if (lt > maxLength) transGrad *= maxLength / lt;
     }
     static void st3(float *d, v3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
-    void updateIrradianceCache() {                                       // rgen:1334-1381
-        uint32_t cacheIndex = C.header.nextUpdateSlot++;
-        if (cacheIndex >= C.header.nextCacheSlot) { C.header.nextUpdateSlot = 0; return; }
-        if (C.cache[cacheIndex].numUpdates < 1) return;
+    int regionIndex() const { return int(py - uint32_t(C.regionY0)) * C.regionNX + int(px - uint32_t(C.regionX0)); }
+    void updateIrradianceCache() {                                       // rgen:1334-1381; slot handed out in pixel order, blend at commit
+        const int cacheIndex = C.updateSlotOfPixel[regionIndex()];
+        if (cacheIndex < 0) return;
+        oracle_ctx::PendingEntry &pe = C.pendingUpdate[regionIndex()];
         v3 rotGrad, transGrad, calculatedColor;
-        float harmonicR = calculateCacheData(v3(C.cacheSpheres[cacheIndex].center), v3(C.cache[cacheIndex].normal), calculatedColor, rotGrad, transGrad);
-        b200pt_cache_data &cd = C.cache[cacheIndex];
-        uint32_t numUpdates = cd.numUpdates;
-        float a = std::min(numUpdates / float(numUpdates + 1), 0.95f);
-        st3(cd.color, mix(calculatedColor, v3(cd.color), a));
-        rotGrad = mix(rotGrad, v3(cd.rotGrad), a);
-        transGrad = mix(transGrad, v3(cd.transGrad), a);
-        clampGradients(rotGrad, transGrad);
-        st3(cd.rotGrad, rotGrad); st3(cd.transGrad, transGrad);
-        if (harmonicR > 0) harmonicR = mixf(harmonicR, cd.harmonicR, a);
-        else harmonicR = cd.harmonicR;
-        harmonicR = std::max(harmonicR, pushC.irradianceCacheMinRadius);
-        cd.harmonicR = harmonicR;
-        C.cacheSpheres[cacheIndex].radius = pushC.irradianceA * harmonicR;
-        cd.numUpdates += 1;
+        pe.harmonicR = calculateCacheData(v3(C.snapSpheres[cacheIndex].center), v3(C.snapCache[cacheIndex].normal), calculatedColor, rotGrad, transGrad);
+        st3(pe.color, calculatedColor); st3(pe.rotGrad, rotGrad); st3(pe.transGrad, transGrad);
+        pe.valid = true;
     }
-    bool createIrradianceCache(v3 origin, v3 normal, v3 &calculatedColor) {   // rgen:1383-1421
-        if (C.header.nextCacheSlot > C.header.maxCaches) return false;
+    bool createIrradianceCache(v3 origin, v3 normal, v3 &calculatedColor) {   // rgen:1383-1421; slot handed out at commit
+        if (C.snapHeader.nextCacheSlot > C.snapHeader.maxCaches) return false;
+        oracle_ctx::PendingEntry pe;
         v3 rotGrad, transGrad;
-        float harmonicR = calculateCacheData(origin, normal, calculatedColor, rotGrad, transGrad);
-        if (harmonicR < 0) return false;
-        uint32_t cacheIndex = C.header.nextCacheSlot++;
-        if (cacheIndex > C.header.maxCaches) return false;
-        if (cacheIndex >= C.cache.size()) return false;   // the reference writes one element past the buffer here (quirk 11)
-        harmonicR = std::max(harmonicR, pushC.irradianceCacheMinRadius);
-        clampGradients(rotGrad, transGrad);
-        b200pt_cache_data &cd = C.cache[cacheIndex];
-        st3(cd.normal, normal); st3(cd.color, calculatedColor);
-        cd.harmonicR = harmonicR;
-        st3(cd.rotGrad, rotGrad); st3(cd.transGrad, transGrad);
-        cd.numUpdates = 1;
-        st3(C.cacheSpheres[cacheIndex].center, origin);
-        C.cacheSpheres[cacheIndex].radius = pushC.irradianceA * harmonicR;
-        return true;
+        pe.harmonicR = calculateCacheData(origin, normal, calculatedColor, rotGrad, transGrad);
+        pe.valid = !(pe.harmonicR < 0);
+        st3(pe.origin, origin); st3(pe.normal, normal); st3(pe.color, calculatedColor); st3(pe.rotGrad, rotGrad); st3(pe.transGrad, transGrad);
+        C.pendingCreate[regionIndex()].push_back(pe);
+        return pe.valid;
     }
 
     void getCameraRay(float pcx, float pcy, v3 &origin, v3 &direction) {  // rgen:1487-1494
@@ -1241,15 +1237,32 @@ void oracle_set_camera(oracle_ctx *C, const float view[16], const float proj[16]
     memcpy(C->view, view, 64); memcpy(C->proj, proj, 64); memcpy(C->viewInverse, viewInv, 64); memcpy(C->projInverse, projInv, 64);
 }
 
-// render the pixels [x0,x1) x [y0,y1) of one frame, sequentially in row-major order (one raygen invocation each)
+// render the pixels [x0,x1) x [y0,y1) of one frame (one raygen invocation each).  Pixels are independent: irradiance-
+// cache lookups read the frame-start snapshot, cache writes are deferred and committed in pixel order afterwards.
 int oracle_render_region(oracle_ctx *C, const b200pt_push_constants *pc, int x0, int y0, int x1, int y1, int num_threads) {
     C->pushC = *pc;
-    const bool shared = pc->useIrradianceCache || pc->useADRRS;   // IC header/cache are shared state: keep it serial
     int nx = x1 - x0, ny = y1 - y0;
     if (nx <= 0 || ny <= 0) return 0;
     uint64_t ext = 0, sh = 0, pv = 0;
     const int total = nx * ny;
-    const int nthreads = (shared || num_threads < 1) ? 1 : num_threads;
+    const int nthreads = num_threads < 1 ? 1 : num_threads;
+    // ---- frame start: snapshot + update slots in pixel order (rgen:1334-1343) ----
+    C->snapHeader = C->header; C->snapCache = C->cache; C->snapSpheres = C->cacheSpheres;
+    C->regionX0 = x0; C->regionY0 = y0; C->regionNX = nx;
+    C->updateSlotOfPixel.assign(size_t(total), -1);
+    C->pendingUpdate.assign(size_t(total), oracle_ctx::PendingEntry{});
+    C->pendingCreate.assign(size_t(total), {});
+    if (pc->useIrradianceCache) {
+        for (int i = 0; i < total; i++) {
+            uint32_t x = uint32_t(x0 + i % nx), y = uint32_t(y0 + i / nx);
+            uint32_t seed = tea(y * uint32_t(C->width) + x, pc->randomUInt);
+            if (!(Pixel::rndS(seed) < pc->irradianceUpdateProb)) continue;
+            uint32_t cacheIndex = C->header.nextUpdateSlot++;
+            if (cacheIndex >= C->snapHeader.nextCacheSlot) { C->header.nextUpdateSlot = 0; continue; }
+            if (cacheIndex >= C->snapCache.size() || C->snapCache[cacheIndex].numUpdates < 1) continue;
+            C->updateSlotOfPixel[size_t(i)] = int32_t(cacheIndex);
+        }
+    }
     std::atomic<int> next(0);
     std::mutex mu;
     auto worker = [&]() {
@@ -1271,6 +1284,47 @@ int oracle_render_region(oracle_ctx *C, const b200pt_push_constants *pc, int x0,
         std::vector<std::thread> pool;
         for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
         for (auto &t : pool) t.join();
+    }
+    // ---- frame end: commit in pixel order ----
+    for (int i = 0; i < total; i++) {                       // updateIrradianceCache, rgen:1351-1380 (blend against the snapshot)
+        const oracle_ctx::PendingEntry &pe = C->pendingUpdate[size_t(i)];
+        if (!pe.valid) continue;
+        const int cacheIndex = C->updateSlotOfPixel[size_t(i)];
+        const b200pt_cache_data &old = C->snapCache[size_t(cacheIndex)];
+        b200pt_cache_data &cd = C->cache[size_t(cacheIndex)];
+        uint32_t numUpdates = old.numUpdates;
+        float a = std::min(numUpdates / float(numUpdates + 1), 0.95f);
+        Pixel::st3(cd.color, mix(v3(pe.color), v3(old.color), a));
+        v3 rotGrad = mix(v3(pe.rotGrad), v3(old.rotGrad), a);
+        v3 transGrad = mix(v3(pe.transGrad), v3(old.transGrad), a);
+        Pixel::clampGradients(pc->irradianceGradientsMaxLength, rotGrad, transGrad);
+        Pixel::st3(cd.rotGrad, rotGrad); Pixel::st3(cd.transGrad, transGrad);
+        float harmonicR = pe.harmonicR;
+        if (harmonicR > 0) harmonicR = mixf(harmonicR, old.harmonicR, a);
+        else harmonicR = old.harmonicR;
+        harmonicR = std::max(harmonicR, pc->irradianceCacheMinRadius);
+        cd.harmonicR = harmonicR;
+        C->cacheSpheres[size_t(cacheIndex)].radius = pc->irradianceA * harmonicR;
+        cd.numUpdates = numUpdates + 1;
+    }
+    for (int i = 0; i < total; i++) {                       // createIrradianceCache, rgen:1394-1420
+        for (const oracle_ctx::PendingEntry &pe : C->pendingCreate[size_t(i)]) {
+            if (!pe.valid) continue;
+            if (C->header.nextCacheSlot > C->header.maxCaches) continue;
+            uint32_t cacheIndex = C->header.nextCacheSlot++;
+            if (cacheIndex > C->header.maxCaches) continue;
+            if (cacheIndex >= C->cache.size()) continue;    // the reference writes one element past the buffer here (quirk 11)
+            float harmonicR = std::max(pe.harmonicR, pc->irradianceCacheMinRadius);
+            v3 rotGrad(pe.rotGrad), transGrad(pe.transGrad);
+            Pixel::clampGradients(pc->irradianceGradientsMaxLength, rotGrad, transGrad);
+            b200pt_cache_data &cd = C->cache[cacheIndex];
+            memcpy(cd.normal, pe.normal, 12); memcpy(cd.color, pe.color, 12);
+            cd.harmonicR = harmonicR;
+            Pixel::st3(cd.rotGrad, rotGrad); Pixel::st3(cd.transGrad, transGrad);
+            cd.numUpdates = 1;
+            memcpy(C->cacheSpheres[cacheIndex].center, pe.origin, 12);
+            C->cacheSpheres[cacheIndex].radius = pc->irradianceA * harmonicR;
+        }
     }
     C->extendRays += ext; C->shadowRays += sh; C->pathVertices += pv;
     return 0;

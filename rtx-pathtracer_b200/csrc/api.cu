@@ -1,6 +1,7 @@
 // libb200pt.so — context management and the C ABI declared in include/b200pt.h.
 // There is NO CPU fallback: every compute entry point needs a CUDA device and fails loudly without one.
 #include "wavefront.cuh"
+#include "ic_kernels.cuh"
 #include "guiding_fit.cuh"
 #include "../host/scene.h"
 #include "../host/bvh.h"
@@ -87,7 +88,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
-    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, resolveGrid = 0;
+    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, resolveGrid = 0;
     TraceTuning tune{64u, 8};
 
     // guiding / IC state
@@ -96,6 +97,14 @@ struct b200pt_ctx {
     DevBuf<b200pt_cache_data> icData;
     DevBuf<b200pt_sphere> icSpheres;
     DevBuf<b200pt_cache_header> icHeader;
+    // IC lookup snapshot + grid, per-pixel IC / split state, ordered-compaction scratch (allocated on first use)
+    DevBuf<float4> icSnapSphere, icSnapNormalR, icSnapColor, icSnapRot, icSnapTrans, icPending, icNewEntries, icSplitData;
+    DevBuf<uint2> icRanges;
+    DevBuf<uint32_t> icCellCount, icCellStart, icCellItems, icSnapHdr, icBlockCounts, icList, icNewCount, icSplitState;
+    DevBuf<int32_t> icUpdSlot;
+    uint32_t *hostIcHdr = nullptr;      // pinned, ICH_NUM
+    ICView icGrid{};
+    int icNumCells = 0;
 
     // batch tracing scratch
     DevBuf<float4> batchRays, batchHits;
@@ -161,6 +170,86 @@ static int ensureQueues(b200pt_ctx *c, int numNEE) {
     return B200PT_OK;
 }
 
+// IC / ADRRS buffers (allocated on the first frame that needs them) and the lookup-grid geometry
+static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
+    const size_t N = size_t(c->numPixels);
+    CUDA_TRY(c->icSnapHdr.alloc(ICH_NUM));
+    CUDA_TRY(c->icBlockCounts.alloc(N / 256 + 2));
+    CUDA_TRY(c->icList.alloc(N));
+    if (needCache) {
+        const size_t S = size_t(std::max(1, c->icSize));
+        CUDA_TRY(c->icSnapSphere.alloc(S)); CUDA_TRY(c->icSnapNormalR.alloc(S)); CUDA_TRY(c->icSnapColor.alloc(S));
+        CUDA_TRY(c->icSnapRot.alloc(S)); CUDA_TRY(c->icSnapTrans.alloc(S)); CUDA_TRY(c->icRanges.alloc(S));
+        CUDA_TRY(c->icCellCount.alloc(size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1));
+        CUDA_TRY(c->icCellStart.alloc(size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1));
+        CUDA_TRY(c->icCellItems.alloc(S * 8));
+        CUDA_TRY(c->icNewCount.alloc(N));
+        CUDA_TRY(c->icNewEntries.alloc(N * IC_MAX_NEW * 2));
+        // uniform grid over the scene box (the same box the guiding regions start from), at most IC_GRID_MAX cells per axis
+        float ext[3], mx = 0.0f;
+        for (int a = 0; a < 3; a++) { ext[a] = c->sceneMax[a] - c->sceneMin[a]; mx = std::max(mx, ext[a]); }
+        const float cell = mx > 0.0f ? mx / float(IC_GRID_MAX) : 1.0f;
+        ICView &g = c->icGrid;
+        c->icNumCells = 1;
+        for (int a = 0; a < 3; a++) {
+            g.gmin[a] = c->sceneMin[a];
+            g.invCell[a] = 1.0f / cell;
+            g.dim[a] = std::min(IC_GRID_MAX, std::max(1, int(ceilf(ext[a] / cell))));
+            c->icNumCells *= g.dim[a];
+        }
+        g.sphere = c->icSnapSphere.p; g.normalR = c->icSnapNormalR.p; g.color = c->icSnapColor.p; g.rotGrad = c->icSnapRot.p; g.transGrad = c->icSnapTrans.p;
+        g.cellStart = c->icCellStart.p; g.cellItems = c->icCellItems.p;
+    }
+    if (splitMode) {
+        CUDA_TRY(c->icSplitState.alloc(N));
+        CUDA_TRY(c->icSplitData.alloc(N * IC_MAX_SPLITS * IC_SPLIT_F4));
+    }
+    return B200PT_OK;
+}
+
+static ICBuffers icBuffers(b200pt_ctx *c) {
+    ICBuffers b{};
+    b.header = c->icHeader.p; b.data = c->icData.p; b.spheres = c->icSpheres.p;
+    b.snapSphere = c->icSnapSphere.p; b.snapNormalR = c->icSnapNormalR.p; b.snapColor = c->icSnapColor.p; b.snapRot = c->icSnapRot.p; b.snapTrans = c->icSnapTrans.p;
+    b.ranges = c->icRanges.p; b.cellCount = c->icCellCount.p; b.cellStart = c->icCellStart.p; b.cellItems = c->icCellItems.p;
+    b.snapHdr = c->icSnapHdr.p; b.blockCounts = c->icBlockCounts.p; b.list = c->icList.p; b.updSlot = c->icUpdSlot.p; b.pending = c->icPending.p;
+    b.icSize = c->icSize; b.numCells = c->icNumCells;
+    return b;
+}
+
+static inline unsigned gridFor(uint64_t n, unsigned block) { return unsigned((n + block - 1) / block); }
+
+// copies the IC snapshot header (entry count, grid size, list count) to the host; the few host decisions of an IC
+// frame (buffer growth, launch shape of the cache-build kernels) are taken on it
+static int readIcHeader(b200pt_ctx *c) {
+    CUDA_TRY(cudaMemcpyAsync(c->hostIcHdr, c->icSnapHdr.p, ICH_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+// ordered list of the pixels that satisfy `pred` -> c->icList, count in hostIcHdr[ICH_LIST_COUNT]
+template <typename Pred>
+static int compactPixels(b200pt_ctx *c, Pred pred) {
+    const unsigned blocks = gridFor(uint64_t(c->numPixels), 256);
+    k_flag_count<<<blocks, 256, 0, c->stream>>>(pred, c->numPixels, c->icBlockCounts.p);
+    k_scan_single_block<<<1, 1024, 0, c->stream>>>(c->icBlockCounts.p, c->icBlockCounts.p, int(blocks), c->icSnapHdr.p + ICH_LIST_COUNT);
+    c->stats.kernel_launches += 2;
+    int rc = readIcHeader(c);
+    if (rc != B200PT_OK) return rc;
+    if (c->hostIcHdr[ICH_LIST_COUNT]) {
+        k_flag_fill<<<blocks, 256, 0, c->stream>>>(pred, c->numPixels, c->icBlockCounts.p, c->icList.p);
+        c->stats.kernel_launches++;
+    }
+    return B200PT_OK;
+}
+
+// launch shape of the cache-build kernels: one entry per warp while the list fits the machine, else one per thread
+static void buildLaunchShape(const b200pt_ctx *c, uint32_t entries, int &grid, int &stride) {
+    const uint32_t warpSlots = uint32_t(c->numSMs) * 16u * 4u;
+    if (entries <= warpSlots) { stride = 32; grid = int(gridFor(entries, 4)); }
+    else { stride = 1; grid = int(gridFor(entries, 128)); }
+}
+
 extern "C" {
 
 const char *b200pt_last_error(void) { return g_lastError.c_str(); }
@@ -197,10 +286,15 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     int occTraceRec = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTraceRec, k_trace<true>, PT_TRACE_BLOCK, 0));
     c->traceGridRec = c->numSMs * std::max(1, occTraceRec);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade<false>, 128, 0));
-    int occShadeGuided = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeGuided, k_shade<true>, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade<false, false>, 128, 0));
+    int occShadeGuided = 0, occShadeIC = 0, occShadeGuidedIC = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeGuided, k_shade<true, false>, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeIC, k_shade<false, true>, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeGuidedIC, k_shade<true, true>, 128, 0));
     c->shadeGridGuided = c->numSMs * std::max(1, occShadeGuided);
+    c->shadeGridIC = c->numSMs * std::max(1, occShadeIC);
+    c->shadeGridGuidedIC = c->numSMs * std::max(1, occShadeGuidedIC);
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostIcHdr), ICH_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
     c->traceGrid = c->numSMs * std::max(1, occTrace);
     c->shadeGrid = c->numSMs * std::max(1, occShade);
@@ -246,6 +340,11 @@ int b200pt_destroy(b200pt_ctx *c) {
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
     c->samples.release(); c->hostSamples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
+    c->icSnapSphere.release(); c->icSnapNormalR.release(); c->icSnapColor.release(); c->icSnapRot.release(); c->icSnapTrans.release();
+    c->icPending.release(); c->icNewEntries.release(); c->icSplitData.release(); c->icRanges.release();
+    c->icCellCount.release(); c->icCellStart.release(); c->icCellItems.release(); c->icSnapHdr.release(); c->icBlockCounts.release();
+    c->icList.release(); c->icNewCount.release(); c->icSplitState.release(); c->icUpdSlot.release();
+    if (c->hostIcHdr) cudaFreeHost(c->hostIcHdr);
     c->guiding.release();
     for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
@@ -379,20 +478,29 @@ int b200pt_set_camera(b200pt_ctx *c, const float view[16], const float proj[16])
     return B200PT_OK;
 }
 
-static inline unsigned gridFor(uint64_t n, unsigned block) { return unsigned((n + block - 1) / block); }
-
 int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     if (!c || !pc) return setError(B200PT_E_INVALID, "b200pt_render_frame: null argument");
     if (!c->hasScene || !c->hasCamera) return setError(B200PT_E_STATE, "b200pt_render_frame: set_scene and set_camera must be called first");
-    if (pc->useIrradianceCache || pc->useADRRS || pc->splitOnFirst || pc->showIrradianceCacheOnly)
-        return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS / splitOnFirst render modes are not implemented in this build");
+    if (pc->showIrradianceCacheOnly || pc->visualizeMode != 0)
+        return setError(B200PT_E_STATE, "b200pt_render_frame: the debug views (visualizeMode, showIrradianceCacheOnly) are not part of this library");
+    const bool useCache = pc->useIrradianceCache || pc->useADRRS;
+    const bool splitMode = (pc->useADRRS && pc->adrrsSplit) || pc->splitOnFirst;
+    const bool icMode = useCache || splitMode;
+    if (useCache && c->icSize < 1) return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS need a context created with ic_size > 0");
+    if (pc->updateGuiding && pc->useIrradianceCache)
+        return setError(B200PT_E_STATE, "b200pt_render_frame: guiding training on irradiance-cache frames is not supported");
     const bool guided = pc->useGuiding || pc->updateGuiding;
     if (guided && !c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_render_frame: guiding needs a scene (region tree)");
     if (pc->numNEE < 1 || pc->samplesPerPixel < 1 || pc->maxDepth < 0 || pc->maxDepth > 60000)
         return setError(B200PT_E_INVALID, "b200pt_render_frame: numNEE, samplesPerPixel must be >= 1 and maxDepth in [0, 60000]");
+    if (useCache && pc->irradianceNumNEE < 1) return setError(B200PT_E_INVALID, "b200pt_render_frame: irradianceNumNEE must be >= 1");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensureQueues(c, pc->enableNEE ? pc->numNEE : 1);
+    // a pixel that finishes a path and starts a split in the same shade pass queues two rounds of light samples
+    int rc = ensureQueues(c, (pc->enableNEE || useCache ? pc->numNEE : 1) * (splitMode ? 2 : 1));
     if (rc != B200PT_OK) return rc;
+    if (icMode) { rc = ensureIC(c, useCache, splitMode); if (rc != B200PT_OK) return rc; }
+    // samples are not collected while splitting: the raygen returns right after resetting them (rgen:1643-1650)
+    const bool earlyReturn = pc->updateGuiding && splitMode;
 
     {   // guiding views: region tree + mixtures, and (training frames) the sample-recording state
         Wavefront &w = c->wf;
@@ -408,6 +516,13 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             w.rec.state = c->recState.p; w.rec.distanceFactor = c->recDistanceFactor.p; w.rec.pathSum = c->recPathSum.p;
             w.shG = c->shG.p;
         }
+        w.ic = ICState{};
+        if (useCache) {
+            w.ic.view = c->icGrid;
+            w.ic.estimate = c->imgEstimate.p;
+            w.ic.newCount = c->icNewCount.p; w.ic.newEntries = c->icNewEntries.p;
+        }
+        if (splitMode) { w.ic.splitState = c->icSplitState.p; w.ic.splitData = c->icSplitData.p; }
     }
     FrameParams fp;
     fp.pc = *pc;
@@ -418,16 +533,54 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     cudaStream_t st = c->stream;
     const uint32_t N = uint32_t(c->numPixels);
     CUDA_TRY(cudaEventRecord(c->evA, st));
+    CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, DST_NUM * sizeof(unsigned long long), st));
+
+    if (useCache) {
+        // frame-start snapshot of the cache + lookup grid (replaces IrradianceCache::updateSpheres, src/IrradianceCache.cpp:81-104)
+        StageTimer t(c, KIND_SHADE);
+        ICBuffers b = icBuffers(c);
+        k_ic_snapshot<<<gridFor(uint64_t(std::max(1, c->icSize)), 256), 256, 0, st>>>(b, c->icGrid);
+        k_ic_cells<false><<<gridFor(uint64_t(c->icNumCells), 256), 256, 0, st>>>(b, c->icGrid);
+        k_scan_single_block<<<1, 1024, 0, st>>>(c->icCellCount.p, c->icCellStart.p, c->icNumCells, c->icSnapHdr.p + ICH_GRID_TOTAL);
+        c->stats.kernel_launches += 2;
+        rc = readIcHeader(c);
+        if (rc != B200PT_OK) return rc;
+        if (c->hostIcHdr[ICH_GRID_TOTAL] > c->icCellItems.n) {
+            CUDA_TRY(c->icCellItems.alloc(size_t(c->hostIcHdr[ICH_GRID_TOTAL]) * 2));
+            c->icGrid.cellItems = c->icCellItems.p; c->wf.ic.view.cellItems = c->icCellItems.p;
+            b = icBuffers(c);
+        }
+        if (c->hostIcHdr[ICH_GRID_TOTAL]) { k_ic_cells<true><<<gridFor(uint64_t(c->icNumCells), 256), 256, 0, st>>>(b, c->icGrid); c->stats.kernel_launches++; }
+    }
+    if (pc->useIrradianceCache && pc->irradianceUpdateProb > 0.0f) {
+        // updateIrradianceCache (rgen:1334-1381) for the pixels whose first random number selects them, before any path
+        PredICUpdate pred{pc->randomUInt, pc->irradianceUpdateProb};
+        rc = compactPixels(c, pred);
+        if (rc != B200PT_OK) return rc;
+        const uint32_t entries = c->hostIcHdr[ICH_LIST_COUNT];
+        if (entries) {
+            StageTimer t(c, KIND_SHADE);
+            CUDA_TRY(c->icUpdSlot.alloc(entries)); CUDA_TRY(c->icPending.alloc(size_t(entries) * 3));
+            ICBuffers b = icBuffers(c);
+            int grid, stride;
+            buildLaunchShape(c, entries, grid, stride);
+            k_ic_update_assign<<<1, 32, 0, st>>>(b);
+            k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride);
+            k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
+            c->stats.kernel_launches += 2;
+        }
+    }
+
     { StageTimer t(c, KIND_SHADE); k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf); }
     c->stats.samples += N;
     uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, DST_NUM * sizeof(unsigned long long), st));
     // Wavefront loop.  Every kernel reads its queue sizes from device memory, so iterations are issued back-to-back;
     // the host only peeks at the counters of iteration i-LAG to learn when the queues have drained.
     int cur = 0;
-    const uint64_t maxIter = uint64_t(fp.samplesPerPixel) * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
-    bool drained = false;
+    const uint64_t pathsPerPixel = uint64_t(fp.samplesPerPixel) + (splitMode ? IC_MAX_SPLITS : 0);
+    const uint64_t maxIter = pathsPerPixel * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
+    bool drained = earlyReturn;
     for (uint64_t iter = 0; !drained; iter++) {
         if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
         {
@@ -435,13 +588,15 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             if (pc->updateGuiding) k_trace<true><<<c->traceGridRec, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
             else k_trace<false><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
         }
-        if (pc->enableNEE && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
+        if ((pc->enableNEE || useCache) && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
         k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
         c->stats.kernel_launches++;
         {
             StageTimer t(c, KIND_SHADE);
-            if (guided) k_shade<true><<<c->shadeGridGuided, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
-            else k_shade<false><<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            if (guided && icMode) k_shade<true, true><<<c->shadeGridGuidedIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            else if (icMode) k_shade<false, true><<<c->shadeGridIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            else if (guided) k_shade<true, false><<<c->shadeGridGuided, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            else k_shade<false, false><<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
         }
         cur = 1 - cur;
         const int slot = int(iter % b200pt_ctx::RING);
@@ -458,8 +613,28 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             drained = hc[CNT_PATH0 + liveQ] == 0 && hc[CNT_PROBE] == 0 && hc[CNT_SHADOW] == 0;
         }
     }
+    if (!earlyReturn) {
+        StageTimer t(c, KIND_SHADE);
+        k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec);
+    }
+    if (useCache && !earlyReturn) {
+        // createIrradianceCache for the entries the frame's paths queued (rgen:1821-1827), slots in pixel order
+        PredICCreate pred{c->icNewCount.p};
+        rc = compactPixels(c, pred);
+        if (rc != B200PT_OK) return rc;
+        const uint32_t entries = c->hostIcHdr[ICH_LIST_COUNT];
+        if (entries) {
+            StageTimer t(c, KIND_SHADE);
+            CUDA_TRY(c->icPending.alloc(size_t(entries) * IC_MAX_NEW * 3));
+            ICBuffers b = icBuffers(c);
+            int grid, stride;
+            buildLaunchShape(c, entries, grid, stride);
+            k_ic_create<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride);
+            k_ic_create_commit<<<1, 32, 0, st>>>(fp, c->wf, b);
+            c->stats.kernel_launches++;
+        }
+    }
     CUDA_TRY(cudaMemcpyAsync(c->hostDstats, c->dstats.p, DST_NUM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    { StageTimer t(c, KIND_SHADE); k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec); }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());

@@ -5,6 +5,7 @@
 #pragma once
 #include "shading.cuh"
 #include "guiding_device.cuh"
+#include "ic_device.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -49,6 +50,7 @@ struct Wavefront {
     unsigned long long *dstats;   // DST_*
     GuidingView guide;       // region tree + mixtures (useGuiding / updateGuiding)
     GuidingRecord rec;       // sample-recording state (updateGuiding); rec.samples == nullptr when not recording
+    ICState ic;              // irradiance cache / ADRRS state (useIrradianceCache / useADRRS / splitOnFirst frames)
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -81,6 +83,11 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= fp.numPixels) return;
     uint32_t seed = tea(uint32_t(p), fp.pc.randomUInt);
+    if (fp.pc.useIrradianceCache) {      // rgen:1639-1641: the update draw; k_ic_update has advanced the stream of the selected pixels
+        if (rnd(seed) < fp.pc.irradianceUpdateProb) seed = wf.seed[p];
+    }
+    if (wf.ic.newCount) wf.ic.newCount[p] = 0u;
+    if (wf.ic.splitState) wf.ic.splitState[p] = 0u;
     const int px = p % fp.width, py = p / fp.width;
     vec3 o, d;
     cameraRay(fp, seed, px, py, o, d);
@@ -231,19 +238,77 @@ __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceSce
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// multipleNEE / nextEventEstimation (rgen:871-877, :601-731) in queue form: the shadow ray and the MIS probe ray of
+// every light sample go to their queues with the contribution they carry; k_trace / k_probe_resolve finish them.
+// T is the throughput the NEE result is multiplied with; cso = currentSampleOffset (guiding training only).
+__device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceScene &sc, const Wavefront &wf, uint32_t &seed, const b200pt_material &mat,
+                                          const HitInfo &info, vec3 origin, vec3 normal, vec3 wi, vec3 T, int pid, bool saveSamples, int cso, uint2 *stack) {
+    const b200pt_push_constants &pc = fp.pc;
+    for (int iNee = 0; iNee < pc.numNEE; iNee++) {
+        vec3 lightDir, lightColor; float lightDistance;
+        const float pdfLights = sampleLights(sc, seed, pc.useVisibleSphereSampling != 0, origin, normal, lightDir, lightColor, lightDistance);
+        const float cosThetaLight = dot(normal, lightDir);
+        const bool traceShadow = cosThetaLight > 0 && pdfLights > 0;
+        bool pushShadow = false, skipProbe = false;
+        vec3 C = V3(0.0f);
+        if (traceShadow) {
+            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, lightDir, true);
+            if (pc.enableMIS) {
+                const float pdfMatL = pdfBSDF(mat, normal, wi, lightDir);
+                const float heuristic = pc.usePowerHeuristic ? powerHeuristic(pdfLights, pdfMatL) : balanceHeuristic(pdfLights, pdfMatL);
+                if (isnan(heuristic)) {
+                    // rgen:653-655 returns before the BSDF probe, but only when the light is visible:
+                    // resolve the visibility here so the RNG stream stays identical (rare)
+                    HitRec sh;
+                    atomicAdd(&wf.counters[CNT_INLINE_SHADOW], 1u);
+                    traceRay<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack, blockDim.x);
+                    if (sh.prim == PT_MISS) skipProbe = true;
+                } else {
+                    C = f * lightColor * heuristic / pdfLights;
+                    pushShadow = true;
+                }
+            } else {
+                C = f * lightColor / pdfLights;
+                pushShadow = true;
+            }
+        }
+        if (pushShadow) {
+            const uint32_t slotS = queuePush(&wf.counters[CNT_SHADOW]);
+            wf.shRayO[slotS] = make_f4(origin, __int_as_float(pid));
+            wf.shRayD[slotS] = make_f4(lightDir, lightDistance * (1 - 0.0001f));
+            wf.shC[slotS] = make_f4(T * (C / float(pc.numNEE)), 0.0f);
+            if (saveSamples) wf.shG[slotS] = make_f4(C / float(pc.numNEE), __int_as_float(cso));
+        }
+        bool pushProbe = false;
+        vec3 bsdfDir = V3(0.0f); float pdfMat = 0.0f;
+        if (pc.enableMIS && !skipProbe) {         // rgen:665-728
+            pdfMat = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, bsdfDir);
+            pushProbe = pdfMat > 0;
+        }
+        if (pushProbe) {
+            const uint32_t slotP = queuePush(&wf.counters[CNT_PROBE]);
+            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, bsdfDir, true);
+            wf.probeRayO[slotP] = make_f4(origin, __int_as_float(cso));
+            wf.probeRayD[slotP] = make_f4(bsdfDir, 0.0f);
+            wf.probeA[slotP] = make_f4(f, pdfMat);
+            wf.probeB[slotP] = make_f4(T, __int_as_float(pid));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
-// GUIDE compiles in guided sampling (pc.useGuiding) and sample recording (pc.updateGuiding)
-template <bool GUIDE>
+// GUIDE compiles in guided sampling (pc.useGuiding) and sample recording (pc.updateGuiding);
+// IC compiles in the irradiance-cache lookup, ADRRS (weight window, Russian roulette, splitting) and the split drain
+template <bool GUIDE, bool IC>
 __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = wf.counters[CNT_SHADE_N];
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
-    const bool active = true;
     bool pushPath = false;
     vec3 outO = V3(0.0f), outD = V3(0.0f);
     int pid = 0;
-
-    if (active) {
+    {
         const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
         const float4 hr = wf.pathHit[qi];
         pid = __float_as_int(ro.w);
@@ -308,87 +373,53 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
             } else {
                 addNext = false;
                 follow = false;
-                if (saveSamples && gst.z != -1) {                     // rgen:1149-1156
-                    wf.rec.samples[sbase + gst.z].distance += info.t * distanceFactor;
-                    if (!isMatAlmostDiscrete(mat)) gst.z = -1;
-                }
-                if (useNEE && neeSupported(mat.type)) {   // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
-                    for (int iNee = 0; iNee < pc.numNEE; iNee++) {
-                        vec3 lightDir, lightColor; float lightDistance;
-                        const float pdfLights = sampleLights(sc, seed, pc.useVisibleSphereSampling != 0, origin, normal, lightDir, lightColor, lightDistance);
-                        const float cosThetaLight = dot(normal, lightDir);
-                        const bool traceShadow = cosThetaLight > 0 && pdfLights > 0;
-                        bool pushShadow = false, skipProbe = false;
-                        vec3 C = V3(0.0f);
-                        if (traceShadow) {
-                            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, lightDir, true);
-                            if (pc.enableMIS) {
-                                const float pdfMatL = pdfBSDF(mat, normal, wi, lightDir);
-                                const float heuristic = pc.usePowerHeuristic ? powerHeuristic(pdfLights, pdfMatL) : balanceHeuristic(pdfLights, pdfMatL);
-                                if (isnan(heuristic)) {
-                                    // rgen:653-655 returns before the BSDF probe, but only when the light is visible:
-                                    // resolve the visibility here so the RNG stream stays identical (rare)
-                                    HitRec sh;
-                                    atomicAdd(&wf.counters[CNT_INLINE_SHADOW], 1u);
-                                    traceRay<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack + threadIdx.x, blockDim.x);
-                                    if (sh.prim == PT_MISS) skipProbe = true;
-                                } else {
-                                    C = f * lightColor * heuristic / pdfLights;
-                                    pushShadow = true;
-                                }
-                            } else {
-                                C = f * lightColor / pdfLights;
-                                pushShadow = true;
+                if (IC && (pc.useIrradianceCache || (pc.useADRRS && depth > 1)) && isICCapable(pc, mat.type)) {      // rgen:1083-1133
+                    vec3 irradianceColor;
+                    if (queryIrradianceCache(wf.ic.view, pc, origin, normal, irradianceColor)) {
+                        if (pc.useADRRS) {
+                            int nSplit;
+                            float q = applyWeightWindow(pc, seed, T, irradianceColor, make_vec3(wf.ic.estimate[pid]), nSplit);
+                            if (nSplit == 1) {
+                                if (rnd(seed) > q) terminated = true;                  // Russian roulette
+                                else T = T / q;
+                            } else if (pc.adrrsSplit) {
+                                const int possibleSplits = IC_MAX_SPLITS - int(wf.ic.splitState[pid] & 0xffffu);
+                                if (nSplit - 1 > possibleSplits) { nSplit = possibleSplits + 1; q = float(nSplit); }
+                                T = T / q;
+                                for (int iSplit = 0; iSplit < nSplit - 1; iSplit++)
+                                    splitPush(wf.ic, pid, origin, normal, wi, T, info.u, info.v, info.matIndex, int(depth), info.isFrontFace);
                             }
+                        } else {
+                            add += T * approxDiffuse(sc, mat, normal, wi, info.u, info.v) * irradianceColor;
+                            if (neeSupported(mat.type)) neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
+                            terminated = true;
                         }
-                        if (pushShadow) {
-                            const uint32_t slotS = queuePush(&wf.counters[CNT_SHADOW]);
-                            wf.shRayO[slotS] = make_f4(origin, __int_as_float(pid));
-                            wf.shRayD[slotS] = make_f4(lightDir, lightDistance * (1 - 0.0001f));
-                            wf.shC[slotS] = make_f4(T * (C / float(pc.numNEE)), 0.0f);
-                            if (saveSamples) wf.shG[slotS] = make_f4(C / float(pc.numNEE), __int_as_float(gst.y));
-                        }
-                        bool pushProbe = false;
-                        vec3 bsdfDir = V3(0.0f); float pdfMat = 0.0f;
-                        if (pc.enableMIS && !skipProbe) {         // rgen:665-728
-                            pdfMat = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, bsdfDir);
-                            pushProbe = pdfMat > 0;
-                        }
-                        if (pushProbe) {
-                            const uint32_t slotP = queuePush(&wf.counters[CNT_PROBE]);
-                            const vec3 f = evalBsdf(sc, mat, info.u, info.v, normal, wi, bsdfDir, true);
-                            wf.probeRayO[slotP] = make_f4(origin, __int_as_float(gst.y));
-                            wf.probeRayD[slotP] = make_f4(bsdfDir, 0.0f);
-                            wf.probeA[slotP] = make_f4(f, pdfMat);
-                            wf.probeB[slotP] = make_f4(T, __int_as_float(pid));
+                    } else if (rnd(seed) < pc.irradianceCreateProb) {                  // createIC is true on every path of main()
+                        const uint32_t k = wf.ic.newCount[pid];
+                        if (k < IC_MAX_NEW) {
+                            wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 0] = make_f4(origin, 0.0f);
+                            wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 1] = make_f4(normal, 0.0f);
+                            wf.ic.newCount[pid] = k + 1u;
                         }
                     }
+                }
+                if (!terminated) {
+                    if (IC && pc.splitOnFirst && depth == 1) {                         // rgen:1135-1139
+                        if (splitPush(wf.ic, pid, origin, normal, wi, T * 0.5f, info.u, info.v, info.matIndex, int(depth), info.isFrontFace)) T *= 0.5f;
+                    }
+                    if (saveSamples && gst.z != -1) {                     // rgen:1149-1156
+                        wf.rec.samples[sbase + gst.z].distance += info.t * distanceFactor;
+                        if (!isMatAlmostDiscrete(mat)) gst.z = -1;
+                    }
+                    if (useNEE && neeSupported(mat.type))                 // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
+                        neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
                 }
             }
 
             // getNewDirection (rgen:923-960) + throughput update (:1169-1177) + sample recording (:1179-1212)
             if (!terminated) {
                 vec3 newDirection = V3(0.0f);
-                float pdf;
-                if (GUIDE && pc.useGuiding && !hasDiscreteDirection(mat.type)) {
-                    const bool parallax = pc.useParallaxCompensation != 0;
-                    const uint32_t iRegion = getGuidingRegion(wf.guide, origin);
-                    if (iRegion == B200PT_INVALID_REGION) pdf = 0.0f;
-                    else {
-                        const b200pt_vmm_theta &vmm = wf.guide.vmms[iRegion];
-                        float pdfMat;
-                        if (rnd(seed) < pc.guidingProb) {
-                            newDirection = sampleVmm(seed, vmm, origin, parallax);
-                            pdfMat = pdfBSDF(mat, normal, wi, newDirection);
-                        } else pdfMat = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
-                        if (dot(newDirection, normal) < 0.0f || pdfMat <= 0.0f) pdf = 0.0f;
-                        else {
-                            const float pdfGuiding = vmmPdf(newDirection, vmm, origin, parallax);
-                            if (isnan(pdfGuiding)) pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
-                            else pdf = mixf(pdfMat, pdfGuiding, pc.guidingProb);
-                        }
-                    }
-                } else pdf = sampleBSDF(seed, mat, wi, normal, info.isFrontFace, newDirection);
+                const float pdf = getNewDirection<GUIDE>(pc, wf.guide, seed, mat, origin, normal, wi, info.isFrontFace, newDirection);
                 if (pdf <= 0.0f) terminated = true;
                 else {
                     const vec3 change = evalBsdf(sc, mat, info.u, info.v, normal, wi, newDirection, info.isFrontFace) / pdf;
@@ -444,6 +475,33 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                 T = V3(1.0f);
                 depth = 0; followCount = 0; addNext = true; follow = false;
                 pushPath = true;
+            } else if (IC && wf.ic.splitState) {
+                // all samples done: drain the pixel's split list, one split per finished path (rgen:1684-1708)
+                const uint32_t ss = wf.ic.splitState[pid];
+                const uint32_t nextSlot = ss & 0xffffu;
+                uint32_t iSplit = ss >> 16;
+                if (iSplit < nextSlot) {
+                    const float4 *sp = wf.ic.splitData + (size_t(pid) * IC_MAX_SPLITS + iSplit) * IC_SPLIT_F4;
+                    const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3], s4 = sp[4];
+                    iSplit++;
+                    HitInfo sinfo;
+                    sinfo.worldPos = make_vec3(s0); sinfo.normal = make_vec3(s1); sinfo.u = s0.w; sinfo.v = s1.w;
+                    sinfo.matIndex = __float_as_int(s2.w); sinfo.t = 0.0f; sinfo.isFrontFace = s4.x != 0.0f; sinfo.isSphere = false; sinfo.instanceIndex = 0u;
+                    const vec3 swi = make_vec3(s2), sT = make_vec3(s3);
+                    const b200pt_material smat = sc.materials[sinfo.matIndex];
+                    if (useNEE && neeSupported(smat.type))      // the split happened before NEE: do it for the split's origin
+                        neeQueued(fp, sc, wf, seed, smat, sinfo, sinfo.worldPos, sinfo.normal, swi, sT, pid, false, 0, stack + threadIdx.x);
+                    vec3 newDirection = V3(0.0f);
+                    const float pdf = getNewDirection<GUIDE>(pc, wf.guide, seed, smat, sinfo.worldPos, sinfo.normal, swi, sinfo.isFrontFace, newDirection);
+                    if (pdf <= 0.0f) iSplit = nextSlot;      // `break`: the remaining splits are dropped
+                    else {
+                        T = sT * evalBsdf(sc, smat, sinfo.u, sinfo.v, sinfo.normal, swi, newDirection, sinfo.isFrontFace) / pdf;
+                        outO = sinfo.worldPos; outD = newDirection;
+                        depth = uint32_t(__float_as_int(s3.w)); followCount = 0; addNext = false; follow = true;
+                        pushPath = true;
+                    }
+                    wf.ic.splitState[pid] = (wf.ic.splitState[pid] & 0xffffu) | (iSplit << 16);
+                }
             }
         } else {
             outO = origin; outD = direction;

@@ -1,0 +1,194 @@
+"""GPU parity of the irradiance cache and ADRRS against the oracle, through the C ABI.
+
+Both sides use the race-free frame semantic described in oracle/tracer_oracle.cpp: lookups read the frame-start cache,
+update / create slots are handed out in pixel order.  Cache entries are matched by their position (a hit point; the
+traversal is bit-exact), values compared within 1e-3 relative: one entry sums 200 paths whose transcendental functions
+differ in the last bit between CUDA and glibc."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+NT = os.cpu_count() or 1
+W, H = 96, 54
+IC_SIZE = 512
+SCENE = "irradianceCache"
+
+
+def _pc(P, frame, **kw):
+    base = dict(randomUInt=P.tea(frame, 77), previousFrames=0, samplesPerPixel=1, enableMIS=1)
+    base.update(kw)
+    return P.default_push_constants(**base)
+
+
+def _prepare_pc(P, frame, **kw):
+    # RayTracingApp::raytrace during the prepare frames (src/RayTracingApp.cpp:1130-1143)
+    return _pc(P, frame, previousFrames=0xFFFFFFFF, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, isIrradiancePrepareFrame=1,
+               irradianceCreateProb=0.02, irradianceUpdateProb=0.005, **kw)
+
+
+def _estimate_pc(P, frame):
+    # RayTracingApp::setEstimateRTSettings (src/RayTracingApp.cpp:1206-1217)
+    return _pc(P, frame, storeEstimate=1, samplesPerPixel=16, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, enableNEE=1, maxDepth=1,
+               maxFollowDiscrete=10, numNEE=5, useADRRS=0, irradianceCreateProb=0.0, irradianceUpdateProb=0.0)
+
+
+def _compare_caches(P, dev, ref, what):
+    (hd, dd, sd), (hr, dr, sr) = dev, ref
+    nd, nr = min(hd.nextCacheSlot, IC_SIZE), min(hr.nextCacheSlot, IC_SIZE)
+    assert nr > 20, what
+    assert abs(int(nd) - int(nr)) <= max(2, nr // 50), (what, nd, nr)
+    # entries created at the first path vertex have bit-identical positions (traversal is bit-exact); deeper vertices
+    # inherit the last-bit differences of CUDA's and glibc's sin/cos, so match by nearest centre
+    cd = sd["center"][:nd].astype(np.float64)
+    matched = bad = 0
+    for i in range(nr):
+        dist = np.linalg.norm(cd - sr["center"][i].astype(np.float64), axis=1)
+        j = int(np.argmin(dist))
+        if dist[j] > 1e-3:
+            continue
+        matched += 1
+        ok = np.abs(dd["normal"][j] - dr["normal"][i]).max() <= 1e-4 and dd["numUpdates"][j] == dr["numUpdates"][i]
+        scale = max(float(np.abs(dr["color"][i]).max()), 1e-6)
+        ok = ok and np.abs(dd["color"][j] - dr["color"][i]).max() <= 1e-3 * scale
+        ok = ok and abs(dd["harmonicR"][j] - dr["harmonicR"][i]) <= 1e-3 * dr["harmonicR"][i]
+        ok = ok and abs(sd["radius"][j] - sr["radius"][i]) <= 1e-3 * sr["radius"][i]
+        for g in ("rotGrad", "transGrad"):
+            gs = max(float(np.abs(dr[g][i]).max()), 1e-2 * scale, 1e-6)
+            ok = ok and np.abs(dd[g][j] - dr[g][i]).max() <= 5e-3 * gs
+        bad += not ok
+    assert matched >= 0.98 * nr, (what, matched, nr)
+    assert bad <= max(1, matched // 50), (what, bad, matched)
+
+
+def _images_close(img, ref, what, frac_needed=0.99, mean_tol=5e-3):
+    img, ref = img[..., :3].astype(np.float64), ref[..., :3].astype(np.float64)
+    assert np.isfinite(img).all(), what
+    rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
+    frac = float((rel <= 1e-4).all(axis=-1).mean())       # north_star: per-path radiance within 1e-4 relative
+    assert frac >= frac_needed, (what, frac)
+    assert abs(img.mean() - ref.mean()) <= mean_tol * max(ref.mean(), 1e-6), (what, img.mean(), ref.mean())
+
+
+def _build_cache(P, o, frames=4):
+    """Reference cache for the lookup tests: a few prepare frames on the oracle."""
+    for f in range(frames):
+        o.render_region(_prepare_pc(P, f), threads=NT)
+    return o.ic_get(P)
+
+
+def test_cache_creation_and_update_match_oracle():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE)
+    for f in range(3):
+        pc = _prepare_pc(P, f)
+        r.render_frame(pc)
+        o.render_region(pc, threads=NT)
+        dev, ref = r.ic_get(), o.ic_get(P)
+        if f > 0:      # frame 0 only creates (empty cache: nothing to update)
+            assert dev[0].nextUpdateSlot == ref[0].nextUpdateSlot, f
+            assert (ref[1]["numUpdates"][:ref[0].nextCacheSlot] > 1).sum() > 0
+        _compare_caches(P, dev, ref, "prepare frame %d" % f)
+        r.ic_put(*ref)      # continue from identical caches
+    st = r.stats()
+    assert st.extend_rays > 0 and st.shadow_rays > 0
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(useIrradianceGradients=1), dict(irradianceCachePerformVisibilityCheck=1, useIrradianceCacheOnGlossy=1)])
+def test_cache_lookup_render_matches_oracle(kw):
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE)
+    cache = _build_cache(P, o)
+    r.ic_put(*cache)
+    pc = _pc(P, 11, samplesPerPixel=2, useIrradianceCache=1, irradianceCreateProb=0.0, irradianceUpdateProb=0.0, **kw)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    _images_close(r.read_image(), o.image(), "IC lookup %r" % (kw,))
+    # nothing was created or updated
+    hdr, data, spheres = r.ic_get()
+    assert hdr.nextCacheSlot == cache[0].nextCacheSlot and np.array_equal(data.view(np.uint8), cache[1].view(np.uint8))
+
+
+def test_estimate_frame_and_adrrs_match_oracle():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE)
+    cache = _build_cache(P, o)
+    r.ic_put(*cache)
+    # estimate frame: 16 spp, depth 1, IC + 5 light samples, stored into the estimate image
+    pc = _estimate_pc(P, 20)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    est_ref = o.image(P.IMAGE_ESTIMATE)
+    _images_close(r.read_image(P.IMAGE_ESTIMATE), est_ref, "estimate frame", frac_needed=0.97)
+    r.write_image(P.IMAGE_ESTIMATE, est_ref)      # identical adjoint inputs for the ADRRS frames
+    for f, kw in enumerate([dict(adrrsSplit=1), dict(adrrsSplit=0), dict(adrrsSplit=1, enableMIS=0, numNEE=2)]):
+        pc = _pc(P, 30 + f, samplesPerPixel=2, useADRRS=1, adrrsS=5.0, irradianceCreateProb=0.0, irradianceUpdateProb=0.0, **kw)
+        r.render_frame(pc)
+        o.render_region(pc, threads=NT)
+        _images_close(r.read_image(), o.image(), "ADRRS %r" % (kw,), frac_needed=0.985)
+
+
+def test_adrrs_frames_keep_creating_cache_entries():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE)
+    cache = _build_cache(P, o, frames=1)
+    r.ic_put(*cache)
+    est = np.full((H, W, 4), 0.5, np.float32)
+    r.write_image(P.IMAGE_ESTIMATE, est)
+    o.set_image(P.IMAGE_ESTIMATE, est)
+    pc = _pc(P, 40, samplesPerPixel=1, useADRRS=1, adrrsSplit=1, irradianceCreateProb=0.05)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    dev, ref = r.ic_get(), o.ic_get(P)
+    assert ref[0].nextCacheSlot > cache[0].nextCacheSlot
+    _compare_caches(P, dev, ref, "creation during an ADRRS frame")
+
+
+def test_split_on_first_matches_oracle():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=0)
+    pc = _pc(P, 50, samplesPerPixel=2, splitOnFirst=1)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    _images_close(r.read_image(), o.image(), "splitOnFirst")
+
+
+def test_cache_fills_up_to_capacity_and_stops():
+    P = helpers.pt()
+    small = 40
+    scene = P.Scene(helpers.scene_path(SCENE))
+    view, proj = scene.camera_matrices(W / H)
+    r = P.Renderer(W, H, small, 0)
+    r.set_scene(scene)
+    r.set_camera(view, proj)
+    for f in range(2):
+        r.render_frame(_prepare_pc(P, f, ))
+    hdr, data, spheres = r.ic_get()
+    assert hdr.nextCacheSlot == small + 1 and hdr.maxCaches == small      # the reference's off-by-one (quirk 11)
+    assert (data["numUpdates"] >= 1).all() and (spheres["radius"] > 0).all()
+
+
+def test_unsupported_modes_fail_loudly():
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, 32, 18, ic_size=0)
+    for kw in (dict(useIrradianceCache=1), dict(useADRRS=1), dict(showIrradianceCacheOnly=1), dict(visualizeMode=3)):
+        with pytest.raises(P.B200ptError):
+            r.render_frame(_pc(P, 0, **kw))
+
+
+def test_guiding_training_returns_early_while_splitting():
+    """rgen:1643-1650: with updateGuiding and a split mode the raygen only invalidates the pixel's samples."""
+    P = helpers.pt()
+    scene = P.Scene(helpers.scene_path(SCENE))
+    view, proj = scene.camera_matrices(32 / 18)
+    r = P.Renderer(32, 18, 0, 2)
+    r.set_scene(scene)
+    r.set_camera(view, proj)
+    r.render_frame(_pc(P, 0))
+    before = r.read_image()
+    r.render_frame(_pc(P, 1, updateGuiding=1, splitOnFirst=1, previousFrames=1))
+    assert np.array_equal(before, r.read_image())
+    assert (r.guiding_get_samples()["flags"] == P.INVALID_REGION).all()
