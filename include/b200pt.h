@@ -413,7 +413,39 @@ int b200pt_mat4_inverse(const float m[16], float out[16]);
 int b200pt_write_exr(const char *path, const float *rgba, int width, int height);
 /* CommonOps::readEXR (src/CommonOps.cpp:40-65): RGBA float (values pass through half like Imf::Rgba) */
 int b200pt_read_exr(const char *path, float **rgba_out, int *width, int *height);
+/* bitmap textures as SceneLoader::addTexture loads them (`stbi_load(path, &w, &h, &channels, 4)`,
+ * src/SceneLoader.cpp:198-207): baseline JPEG or PNG -> RGBA8, row 0 first; release with b200pt_free */
+int b200pt_read_image_file(const char *path, uint8_t **rgba_out, int *width, int *height);
 void b200pt_free(void *p);
+
+/* ---- frame driver: the per-frame host logic of RayTracingApp ------------------------------------
+ * RayTracingApp::raytrace (src/RayTracingApp.cpp:1120-1170) decides each frame's push constants from the user's
+ * settings: previousFrames (running mean), the irradiance-cache prepare frames (1 spp, IC on, ADRRS postponed),
+ * the one estimate frame that ADRRS needs (setEstimateRTSettings, :1206-1217) and the restore afterwards;
+ * RayTracingApp::drawCallback (:120-157) stops guiding training after numGuidingOptimizations updates and counts the
+ * samples of the "collect N samples" evaluation (:159-186).  Pure host state, no device work: usable without a GPU. */
+typedef struct b200pt_app {
+    b200pt_push_constants settings;          /* rtPushConstants: what the user edits (the ImGui panel of the reference) */
+    int32_t accumulateResults;               /* RayTracingApp.h:147 (the evaluation modes switch it on, :93,98) */
+    int32_t hasInputChanged;                 /* set it after editing `settings`: restarts the running mean */
+    int32_t irradianceCachePrepareFrames;    /* RayTracingApp.h:175, default 50 */
+    int32_t currentPrepareFrames;
+    int32_t numGuidingOptimizations;         /* RayTracingApp.h:180, default 6; -1 = keep training */
+    int32_t currentGuidingOptimizations;     /* -1 = not training */
+    int32_t loadBackupNextIteration;
+    int32_t activateADRRSAfterPrepareFrames;
+    int64_t evalCurrentSamples;              /* samples per pixel that count for the image (prepare frames do not) */
+    b200pt_push_constants backupPushConstant;
+} b200pt_app;
+void b200pt_app_init(b200pt_app *app);                       /* reference defaults, previousFrames = -1 */
+void b200pt_app_scene_switched(b200pt_app *app);             /* sceneSwitcher, :327-367: currentPrepareFrames = 0, input changed */
+/* start of a frame: advances the state machine and returns the constants to render with (copy of app->settings) */
+void b200pt_app_begin_frame(b200pt_app *app, uint32_t frame_seed, b200pt_push_constants *frame_pc);
+/* end of a frame: guiding-optimisation bookkeeping and sample accounting; returns 1 when PathGuiding::update must
+ * run on the frame's samples (drawCallback :143-154) */
+int b200pt_app_end_frame(b200pt_app *app);
+/* begin_frame + b200pt_render_frame + end_frame (+ b200pt_guiding_update with `guiding_params` when due) */
+int b200pt_app_draw_frame(b200pt_app *app, b200pt_ctx *ctx, uint32_t frame_seed, const b200pt_guiding_params *guiding_params);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,14 @@ class GuidingParams(C.Structure):
                 ("maxKappa", C.c_float), ("vPrior", C.c_float), ("rPrior", C.c_float), ("rPriorWeight", C.c_float)]
 
 
+class AppState(C.Structure):
+    """b200pt_app — the per-frame host state of RayTracingApp (src/RayTracingApp.h:147-189)."""
+    _fields_ = [("settings", PushConstants), ("accumulateResults", C.c_int32), ("hasInputChanged", C.c_int32),
+                ("irradianceCachePrepareFrames", C.c_int32), ("currentPrepareFrames", C.c_int32), ("numGuidingOptimizations", C.c_int32),
+                ("currentGuidingOptimizations", C.c_int32), ("loadBackupNextIteration", C.c_int32), ("activateADRRSAfterPrepareFrames", C.c_int32),
+                ("evalCurrentSamples", C.c_int64), ("backupPushConstant", PushConstants)]
+
+
 class Stats(C.Structure):
     _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("path_vertices", C.c_uint64), ("samples", C.c_uint64),
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("launches_extend", C.c_uint64),
@@ -149,7 +157,8 @@ EXPORTS = [
     "b200pt_guiding_sample_capacity", "b200pt_guiding_get_samples_device", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
     "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
-    "b200pt_read_exr", "b200pt_free"]
+    "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
+    "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
 
@@ -212,6 +221,15 @@ def lib():
         L.b200pt_write_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         L.b200pt_read_exr.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200pt_free.argtypes = [C.c_void_p]
+        L.b200pt_read_image_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.b200pt_app_init.restype = None
+        L.b200pt_app_init.argtypes = [C.POINTER(AppState)]
+        L.b200pt_app_scene_switched.restype = None
+        L.b200pt_app_scene_switched.argtypes = [C.POINTER(AppState)]
+        L.b200pt_app_begin_frame.restype = None
+        L.b200pt_app_begin_frame.argtypes = [C.POINTER(AppState), C.c_uint32, C.POINTER(PushConstants)]
+        L.b200pt_app_end_frame.argtypes = [C.POINTER(AppState)]
+        L.b200pt_app_draw_frame.argtypes = [C.POINTER(AppState), C.c_void_p, C.c_uint32, C.POINTER(GuidingParams)]
         _lib = L
     return _lib
 
@@ -472,6 +490,54 @@ class Renderer:
             self.close()
         except Exception:
             pass
+
+
+class App:
+    """Frame driver: RayTracingApp::raytrace / drawCallback without the window (include/b200pt.h, b200pt_app_*).
+    `settings` is the user's RtPushConstant (edit it, then call input_changed()); draw_frame renders one frame."""
+
+    def __init__(self, renderer=None, accumulate=True, **settings):
+        self.state = AppState()
+        lib().b200pt_app_init(C.byref(self.state))
+        self.state.accumulateResults = int(accumulate)
+        self.renderer = renderer
+        for k, v in settings.items():
+            if not hasattr(self.state.settings, k):
+                raise AttributeError("no push constant named %r" % k)
+            setattr(self.state.settings, k, v)
+
+    @property
+    def settings(self):
+        return self.state.settings
+
+    def input_changed(self):
+        self.state.hasInputChanged = 1
+
+    def scene_switched(self):
+        lib().b200pt_app_scene_switched(C.byref(self.state))
+
+    def begin_frame(self, frame_seed):
+        pc = PushConstants()
+        lib().b200pt_app_begin_frame(C.byref(self.state), C.c_uint32(frame_seed), C.byref(pc))
+        return pc
+
+    def end_frame(self):
+        return bool(lib().b200pt_app_end_frame(C.byref(self.state)))
+
+    def draw_frame(self, frame_seed, guiding_params=None):
+        gp = C.byref(guiding_params) if guiding_params is not None else None
+        _check(lib().b200pt_app_draw_frame(C.byref(self.state), self.renderer._h, C.c_uint32(frame_seed), gp))
+
+
+def read_image_file(path):
+    """Baseline JPEG / PNG -> (H, W, 4) uint8, as the scene loader decodes bitmap textures."""
+    p = C.POINTER(C.c_uint8)()
+    w, h = C.c_int(), C.c_int()
+    _check(lib().b200pt_read_image_file(os.fsencode(path), C.byref(p), C.byref(w), C.byref(h)))
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().b200pt_free(p)
 
 
 def write_exr(path, rgba):

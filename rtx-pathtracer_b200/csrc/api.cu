@@ -973,6 +973,16 @@ int b200pt_read_exr(const char *path, float **rgba_out, int *width, int *height)
     } catch (const std::exception &e) { return setError(B200PT_E_IO, std::string("b200pt_read_exr: ") + e.what()); }
     return B200PT_OK;
 }
+int b200pt_read_image_file(const char *path, uint8_t **rgba_out, int *width, int *height) {
+    if (!path || !rgba_out || !width || !height) return setError(B200PT_E_INVALID, "b200pt_read_image_file: bad argument");
+    try {
+        std::vector<uint8_t> px;
+        decodeImageFile(path, *width, *height, px);
+        *rgba_out = static_cast<uint8_t *>(malloc(px.size()));
+        memcpy(*rgba_out, px.data(), px.size());
+    } catch (const std::exception &e) { return setError(B200PT_E_IO, std::string("b200pt_read_image_file: ") + e.what()); }
+    return B200PT_OK;
+}
 void b200pt_free(void *p) { free(p); }
 
 }  // extern "C"

@@ -1,8 +1,10 @@
 // Headless command line of the path tracer.  Keeps the reference's positional interface
 //   rtx_raytracer WIDTH HEIGHT IC_SIZE GUIDING_SPLITS scenes...      (src/main.cpp:8-35)
 // and replaces the ImGui panels (src/RayTracingApp.cpp:932-1118) with --<RtPushConstant field>=value overrides.
-// Instead of presenting a window it renders `--frames` frames of `--samplesPerPixel` spp per scene and writes an EXR
-// whose name follows RayTracingApp::getModeString (src/RayTracingApp.cpp:288-316).
+// Instead of presenting a window it runs the reference's "collect N samples" evaluation (src/RayTracingApp.cpp:159-186):
+// frames of `--samplesPerPixel` spp through the frame driver (b200pt_app_*: IC prepare frames, the ADRRS estimate
+// frame, the guiding-optimisation limit) until `--frames` x spp samples are in the image, then writes an EXR whose name
+// follows RayTracingApp::getModeString (src/RayTracingApp.cpp:288-316).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,7 +26,8 @@ static const Field kFields[] = {
 
 static void printHelp() {
     printf("Required parameters: WIDTH HEIGHT IC_SIZE GUIDING_SPLITS Scenes ...\n");
-    printf("Options: --frames=N --seed=S --out=FILE.exr --device=D and --<pushConstantField>=value, e.g. --samplesPerPixel=16 --enableMIS=1\n");
+    printf("Options: --frames=N --seed=S --out=FILE.exr --device=D --prepareFrames=N --numGuidingOptimizations=N\n");
+    printf("         and --<pushConstantField>=value, e.g. --samplesPerPixel=16 --enableMIS=1 --useADRRS=1\n");
 }
 
 // frame seed stream: the reference draws randomUInt from glm::linearRand (quirk 10); we take tea(frame, seed)
@@ -45,8 +48,10 @@ int main(int argc, char **argv) {
     int width = std::stoi(positional[0]), height = std::stoi(positional[1]);
     int icSize = std::stoi(positional[2]), guidingSplits = std::stoi(positional[3]);
 
-    b200pt_push_constants pc;
-    b200pt_default_push_constants(&pc);
+    b200pt_app app;
+    b200pt_app_init(&app);
+    app.accumulateResults = 1;      // the evaluation modes switch it on (src/RayTracingApp.cpp:93,98)
+    b200pt_push_constants &pc = app.settings;
     int frames = 1, device = 0;
     uint32_t seed = 0xC0FFEEu;
     std::string out;
@@ -58,6 +63,8 @@ int main(int argc, char **argv) {
         else if (key == "seed") seed = uint32_t(std::stoul(val, nullptr, 0));
         else if (key == "out") out = val;
         else if (key == "device") device = std::stoi(val);
+        else if (key == "prepareFrames") app.irradianceCachePrepareFrames = std::stoi(val);
+        else if (key == "numGuidingOptimizations") app.numGuidingOptimizations = std::stoi(val);
         else {
             bool found = false;
             for (const Field &f : kFields)
@@ -90,18 +97,22 @@ int main(int argc, char **argv) {
         printf("Startup time: %lld milliseconds\n", (long long)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
         b200pt_stats_reset(ctx);
         bool ok = true;
-        for (int f = 0; f < frames && ok; f++) {
-            pc.randomUInt = tea(uint32_t(f), seed);
-            pc.previousFrames = uint32_t(f);     // accumulateResults = true: running mean over frames (RayTracingApp.cpp:1123-1127)
-            if (b200pt_render_frame(ctx, &pc) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); ok = false; }
+        const b200pt_push_constants userSettings = pc;
+        b200pt_app_scene_switched(&app);
+        pc.previousFrames = 0xFFFFFFFFu;
+        app.evalCurrentSamples = 0;
+        const long long wanted = (long long)frames * pc.samplesPerPixel;
+        int drawn = 0;
+        for (uint32_t f = 0; app.evalCurrentSamples < wanted && ok; f++, drawn++) {
+            if (b200pt_app_draw_frame(&app, ctx, tea(f, seed), nullptr) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); ok = false; }
         }
         auto t2 = std::chrono::high_resolution_clock::now();
         if (ok) {
             b200pt_stats st;
             b200pt_stats_get(ctx, &st);
             long long ms = (long long)std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count();
-            int spp = frames * pc.samplesPerPixel;
-            printf("Collecting %d samples took %lld milliseconds with %d samples per pixel per frame\n", spp, ms, pc.samplesPerPixel);
+            int spp = frames * userSettings.samplesPerPixel;
+            printf("Collecting %d samples took %lld milliseconds with %d samples per pixel per frame (%d frames drawn)\n", spp, ms, userSettings.samplesPerPixel, drawn);
             printf("rays: %llu extend + %llu shadow, %.1f Mrays/s (device time %.1f ms), %.2f spp/s\n", (unsigned long long)st.extend_rays,
                    (unsigned long long)st.shadow_rays, double(st.extend_rays + st.shadow_rays) / (double(st.ms_total) * 1e3), st.ms_total,
                    spp / (double(st.ms_total) * 1e-3));
@@ -121,6 +132,7 @@ int main(int argc, char **argv) {
             if (b200pt_write_exr(file.c_str(), img.data(), width, height) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); status = EXIT_FAILURE; }
             else printf("Wrote file %s\n", file.c_str());
         } else status = EXIT_FAILURE;
+        pc = userSettings;      // the next scene starts from the user's settings again
         b200pt_scene_free(scene);
     }
     b200pt_destroy(ctx);

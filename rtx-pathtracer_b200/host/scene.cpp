@@ -582,8 +582,14 @@ int Scene::addTexture(const std::string &name) {   // src/SceneLoader.cpp:184-23
     size_t bs = ps.find('\\');
     if (bs != std::string::npos) ps.replace(bs, 1, "/");
     path = std::filesystem::path(ps).lexically_normal();
-    // Image decoding (JPG/PNG via stb_image in the reference) is not part of the hot path yet: SURVEY §8(f) item 2.
-    throw std::runtime_error("Could not load texture file " + path.string() + " (bitmap textures: not implemented yet)");
+    TextureImage t;
+    t.format = B200PT_TEX_RGBA8_SRGB;       // vk::Format::eR8G8B8A8Srgb, 4 channels forced (stbi_load(..., 4))
+    t.path = path.string();
+    decodeImageFile(t.path, t.width, t.height, t.rgba8);
+    textures.push_back(std::move(t));
+    const int textureIndex = int(textures.size()) - 1;
+    pathTextureId[path.string()] = textureIndex;      // sic: keyed by the normalised path, looked up by the raw one (:189,233)
+    return textureIndex;
 }
 
 void Scene::parseMitsubaSceneFile(const std::string &filepath) {

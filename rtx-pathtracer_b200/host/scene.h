@@ -26,6 +26,9 @@ struct TextureImage {
     std::string path;
 };
 
+// JPEG (baseline) / PNG file -> RGBA8, row 0 first (host/image_decode.cpp; stands in for stbi_load(path, .., 4))
+void decodeImageFile(const std::string &path, int &width, int &height, std::vector<uint8_t> &rgba);
+
 // CDF-walk sampler with a default-seeded std::mt19937 — src/WeightedSampler.{h,cpp}
 class WeightedSampler {
 public:
