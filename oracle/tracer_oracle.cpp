@@ -114,7 +114,7 @@ struct HitInfo {    // raycommon.glsl:1-13
     uint32_t instanceIndex = 0;
 };
 
-struct Tex { int w = 0, h = 0; std::vector<float> px; };   // linear RGBA float
+struct Tex { int w = 0, h = 0; bool hasAlpha = false; std::vector<float> px; };   // linear RGBA float; hasAlpha: some texel is not opaque
 
 struct AccelNode { float lo[3], hi[3]; int left, right; uint32_t first, count; };
 
@@ -299,6 +299,9 @@ struct Pixel {
         const b200pt_vertex &v0 = C.vertices[iModel][ind[0]], &v1 = C.vertices[iModel][ind[1]], &v2 = C.vertices[iModel][ind[2]];
         const b200pt_material &mat = C.mats[v0.materialIndex];
         if (mat.textureIdDiffuse == -1) return false;
+        // a fully opaque texture filters to alpha = 1 (give or take one rounding) and rnd() < 1: the test cannot reject
+        // (except with probability 2^-24 per hit when the bilinear weights round to 1 - 2^-24); both sides skip it
+        if (!C.textures[mat.textureIdDiffuse].hasAlpha) return false;
         float bx = 1.0f - bu - bv;
         float tu = v0.texCoord[0] * bx + v1.texCoord[0] * bu + v2.texCoord[0] * bv;
         float tv = v0.texCoord[1] * bx + v1.texCoord[1] * bu + v2.texCoord[1] * bv;
@@ -1197,8 +1200,9 @@ int oracle_set_scene(oracle_ctx *C, const b200pt_scene_desc *s) {
         }
         C->textures.push_back(std::move(tx));
     }
+    for (auto &t : C->textures) { t.hasAlpha = false; for (size_t p = 3; p < t.px.size(); p += 4) if (t.px[p] < 1.0f) { t.hasAlpha = true; break; } }
     C->anyTextured = false;
-    for (auto &m : C->mats) if (m.textureIdDiffuse != -1) C->anyTextured = true;
+    for (auto &m : C->mats) if (m.textureIdDiffuse != -1 && m.textureIdDiffuse < int(C->textures.size()) && C->textures[m.textureIdDiffuse].hasAlpha) C->anyTextured = true;
     // world-space triangles: same formula and operation order as the product's host code (IEEE, no contraction)
     C->tri.clear(); C->primInstance.clear(); C->primLocal.clear();
     std::vector<float> lo, hi;

@@ -63,6 +63,9 @@ struct b200pt_ctx {
     DevBuf<b200pt_face_sample> randomTriIndex;
     DevBuf<b200pt_sphere> spheres;
     DevBuf<DeviceTexture> textures;
+    DevBuf<AlphaTexture> alphaTextures;
+    DevBuf<int> alphaMaterialTexture;
+    DevBuf<AlphaScene> alphaScene;
     DeviceScene dscene{};
     float sceneMin[3], sceneMax[3];
     int bvhDepth = 0;
@@ -98,9 +101,9 @@ struct b200pt_ctx {
     DevBuf<b200pt_sphere> icSpheres;
     DevBuf<b200pt_cache_header> icHeader;
     // IC lookup snapshot + grid, per-pixel IC / split state, ordered-compaction scratch (allocated on first use)
-    DevBuf<float4> icSnapSphere, icSnapNormalR, icSnapColor, icSnapRot, icSnapTrans, icPending, icNewEntries, icSplitData;
+    DevBuf<float4> icSnapSphere, icSnapNormalR, icSnapColor, icSnapRot, icSnapTrans, icPending, icNewEntries, icSplitData, icCellSpheres;
     DevBuf<uint2> icRanges;
-    DevBuf<uint32_t> icCellCount, icCellStart, icCellItems, icSnapHdr, icBlockCounts, icList, icNewCount, icSplitState;
+    DevBuf<uint32_t> icCellCount, icCellStart, icCellItems, icSnapHdr, icBlockCounts, icList, icNewCount, icSplitState, icValidFlags, icValidOffsets;
     DevBuf<int32_t> icUpdSlot;
     uint32_t *hostIcHdr = nullptr;      // pinned, ICH_NUM
     ICView icGrid{};
@@ -182,7 +185,7 @@ static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
         CUDA_TRY(c->icSnapRot.alloc(S)); CUDA_TRY(c->icSnapTrans.alloc(S)); CUDA_TRY(c->icRanges.alloc(S));
         CUDA_TRY(c->icCellCount.alloc(size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1));
         CUDA_TRY(c->icCellStart.alloc(size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1));
-        CUDA_TRY(c->icCellItems.alloc(S * 8));
+        CUDA_TRY(c->icCellItems.alloc(S * 8)); CUDA_TRY(c->icCellSpheres.alloc(S * 8));
         CUDA_TRY(c->icNewCount.alloc(N));
         CUDA_TRY(c->icNewEntries.alloc(N * IC_MAX_NEW * 2));
         // uniform grid over the scene box (the same box the guiding regions start from), at most IC_GRID_MAX cells per axis
@@ -198,7 +201,7 @@ static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
             c->icNumCells *= g.dim[a];
         }
         g.sphere = c->icSnapSphere.p; g.normalR = c->icSnapNormalR.p; g.color = c->icSnapColor.p; g.rotGrad = c->icSnapRot.p; g.transGrad = c->icSnapTrans.p;
-        g.cellStart = c->icCellStart.p; g.cellItems = c->icCellItems.p;
+        g.cellStart = c->icCellStart.p; g.cellItems = c->icCellItems.p; g.cellSpheres = c->icCellSpheres.p;
     }
     if (splitMode) {
         CUDA_TRY(c->icSplitState.alloc(N));
@@ -211,7 +214,8 @@ static ICBuffers icBuffers(b200pt_ctx *c) {
     ICBuffers b{};
     b.header = c->icHeader.p; b.data = c->icData.p; b.spheres = c->icSpheres.p;
     b.snapSphere = c->icSnapSphere.p; b.snapNormalR = c->icSnapNormalR.p; b.snapColor = c->icSnapColor.p; b.snapRot = c->icSnapRot.p; b.snapTrans = c->icSnapTrans.p;
-    b.ranges = c->icRanges.p; b.cellCount = c->icCellCount.p; b.cellStart = c->icCellStart.p; b.cellItems = c->icCellItems.p;
+    b.ranges = c->icRanges.p; b.cellCount = c->icCellCount.p; b.cellStart = c->icCellStart.p; b.cellItems = c->icCellItems.p; b.cellSpheres = c->icCellSpheres.p;
+    b.validFlags = c->icValidFlags.p; b.validOffsets = c->icValidOffsets.p;
     b.snapHdr = c->icSnapHdr.p; b.blockCounts = c->icBlockCounts.p; b.list = c->icList.p; b.updSlot = c->icUpdSlot.p; b.pending = c->icPending.p;
     b.icSize = c->icSize; b.numCells = c->icNumCells;
     return b;
@@ -330,6 +334,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->nodes.release(); c->tris.release(); c->sphereGeom.release(); c->texels.release(); c->vertices.release(); c->indices.release();
     c->modelVertexOffset.release(); c->modelIndexOffset.release(); c->randomLightIndex.release(); c->primVerts.release();
     c->materials.release(); c->instances.release(); c->lights.release(); c->randomTriIndex.release(); c->spheres.release(); c->textures.release();
+    c->alphaTextures.release(); c->alphaMaterialTexture.release(); c->alphaScene.release();
     c->imgOutput.release(); c->imgAccum.release(); c->imgEstimate.release();
     for (int i = 0; i < 2; i++) { c->pathRayO[i].release(); c->pathRayD[i].release(); }
     c->pathHit.release(); c->probeRayO.release(); c->probeRayD.release(); c->probeHit.release(); c->probeA.release(); c->probeB.release();
@@ -344,6 +349,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->icPending.release(); c->icNewEntries.release(); c->icSplitData.release(); c->icRanges.release();
     c->icCellCount.release(); c->icCellStart.release(); c->icCellItems.release(); c->icSnapHdr.release(); c->icBlockCounts.release();
     c->icList.release(); c->icNewCount.release(); c->icSplitState.release(); c->icUpdSlot.release();
+    c->icCellSpheres.release(); c->icValidFlags.release(); c->icValidOffsets.release();
     if (c->hostIcHdr) cudaFreeHost(c->hostIcHdr);
     c->guiding.release();
     for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
@@ -407,6 +413,28 @@ int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
         buildBvh8(world.data(), numTris, bvh);
         if (bvh.maxDepth > PT_STACK_LOCAL) return setError(B200PT_E_INVALID, "b200pt_set_scene: BVH too deep for the traversal stack");
         c->bvhDepth = bvh.maxDepth;
+        // alpha test (raytrace.rahit): a texture takes part when one of its texels is not opaque; triangles whose
+        // material (of vertex 0, quirk 4) has such a diffuse texture carry a flag in the packed triangle
+        std::vector<char> texHasAlpha(size_t(s->num_textures), 0);
+        for (int t = 0; t < s->num_textures; t++) {
+            const b200pt_texture &tx = s->textures[t];
+            if (tx.width <= 0 || tx.height <= 0 || !tx.pixels) continue;
+            const size_t np = size_t(tx.width) * tx.height;
+            if (tx.format == B200PT_TEX_RGBA32F) { const float *px = static_cast<const float *>(tx.pixels); for (size_t p = 0; p < np; p++) if (px[4 * p + 3] < 1.0f) { texHasAlpha[t] = 1; break; } }
+            else { const uint8_t *px = static_cast<const uint8_t *>(tx.pixels); for (size_t p = 0; p < np; p++) if (px[4 * p + 3] != 255) { texHasAlpha[t] = 1; break; } }
+        }
+        bool anyAlpha = false;
+        std::vector<int> matTex(size_t(std::max(1, s->num_materials)), -1);
+        for (int i = 0; i < s->num_materials; i++) {
+            const int t = s->materials[i].textureIdDiffuse;
+            if (t >= 0 && t < s->num_textures && texHasAlpha[t]) { matTex[i] = t; anyAlpha = true; }
+        }
+        if (anyAlpha) {
+            for (PackedTri &pt : bvh.tris) {
+                const int mi = verts[size_t(primVerts[pt.prim].x)].materialIndex;
+                if (mi >= 0 && mi < s->num_materials && matTex[mi] != -1) { uint32_t one = 1u; memcpy(&pt.pad0, &one, 4); }
+            }
+        }
 
         cudaStream_t st = c->stream;
         CUDA_TRY(c->nodes.upload(reinterpret_cast<const float4 *>(bvh.nodes.data()), bvh.nodes.size() * 5, st));
@@ -445,11 +473,22 @@ int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
         std::vector<DeviceTexture> dts(size_t(s->num_textures));
         for (int t = 0; t < s->num_textures; t++) { dts[t].texels = c->texels.p + texOff[t]; dts[t].width = s->textures[t].width; dts[t].height = s->textures[t].height; }
         CUDA_TRY(c->textures.upload(dts.data(), dts.size(), st));
+        AlphaScene as{};
+        if (anyAlpha) {
+            std::vector<AlphaTexture> ats(size_t(s->num_textures));
+            for (int t = 0; t < s->num_textures; t++) { ats[t].texels = dts[t].texels; ats[t].width = dts[t].width; ats[t].height = dts[t].height; }
+            CUDA_TRY(c->alphaTextures.upload(ats.data(), ats.size(), st));
+            CUDA_TRY(c->alphaMaterialTexture.upload(matTex.data(), matTex.size(), st));
+            as.primVerts = c->primVerts.p; as.vertices = reinterpret_cast<const float4 *>(c->vertices.p);
+            as.materialTexture = c->alphaMaterialTexture.p; as.textures = c->alphaTextures.p;
+            CUDA_TRY(c->alphaScene.upload(&as, 1, st));
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
 
         DeviceScene &d = c->dscene;
         d.trace.nodes = c->nodes.p; d.trace.tris = c->tris.p; d.trace.spheres = c->sphereGeom.p;
         d.trace.numTris = numTris; d.trace.numSpheres = uint32_t(s->num_spheres);
+        d.trace.alpha = anyAlpha ? c->alphaScene.p : nullptr; d.trace.alphaSeed = 0u;
         d.vertices = c->vertices.p; d.indices = c->indices.p; d.modelVertexOffset = c->modelVertexOffset.p; d.modelIndexOffset = c->modelIndexOffset.p;
         d.primVerts = c->primVerts.p; d.materials = c->materials.p; d.instances = c->instances.p; d.lights = c->lights.p;
         d.randomLightIndex = c->randomLightIndex.p; d.randomTriIndex = c->randomTriIndex.p; d.spheres = c->spheres.p; d.textures = c->textures.p;
@@ -532,6 +571,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
 
     cudaStream_t st = c->stream;
     const uint32_t N = uint32_t(c->numPixels);
+    c->dscene.trace.alphaSeed = pc->randomUInt;
     CUDA_TRY(cudaEventRecord(c->evA, st));
     CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, DST_NUM * sizeof(unsigned long long), st));
 
@@ -547,7 +587,9 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         if (rc != B200PT_OK) return rc;
         if (c->hostIcHdr[ICH_GRID_TOTAL] > c->icCellItems.n) {
             CUDA_TRY(c->icCellItems.alloc(size_t(c->hostIcHdr[ICH_GRID_TOTAL]) * 2));
+            CUDA_TRY(c->icCellSpheres.alloc(size_t(c->hostIcHdr[ICH_GRID_TOTAL]) * 2));
             c->icGrid.cellItems = c->icCellItems.p; c->wf.ic.view.cellItems = c->icCellItems.p;
+            c->icGrid.cellSpheres = c->icCellSpheres.p; c->wf.ic.view.cellSpheres = c->icCellSpheres.p;
             b = icBuffers(c);
         }
         if (c->hostIcHdr[ICH_GRID_TOTAL]) { k_ic_cells<true><<<gridFor(uint64_t(c->icNumCells), 256), 256, 0, st>>>(b, c->icGrid); c->stats.kernel_launches++; }
@@ -625,13 +667,15 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         const uint32_t entries = c->hostIcHdr[ICH_LIST_COUNT];
         if (entries) {
             StageTimer t(c, KIND_SHADE);
-            CUDA_TRY(c->icPending.alloc(size_t(entries) * IC_MAX_NEW * 3));
+            const size_t slots = size_t(entries) * IC_MAX_NEW;
+            CUDA_TRY(c->icPending.alloc(slots * 3)); CUDA_TRY(c->icValidFlags.alloc(slots)); CUDA_TRY(c->icValidOffsets.alloc(slots + 1));
             ICBuffers b = icBuffers(c);
             int grid, stride;
             buildLaunchShape(c, entries, grid, stride);
             k_ic_create<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride);
-            k_ic_create_commit<<<1, 32, 0, st>>>(fp, c->wf, b);
-            c->stats.kernel_launches++;
+            k_scan_single_block<<<1, 1024, 0, st>>>(c->icValidFlags.p, c->icValidOffsets.p, int(slots), nullptr);
+            k_ic_create_commit<<<gridFor(slots, 256), 256, 0, st>>>(fp, c->wf, b);
+            c->stats.kernel_launches += 2;
         }
     }
     CUDA_TRY(cudaMemcpyAsync(c->hostDstats, c->dstats.p, DST_NUM * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

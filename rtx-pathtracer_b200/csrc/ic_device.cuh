@@ -31,6 +31,8 @@ struct ICView {
     const float4 *transGrad;  // snapshot: transGrad.xyz
     const uint32_t *cellStart;   // [cells + 1]
     const uint32_t *cellItems;   // cache indices, ascending inside a cell
+    const float4 *cellSpheres;   // the same lists with the sphere (center, radius) in line: the containment test of a
+                                 // lookup streams these without a dependent index -> sphere load
     float gmin[3], invCell[3];
     int dim[3];
 };
@@ -70,25 +72,34 @@ __device__ __forceinline__ bool queryIrradianceCache(const ICView &ic, const b20
     const uint32_t b = __ldg(&ic.cellStart[cell]), e = __ldg(&ic.cellStart[cell + 1]);
     vec3 cacheValueSum = V3(0.0f);
     float totalWeight = 0.0f;
-    for (uint32_t k = b; k < e; k++) {
-        const uint32_t i = __ldg(&ic.cellItems[k]);
-        const float4 s = __ldg(&ic.sphere[i]);
-        const vec3 oc = origin - make_vec3(s);
-        if (!(length(oc) <= s.w)) continue;                                         // irradiance.rint:15-20
-        const float4 nr = __ldg(&ic.normalR[i]);
-        const vec3 cn = make_vec3(nr);
-        float weight = 1.0f / (length(oc) / nr.w + sqrtf(1.0f - dot(normal, cn)));   // irradiance.rahit:18-21
-        if (isnan(weight) || isinf(weight)) weight = 1000000.0f;
-        const bool vis = -0.001f <= dot(oc, (normal + cn) / 2.0f);
-        if (weight <= 1.0f / pc.irradianceA || (pc.irradianceCachePerformVisibilityCheck && !vis)) continue;
-        const vec3 c = make_vec3(__ldg(&ic.color[i]));
-        if (pc.useIrradianceGradients) {
-            const float E = length(c);
-            const vec3 col = E != 0.0f ? normalize(c) : V3(0.0f);
-            const vec3 adjusted = col * (E + dot(cross(cn, normal), make_vec3(__ldg(&ic.rotGrad[i]))) + dot(oc, make_vec3(__ldg(&ic.transGrad[i]))));
-            cacheValueSum += weight * adjusted;
-        } else cacheValueSum += weight * c;
-        totalWeight += weight;
+    for (uint32_t k0 = b; k0 < e; k0 += 4) {
+        // four independent 128-bit loads in flight per round (the list is walked in order: ascending cache index)
+        float4 s4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) s4[j] = __ldg(&ic.cellSpheres[min(k0 + j, e - 1u)]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (k0 + j >= e) break;
+            const float4 s = s4[j];
+            const vec3 oc = origin - make_vec3(s);
+            const float dist = length(oc);
+            if (!(dist <= s.w)) continue;                                               // irradiance.rint:15-20
+            const uint32_t i = __ldg(&ic.cellItems[k0 + j]);
+            const float4 nr = __ldg(&ic.normalR[i]);
+            const vec3 cn = make_vec3(nr);
+            float weight = 1.0f / (dist / nr.w + sqrtf(1.0f - dot(normal, cn)));         // irradiance.rahit:18-21
+            if (isnan(weight) || isinf(weight)) weight = 1000000.0f;
+            const bool vis = -0.001f <= dot(oc, (normal + cn) / 2.0f);
+            if (weight <= 1.0f / pc.irradianceA || (pc.irradianceCachePerformVisibilityCheck && !vis)) continue;
+            const vec3 c = make_vec3(__ldg(&ic.color[i]));
+            if (pc.useIrradianceGradients) {
+                const float E = length(c);
+                const vec3 col = E != 0.0f ? normalize(c) : V3(0.0f);
+                const vec3 adjusted = col * (E + dot(cross(cn, normal), make_vec3(__ldg(&ic.rotGrad[i]))) + dot(oc, make_vec3(__ldg(&ic.transGrad[i]))));
+                cacheValueSum += weight * adjusted;
+            } else cacheValueSum += weight * c;
+            totalWeight += weight;
+        }
     }
     if (totalWeight > 0.0f) { color = cacheValueSum / totalWeight; return true; }
     return false;

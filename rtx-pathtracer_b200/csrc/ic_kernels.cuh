@@ -6,7 +6,7 @@
 namespace b200pt {
 
 // snapshot header (device): what the frame's lookups see
-enum { ICH_COUNT = 0, ICH_MAX = 1, ICH_NEXT_UPDATE = 2, ICH_GRID_TOTAL = 3, ICH_LIST_COUNT = 4, ICH_NUM = 8 };
+enum { ICH_COUNT = 0, ICH_MAX = 1, ICH_NEXT_UPDATE = 2, ICH_GRID_TOTAL = 3, ICH_LIST_COUNT = 4, ICH_NEXT_CACHE = 5, ICH_NUM = 8 };
 
 struct ICBuffers {      // raw device pointers of one context (host keeps ownership, api.cu)
     b200pt_cache_header *header;      // live, binding 13 header
@@ -15,10 +15,12 @@ struct ICBuffers {      // raw device pointers of one context (host keeps owners
     float4 *snapSphere, *snapNormalR, *snapColor, *snapRot, *snapTrans;
     uint2 *ranges;                    // per snapshot entry: packed cell range (lo xyz bytes, hi xyz bytes)
     uint32_t *cellCount, *cellStart, *cellItems;
+    float4 *cellSpheres;              // per cell-list item: center.xyz, radius
     uint32_t *snapHdr;                // ICH_*
     uint32_t *blockCounts;            // ordered compaction scratch
     uint32_t *list;                   // compacted pixel ids (pixel order)
     int32_t *updSlot;                 // per list entry: cache index to update or -1
+    uint32_t *validFlags, *validOffsets;   // create: per (list entry, k) 1 when the entry is to be appended; exclusive scan
     float4 *pending;                  // per list entry (update) / per (list entry, k) (create): 3 float4
     int icSize;
     int numCells;
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(256) k_ic_snapshot(ICBuffers b, ICView grid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t next = b.header->nextCacheSlot, mx = b.header->maxCaches;
     const uint32_t count = min(min(next, mx), uint32_t(b.icSize));
-    if (i == 0) { b.snapHdr[ICH_COUNT] = count; b.snapHdr[ICH_MAX] = mx; b.snapHdr[ICH_NEXT_UPDATE] = b.header->nextUpdateSlot; b.snapHdr[ICH_GRID_TOTAL] = 0; b.snapHdr[ICH_LIST_COUNT] = 0; }
+    if (i == 0) { b.snapHdr[ICH_COUNT] = count; b.snapHdr[ICH_MAX] = mx; b.snapHdr[ICH_NEXT_UPDATE] = b.header->nextUpdateSlot; b.snapHdr[ICH_GRID_TOTAL] = 0; b.snapHdr[ICH_LIST_COUNT] = 0; b.snapHdr[ICH_NEXT_CACHE] = next; }
     if (uint32_t(i) >= count) return;
     const b200pt_sphere s = b.spheres[i];
     const b200pt_cache_data d = b.data[i];
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) k_ic_cells(ICBuffers b, ICView grid) {
             for (uint32_t k = 0; k < m; k++) {
                 const uint2 r = tile[k];
                 if ((__vcmpgeu4(cp, r.x) & __vcmpleu4(cp, r.y)) == 0xffffffffu) {
-                    if (FILL) b.cellItems[out++] = base + k; else n++;
+                    if (FILL) { b.cellItems[out] = base + k; b.cellSpheres[out] = b.snapSphere[base + k]; out++; } else n++;
                 }
             }
         }
@@ -213,13 +215,14 @@ __global__ void __launch_bounds__(128) k_ic_create(FrameParams fp, DeviceScene s
         InlineTracer tr(fp.pc, sc, wf.ic, wf.guide, stack + threadIdx.x, blockDim.x, pid, wf.seed[pid]);
         for (uint32_t k = 0; k < IC_MAX_NEW; k++) {
             float4 *pe = b.pending + (size_t(e) * IC_MAX_NEW + k) * 3;
-            if (k >= cnt || full) { pe[1].w = 0.0f; continue; }
+            if (k >= cnt || full) { b.validFlags[size_t(e) * IC_MAX_NEW + k] = 0u; continue; }
             const float4 o = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 0], nn = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 1];
             vec3 color, rotGrad, transGrad;
             const float harmonicR = tr.calculateCacheData(make_vec3(o), make_vec3(nn), color, rotGrad, transGrad);
             pe[0] = make_f4(color, harmonicR);
-            pe[1] = make_f4(rotGrad, harmonicR < 0.0f ? 0.0f : 1.0f);      // w: entry valid
+            pe[1] = make_f4(rotGrad, 0.0f);
             pe[2] = make_f4(transGrad, 0.0f);
+            b.validFlags[size_t(e) * IC_MAX_NEW + k] = harmonicR < 0.0f ? 0u : 1u;      // rgen:1391-1393
         }
         wf.seed[pid] = tr.seed;
         atomicAdd(&wf.dstats[DST_EXTEND], (unsigned long long)tr.extendRays);
@@ -228,37 +231,34 @@ __global__ void __launch_bounds__(128) k_ic_create(FrameParams fp, DeviceScene s
     }
 }
 
-// cache slots in pixel order (`header.nextCacheSlot++`), including the reference's off-by-one at the end of the buffer
-__global__ void k_ic_create_commit(FrameParams fp, Wavefront wf, ICBuffers b) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint32_t n = b.snapHdr[ICH_LIST_COUNT];
-    uint32_t next = b.header->nextCacheSlot;
-    const uint32_t maxCaches = b.header->maxCaches;
-    for (uint32_t e = 0; e < n; e++) {
-        const int pid = int(b.list[e]);
-        for (uint32_t k = 0; k < IC_MAX_NEW; k++) {
-            const float4 *pe = b.pending + (size_t(e) * IC_MAX_NEW + k) * 3;
-            if (pe[1].w == 0.0f) continue;
-            if (next > maxCaches) continue;
-            const uint32_t ci = next++;
-            if (ci > maxCaches || ci >= uint32_t(b.icSize)) continue;      // quirk 11: the reference writes one element past the buffer
-            const float harmonicR = fmaxf(pe[0].w, fp.pc.irradianceCacheMinRadius);
-            vec3 rotGrad = make_vec3(pe[1]), transGrad = make_vec3(pe[2]);
-            clampGradients(fp.pc.irradianceGradientsMaxLength, rotGrad, transGrad);
-            const float4 o = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 0], nn = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 1];
-            b200pt_cache_data &cd = b.data[ci];
-            cd.normal[0] = nn.x; cd.normal[1] = nn.y; cd.normal[2] = nn.z;
-            cd.color[0] = pe[0].x; cd.color[1] = pe[0].y; cd.color[2] = pe[0].z;
-            cd.harmonicR = harmonicR;
-            cd.rotGrad[0] = rotGrad.x; cd.rotGrad[1] = rotGrad.y; cd.rotGrad[2] = rotGrad.z;
-            cd.transGrad[0] = transGrad.x; cd.transGrad[1] = transGrad.y; cd.transGrad[2] = transGrad.z;
-            cd.numUpdates = 1u;
-            b200pt_sphere &s = b.spheres[ci];
-            s.center[0] = o.x; s.center[1] = o.y; s.center[2] = o.z;
-            s.radius = fp.pc.irradianceA * harmonicR;
-        }
-    }
-    b.header->nextCacheSlot = next;
+// cache slots in pixel order (`header.nextCacheSlot++`): the j-th valid entry of the ordered list gets slot start + j
+// (validOffsets = exclusive scan of validFlags), including the reference's off-by-one at the end of the buffer
+// (rgen:1384,1397: the slot counter may reach maxCaches + 1, the entry at index maxCaches is dropped — quirk 11)
+__global__ void __launch_bounds__(256) k_ic_create_commit(FrameParams fp, Wavefront wf, ICBuffers b) {
+    const uint32_t n = b.snapHdr[ICH_LIST_COUNT] * IC_MAX_NEW;
+    const uint32_t start = b.snapHdr[ICH_NEXT_CACHE], maxCaches = b.snapHdr[ICH_MAX];
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 && start <= maxCaches) b.header->nextCacheSlot = min(start + b.validOffsets[n], maxCaches + 1u);
+    if (idx >= n || start > maxCaches || !b.validFlags[idx]) return;
+    const uint32_t ci = start + b.validOffsets[idx];
+    if (ci > maxCaches || ci >= uint32_t(b.icSize)) return;
+    const uint32_t e = idx / IC_MAX_NEW, k = idx % IC_MAX_NEW;
+    const int pid = int(b.list[e]);
+    const float4 *pe = b.pending + size_t(idx) * 3;
+    const float harmonicR = fmaxf(pe[0].w, fp.pc.irradianceCacheMinRadius);
+    vec3 rotGrad = make_vec3(pe[1]), transGrad = make_vec3(pe[2]);
+    clampGradients(fp.pc.irradianceGradientsMaxLength, rotGrad, transGrad);
+    const float4 o = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 0], nn = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 1];
+    b200pt_cache_data &cd = b.data[ci];
+    cd.normal[0] = nn.x; cd.normal[1] = nn.y; cd.normal[2] = nn.z;
+    cd.color[0] = pe[0].x; cd.color[1] = pe[0].y; cd.color[2] = pe[0].z;
+    cd.harmonicR = harmonicR;
+    cd.rotGrad[0] = rotGrad.x; cd.rotGrad[1] = rotGrad.y; cd.rotGrad[2] = rotGrad.z;
+    cd.transGrad[0] = transGrad.x; cd.transGrad[1] = transGrad.y; cd.transGrad[2] = transGrad.z;
+    cd.numUpdates = 1u;
+    b200pt_sphere &s = b.spheres[ci];
+    s.center[0] = o.x; s.center[1] = o.y; s.center[2] = o.z;
+    s.radius = fp.pc.irradianceA * harmonicR;
 }
 
 }  // namespace b200pt

@@ -13,12 +13,24 @@
 
 namespace b200pt {
 
+// what the stochastic alpha test of textured triangles needs (raytrace.rahit:22-46); nullptr in TraceScene when no
+// texture of the scene has a texel with alpha < 1 (then no triangle carries the alpha flag either)
+struct AlphaTexture { const float4 *texels; int width, height; };
+struct AlphaScene {
+    const int4 *primVerts;            // per global triangle: global vertex ids v0,v1,v2 + instance
+    const float4 *vertices;           // b200pt_vertex as 3 float4: pos|-, normal|-, texCoord.xy materialIndex -
+    const int *materialTexture;       // per material: textureIdDiffuse
+    const AlphaTexture *textures;
+};
+
 struct TraceScene {
     const float4 *nodes;      // 5 float4 per Bvh8Node
-    const float4 *tris;       // 3 float4 per PackedTri
+    const float4 *tris;       // 3 float4 per PackedTri (e1.w != 0: triangle of an alpha-tested material)
     const float4 *spheres;    // center.xyz, radius
+    const AlphaScene *alpha;
     uint32_t numTris;
     uint32_t numSpheres;
+    uint32_t alphaSeed;       // pushC.randomUInt of the frame (the any-hit shader seeds its own stream with it)
 };
 
 struct HitRec { float t; uint32_t prim; float u, v; };
@@ -64,6 +76,34 @@ __device__ __forceinline__ bool intersectSphereExact(const float4 s, const vec3 
 }
 
 __device__ __forceinline__ uint32_t byteOf(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
+
+// raytrace.rahit:22-46 — any-hit shader of the (non-opaque) triangle geometry: a hit on a textured material is ignored
+// when rnd(seed) > alpha, seed = tea(uint(uv.x * 1e8 + rayOrigin.x * t), pushC.randomUInt).  Runs for closest-hit and
+// shadow rays alike.  Out of line: only scenes with a non-opaque texel ever get here.
+__device__ __noinline__ bool alphaRejects(const TraceScene &sc, uint32_t prim, float bu, float bv, float ox, float t) {
+    const AlphaScene &A = *sc.alpha;
+    const int4 pv = __ldg(&A.primVerts[prim]);
+    const float4 t0 = __ldg(&A.vertices[3 * pv.x + 2]), t1 = __ldg(&A.vertices[3 * pv.y + 2]), t2 = __ldg(&A.vertices[3 * pv.z + 2]);
+    const int tex = __ldg(&A.materialTexture[__float_as_int(t0.z)]);      // material of v0 (quirk 4)
+    if (tex == -1) return false;
+    const float bx = 1.0f - bu - bv;
+    const float tu = t0.x * bx + t1.x * bu + t2.x * bv;
+    const float tv = t0.y * bx + t1.y * bu + t2.y * bv;
+    uint32_t seed = tea(uint32_t(tu * 100000000.0f + ox * t), sc.alphaSeed);   // float -> uint saturates (negative, NaN -> 0), like the oracle
+    // sampler2D: linear filter, repeat (the alpha channel only)
+    const AlphaTexture T = A.textures[tex];
+    const float x = tu * float(T.width) - 0.5f, y = tv * float(T.height) - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    int x0 = int(fx) % T.width, y0 = int(fy) % T.height;
+    if (x0 < 0) x0 += T.width;
+    if (y0 < 0) y0 += T.height;
+    const int x1 = x0 + 1 == T.width ? 0 : x0 + 1, y1 = y0 + 1 == T.height ? 0 : y0 + 1;
+    const float a = __ldg(&T.texels[y0 * T.width + x0]).w, b = __ldg(&T.texels[y0 * T.width + x1]).w;
+    const float c = __ldg(&T.texels[y1 * T.width + x0]).w, d = __ldg(&T.texels[y1 * T.width + x1]).w;
+    const float alpha = (a * (1 - ax) + b * ax) * (1 - ay) + (c * (1 - ax) + d * ax) * ay;
+    return rnd(seed) > alpha;
+}
 
 // Traversal is written as an explicit per-lane state machine (init / step) so that the persistent trace kernel can
 // hand a lane a NEW ray as soon as its current one is finished (dynamic ray fetch), instead of idling until the slowest
@@ -192,8 +232,10 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
         if (intersectTriExact(a, b, c, o, d, t, u, v)) {
             const uint32_t id = __float_as_uint(a.w);
             if (t > s.tmin && t < s.tmax && (t < s.best || (t == s.best && id < s.hit.prim))) {
-                s.best = t; s.hit.t = t; s.hit.prim = id; s.hit.u = u; s.hit.v = v;
-                if (ANY) return true;
+                if (__float_as_uint(b.w) == 0u || !alphaRejects(sc, id, u, v, o.x, t)) {
+                    s.best = t; s.hit.t = t; s.hit.prim = id; s.hit.u = u; s.hit.v = v;
+                    if (ANY) return true;
+                }
             }
         }
     }

@@ -28,6 +28,20 @@ def frame_seed(step, rank, world, seed):
     return tea(step * world + rank, seed)
 
 
+def app_frame_seed(app_state, step, rank, world, seed):
+    """Seed of the next frame when the frames are drawn through the frame driver (b200pt_app_*).  Irradiance-cache
+    prepare frames and the ADRRS estimate frame get the SAME seed on every rank, so all ranks build identical caches and
+    estimate images without any communication; every other frame is sharded like frame_seed().
+    `app_state` is the driver's state BEFORE begin_frame (the condition mirrors src/RayTracingApp.cpp:1130-1150)."""
+    st = app_state
+    uses_cache = bool(st.settings.useIrradianceCache or st.settings.useADRRS)
+    prepare = uses_cache and st.currentPrepareFrames < st.irradianceCachePrepareFrames
+    estimate = uses_cache and bool(st.activateADRRSAfterPrepareFrames) and st.currentPrepareFrames == st.irradianceCachePrepareFrames
+    if prepare or estimate:
+        return tea(step, seed ^ 0x1C1C1C1C)
+    return frame_seed(step, rank, world, seed)
+
+
 def global_frame_indices(steps, rank, world):
     return [s * world + rank for s in range(steps)]
 

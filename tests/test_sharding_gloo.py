@@ -77,3 +77,27 @@ def test_single_process_passthrough():
     r = torch.zeros((4, 40), dtype=torch.uint8)
     assert S.allgather_samples(r) is r
     assert S.frame_seed(2, 1, 4, 7) == helpers.pt().tea(9, 7)
+
+
+def test_app_frame_seed_schedule_is_common_during_ic_preparation():
+    """Prepare frames and the ADRRS estimate frame: same seed on every rank (identical caches without communication);
+    afterwards the frames are sharded by global frame index.  Pure host logic."""
+    P, S = helpers.pt(), _sharding()
+    world = 4
+    seeds = []
+    for rank in range(world):
+        app = P.App(accumulate=True, useADRRS=1, samplesPerPixel=2)
+        app.state.irradianceCachePrepareFrames = 3
+        mine = []
+        for step in range(7):
+            sd = S.app_frame_seed(app.state, step, rank, world, SEED)
+            pc = app.begin_frame(sd)
+            mine.append((sd, pc.isIrradiancePrepareFrame, pc.storeEstimate, pc.useADRRS))
+            app.end_frame()
+        seeds.append(mine)
+    for step in range(4):                    # 3 prepare frames + the estimate frame
+        assert len({seeds[r][step][0] for r in range(world)}) == 1
+    assert [seeds[0][s][1] for s in range(7)] == [1, 1, 1, 0, 0, 0, 0] and seeds[0][3][2] == 1
+    for step in range(5, 7):                 # (step 4 re-uses the estimate frame's seed: reference behaviour, see test_app_driver)
+        assert len({seeds[r][step][0] for r in range(world)}) == world
+        assert all(seeds[r][step][0] == S.frame_seed(step, r, world, SEED) and seeds[r][step][3] == 1 for r in range(world))

@@ -55,6 +55,37 @@ def test_any_hit_matches_oracle(scene_name):
     assert 0.02 < np.mean(c["prim"] != MISS) < 0.98
 
 
+def test_alpha_cutout_any_hit_shader():
+    """raytrace.rahit:22-46: hits on a material whose diffuse texture has transparent texels are ignored stochastically
+    (own RNG stream seeded from uv, ray origin, t and the frame seed) — for closest-hit and for shadow rays."""
+    P = helpers.pt()
+    w, h = 192, 108
+    scene, r, o = helpers.make_pair("alphaLeaf", w, h)
+    prim = helpers.camera_rays(scene, w, h, seed=9)
+    down = prim.copy()                      # a second batch straight down through the card, starting above it
+    rng = np.random.default_rng(3)
+    down["origin"] = np.stack([rng.uniform(-1.6, 1.6, len(down)), np.full(len(down), 3.0), rng.uniform(-1.6, 1.6, len(down))], -1).astype(np.float32)
+    down["dir"] = [0, -1, 0]
+    for seed in (0, 0x12345678):           # the batch API uses the seed of the last rendered frame (0 before any)
+        if seed:
+            pc = P.default_push_constants(randomUInt=seed, previousFrames=0, samplesPerPixel=1)
+            r.render_frame(pc)
+            o.render_region(pc, x1=1, y1=1)
+        for rays in (prim, down):
+            for any_hit in (False, True):
+                g, c = r.trace_rays(rays, any_hit=any_hit), o.trace_rays(rays, any_hit=any_hit, threads=NT)
+                if any_hit:
+                    assert np.array_equal(g["prim"] != MISS, c["prim"] != MISS)
+                else:
+                    assert np.array_equal(g["prim"], c["prim"])
+    # the card (prims 2, 3) stops some of the vertical rays and lets most through to the floor (78 % of the texels are clear)
+    g = r.trace_rays(down)
+    card = np.isin(g["prim"], (2, 3)).mean()
+    assert 0.05 < card < 0.5 and np.isin(g["prim"], (0, 1)).mean() > 0.4
+    r2, o2, gi, ci = _render_both("alphaLeaf", 160, 90, samplesPerPixel=2, enableNEE=1, enableMIS=1, maxDepth=6)
+    _assert_radiance_parity(gi, ci, 0.99)
+
+
 def test_edge_cases_empty_and_degenerate_rays():
     P = helpers.pt()
     scene, r, o = helpers.make_pair("veachMIS", 16, 16)

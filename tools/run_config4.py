@@ -23,6 +23,7 @@ def run(name, **settings):
     r.set_scene(scene)
     r.set_camera(view, proj)
     t_scene = time.time() - t0
+    r.set_stage_timing(True)
     app = P.App(r, accumulate=True, samplesPerPixel=SPP, enableNEE=1, enableMIS=1, **settings)
     phases = []
 
@@ -33,7 +34,7 @@ def run(name, **settings):
             app.draw_frame(P.tea(len(phases) * 1000 + _, 0xC0FFEE))
         st = r.stats()
         hdr = r.ic_get()[0] if r.ic_size else None
-        phases.append(dict(phase=label, frames=n, wall_ms=round((time.time() - t) * 1e3, 1), device_ms=round(st.ms_total, 1),
+        phases.append(dict(phase=label, frames=n, wall_ms=round((time.time() - t) * 1e3, 1), device_ms=round(st.ms_total, 1), trace_ms=round(st.ms_extend + st.ms_shadow, 1), shade_and_ic_ms=round(st.ms_shade, 1),
                            Mrays_per_s=round((st.extend_rays + st.shadow_rays) / max(st.ms_total, 1e-6) / 1e3, 1), extend=st.extend_rays,
                            shadow=st.shadow_rays, launches=st.kernel_launches, cache_entries=(hdr.nextCacheSlot if hdr else 0)))
 
