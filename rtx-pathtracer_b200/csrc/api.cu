@@ -91,7 +91,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
-    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, resolveGrid = 0;
+    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, resolveGrid = 0, icQueryGrid = 0;
     TraceTuning tune{64u, 8};
 
     // guiding / IC state
@@ -101,7 +101,7 @@ struct b200pt_ctx {
     DevBuf<b200pt_sphere> icSpheres;
     DevBuf<b200pt_cache_header> icHeader;
     // IC lookup snapshot + grid, per-pixel IC / split state, ordered-compaction scratch (allocated on first use)
-    DevBuf<float4> icSnapSphere, icSnapNormalR, icSnapColor, icSnapRot, icSnapTrans, icPending, icNewEntries, icSplitData, icCellSpheres;
+    DevBuf<float4> icSnapSphere, icSnapNormalR, icSnapColor, icSnapRot, icSnapTrans, icPending, icNewEntries, icSplitData, icCellSpheres, icQueryResult;
     DevBuf<uint2> icRanges;
     DevBuf<uint32_t> icCellCount, icCellStart, icCellItems, icSnapHdr, icBlockCounts, icList, icNewCount, icSplitState, icValidFlags, icValidOffsets;
     DevBuf<int32_t> icUpdSlot;
@@ -188,6 +188,7 @@ static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
         CUDA_TRY(c->icCellItems.alloc(S * 8)); CUDA_TRY(c->icCellSpheres.alloc(S * 8));
         CUDA_TRY(c->icNewCount.alloc(N));
         CUDA_TRY(c->icNewEntries.alloc(N * IC_MAX_NEW * 2));
+        CUDA_TRY(c->icQueryResult.alloc(N));
         // uniform grid over the scene box (the same box the guiding regions start from), at most IC_GRID_MAX cells per axis
         float ext[3], mx = 0.0f;
         for (int a = 0; a < 3; a++) { ext[a] = c->sceneMax[a] - c->sceneMin[a]; mx = std::max(mx, ext[a]); }
@@ -286,9 +287,9 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
     c->numSMs = prop.multiProcessorCount;
     int occTrace = 0, occShade = 0, occResolve = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace<false>, PT_TRACE_BLOCK, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, k_trace<false, 0>, PT_TRACE_BLOCK, 0));
     int occTraceRec = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTraceRec, k_trace<true>, PT_TRACE_BLOCK, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTraceRec, k_trace<true, 0>, PT_TRACE_BLOCK, 0));
     c->traceGridRec = c->numSMs * std::max(1, occTraceRec);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShade, k_shade<false, false>, 128, 0));
     int occShadeGuided = 0, occShadeIC = 0, occShadeGuidedIC = 0;
@@ -298,6 +299,9 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->shadeGridGuided = c->numSMs * std::max(1, occShadeGuided);
     c->shadeGridIC = c->numSMs * std::max(1, occShadeIC);
     c->shadeGridGuidedIC = c->numSMs * std::max(1, occShadeGuidedIC);
+    int occQuery = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQuery, k_ic_query, 256, 0));
+    c->icQueryGrid = c->numSMs * std::max(1, occQuery);
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostIcHdr), ICH_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
     c->traceGrid = c->numSMs * std::max(1, occTrace);
@@ -349,7 +353,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->icPending.release(); c->icNewEntries.release(); c->icSplitData.release(); c->icRanges.release();
     c->icCellCount.release(); c->icCellStart.release(); c->icCellItems.release(); c->icSnapHdr.release(); c->icBlockCounts.release();
     c->icList.release(); c->icNewCount.release(); c->icSplitState.release(); c->icUpdSlot.release();
-    c->icCellSpheres.release(); c->icValidFlags.release(); c->icValidOffsets.release();
+    c->icCellSpheres.release(); c->icValidFlags.release(); c->icValidOffsets.release(); c->icQueryResult.release();
     if (c->hostIcHdr) cudaFreeHost(c->hostIcHdr);
     c->guiding.release();
     for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
@@ -559,7 +563,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         if (useCache) {
             w.ic.view = c->icGrid;
             w.ic.estimate = c->imgEstimate.p;
-            w.ic.newCount = c->icNewCount.p; w.ic.newEntries = c->icNewEntries.p;
+            w.ic.newCount = c->icNewCount.p; w.ic.newEntries = c->icNewEntries.p; w.ic.queryResult = c->icQueryResult.p;
         }
         if (splitMode) { w.ic.splitState = c->icSplitState.p; w.ic.splitData = c->icSplitData.p; }
     }
@@ -627,12 +631,19 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
         if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
         {
             StageTimer t(c, KIND_EXTEND);
-            if (pc->updateGuiding) k_trace<true><<<c->traceGridRec, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
-            else k_trace<false><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+            const bool alpha = c->dscene.trace.alpha != nullptr;     // some texture of the scene has a transparent texel
+            if (pc->updateGuiding) {
+                if (alpha) k_trace<true, 1><<<c->traceGridRec, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+                else k_trace<true, 0><<<c->traceGridRec, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+            } else {
+                if (alpha) k_trace<false, 1><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+                else k_trace<false, 0><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
+            }
         }
         if ((pc->enableNEE || useCache) && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
         k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
         c->stats.kernel_launches++;
+        if (useCache) { StageTimer t(c, KIND_SHADE); k_ic_query<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur); }
         {
             StageTimer t(c, KIND_SHADE);
             if (guided && icMode) k_shade<true, true><<<c->shadeGridGuidedIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
@@ -738,8 +749,12 @@ int b200pt_trace_rays_device(b200pt_ctx *c, const void *rays, int64_t n, void *h
     CUDA_TRY(cudaSetDevice(c->device));
     if (n > int64_t(0x7fffffff)) return setError(B200PT_E_INVALID, "b200pt_trace_rays_device: at most 2^31-1 rays per call");
     CUDA_TRY(cudaMemsetAsync(c->batchCounter.p, 0, sizeof(uint32_t), c->stream));
-    k_trace_batch<<<c->traceGrid, PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), uint32_t(n),
-                                                                 any_hit, c->batchCounter.p, c->tune);
+    if (c->dscene.trace.alpha)
+        k_trace_batch<1><<<c->traceGrid, PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), uint32_t(n),
+                                                                           any_hit, c->batchCounter.p, c->tune);
+    else
+        k_trace_batch<0><<<c->traceGrid, PT_TRACE_BLOCK, 0, c->stream>>>(c->dscene.trace, static_cast<const float4 *>(rays), static_cast<float4 *>(hits), uint32_t(n),
+                                                                            any_hit, c->batchCounter.p, c->tune);
     c->stats.kernel_launches++;
     if (any_hit) { c->stats.shadow_rays += uint64_t(n); c->stats.launches_shadow++; } else { c->stats.extend_rays += uint64_t(n); c->stats.launches_extend++; }
     CUDA_TRY(cudaGetLastError());

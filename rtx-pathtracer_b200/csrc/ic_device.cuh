@@ -41,6 +41,7 @@ struct ICView {
 struct ICState {
     ICView view;
     const float4 *estimate;   // estimate image (binding 14), read by ADRRS
+    float4 *queryResult;      // per path-queue entry of the current iteration: irradiance rgb, w = 1 when the lookup found something (k_ic_query)
     uint32_t *newCount;       // [pixel] nextNewIrradianceCacheSlot
     float4 *newEntries;       // [(pixel * IC_MAX_NEW + k) * 2]: origin, normal
     uint32_t *splitState;     // [pixel] nextSplitSlot | (index of the next split to drain) << 16; nullptr when no split mode is on

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t byteOf(uint32_t x, int i) { return (x >> (8 
 // raytrace.rahit:22-46 — any-hit shader of the (non-opaque) triangle geometry: a hit on a textured material is ignored
 // when rnd(seed) > alpha, seed = tea(uint(uv.x * 1e8 + rayOrigin.x * t), pushC.randomUInt).  Runs for closest-hit and
 // shadow rays alike.  Out of line: only scenes with a non-opaque texel ever get here.
-__device__ __noinline__ bool alphaRejects(const TraceScene &sc, uint32_t prim, float bu, float bv, float ox, float t) {
+__device__ __forceinline__ bool alphaRejectsInline(const TraceScene &sc, uint32_t prim, float bu, float bv, float ox, float t) {
     const AlphaScene &A = *sc.alpha;
     const int4 pv = __ldg(&A.primVerts[prim]);
     const float4 t0 = __ldg(&A.vertices[3 * pv.x + 2]), t1 = __ldg(&A.vertices[3 * pv.y + 2]), t2 = __ldg(&A.vertices[3 * pv.z + 2]);
@@ -103,6 +103,9 @@ __device__ __noinline__ bool alphaRejects(const TraceScene &sc, uint32_t prim, f
     const float c = __ldg(&T.texels[y1 * T.width + x0]).w, d = __ldg(&T.texels[y1 * T.width + x1]).w;
     const float alpha = (a * (1 - ax) + b * ax) * (1 - ay) + (c * (1 - ax) + d * ax) * ay;
     return rnd(seed) > alpha;
+}
+__device__ __noinline__ bool alphaRejects(const TraceScene &sc, uint32_t prim, float bu, float bv, float ox, float t) {
+    return alphaRejectsInline(sc, prim, bu, bv, ox, t);
 }
 
 // Traversal is written as an explicit per-lane state machine (init / step) so that the persistent trace kernel can
@@ -152,6 +155,10 @@ __device__ __forceinline__ bool travInit(Trav &s, const TraceScene &sc, const ve
 #ifndef PT_TRI_CAP
 #define PT_TRI_CAP 0          // compile-time: 0 = no cap (test every triangle of the group in this step)
 #endif
+// ALPHA compiles the alpha test of textured triangles in (scenes without a transparent texel run the plain kernel):
+// 0 = none, 1 = out-of-line call (the trace kernels: keeps their register count), 2 = in line (callers that must not
+// contain an ABI call: a CALL anywhere in the shade kernel costs it 7 % even when it is never executed)
+template <int ALPHA>
 __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *smemStack, uint2 *localStack, const int stride, const bool ANY) {
     const vec3 o = s.o, d = s.d;
     uint2 cur = s.cur;
@@ -232,7 +239,7 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
         if (intersectTriExact(a, b, c, o, d, t, u, v)) {
             const uint32_t id = __float_as_uint(a.w);
             if (t > s.tmin && t < s.tmax && (t < s.best || (t == s.best && id < s.hit.prim))) {
-                if (__float_as_uint(b.w) == 0u || !alphaRejects(sc, id, u, v, o.x, t)) {
+                if (!ALPHA || __float_as_uint(b.w) == 0u || !(ALPHA == 2 ? alphaRejectsInline(sc, id, u, v, o.x, t) : alphaRejects(sc, id, u, v, o.x, t))) {
                     s.best = t; s.hit.t = t; s.hit.prim = id; s.hit.u = u; s.hit.v = v;
                     if (ANY) return true;
                 }
@@ -262,14 +269,29 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
 }
 
 // whole-ray convenience wrapper (used for the rare in-line visibility rays of the shade kernel)
-template <bool ANY>
-__device__ __forceinline__ void traceRay(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
-                                         HitRec &hit, uint2 *smemStack, const int stride) {
+template <bool ANY, int ALPHA>
+__device__ __forceinline__ void traceRayT(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                          HitRec &hit, uint2 *smemStack, const int stride) {
     Trav s;
     uint2 localStack[PT_STACK_LOCAL];
     bool done = travInit(s, sc, o, d, tmin, tmax, ANY);
-    while (!done) done = travStep(s, sc, smemStack, localStack, stride, ANY);
+    while (!done) done = travStep<ALPHA>(s, sc, smemStack, localStack, stride, ANY);
     hit = s.hit;
+}
+// out of line on purpose: the callers (the rare in-line visibility ray of the shade kernel, the serial cache-build
+// tracer) keep their registers for their own work and share one copy of the traversal code
+template <bool ANY>
+__device__ __noinline__ void traceRay(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                      HitRec &hit, uint2 *smemStack, const int stride) {
+    if (sc.alpha) traceRayT<ANY, 2>(sc, o, d, tmin, tmax, hit, smemStack, stride);
+    else traceRayT<ANY, 0>(sc, o, d, tmin, tmax, hit, smemStack, stride);
+}
+// the same, in line (no ABI call in the caller)
+template <bool ANY>
+__device__ __forceinline__ void traceRayInline(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                               HitRec &hit, uint2 *smemStack, const int stride) {
+    if (sc.alpha) traceRayT<ANY, 2>(sc, o, d, tmin, tmax, hit, smemStack, stride);
+    else traceRayT<ANY, 0>(sc, o, d, tmin, tmax, hit, smemStack, stride);
 }
 
 // Persistent-warp ray loop with dynamic fetch.  `total` rays are numbered 0..total-1; warps take chunks of `chunk`
@@ -277,7 +299,7 @@ __device__ __forceinline__ void traceRay(const TraceScene &sc, const vec3 o, con
 // lane whose ray is finished gets the warp's next ray once at least `refillMin` lanes are idle (or the whole warp is).
 // IO::load(idx, o, d, tmin, tmax, any) reads ray idx, IO::store(idx, hit, any) consumes the result; results are keyed
 // by ray index, so the output does not depend on which lane traced which ray.
-template <typename IO>
+template <int ALPHA, typename IO>
 __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &io, const uint32_t total, uint32_t *workCounter,
                                                 const uint32_t chunk, const int refillMin, uint2 *smemStack) {
     const unsigned lane = threadIdx.x & 31u;
@@ -311,7 +333,7 @@ __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &
             wBase = min(wEnd, wBase + uint32_t(__popc(idle)));
         }
         if (active) {
-            if (travStep(s, sc, smemStack, localStack, stride, any)) {
+            if (travStep<ALPHA>(s, sc, smemStack, localStack, stride, any)) {
                 io.store(rayIdx, s.hit, any);
                 active = false;
             }

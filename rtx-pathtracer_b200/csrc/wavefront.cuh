@@ -145,7 +145,7 @@ struct WavefrontRayIO {
     }
 };
 
-template <bool REC>
+template <bool REC, int ALPHA>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefront wf, int cur, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
     WavefrontRayIO<REC> io;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefro
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
     while (chunk > 32 && total / chunk < warps) chunk >>= 1;
-    tracePersistent(sc, io, total, &wf.counters[CNT_WORK_TRACE], chunk, tune.refillMin, stack + threadIdx.x);
+    tracePersistent<ALPHA>(sc, io, total, &wf.counters[CNT_WORK_TRACE], chunk, tune.refillMin, stack + threadIdx.x);
 }
 
 // generic ray batch for the traversal-only parity hook (b200pt_trace_rays): same persistent loop
@@ -172,6 +172,7 @@ struct BatchRayIO {
     }
     __device__ __forceinline__ void store(uint32_t idx, const HitRec &h, bool) const { hits[idx] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v); }
 };
+template <int ALPHA>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, uint32_t n,
                                                                 int any, uint32_t *workCounter, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, c
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
     while (chunk > 32 && n / chunk < warps) chunk >>= 1;
-    tracePersistent(sc, io, n, workCounter, chunk, tune.refillMin, stack + threadIdx.x);
+    tracePersistent<ALPHA>(sc, io, n, workCounter, chunk, tune.refillMin, stack + threadIdx.x);
 }
 
 // between trace and shade of one iteration: fold the queue sizes into the 64-bit statistics, publish the shade count
@@ -238,6 +239,32 @@ __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceSce
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// irradiance-cache lookups of one wavefront iteration (IC / ADRRS frames), run between trace and shade.  The lookup is a
+// chain of dependent loads over a cell list of some tens of entries; inside the 128-register shade kernel (4 CTAs per
+// SM) it was latency bound — issue slots 12 % busy, 60 % of the kernel's instructions (profiles/r01c_ncu_shade_ic.txt).
+// As a kernel of its own it runs at full occupancy and the shade kernel just reads the result.
+__global__ void __launch_bounds__(256) k_ic_query(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
+    const uint32_t n = wf.counters[CNT_SHADE_N];
+    const b200pt_push_constants &pc = fp.pc;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+        const float4 hr = wf.pathHit[qi];
+        HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
+        if (h.prim == PT_MISS) continue;
+        const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
+        const int pid = __float_as_int(ro.w);
+        const uint32_t depth = (wf.state[pid] & 0xffffu) + 1u;
+        if (!(pc.useIrradianceCache || (pc.useADRRS && depth > 1))) continue;
+        HitInfo info;
+        computeHitInfo(sc, h, make_vec3(ro), make_vec3(rd), info);
+        const int type = sc.materials[info.matIndex].type;
+        if (hasDiscreteDirection(type) || !isICCapable(pc, type)) continue;
+        vec3 irr = V3(0.0f);
+        const bool found = queryIrradianceCache(wf.ic.view, pc, info.worldPos, info.normal, irr);
+        wf.ic.queryResult[qi] = make_f4(irr, found ? 1.0f : 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // multipleNEE / nextEventEstimation (rgen:871-877, :601-731) in queue form: the shadow ray and the MIS probe ray of
 // every light sample go to their queues with the contribution they carry; k_trace / k_probe_resolve finish them.
 // T is the throughput the NEE result is multiplied with; cso = currentSampleOffset (guiding training only).
@@ -261,7 +288,7 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
                     // resolve the visibility here so the RNG stream stays identical (rare)
                     HitRec sh;
                     atomicAdd(&wf.counters[CNT_INLINE_SHADOW], 1u);
-                    traceRay<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack, blockDim.x);
+                    traceRayInline<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack, blockDim.x);
                     if (sh.prim == PT_MISS) skipProbe = true;
                 } else {
                     C = f * lightColor * heuristic / pdfLights;
@@ -300,8 +327,11 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
 // shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
 // GUIDE compiles in guided sampling (pc.useGuiding) and sample recording (pc.updateGuiding);
 // IC compiles in the irradiance-cache lookup, ADRRS (weight window, Russian roulette, splitting) and the split drain
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 5        // 96 registers, ~200 B of spills: 5 CTAs per SM beat 4 without spills by 5 % (tools/tune_variants.sh)
+#endif
 template <bool GUIDE, bool IC>
-__global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
+__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = wf.counters[CNT_SHADE_N];
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
@@ -374,8 +404,9 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, DeviceScene sc, W
                 addNext = false;
                 follow = false;
                 if (IC && (pc.useIrradianceCache || (pc.useADRRS && depth > 1)) && isICCapable(pc, mat.type)) {      // rgen:1083-1133
-                    vec3 irradianceColor;
-                    if (queryIrradianceCache(wf.ic.view, pc, origin, normal, irradianceColor)) {
+                    const float4 icq = wf.ic.queryResult[qi];        // queryIrradianceCache, done by k_ic_query for this queue entry
+                    const vec3 irradianceColor = make_vec3(icq);
+                    if (icq.w != 0.0f) {
                         if (pc.useADRRS) {
                             int nSplit;
                             float q = applyWeightWindow(pc, seed, T, irradianceColor, make_vec3(wf.ic.estimate[pid]), nSplit);

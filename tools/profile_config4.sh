@@ -6,4 +6,4 @@ python tools/run_config4.py 1920 1080 4 4 > gpurun_out/config4_stage.jsonl 2> gp
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/config4_launches.csv \
     python tools/run_config4_short.py > gpurun_out/config4_under_ncu.log 2>&1
 python tools/ncu_summary.py launches gpurun_out/config4_launches.csv > gpurun_out/config4_launch_summary.txt 2>&1 || true
-cat gpurun_out/config4_stage.jsonl; tail -30 gpurun_out/config4_launch_summary.txt
+rm -f gpurun_out/config4_launches.csv; cat gpurun_out/config4_stage.jsonl; tail -30 gpurun_out/config4_launch_summary.txt
