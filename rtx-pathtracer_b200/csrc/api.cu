@@ -113,6 +113,7 @@ struct b200pt_ctx {
     DevBuf<float4> batchRays, batchHits;
 
     b200pt_stats stats{};
+    FILE *dumpIters = nullptr;          // B200PT_DUMP_ITERS=file: queue sizes after every wavefront iteration (tuning aid)
 
     // optional per-kernel timing: (kind, start event, stop event) triples resolved at the end of a frame
     bool stageTiming = false;
@@ -307,6 +308,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->traceGrid = c->numSMs * std::max(1, occTrace);
     c->shadeGrid = c->numSMs * std::max(1, occShade);
     c->resolveGrid = c->numSMs * std::max(1, occResolve);
+    if (const char *e = getenv("B200PT_DUMP_ITERS")) c->dumpIters = fopen(e, "w");
     if (const char *e = getenv("B200PT_TRACE_CHUNK")) c->tune.chunk = uint32_t(std::max(32, atoi(e)));
     if (const char *e = getenv("B200PT_TRACE_REFILL")) c->tune.refillMin = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("B200PT_TRACE_GRID_PER_SM")) c->traceGrid = c->numSMs * std::max(1, atoi(e));
@@ -347,6 +349,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->seed.release(); c->state.release(); c->sampleIdx.release(); c->counters.release(); c->dstats.release(); c->batchCounter.release();
     for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
+    if (c->dumpIters) fclose(c->dumpIters);
     c->samples.release(); c->hostSamples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
     c->icSnapSphere.release(); c->icSnapNormalR.release(); c->icSnapColor.release(); c->icSnapRot.release(); c->icSnapTrans.release();
@@ -664,6 +667,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             if (hc[CNT_PATH0 + liveQ] > N || hc[CNT_PROBE] > N * uint32_t(c->queueNEE) || hc[CNT_SHADOW] > N * uint32_t(c->queueNEE))
                 return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
             drained = hc[CNT_PATH0 + liveQ] == 0 && hc[CNT_PROBE] == 0 && hc[CNT_SHADOW] == 0;
+            if (c->dumpIters) fprintf(c->dumpIters, "%llu %u %u %u\n", (unsigned long long)(iter - b200pt_ctx::LAG), hc[CNT_PATH0 + liveQ], hc[CNT_PROBE], hc[CNT_SHADOW]);
         }
     }
     if (!earlyReturn) {
