@@ -26,7 +26,7 @@ static const Field kFields[] = {
 
 static void printHelp() {
     printf("Required parameters: WIDTH HEIGHT IC_SIZE GUIDING_SPLITS Scenes ...\n");
-    printf("Options: --frames=N --seed=S --out=FILE.exr --device=D --prepareFrames=N --numGuidingOptimizations=N\n");
+    printf("Options: --frames=N | --seconds=S, --seed=S --out=FILE.exr --device=D --prepareFrames=N --numGuidingOptimizations=N\n");
     printf("         and --<pushConstantField>=value, e.g. --samplesPerPixel=16 --enableMIS=1 --useADRRS=1\n");
 }
 
@@ -53,6 +53,7 @@ int main(int argc, char **argv) {
     app.accumulateResults = 1;      // the evaluation modes switch it on (src/RayTracingApp.cpp:93,98)
     b200pt_push_constants &pc = app.settings;
     int frames = 1, device = 0;
+    double seconds = 0.0;           // > 0: the reference's "collect for N seconds" evaluation (src/RayTracingApp.cpp:188-218)
     uint32_t seed = 0xC0FFEEu;
     std::string out;
     for (const std::string &o : options) {
@@ -63,6 +64,7 @@ int main(int argc, char **argv) {
         else if (key == "seed") seed = uint32_t(std::stoul(val, nullptr, 0));
         else if (key == "out") out = val;
         else if (key == "device") device = std::stoi(val);
+        else if (key == "seconds") seconds = std::stod(val);
         else if (key == "prepareFrames") app.irradianceCachePrepareFrames = std::stoi(val);
         else if (key == "numGuidingOptimizations") app.numGuidingOptimizations = std::stoi(val);
         else {
@@ -103,7 +105,9 @@ int main(int argc, char **argv) {
         app.evalCurrentSamples = 0;
         const long long wanted = (long long)frames * pc.samplesPerPixel;
         int drawn = 0;
-        for (uint32_t f = 0; app.evalCurrentSamples < wanted && ok; f++, drawn++) {
+        for (uint32_t f = 0; ok; f++, drawn++) {
+            if (seconds > 0.0) { if (std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t1).count() >= seconds) break; }
+            else if (app.evalCurrentSamples >= wanted) break;
             if (b200pt_app_draw_frame(&app, ctx, tea(f, seed), nullptr) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); ok = false; }
         }
         auto t2 = std::chrono::high_resolution_clock::now();
@@ -111,7 +115,8 @@ int main(int argc, char **argv) {
             b200pt_stats st;
             b200pt_stats_get(ctx, &st);
             long long ms = (long long)std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count();
-            int spp = frames * userSettings.samplesPerPixel;
+            int spp = seconds > 0.0 ? int(app.evalCurrentSamples) : frames * userSettings.samplesPerPixel;
+            if (seconds > 0.0) printf("Collected %d in %g\n", spp, seconds);
             printf("Collecting %d samples took %lld milliseconds with %d samples per pixel per frame (%d frames drawn)\n", spp, ms, userSettings.samplesPerPixel, drawn);
             printf("rays: %llu extend + %llu shadow, %.1f Mrays/s (device time %.1f ms), %.2f spp/s\n", (unsigned long long)st.extend_rays,
                    (unsigned long long)st.shadow_rays, double(st.extend_rays + st.shadow_rays) / (double(st.ms_total) * 1e3), st.ms_total,
@@ -123,10 +128,11 @@ int main(int argc, char **argv) {
                 std::string base = scenePath.substr(scenePath.find_last_of('/') + 1);
                 base = base.substr(0, base.find_last_of('.'));
                 std::string mode;
-                if (pc.enableNEE) { mode += "_NEE"; if (pc.enableMIS) mode += "_MIS"; }
-                if (pc.useIrradianceCache) mode += "_IC";
-                if (pc.useADRRS) mode += "_ADRRS";
-                if (pc.useGuiding) { mode += "_Guiding"; if (pc.useParallaxCompensation) mode += "_Parallax"; }
+                const b200pt_push_constants &us = userSettings;     // (the driver may be in the middle of a prepare / estimate frame)
+                if (us.enableNEE) { mode += "_NEE"; if (us.enableMIS) mode += "_MIS"; }
+                if (us.useIrradianceCache) mode += "_IC";
+                if (us.useADRRS) mode += "_ADRRS";
+                if (us.useGuiding) { mode += "_Guiding"; if (us.useParallaxCompensation) mode += "_Parallax"; }
                 file = base + mode + "_" + std::to_string(spp) + "samples.exr";
             }
             if (b200pt_write_exr(file.c_str(), img.data(), width, height) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); status = EXIT_FAILURE; }
