@@ -46,7 +46,8 @@ def has_gpu():
 
 
 def scene_path(name):
-    return os.path.join(SCENES, name, name + ".xml")
+    xml = os.path.join(SCENES, name, name + ".xml")
+    return xml if os.path.exists(xml) else os.path.join(SCENES, name, name + ".json")     # the reference's two scene formats
 
 
 def make_pair(scene_name, width, height, ic_size=0, guiding_splits=0, accel=True, gpu=True):

@@ -13,7 +13,7 @@ MISS = 0xFFFFFFFF
 NT = os.cpu_count() or 1
 
 
-@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML"])
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML", "test-scene", "envSynthetic"])
 def test_closest_hit_bit_exact(scene_name):
     w, h = 256, 144
     scene, r, o = helpers.make_pair(scene_name, w, h, accel=True)
@@ -24,7 +24,7 @@ def test_closest_hit_bit_exact(scene_name):
         c = o.trace_rays(rays, threads=NT)
         assert np.array_equal(g["prim"], c["prim"]), "%s: %d primitive ids differ" % (name, np.sum(g["prim"] != c["prim"]))
         hit = c["prim"] != MISS
-        assert hit.mean() > 0.3
+        assert hit.mean() > 0.2
         # t, u, v are computed with identical individually-rounded operations: bit-exact
         for f in ("t", "u", "v"):
             assert np.array_equal(g[f][hit].view(np.uint32), c[f][hit].view(np.uint32)), f
@@ -161,6 +161,27 @@ def test_radiance_parity_sponza_textured():
     assert c.mean() > 0
     r, o, g, c = _render_both("sponzaXML", 128, 72, samplesPerPixel=2, enableNEE=1, enableMIS=1, maxDepth=8)
     _assert_radiance_parity(g, c, 0.85)
+
+
+@pytest.mark.parametrize("mode", ["nee_mis", "nee", "bsdf"])
+def test_radiance_parity_json_scene_instances_point_and_mesh_lights(mode):
+    """The reference's JSON test scene: 14 instances with rotation and non-uniform scale (normalTransform), two mesh
+    lights (per-light face tables, quirk 5) and two point lights, MTL materials (diffuse, Phong, glass, mirror, light),
+    PNG + JPEG textures."""
+    over = dict(nee_mis=dict(enableNEE=1, enableMIS=1), nee=dict(enableNEE=1, enableMIS=0), bsdf=dict(enableNEE=0))[mode]
+    r, o, g, c = _render_both("test-scene", 160, 90, samplesPerPixel=2, maxDepth=8, **over)
+    _assert_radiance_parity(g, c, 0.985)
+    assert c.mean() > 0
+
+
+@pytest.mark.parametrize("mode", ["nee_mis", "nee", "bsdf"])
+def test_radiance_parity_environment_map(mode):
+    """Environment emitter: lat-long lookup on a miss (raytrace.rmiss), uniform-hemisphere light sampling with the stub
+    pdf (quirk 7), MIS probe misses; plus a sphere light."""
+    over = dict(nee_mis=dict(enableNEE=1, enableMIS=1), nee=dict(enableNEE=1, enableMIS=0), bsdf=dict(enableNEE=0))[mode]
+    r, o, g, c = _render_both("envSynthetic", 160, 90, samplesPerPixel=2, maxDepth=6, **over)
+    _assert_radiance_parity(g, c, 0.99)
+    assert c.mean() > 0.05
 
 
 def test_accumulation_over_frames_matches_oracle():
