@@ -351,6 +351,8 @@ typedef struct b200pt_guiding_params {
     float vPrior;                      /* 0.01 */
     float rPrior;                      /* 0 */
     float rPriorWeight;                /* 1 */
+    int32_t splitRegions;              /* PathGuiding::splitRegions, src/PathGuiding.h:121 — 0: adaptive region refinement off */
+    float samplesForRegionSplit;       /* 10000, src/PathGuiding.h:122: a region whose mixture saw more samples is halved */
 } b200pt_guiding_params;
 void b200pt_default_guiding_params(b200pt_guiding_params *p);
 

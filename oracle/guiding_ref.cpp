@@ -133,6 +133,14 @@ void computeEigenValuesVectors(const lightpmm::Matrix2x2 &covmat, float eigenVal
     }
 }
 
+static void splitAabb(const b200pt_aabb &b, b200pt_aabb &l, b200pt_aabb &r) {        // Aabb::splitAabb, Shapes.h:32-46
+    const float size[3] = {b.max[0] - b.min[0], b.max[1] - b.min[1], b.max[2] - b.min[2]};
+    const int axis = size[0] > size[1] ? (size[0] > size[2] ? 0 : 2) : (size[1] > size[2] ? 1 : 2);
+    l = b; r = b;
+    l.max[axis] -= 0.5f * size[axis];
+    r.min[axis] += 0.5f * size[axis];
+}
+
 struct RefGuiding {
     uint32_t regionCount = 0;
     bool firstFit = true;
@@ -170,14 +178,7 @@ struct RefGuiding {
         aabbs.assign(1, scene);
         for (int i = 0; i < splits; i++) {
             std::vector<b200pt_aabb> next;
-            for (const b200pt_aabb &b : aabbs) {                                     // Aabb::splitAabb, Shapes.h:32-46
-                const float size[3] = {b.max[0] - b.min[0], b.max[1] - b.min[1], b.max[2] - b.min[2]};
-                const int axis = size[0] > size[1] ? (size[0] > size[2] ? 0 : 2) : (size[1] > size[2] ? 1 : 2);
-                b200pt_aabb l = b, r = b;
-                l.max[axis] -= 0.5f * size[axis];
-                r.min[axis] += 0.5f * size[axis];
-                next.push_back(l); next.push_back(r);
-            }
+            for (const b200pt_aabb &b : aabbs) { b200pt_aabb l, r; splitAabb(b, l, r); next.push_back(l); next.push_back(r); }
             aabbs.swap(next);
         }
         regionCount = uint32_t(aabbs.size());
@@ -454,6 +455,22 @@ struct RefGuiding {
             for (auto &t : pool) t.join();
         }
         firstFit = false;
+        // Check for regions to split (PathGuiding.cpp:291-300) + splitRegion (:328-348)
+        const uint32_t currentRegionCount = regionCount;
+        for (uint32_t r = 0; r < currentRegionCount; r++) {
+            if (gp.splitRegions && pmms[r].m_numSamples > gp.samplesForRegionSplit) {
+                b200pt_aabb left, right;
+                splitAabb(aabbs[r], left, right);
+                aabbs[r] = left;
+                aabbs.push_back(right);
+                const float decayTerm = 0.25f;
+                pmms[r].m_numSamples *= decayTerm;
+                pmms[r].m_sampleWeight *= decayTerm;
+                pmms.push_back(pmms[r]);
+                extra.push_back(extra[r]);
+                regionCount++;
+            }
+        }
         syncThetas();
     }
 };

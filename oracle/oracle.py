@@ -182,6 +182,7 @@ class GuidingRef:
     def update(self, samples, threads=1):
         a = np.ascontiguousarray(samples, dtype=DIRECTIONAL_DATA_DTYPE)
         glib().refguiding_update(self._h, a.ctypes.data, a.shape[0], threads)
+        self.region_count = glib().refguiding_region_count(self._h)      # adaptive refinement may have split regions
 
     def vmms(self):
         out = np.empty(self.region_count, dtype=VMM_THETA_DTYPE)

@@ -110,7 +110,8 @@ class GuidingParams(C.Structure):
                 ("minSamplesForSplitting", C.c_int32), ("minSamplesForPostSplitFitting", C.c_int32),
                 ("splitMinDivergence", C.c_float), ("mergeMaxDivergence", C.c_float), ("numInitialComponents", C.c_int32),
                 ("minItr", C.c_int32), ("maxItr", C.c_int32), ("relLogLikelihoodThreshold", C.c_float), ("initKappa", C.c_float),
-                ("maxKappa", C.c_float), ("vPrior", C.c_float), ("rPrior", C.c_float), ("rPriorWeight", C.c_float)]
+                ("maxKappa", C.c_float), ("vPrior", C.c_float), ("rPrior", C.c_float), ("rPriorWeight", C.c_float),
+                ("splitRegions", C.c_int32), ("samplesForRegionSplit", C.c_float)]
 
 
 class AppState(C.Structure):

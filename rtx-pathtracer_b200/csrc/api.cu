@@ -551,6 +551,9 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     {   // guiding views: region tree + mixtures, and (training frames) the sample-recording state
         Wavefront &w = c->wf;
         w.guide.levels = c->guiding.levelAabbs; w.guide.vmms = c->guiding.vmms; w.guide.splits = c->guiding.splits;
+        w.guide.aabbs = c->guiding.aabbs;
+        w.guide.spawnFirst = c->guiding.hasSpawns ? c->guiding.spawnFirst : nullptr;
+        w.guide.spawnNext = c->guiding.hasSpawns ? c->guiding.spawnNext : nullptr;
         w.rec = GuidingRecord{};
         if (pc->updateGuiding) {
             const size_t N16 = size_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL;
@@ -823,6 +826,7 @@ void b200pt_default_guiding_params(b200pt_guiding_params *p) {
     p->splitMinDivergence = 0.5f; p->mergeMaxDivergence = 0.025f;
     p->numInitialComponents = 8; p->minItr = 1; p->maxItr = 100; p->relLogLikelihoodThreshold = 0.005f;
     p->initKappa = 5.0f; p->maxKappa = 50000.0f; p->vPrior = 0.01f; p->rPrior = 0.0f; p->rPriorWeight = 1.0f;
+    p->splitRegions = 0; p->samplesForRegionSplit = 10000.0f;
 }
 
 int b200pt_guiding_update(b200pt_ctx *c, const b200pt_guiding_params *params) {

@@ -18,6 +18,11 @@ struct GuidingView {
     const b200pt_aabb *levels;        // all levels concatenated: level L starts at (2^L - 1)
     const b200pt_vmm_theta *vmms;     // binding 16
     int splits;
+    // adaptive refinement (PathGuiding::splitRegion, src/PathGuiding.cpp:328-348): a split region keeps its index and the
+    // left half of its box, the right half becomes a new region at the end of the array.  spawnFirst[r] / spawnNext[c]
+    // chain the regions that were cut off region r (newest first); both nullptr until the first split.
+    const b200pt_aabb *aabbs;         // binding 15: the current box of every region
+    const int32_t *spawnFirst, *spawnNext;
 };
 
 __device__ __forceinline__ bool aabbContains(const b200pt_aabb &b, vec3 p) {   // raytrace.guiding.rint:15-17: min(aabb.min, p) == aabb.min && max(aabb.max, p) == aabb.max
@@ -25,36 +30,50 @@ __device__ __forceinline__ bool aabbContains(const b200pt_aabb &b, vec3 p) {   /
            fmaxf(b.max[0], p.x) == b.max[0] && fmaxf(b.max[1], p.y) == b.max[1] && fmaxf(b.max[2], p.z) == b.max[2];
 }
 
+// region of a point inside base leaf `base` of the halving tree: the leaf itself, or — after adaptive splits — the
+// lowest-index region among the leaf and everything that was cut off it whose current box contains the point
+__device__ __forceinline__ uint32_t guidingLeafRegion(const GuidingView &g, uint32_t base, vec3 p) {
+    if (!g.spawnFirst) return base;
+    uint32_t best = B200PT_INVALID_REGION;
+    int32_t stack[12];
+    int sp = 0;
+    stack[sp++] = int32_t(base);
+    while (sp) {
+        const int32_t r = stack[--sp];
+        if (uint32_t(r) < best && aabbContains(g.aabbs[r], p)) best = uint32_t(r);
+        for (int32_t c = g.spawnFirst[r]; c >= 0; c = g.spawnNext[c]) if (sp < 12) stack[sp++] = c;
+    }
+    return best;
+}
+
 __device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 p) {
     if (!aabbContains(g.levels[0], p)) return B200PT_INVALID_REGION;
-    if (g.splits == 0) return 0u;
     int level = 0;
     uint32_t node = 0;
     uint32_t triedRight = 0;          // bit L: the right child of the node on the current path at level L was entered
     for (;;) {
-        // descend: prefer the left child
-        const b200pt_aabb *next = g.levels + ((1u << (level + 1)) - 1u);
-        const uint32_t l = 2u * node, r = l + 1u;
-        if (!((triedRight >> level) & 1u) && aabbContains(next[l], p)) {
-            node = l; level++;
-        } else if (!((triedRight >> level) & 1u) && aabbContains(next[r], p)) {
-            triedRight |= 1u << level;
-            node = r; level++;
+        if (level == g.splits) {
+            const uint32_t r = guidingLeafRegion(g, node, p);
+            if (r != B200PT_INVALID_REGION) return r;
         } else {
-            // dead end (or both children exhausted): back up to the nearest ancestor whose right child is untried
-            for (;;) {
-                if (level == 0) return B200PT_INVALID_REGION;
-                const bool cameFromLeft = (node & 1u) == 0u;
-                triedRight &= ~(1u << level);
-                level--; node >>= 1;
-                if (cameFromLeft && !((triedRight >> level) & 1u)) {
-                    const b200pt_aabb *nx = g.levels + ((1u << (level + 1)) - 1u);
-                    if (aabbContains(nx[2u * node + 1u], p)) { triedRight |= 1u << level; node = 2u * node + 1u; level++; break; }
-                    triedRight |= 1u << level;      // right child does not contain p either: keep backing up
-                }
+            // descend: prefer the left child
+            const b200pt_aabb *next = g.levels + ((1u << (level + 1)) - 1u);
+            const uint32_t l = 2u * node, r = l + 1u;
+            if (!((triedRight >> level) & 1u) && aabbContains(next[l], p)) { node = l; level++; continue; }
+            if (!((triedRight >> level) & 1u) && aabbContains(next[r], p)) { triedRight |= 1u << level; node = r; level++; continue; }
+        }
+        // dead end (or both children exhausted): back up to the nearest ancestor whose right child is untried
+        for (;;) {
+            if (level == 0) return B200PT_INVALID_REGION;
+            const bool cameFromLeft = (node & 1u) == 0u;
+            triedRight &= ~(1u << level);
+            level--; node >>= 1;
+            if (cameFromLeft && !((triedRight >> level) & 1u)) {
+                const b200pt_aabb *nx = g.levels + ((1u << (level + 1)) - 1u);
+                triedRight |= 1u << level;
+                if (aabbContains(nx[2u * node + 1u], p)) { node = 2u * node + 1u; level++; break; }
             }
         }
-        if (level == g.splits) return node;
     }
 }
 

@@ -422,9 +422,26 @@ int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stre
         if (_e != cudaSuccess) { error = std::string(#expr) + ": " + cudaGetErrorString(_e); return B200PT_E_CUDA; } \
     } while (0)
 
+// PathGuiding::splitRegion (src/PathGuiding.cpp:328-348), device half: decay the split mixture's sample counters, then the
+// new region starts as a copy of it (mixture, extra statistics, packed VMM_Theta)
+__global__ void __launch_bounds__(128) k_guiding_split_regions(GMix *mixes, b200pt_vmm_theta *vmms, const int2 *pairs) {
+    const int2 pr = pairs[blockIdx.x];
+    if (threadIdx.x == 0) {
+        const float decayTerm = 0.25f;
+        mixes[pr.x].numSamples *= decayTerm;
+        mixes[pr.x].sampleWeight *= decayTerm;
+    }
+    __syncthreads();
+    const uint32_t *ms = reinterpret_cast<const uint32_t *>(&mixes[pr.x]); uint32_t *md = reinterpret_cast<uint32_t *>(&mixes[pr.y]);
+    for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += blockDim.x) md[i] = ms[i];
+    const uint32_t *vs = reinterpret_cast<const uint32_t *>(&vmms[pr.x]); uint32_t *vd = reinterpret_cast<uint32_t *>(&vmms[pr.y]);
+    for (uint32_t i = threadIdx.x; i < sizeof(b200pt_vmm_theta) / 4; i += blockDim.x) vd[i] = vs[i];
+}
+
 int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream) {
     release();
     regionCount = 1 << splits;
+    maxRegions = std::max(regionCount, 1024);       // room for adaptive splits up to what the device sort handles
     b200pt_aabb scene;
     for (int a = 0; a < 3; a++) {   // Aabb::addEpsilon, src/Shapes.h:48-53
         float extent = sceneMax[a] - sceneMin[a];
@@ -445,12 +462,18 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&levelAabbs), allLevels.size() * sizeof(b200pt_aabb)));
     G_TRY(cudaMemcpyAsync(levelAabbs, allLevels.data(), allLevels.size() * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
     G_TRY(cudaStreamSynchronize(stream));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(regionCount) * sizeof(b200pt_aabb)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(regionCount) * sizeof(b200pt_vmm_theta)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&mixes), size_t(regionCount) * sizeof(GMix)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionTotal), size_t(regionCount) * sizeof(uint32_t)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionOffset), size_t(regionCount + 1) * sizeof(uint32_t)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&activeRegions), size_t(regionCount) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(maxRegions) * sizeof(b200pt_aabb)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(maxRegions) * sizeof(b200pt_vmm_theta)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&mixes), size_t(maxRegions) * sizeof(GMix)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionTotal), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionOffset), size_t(maxRegions + 1) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&spawnFirst), size_t(maxRegions) * sizeof(int32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&spawnNext), size_t(maxRegions) * sizeof(int32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&splitPairs), size_t(maxRegions) * sizeof(int2)));
+    hostSpawnFirst.assign(size_t(maxRegions), -1); hostSpawnNext.assign(size_t(maxRegions), -1); hasSpawns = false;
+    G_TRY(cudaMemsetAsync(spawnFirst, 0xff, size_t(maxRegions) * sizeof(int32_t), stream));
+    G_TRY(cudaMemsetAsync(spawnNext, 0xff, size_t(maxRegions) * sizeof(int32_t), stream));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&activeRegions), size_t(maxRegions) * sizeof(uint32_t)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&devScalars), 4 * sizeof(unsigned long long)));
     G_TRY(cudaMallocHost(reinterpret_cast<void **>(&hostScalars), 4 * sizeof(unsigned long long)));
     G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
@@ -486,7 +509,7 @@ int GuidingState::ensureCapacity(int64_t numSamples) {
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&dirw), n * sizeof(float4)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&pdfDist), n * sizeof(float2)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&srcIndex), n * sizeof(uint32_t)));
-    G_TRY(cudaMalloc(reinterpret_cast<void **>(&tileCounts), tiles * size_t(regionCount) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&tileCounts), tiles * size_t(maxRegions) * sizeof(uint32_t)));
     capacity = numSamples;
     return B200PT_OK;
 }
@@ -559,6 +582,7 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     firstFit = false;
     lastValidSamples = validCount;
+    if (params.splitRegions) { int rcs = splitRegions(params, stream); if (rcs != B200PT_OK) return rcs; }
     if (getenv("B200PT_GUIDING_PROFILE")) {   // per-region cost distribution (development aid)
         std::vector<GMix> hm;
         hm.resize(size_t(regionCount));
@@ -580,6 +604,40 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
         stats->kernel_launches += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
         stats->launches_guiding += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
     }
+    return B200PT_OK;
+}
+
+// "Check for regions to split" of PathGuiding::update (src/PathGuiding.cpp:291-300): every region whose mixture has
+// seen more than samplesForRegionSplit samples is halved along its longest axis; it keeps the left half, the right
+// half is appended as a new region that starts from a copy of the mixture (splitRegion, :328-348)
+int GuidingState::splitRegions(const b200pt_guiding_params &params, cudaStream_t stream) {
+    std::vector<float> numSamples;
+    numSamples.resize(size_t(regionCount));
+    G_TRY(cudaMemcpy2DAsync(numSamples.data(), sizeof(float), &mixes[0].numSamples, sizeof(GMix), sizeof(float), size_t(regionCount), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    std::vector<int2> pairs;
+    const int currentRegionCount = regionCount;
+    for (int r = 0; r < currentRegionCount; r++) {
+        if (!(numSamples[size_t(r)] > params.samplesForRegionSplit)) continue;
+        if (regionCount >= maxRegions) break;          // the device sort handles at most 1024 regions: refinement stops there
+        b200pt_aabb l, rr;
+        splitAabb(hostAabbs[size_t(r)], l, rr);
+        hostAabbs[size_t(r)] = l;
+        hostAabbs.push_back(rr);
+        const int nr = regionCount++;
+        hostSpawnNext[size_t(nr)] = hostSpawnFirst[size_t(r)];
+        hostSpawnFirst[size_t(r)] = nr;
+        pairs.push_back(make_int2(r, nr));
+    }
+    if (pairs.empty()) return B200PT_OK;
+    G_TRY(cudaMemcpyAsync(splitPairs, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+    k_guiding_split_regions<<<unsigned(pairs.size()), 128, 0, stream>>>(mixes, vmms, splitPairs);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(spawnFirst, hostSpawnFirst.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(spawnNext, hostSpawnNext.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    hasSpawns = true;
     return B200PT_OK;
 }
 
@@ -623,6 +681,11 @@ void GuidingState::release() {
     if (aabbs) cudaFree(aabbs);
     if (levelAabbs) cudaFree(levelAabbs);
     levelAabbs = nullptr;
+    if (spawnFirst) cudaFree(spawnFirst);
+    if (spawnNext) cudaFree(spawnNext);
+    if (splitPairs) cudaFree(splitPairs);
+    spawnFirst = nullptr; spawnNext = nullptr; splitPairs = nullptr; hasSpawns = false; maxRegions = 0;
+    hostSpawnFirst.clear(); hostSpawnNext.clear();
     if (vmms) cudaFree(vmms);
     if (mixes) cudaFree(mixes);
     if (regionTotal) cudaFree(regionTotal);

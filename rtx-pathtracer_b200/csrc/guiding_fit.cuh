@@ -13,8 +13,13 @@ struct GMix;
 struct GuidingState {
     bool ready = false;
     bool firstFit = true;                  // PathGuiding::firstFit (global: cleared by the first update)
-    int regionCount = 0;
+    int regionCount = 0;                   // grows when regions are split adaptively (PathGuiding::splitRegion)
+    int maxRegions = 0;                    // capacity of every per-region buffer
     std::vector<b200pt_aabb> hostAabbs;
+    std::vector<int32_t> hostSpawnFirst, hostSpawnNext;
+    int32_t *spawnFirst = nullptr, *spawnNext = nullptr;   // device; consulted by the tracer once hasSpawns
+    bool hasSpawns = false;
+    int2 *splitPairs = nullptr;            // device scratch: (source region, new region) of one update's splits
     int splits = 0;
     b200pt_aabb *aabbs = nullptr;          // device, binding 15
     b200pt_aabb *levelAabbs = nullptr;     // device: all 2^(splits+1)-1 boxes of the halving tree, level by level
@@ -34,6 +39,7 @@ struct GuidingState {
     int reset(const b200pt_guiding_params &params, cudaStream_t stream);
     int ensureCapacity(int64_t numSamples);
     int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats);
+    int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);      // PathGuiding.cpp:291-300, :328-348
     int getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream);
     int getSorted(b200pt_directional_data *out, uint32_t *offsets, const b200pt_directional_data *rawDevice, cudaStream_t stream);
     void release();

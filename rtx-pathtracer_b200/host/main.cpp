@@ -27,6 +27,7 @@ static const Field kFields[] = {
 static void printHelp() {
     printf("Required parameters: WIDTH HEIGHT IC_SIZE GUIDING_SPLITS Scenes ...\n");
     printf("Options: --frames=N | --seconds=S, --seed=S --out=FILE.exr --device=D --prepareFrames=N --numGuidingOptimizations=N\n");
+    printf("         --splitRegions=0|1 --samplesForRegionSplit=N --splitAndMerge=0|1 (guiding refit)\n");
     printf("         and --<pushConstantField>=value, e.g. --samplesPerPixel=16 --enableMIS=1 --useADRRS=1\n");
 }
 
@@ -52,6 +53,8 @@ int main(int argc, char **argv) {
     b200pt_app_init(&app);
     app.accumulateResults = 1;      // the evaluation modes switch it on (src/RayTracingApp.cpp:93,98)
     b200pt_push_constants &pc = app.settings;
+    b200pt_guiding_params gparams;      // PathGuiding's knobs (the "Guiding" ImGui panel, src/RayTracingApp.cpp:1060-1090)
+    b200pt_default_guiding_params(&gparams);
     int frames = 1, device = 0;
     double seconds = 0.0;           // > 0: the reference's "collect for N seconds" evaluation (src/RayTracingApp.cpp:188-218)
     uint32_t seed = 0xC0FFEEu;
@@ -65,6 +68,9 @@ int main(int argc, char **argv) {
         else if (key == "out") out = val;
         else if (key == "device") device = std::stoi(val);
         else if (key == "seconds") seconds = std::stod(val);
+        else if (key == "splitRegions") gparams.splitRegions = std::stoi(val);
+        else if (key == "samplesForRegionSplit") gparams.samplesForRegionSplit = std::stof(val);
+        else if (key == "splitAndMerge") gparams.splitAndMerge = std::stoi(val);
         else if (key == "prepareFrames") app.irradianceCachePrepareFrames = std::stoi(val);
         else if (key == "numGuidingOptimizations") app.numGuidingOptimizations = std::stoi(val);
         else {
@@ -108,7 +114,8 @@ int main(int argc, char **argv) {
         for (uint32_t f = 0; ok; f++, drawn++) {
             if (seconds > 0.0) { if (std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t1).count() >= seconds) break; }
             else if (app.evalCurrentSamples >= wanted) break;
-            if (b200pt_app_draw_frame(&app, ctx, tea(f, seed), nullptr) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); ok = false; }
+            gparams.useParallaxCompensation = pc.useParallaxCompensation;
+            if (b200pt_app_draw_frame(&app, ctx, tea(f, seed), &gparams) != B200PT_OK) { fprintf(stderr, "%s\n", b200pt_last_error()); ok = false; }
         }
         auto t2 = std::chrono::high_resolution_clock::now();
         if (ok) {

@@ -171,3 +171,35 @@ def test_closed_loop_training_then_guided_render_is_unbiased():
     blk = lambda a: a.reshape(h // 8, 8, w // 8, 8, 3).mean(axis=(1, 3))
     rel = np.abs(blk(imgs["guided"]) - blk(imgs["plain"])) / (blk(imgs["plain"]) + 1e-2)
     assert np.median(rel) < 0.03 and rel.mean() < 0.06
+
+
+def test_region_lookup_after_adaptive_splits_matches_oracle():
+    """After PathGuiding::splitRegion the regions are no longer the leaves of the halving tree: the tracer's lookup
+    walks the tree to a base leaf and then through the regions cut off it; the oracle scans all boxes linearly."""
+    P, scene, r, o = _pair("cornell-dielectric", 3)
+    gp = P.default_guiding_params(splitRegions=1, samplesForRegionSplit=1500.0)
+    for rnd in range(3):          # three refits on synthetic samples: 8 -> 16 -> ... regions
+        aabbs = r.guiding_aabbs()
+        r.guiding_update_host(guiding_data.make_batch(aabbs, [2000 if i % 2 == 0 else 900 for i in range(len(aabbs))], 50 + rnd), gp)
+    aabbs = r.guiding_aabbs()
+    assert len(aabbs) > 12
+    r.guiding_put_vmms(_synthetic_vmms(P, aabbs, 11))
+    o.set_guiding(aabbs, r.guiding_get_vmms())
+    # training frame: the recorded region ids come from the lookup
+    pc = P.default_push_constants(randomUInt=P.tea(3, 0xC0FFEE), previousFrames=0, samplesPerPixel=2, enableMIS=1, updateGuiding=1)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    g = r.guiding_get_samples().reshape(H * W, 16)
+    c = o.samples(P.DIRECTIONAL_DATA_DTYPE).reshape(H * W, 16)
+    gv, cv = g["flags"] != INVALID, c["flags"] != INVALID
+    same = (gv == cv).all(axis=1)
+    assert same.mean() >= 0.99
+    assert np.where(gv & cv, g["flags"] == c["flags"], True).all(axis=1)[same].mean() >= 0.999
+    assert len(np.unique(c["flags"][cv])) > 8 and c["flags"][cv].max() >= 8          # spawned regions are in use
+    # guided frame: sampling from the mixtures of the looked-up regions
+    pc = P.default_push_constants(randomUInt=P.tea(4, 0xC0FFEE), previousFrames=0, samplesPerPixel=2, enableMIS=1, useGuiding=1, guidingProb=0.5)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    gi, ci = r.read_image()[..., :3].astype(np.float64), o.image()[..., :3].astype(np.float64)
+    rel = np.abs(gi - ci) / np.maximum(np.abs(ci), 1e-3)
+    assert (rel <= 1e-4).all(axis=-1).mean() >= 0.985
