@@ -390,6 +390,31 @@ int b200pt_guiding_get_state(b200pt_ctx *ctx, int region, float scalars5[5], flo
 /* known-answer hook: lightpmm::exp (PMM_APPROX_EXP fastexp, pmm-vcl.h:157-184) as evaluated by the device code */
 int b200pt_guiding_fastexp(b200pt_ctx *ctx, const float *in_host, float *out_host, int n);
 
+/* ---- checkpoint / resume ------------------------------------------------
+ * Everything a later frame depends on: the three images, the irradiance cache (header, data, spheres) and the guiding
+ * state (region boxes incl. adaptive splits, mixtures with their running statistics, packed VMM_Thetas, firstFit).  The
+ * frame driver's state is the plain struct b200pt_app, which the host stores itself.  A context that loads a
+ * checkpoint must have been created with the same width, height, ic_size and guiding_splits and have its scene set;
+ * frames rendered after b200pt_load_state are bit-identical to those of the run that saved it. */
+int b200pt_save_state(b200pt_ctx *ctx, const char *path);
+int b200pt_load_state(b200pt_ctx *ctx, const char *path);
+
+/* ---- multi-GPU (ours: the reference is single-GPU) -----------------------------------------------
+ * One context per GPU and per process; the image shards by sample index: every rank renders disjoint
+ * frames of the full image, the running means are combined with one NCCL all-reduce, and guiding training frames
+ * all-gather their DirectionalData buffers so that every rank refits on the identical concatenation.  NCCL is loaded
+ * with dlopen("libnccl.so.2") on first use; B200PT_E_STATE when it is not installed. */
+#define B200PT_COMM_ID_BYTES 128
+int b200pt_comm_unique_id(char id[B200PT_COMM_ID_BYTES]);      /* ncclGetUniqueId: call on one rank, hand the bytes to the others */
+int b200pt_comm_init(b200pt_ctx *ctx, const char id[B200PT_COMM_ID_BYTES], int rank, int nranks);
+int b200pt_comm_destroy(b200pt_ctx *ctx);
+/* image `which` of every rank becomes sum_r(frames_r * image_r) / sum_r(frames_r): the mean over all frames of all ranks */
+int b200pt_reduce_image(b200pt_ctx *ctx, int which, int frames_local);
+/* all-gather of the ranks' DirectionalData buffers (rank order) into the context; *total_out = records gathered */
+int b200pt_allgather_samples(b200pt_ctx *ctx, int64_t *total_out);
+/* b200pt_allgather_samples + b200pt_guiding_update on the gathered records: identical mixtures on every rank, no broadcast */
+int b200pt_guiding_update_all_ranks(b200pt_ctx *ctx, const b200pt_guiding_params *params);
+
 /* ---- irradiance cache parity hooks (bindings 10,12,13) ---------------------------------------- */
 int b200pt_ic_get(b200pt_ctx *ctx, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n);
 int b200pt_ic_put(b200pt_ctx *ctx, const b200pt_cache_header *hdr, const b200pt_cache_data *data,

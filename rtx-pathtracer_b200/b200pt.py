@@ -159,6 +159,7 @@ EXPORTS = [
     "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
+    "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks",
     "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
@@ -223,6 +224,14 @@ def lib():
         L.b200pt_read_exr.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200pt_free.argtypes = [C.c_void_p]
         L.b200pt_read_image_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.b200pt_save_state.argtypes = [C.c_void_p, C.c_char_p]
+        L.b200pt_load_state.argtypes = [C.c_void_p, C.c_char_p]
+        L.b200pt_comm_unique_id.argtypes = [C.c_char_p]
+        L.b200pt_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.b200pt_comm_destroy.argtypes = [C.c_void_p]
+        L.b200pt_reduce_image.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b200pt_allgather_samples.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.b200pt_guiding_update_all_ranks.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_app_init.restype = None
         L.b200pt_app_init.argtypes = [C.POINTER(AppState)]
         L.b200pt_app_scene_switched.restype = None
@@ -248,6 +257,16 @@ def default_push_constants(**overrides):
             raise AttributeError("no push constant named %r" % k)
         setattr(pc, k, v)
     return pc
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId as 128 bytes: create on one rank, send to the others (any side channel), pass to Renderer.comm_init."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().b200pt_comm_unique_id(buf))
+    return buf.raw
 
 
 def default_guiding_params(**overrides):
@@ -467,6 +486,31 @@ class Renderer:
         out = np.empty_like(a)
         _check(lib().b200pt_guiding_fastexp(self._h, a.ctypes.data, out.ctypes.data, a.size))
         return out
+
+    def save_state(self, path):
+        _check(lib().b200pt_save_state(self._h, os.fsencode(path)))
+
+    def load_state(self, path):
+        _check(lib().b200pt_load_state(self._h, os.fsencode(path)))
+
+    # multi-GPU (native NCCL path of the C ABI; sharding.py is the torch.distributed variant)
+    def comm_init(self, unique_id, rank, nranks):
+        _check(lib().b200pt_comm_init(self._h, unique_id, rank, nranks))
+
+    def comm_destroy(self):
+        _check(lib().b200pt_comm_destroy(self._h))
+
+    def reduce_image(self, which=IMAGE_OUTPUT, frames_local=1):
+        _check(lib().b200pt_reduce_image(self._h, which, frames_local))
+
+    def allgather_samples(self):
+        n = C.c_int64()
+        _check(lib().b200pt_allgather_samples(self._h, C.byref(n)))
+        return n.value
+
+    def guiding_update_all_ranks(self, params=None):
+        p = params if params is not None else default_guiding_params()
+        _check(lib().b200pt_guiding_update_all_ranks(self._h, C.byref(p)))
 
     # irradiance cache
     def ic_get(self):

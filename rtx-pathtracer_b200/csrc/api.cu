@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace b200pt;
 
@@ -26,6 +28,32 @@ static int setError(int code, const std::string &msg) { g_lastError = msg; retur
     } while (0)
 
 namespace {
+// NCCL entry points, resolved at run time so that the library loads on machines without NCCL
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) return false;
+#define B200PT_NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(handle, name)); if (!field) { dlclose(handle); handle = nullptr; return false; }
+        B200PT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") B200PT_NCCL_SYM(CommInitRank, "ncclCommInitRank") B200PT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        B200PT_NCCL_SYM(AllReduce, "ncclAllReduce") B200PT_NCCL_SYM(AllGather, "ncclAllGather") B200PT_NCCL_SYM(GroupStart, "ncclGroupStart")
+        B200PT_NCCL_SYM(GroupEnd, "ncclGroupEnd") B200PT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef B200PT_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr; size_t n = 0;
@@ -111,6 +139,13 @@ struct b200pt_ctx {
 
     // batch tracing scratch
     DevBuf<float4> batchRays, batchHits;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int commRank = 0, commRanks = 1;
+    DevBuf<float4> commImage;
+    DevBuf<float> commCount;
+    DevBuf<b200pt_directional_data> commSamples;
 
     b200pt_stats stats{};
     FILE *dumpIters = nullptr;          // B200PT_DUMP_ITERS=file: queue sizes after every wavefront iteration (tuning aid)
@@ -350,6 +385,8 @@ int b200pt_destroy(b200pt_ctx *c) {
     for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
     if (c->dumpIters) fclose(c->dumpIters);
+    if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
+    c->commImage.release(); c->commCount.release(); c->commSamples.release();
     c->samples.release(); c->hostSamples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
     c->icSnapSphere.release(); c->icSnapNormalR.release(); c->icSnapColor.release(); c->icSnapRot.release(); c->icSnapTrans.release();
@@ -929,6 +966,151 @@ int b200pt_guiding_put_samples(b200pt_ctx *c, const b200pt_directional_data *in,
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(c->samples.p, in, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+// ---- checkpoint / resume -------------------------------------------------------------------------------------------
+static const char kStateMagic[8] = {'B', '2', 'P', 'T', 'S', 'T', '0', '1'};
+
+int b200pt_save_state(b200pt_ctx *c, const char *path) {
+    if (!c || !path) return setError(B200PT_E_INVALID, "b200pt_save_state: null argument");
+    if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_save_state: set_scene must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) return setError(B200PT_E_IO, std::string("b200pt_save_state: cannot open ") + path);
+    const int32_t hdr[4] = {c->width, c->height, c->icSize, c->guidingSplits};
+    const size_t N = size_t(c->numPixels), S = size_t(c->icSize);
+    std::vector<float4> img(N);
+    std::vector<b200pt_cache_data> icd(S);
+    std::vector<b200pt_sphere> ics(S);
+    b200pt_cache_header ich;
+    bool ok = fwrite(kStateMagic, 8, 1, f) == 1 && fwrite(hdr, sizeof(hdr), 1, f) == 1;
+    for (int which = 0; which < 3 && ok; which++) {
+        if (cudaMemcpy(img.data(), imagePtr(c, which), N * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); return setError(B200PT_E_CUDA, "b200pt_save_state: image read-back failed"); }
+        ok = fwrite(img.data(), sizeof(float4), N, f) == N;
+    }
+    int rc = b200pt_ic_get(c, &ich, S ? icd.data() : nullptr, S ? ics.data() : nullptr, int(S));
+    if (rc != B200PT_OK) { fclose(f); return rc; }
+    ok = ok && fwrite(&ich, sizeof(ich), 1, f) == 1 && fwrite(icd.data(), sizeof(b200pt_cache_data), S, f) == S && fwrite(ics.data(), sizeof(b200pt_sphere), S, f) == S;
+    if (ok) { rc = c->guiding.save(f, c->stream); if (rc != B200PT_OK) { fclose(f); return setError(rc, "b200pt_save_state: " + c->guiding.error); } }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return setError(B200PT_E_IO, std::string("b200pt_save_state: write failed: ") + path);
+    return B200PT_OK;
+}
+
+int b200pt_load_state(b200pt_ctx *c, const char *path) {
+    if (!c || !path) return setError(B200PT_E_INVALID, "b200pt_load_state: null argument");
+    if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_load_state: set_scene must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FILE *f = fopen(path, "rb");
+    if (!f) return setError(B200PT_E_IO, std::string("b200pt_load_state: cannot open ") + path);
+    char magic[8]; int32_t hdr[4];
+    if (fread(magic, 8, 1, f) != 1 || memcmp(magic, kStateMagic, 8) != 0 || fread(hdr, sizeof(hdr), 1, f) != 1) { fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: not a b200pt checkpoint"); }
+    if (hdr[0] != c->width || hdr[1] != c->height || hdr[2] != c->icSize || hdr[3] != c->guidingSplits) {
+        fclose(f); return setError(B200PT_E_INVALID, "b200pt_load_state: the checkpoint was written by a context of a different size (width, height, ic_size, guiding_splits)");
+    }
+    const size_t N = size_t(c->numPixels), S = size_t(c->icSize);
+    std::vector<float4> img(N);
+    for (int which = 0; which < 3; which++) {
+        if (fread(img.data(), sizeof(float4), N, f) != N) { fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: truncated checkpoint"); }
+        if (cudaMemcpy(imagePtr(c, which), img.data(), N * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) { fclose(f); return setError(B200PT_E_CUDA, "b200pt_load_state: image upload failed"); }
+    }
+    std::vector<b200pt_cache_data> icd(S);
+    std::vector<b200pt_sphere> ics(S);
+    b200pt_cache_header ich;
+    if (fread(&ich, sizeof(ich), 1, f) != 1 || fread(icd.data(), sizeof(b200pt_cache_data), S, f) != S || fread(ics.data(), sizeof(b200pt_sphere), S, f) != S) {
+        fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: truncated checkpoint");
+    }
+    int rc = b200pt_ic_put(c, &ich, S ? icd.data() : nullptr, S ? ics.data() : nullptr, int(S));
+    if (rc == B200PT_OK) { rc = c->guiding.load(f, c->stream); if (rc != B200PT_OK) setError(rc, "b200pt_load_state: " + c->guiding.error); }
+    fclose(f);
+    return rc;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------------------------
+#define NCCL_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        ncclResult_t _r = (expr);                                                                          \
+        if (_r != ncclSuccess) return setError(B200PT_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+int b200pt_comm_unique_id(char id[B200PT_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= B200PT_COMM_ID_BYTES, "ncclUniqueId does not fit the ABI's id buffer");
+    if (!id) return setError(B200PT_E_INVALID, "b200pt_comm_unique_id: null argument");
+    if (!g_nccl.load()) return setError(B200PT_E_STATE, "b200pt_comm_unique_id: libnccl.so.2 not found");
+    ncclUniqueId uid;
+    NCCL_TRY(g_nccl.GetUniqueId(&uid));
+    memset(id, 0, B200PT_COMM_ID_BYTES);
+    memcpy(id, &uid, sizeof(uid));
+    return B200PT_OK;
+}
+int b200pt_comm_init(b200pt_ctx *c, const char id[B200PT_COMM_ID_BYTES], int rank, int nranks) {
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return setError(B200PT_E_INVALID, "b200pt_comm_init: bad argument");
+    if (!g_nccl.load()) return setError(B200PT_E_STATE, "b200pt_comm_init: libnccl.so.2 not found");
+    if (c->comm) return setError(B200PT_E_STATE, "b200pt_comm_init: communicator already initialised");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+    c->commRank = rank; c->commRanks = nranks;
+    return B200PT_OK;
+}
+int b200pt_comm_destroy(b200pt_ctx *c) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_comm_destroy: null argument");
+    if (c->comm) { CUDA_TRY(cudaSetDevice(c->device)); CUDA_TRY(cudaStreamSynchronize(c->stream)); NCCL_TRY(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; }
+    c->commRank = 0; c->commRanks = 1;
+    return B200PT_OK;
+}
+
+}  // extern "C"
+__global__ void __launch_bounds__(256) k_comm_scale(const float4 *__restrict__ img, float4 *__restrict__ out, int n, float w, float *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = w;
+    if (i < n) { const float4 v = img[i]; out[i] = make_float4(v.x * w, v.y * w, v.z * w, v.w * w); }
+}
+__global__ void __launch_bounds__(256) k_comm_normalise(const float4 *__restrict__ acc, float4 *__restrict__ img, int n, const float *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float t = *count;
+    if (i < n) { const float4 v = acc[i]; img[i] = make_float4(v.x / t, v.y / t, v.z / t, v.w / t); }
+}
+extern "C" {
+
+int b200pt_reduce_image(b200pt_ctx *c, int which, int frames_local) {
+    if (!c || !imagePtr(c, which) || frames_local < 0) return setError(B200PT_E_INVALID, "b200pt_reduce_image: bad argument");
+    if (!c->comm) return setError(B200PT_E_STATE, "b200pt_reduce_image: b200pt_comm_init must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int n = c->numPixels;
+    CUDA_TRY(c->commImage.alloc(size_t(n))); CUDA_TRY(c->commCount.alloc(1));
+    k_comm_scale<<<gridFor(uint64_t(n), 256), 256, 0, c->stream>>>(imagePtr(c, which), c->commImage.p, n, float(frames_local), c->commCount.p);
+    NCCL_TRY(g_nccl.GroupStart());
+    NCCL_TRY(g_nccl.AllReduce(c->commImage.p, c->commImage.p, size_t(n) * 4, ncclFloat, ncclSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(c->commCount.p, c->commCount.p, 1, ncclFloat, ncclSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    k_comm_normalise<<<gridFor(uint64_t(n), 256), 256, 0, c->stream>>>(c->commImage.p, imagePtr(c, which), n, c->commCount.p);
+    c->stats.kernel_launches += 2;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    return B200PT_OK;
+}
+int b200pt_allgather_samples(b200pt_ctx *c, int64_t *total_out) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_allgather_samples: null argument");
+    if (!c->comm) return setError(B200PT_E_STATE, "b200pt_allgather_samples: b200pt_comm_init must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t per = size_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL;      // every rank renders the same resolution
+    CUDA_TRY(c->commSamples.alloc(per * size_t(c->commRanks)));
+    NCCL_TRY(g_nccl.AllGather(c->samples.p, c->commSamples.p, per * sizeof(b200pt_directional_data), ncclChar, c->comm, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (total_out) *total_out = int64_t(per * size_t(c->commRanks));
+    return B200PT_OK;
+}
+int b200pt_guiding_update_all_ranks(b200pt_ctx *c, const b200pt_guiding_params *params) {
+    if (!c || !params) return setError(B200PT_E_INVALID, "b200pt_guiding_update_all_ranks: null argument");
+    if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update_all_ranks: set_scene must be called first");
+    int64_t total = 0;
+    int rc = b200pt_allgather_samples(c, &total);
+    if (rc != B200PT_OK) return rc;
+    rc = c->guiding.update(c->commSamples.p, total, *params, c->stream, &c->stats);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_all_ranks: " + c->guiding.error);
     return B200PT_OK;
 }
 

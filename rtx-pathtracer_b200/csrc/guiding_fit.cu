@@ -641,6 +641,53 @@ int GuidingState::splitRegions(const b200pt_guiding_params &params, cudaStream_t
     return B200PT_OK;
 }
 
+// checkpoint of the guiding state (b200pt_save_state / b200pt_load_state)
+int GuidingState::save(FILE *f, cudaStream_t stream) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    const int32_t hdr[6] = {splits, regionCount, maxRegions, firstFit ? 1 : 0, hasSpawns ? 1 : 0, int32_t(sizeof(GMix))};
+    std::vector<char> mixBuf(size_t(regionCount) * sizeof(GMix));
+    std::vector<b200pt_vmm_theta> vmmBuf;
+    vmmBuf.resize(size_t(regionCount));
+    G_TRY(cudaMemcpyAsync(mixBuf.data(), mixes, mixBuf.size(), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaMemcpyAsync(vmmBuf.data(), vmms, vmmBuf.size() * sizeof(b200pt_vmm_theta), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(&lastParams, sizeof(lastParams), 1, f) == 1 &&
+              fwrite(hostAabbs.data(), sizeof(b200pt_aabb), size_t(regionCount), f) == size_t(regionCount) &&
+              fwrite(hostSpawnFirst.data(), sizeof(int32_t), size_t(regionCount), f) == size_t(regionCount) &&
+              fwrite(hostSpawnNext.data(), sizeof(int32_t), size_t(regionCount), f) == size_t(regionCount) &&
+              fwrite(mixBuf.data(), 1, mixBuf.size(), f) == mixBuf.size() &&
+              fwrite(vmmBuf.data(), sizeof(b200pt_vmm_theta), vmmBuf.size(), f) == vmmBuf.size();
+    if (!ok) { error = "write failed"; return B200PT_E_IO; }
+    return B200PT_OK;
+}
+int GuidingState::load(FILE *f, cudaStream_t stream) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    int32_t hdr[6];
+    if (fread(hdr, sizeof(hdr), 1, f) != 1) { error = "truncated checkpoint"; return B200PT_E_IO; }
+    if (hdr[0] != splits || hdr[2] != maxRegions || hdr[5] != int32_t(sizeof(GMix)) || hdr[1] < (1 << splits) || hdr[1] > maxRegions) {
+        error = "checkpoint belongs to a different guiding configuration"; return B200PT_E_INVALID;
+    }
+    const int n = hdr[1];
+    std::vector<b200pt_aabb> ab; ab.resize(size_t(n));
+    std::vector<int32_t> sf(size_t(maxRegions), -1), sn(size_t(maxRegions), -1);
+    std::vector<char> mixBuf(size_t(n) * sizeof(GMix));
+    std::vector<b200pt_vmm_theta> vmmBuf; vmmBuf.resize(size_t(n));
+    b200pt_guiding_params gp;
+    bool ok = fread(&gp, sizeof(gp), 1, f) == 1 && fread(ab.data(), sizeof(b200pt_aabb), size_t(n), f) == size_t(n) &&
+              fread(sf.data(), sizeof(int32_t), size_t(n), f) == size_t(n) && fread(sn.data(), sizeof(int32_t), size_t(n), f) == size_t(n) &&
+              fread(mixBuf.data(), 1, mixBuf.size(), f) == mixBuf.size() && fread(vmmBuf.data(), sizeof(b200pt_vmm_theta), vmmBuf.size(), f) == vmmBuf.size();
+    if (!ok) { error = "truncated checkpoint"; return B200PT_E_IO; }
+    regionCount = n; firstFit = hdr[3] != 0; hasSpawns = hdr[4] != 0; lastParams = gp;
+    hostAabbs = ab; hostSpawnFirst = sf; hostSpawnNext = sn;
+    G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(n) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(spawnFirst, hostSpawnFirst.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(spawnNext, hostSpawnNext.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(mixes, mixBuf.data(), mixBuf.size(), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(vmms, vmmBuf.data(), vmmBuf.size() * sizeof(b200pt_vmm_theta), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    return B200PT_OK;
+}
+
 int GuidingState::getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream) {
     if (!ready || region < 0 || region >= regionCount) { error = "bad region"; return B200PT_E_INVALID; }
     GMix m;

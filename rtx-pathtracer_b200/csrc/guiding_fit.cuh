@@ -2,6 +2,7 @@
 // scratch buffers of the on-device sample sort (SampleCollector::getSortedData, src/SampleCollector.cpp:76-131).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <string>
 #include <vector>
 #include "../../include/b200pt.h"
@@ -39,7 +40,9 @@ struct GuidingState {
     int reset(const b200pt_guiding_params &params, cudaStream_t stream);
     int ensureCapacity(int64_t numSamples);
     int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats);
-    int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);      // PathGuiding.cpp:291-300, :328-348
+    int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);
+    int save(FILE *f, cudaStream_t stream);          // checkpoint: regions, spawn chains, mixtures, packed VMMs
+    int load(FILE *f, cudaStream_t stream);      // PathGuiding.cpp:291-300, :328-348
     int getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream);
     int getSorted(b200pt_directional_data *out, uint32_t *offsets, const b200pt_directional_data *rawDevice, cudaStream_t stream);
     void release();
