@@ -3,6 +3,7 @@
 // Reader: HALF/FLOAT channels, compression NONE / ZIPS / ZIP (what Mitsuba and the reference app write).
 // PIZ (used by the scenes' envmap.exr files) is not implemented yet — reported as an error, never silently skipped.
 #include "scene.h"
+#include <algorithm>
 #include <cstring>
 #include <cstdio>
 #include <fstream>
@@ -101,6 +102,186 @@ void writeExrRGB(const std::string &path, const float *rgba, int width, int heig
     if (!out) throw std::runtime_error("Write failed: " + path);
 }
 
+// ---- PIZ decompression (OpenEXR compression type 4) -------------------------------------------------------------------
+// Independent implementation of the published format: a chunk holds, for all channels of up to 32 scanlines, 16-bit
+// words that were (1) mapped to a dense range through a bitmap of the values that occur, (2) transformed by a 2-D Haar
+// style wavelet (14-bit or 16-bit modular variant, chosen by the largest mapped value) and (3) Huffman coded with a
+// canonical code whose length table is itself packed (6-bit lengths, zero runs) and one symbol reserved for run lengths.
+namespace {
+const int kHufEncBits = 16, kHufEncSize = (1 << kHufEncBits) + 1;
+
+struct PizBits {            // MSB-first bit reader
+    const unsigned char *p, *end;
+    uint64_t c = 0;
+    int lc = 0;
+    uint32_t get(int n) {
+        while (lc < n) { c = (c << 8) | (p < end ? *p : 0); p++; lc += 8; }
+        lc -= n;
+        return uint32_t((c >> lc) & ((uint64_t(1) << n) - 1));
+    }
+};
+
+// canonical Huffman code from code lengths: codes of equal length are consecutive, shorter codes have larger prefixes
+void pizCanonicalCodes(std::vector<uint64_t> &hcode) {
+    uint64_t n[59] = {0};
+    for (uint64_t l : hcode) n[l]++;
+    uint64_t c = 0;
+    for (int i = 58; i > 0; i--) { const uint64_t nc = (c + n[i]) >> 1; n[i] = c; c = nc; }
+    for (uint64_t &h : hcode) { const uint64_t l = h; if (l > 0) h = l | (n[l]++ << 6); }
+}
+
+void pizHufDecode(const unsigned char *src, size_t srcLen, uint16_t *out, size_t outLen) {
+    if (srcLen < 20) throw std::runtime_error("EXR/PIZ: truncated Huffman block");
+    uint32_t im, iM, nBits;
+    memcpy(&im, src, 4); memcpy(&iM, src + 4, 4); memcpy(&nBits, src + 12, 4);
+    if (im >= uint32_t(kHufEncSize) || iM >= uint32_t(kHufEncSize) || im > iM) throw std::runtime_error("EXR/PIZ: bad Huffman header");
+    // packed code-length table: 6 bits per symbol; 59..62 = run of 2..5 zeros, 63 = run of (next 8 bits) + 6 zeros
+    std::vector<uint64_t> hcode(size_t(kHufEncSize), 0);
+    PizBits tb{src + 20, src + srcLen};
+    for (uint32_t i = im; i <= iM; i++) {
+        const uint32_t l = tb.get(6);
+        hcode[i] = l;
+        if (l == 63) {
+            uint32_t zerun = tb.get(8) + 6;
+            if (i + zerun > iM + 1) throw std::runtime_error("EXR/PIZ: bad code table");
+            while (zerun--) hcode[i++] = 0;
+            i--;
+        } else if (l >= 59) {
+            uint32_t zerun = l - 59 + 2;
+            if (i + zerun > iM + 1) throw std::runtime_error("EXR/PIZ: bad code table");
+            while (zerun--) hcode[i++] = 0;
+            i--;
+        }
+    }
+    const unsigned char *dataStart = tb.p - (tb.lc / 8);       // the table ends on a byte boundary of what was consumed
+    pizCanonicalCodes(hcode);
+    // decoding tables by length: first code and first symbol index per length (symbols ordered by code)
+    struct Sym { uint64_t code; int len; uint32_t sym; };
+    std::vector<Sym> syms;
+    for (uint32_t i = im; i <= iM; i++) if (hcode[i] & 63) syms.push_back({hcode[i] >> 6, int(hcode[i] & 63), i});
+    std::vector<std::vector<Sym>> byLen(59);
+    for (const Sym &sy : syms) byLen[size_t(sy.len)].push_back(sy);
+    for (auto &v : byLen) std::sort(v.begin(), v.end(), [](const Sym &a, const Sym &b) { return a.code < b.code; });
+    PizBits db{dataStart, src + srcLen};
+    const uint32_t rlc = iM;                                   // run-length symbol
+    size_t o = 0;
+    uint64_t bitsLeft = nBits;
+    while (bitsLeft > 0 && o <= outLen) {
+        uint64_t code = 0;
+        int len = 0;
+        uint32_t sym = 0xffffffffu;
+        while (len < 58 && bitsLeft > 0) {
+            code = (code << 1) | db.get(1); len++; bitsLeft--;
+            const auto &v = byLen[size_t(len)];
+            if (!v.empty() && code >= v.front().code && code <= v.back().code) { sym = v[size_t(code - v.front().code)].sym; break; }
+        }
+        if (sym == 0xffffffffu) break;                         // trailing padding bits
+        if (sym == rlc) {
+            if (bitsLeft < 8 || o == 0) throw std::runtime_error("EXR/PIZ: bad run");
+            uint32_t run = db.get(8); bitsLeft -= 8;
+            if (o + run > outLen) throw std::runtime_error("EXR/PIZ: run past the end");
+            const uint16_t prev = out[o - 1];
+            while (run--) out[o++] = prev;
+        } else {
+            if (o >= outLen) throw std::runtime_error("EXR/PIZ: too much data");
+            out[o++] = uint16_t(sym);
+        }
+    }
+    if (o != outLen) throw std::runtime_error("EXR/PIZ: Huffman data ends early");
+}
+
+inline void wdec14(uint16_t l, uint16_t h, uint16_t &a, uint16_t &b) {
+    const int16_t ls = int16_t(l), hs = int16_t(h);
+    const int hi = hs, ai = ls + (hi & 1) + (hi >> 1);
+    a = uint16_t(int16_t(ai)); b = uint16_t(int16_t(ai - hi));
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t &a, uint16_t &b) {
+    const int m = l, d = h;
+    const int bb = (m - (d >> 1)) & 0xffff;
+    const int aa = (d + bb - 0x8000) & 0xffff;
+    b = uint16_t(bb); a = uint16_t(aa);
+}
+void pizWaveletDecode(uint16_t *in, int nx, int ox, int ny, int oy, uint16_t mx) {
+    const bool w14 = mx < (1 << 14);
+    const int n = std::min(nx, ny);
+    int p = 1;
+    while (p <= n) p <<= 1;
+    p >>= 1;
+    int p2 = p;
+    p >>= 1;
+    while (p >= 1) {
+        uint16_t *py = in, *ey = in + ptrdiff_t(oy) * (ny - p2);
+        const int oy1 = oy * p, oy2 = oy * p2, ox1 = ox * p, ox2 = ox * p2;
+        uint16_t i00, i01, i10, i11;
+        for (; py <= ey; py += oy2) {
+            uint16_t *px = py, *ex = py + ptrdiff_t(ox) * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+                if (w14) { wdec14(*px, *p10, i00, i10); wdec14(*p01, *p11, i01, i11); wdec14(i00, i01, *px, *p01); wdec14(i10, i11, *p10, *p11); }
+                else { wdec16(*px, *p10, i00, i10); wdec16(*p01, *p11, i01, i11); wdec16(i00, i01, *px, *p01); wdec16(i10, i11, *p10, *p11); }
+            }
+            if (nx & p) {
+                uint16_t *p10 = px + oy1;
+                if (w14) wdec14(*px, *p10, i00, *p10); else wdec16(*px, *p10, i00, *p10);
+                *px = i00;
+            }
+        }
+        if (ny & p) {
+            uint16_t *px = py, *ex = py + ptrdiff_t(ox) * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t *p01 = px + ox1;
+                if (w14) wdec14(*px, *p01, i00, *p01); else wdec16(*px, *p01, i00, *p01);
+                *px = i00;
+            }
+        }
+        p2 = p;
+        p >>= 1;
+    }
+}
+
+// one PIZ chunk -> raw scanline bytes (channels interleaved per scanline like the uncompressed layout)
+void pizDecompress(const unsigned char *src, size_t srcLen, unsigned char *dst, size_t dstLen, int width, int lines, const std::vector<int> &wordsPerPixel) {
+    if (srcLen < 4) throw std::runtime_error("EXR/PIZ: truncated chunk");
+    uint16_t minNonZero, maxNonZero;
+    memcpy(&minNonZero, src, 2); memcpy(&maxNonZero, src + 2, 2);
+    size_t pos = 4;
+    std::vector<unsigned char> bitmap(8192, 0);
+    if (minNonZero <= maxNonZero) {
+        const size_t nb = size_t(maxNonZero) - minNonZero + 1;
+        if (maxNonZero >= 8192 || pos + nb > srcLen) throw std::runtime_error("EXR/PIZ: bad bitmap");
+        memcpy(&bitmap[minNonZero], src + pos, nb);
+        pos += nb;
+    }
+    std::vector<uint16_t> lut(65536, 0);                     // reverse LUT: dense index -> value (zero always occurs)
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < 65536; i++) if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = uint16_t(i);
+    const uint16_t maxValue = uint16_t(k - 1);
+    if (pos + 4 > srcLen) throw std::runtime_error("EXR/PIZ: truncated chunk");
+    int32_t length;
+    memcpy(&length, src + pos, 4); pos += 4;
+    if (length < 0 || pos + size_t(length) > srcLen) throw std::runtime_error("EXR/PIZ: bad Huffman length");
+    const size_t words = dstLen / 2;
+    std::vector<uint16_t> tmp(words);
+    pizHufDecode(src + pos, size_t(length), tmp.data(), words);
+    // planes: channel after channel, each lines x width x wordsPerPixel; wavelet per 16-bit component
+    size_t start = 0;
+    std::vector<size_t> starts;
+    for (int wp : wordsPerPixel) {
+        starts.push_back(start);
+        for (int j = 0; j < wp; j++) pizWaveletDecode(tmp.data() + start + j, width, wp, lines, width * wp, maxValue);
+        start += size_t(width) * lines * wp;
+    }
+    for (uint16_t &v : tmp) v = lut[v];
+    unsigned char *o = dst;
+    for (int y = 0; y < lines; y++)
+        for (size_t c = 0; c < wordsPerPixel.size(); c++) {
+            const size_t n = size_t(width) * wordsPerPixel[c];
+            memcpy(o, tmp.data() + starts[c] + size_t(y) * n, n * 2);
+            o += n * 2;
+        }
+}
+}  // namespace
+
 void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, int &height, bool viaHalf) {
     std::ifstream in(path, std::ios::binary);
     if (!in) throw std::runtime_error("Cannot open EXR file " + path);
@@ -138,7 +319,8 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
     int linesPerBlock;
     if (comp == 0 || comp == 2) linesPerBlock = 1;
     else if (comp == 3) linesPerBlock = 16;
-    else throw std::runtime_error("EXR: compression type " + std::to_string(comp) + " not supported (only NONE/ZIPS/ZIP): " + path);
+    else if (comp == 4) linesPerBlock = 32;
+    else throw std::runtime_error("EXR: compression type " + std::to_string(comp) + " not supported (only NONE/ZIPS/ZIP/PIZ): " + path);
     size_t bytesPerLine = 0;
     for (auto &c : chans) {
         if (c.type != 1 && c.type != 2) throw std::runtime_error("EXR: only HALF/FLOAT channels supported");
@@ -159,7 +341,12 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
         const unsigned char *src = reinterpret_cast<const unsigned char *>(data.data() + off + 8);
         raw.resize(expect);
         if (comp == 0 || size_t(sz) == expect) memcpy(raw.data(), src, expect);
-        else {
+        else if (comp == 4) {
+            std::vector<int> wordsPerPixel;
+            for (auto &c : chans) wordsPerPixel.push_back(c.type == 1 ? 1 : 2);
+            if (off + 8 + size_t(sz) > data.size()) throw std::runtime_error("EXR: bad chunk size");
+            pizDecompress(src, size_t(sz), raw.data(), expect, width, lines, wordsPerPixel);
+        } else {
             tmp.resize(expect);
             uLongf dl = uLongf(expect);
             if (uncompress(tmp.data(), &dl, src, uLong(sz)) != Z_OK || dl != expect) throw std::runtime_error("EXR: zlib error");

@@ -65,3 +65,17 @@ def test_sponza_scene_loads_with_textures():
     assert d.num_textures == 11                                            # slot 0 (env map) + 10 JPGs
     used = {d.materials[i].textureIdDiffuse for i in range(d.num_materials)}
     assert used - {-1} == set(range(1, 11))
+
+
+EXR_DIGESTS = json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "exr_digests.json")))
+
+
+@pytest.mark.parametrize("rel", sorted(EXR_DIGESTS))
+def test_exr_reader_matches_openexr_digest(rel):
+    """host/exr.cpp against OpenEXR's own decode (digests made with tests/golden/make_exr_digests.py): the reference's
+    PIZ-compressed environment map and the uncompressed file our writer produces."""
+    img = helpers.pt().read_exr(os.path.join(helpers.ROOT, rel))
+    want = EXR_DIGESTS[rel]
+    assert img.shape == (want["height"], want["width"], 4)
+    assert hashlib.sha256(np.ascontiguousarray(img[..., :3]).tobytes()).hexdigest() == want["sha256"]
+    assert {EXR_DIGESTS[k]["compression"] for k in EXR_DIGESTS} >= {0, 4}

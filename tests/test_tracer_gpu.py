@@ -13,7 +13,7 @@ MISS = 0xFFFFFFFF
 NT = os.cpu_count() or 1
 
 
-@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML", "test-scene", "envSynthetic"])
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML", "test-scene", "envSynthetic", "envMap", "testSpheres"])
 def test_closest_hit_bit_exact(scene_name):
     w, h = 256, 144
     scene, r, o = helpers.make_pair(scene_name, w, h, accel=True)
@@ -24,7 +24,7 @@ def test_closest_hit_bit_exact(scene_name):
         c = o.trace_rays(rays, threads=NT)
         assert np.array_equal(g["prim"], c["prim"]), "%s: %d primitive ids differ" % (name, np.sum(g["prim"] != c["prim"]))
         hit = c["prim"] != MISS
-        assert hit.mean() > 0.2
+        assert hit.mean() > (0.05 if scene_name == "testSpheres" else 0.2)
         # t, u, v are computed with identical individually-rounded operations: bit-exact
         for f in ("t", "u", "v"):
             assert np.array_equal(g[f][hit].view(np.uint32), c[f][hit].view(np.uint32)), f
@@ -180,6 +180,15 @@ def test_radiance_parity_environment_map(mode):
     pdf (quirk 7), MIS probe misses; plus a sphere light."""
     over = dict(nee_mis=dict(enableNEE=1, enableMIS=1), nee=dict(enableNEE=1, enableMIS=0), bsdf=dict(enableNEE=0))[mode]
     r, o, g, c = _render_both("envSynthetic", 160, 90, samplesPerPixel=2, maxDepth=6, **over)
+    _assert_radiance_parity(g, c, 0.99)
+    assert c.mean() > 0.05
+
+
+@pytest.mark.parametrize("scene_name", ["envMap", "testSpheres"])
+def test_radiance_parity_reference_envmap_scenes(scene_name):
+    """The reference's own environment-map scenes (PIZ-compressed 512x256 lat-long map): a diffuse ball, and a lone
+    conductor sphere — a scene without a single triangle."""
+    r, o, g, c = _render_both(scene_name, 160, 90, samplesPerPixel=2, enableNEE=1, enableMIS=1, maxDepth=6)
     _assert_radiance_parity(g, c, 0.99)
     assert c.mean() > 0.05
 
