@@ -390,6 +390,15 @@ int b200pt_guiding_get_state(b200pt_ctx *ctx, int region, float scalars5[5], flo
 /* known-answer hook: lightpmm::exp (PMM_APPROX_EXP fastexp, pmm-vcl.h:157-184) as evaluated by the device code */
 int b200pt_guiding_fastexp(b200pt_ctx *ctx, const float *in_host, float *out_host, int n);
 
+/* ---- AOVs ---------------------------------------------------------------
+ * The quantities behind the reference's depth / split debug views (shaders/raytrace.rgen:1653-1655, :1677-1679,
+ * :1705-1707, :1722-1741) as a per-pixel RGBA32F layer of the LAST rendered frame instead of a view mode:
+ * x = maxReachedDepth, y = depthSum, z = depthsCounter (paths incl. drained splits), w = nextSplitSlot.
+ * VISU_DEPTH_MAX = x / maxDepth, VISU_DEPTH_AVERAGE = y / z / maxDepth, VISU_SPLITS = w / 10; the estimate image is
+ * B200PT_IMAGE_ESTIMATE.  Off by default (costs one read-modify-write per finished path). */
+int b200pt_set_aovs(b200pt_ctx *ctx, int enabled);
+int b200pt_read_aovs(b200pt_ctx *ctx, float *rgba);
+
 /* ---- checkpoint / resume ------------------------------------------------
  * Everything a later frame depends on: the three images, the irradiance cache (header, data, spheres) and the guiding
  * state (region boxes incl. adaptive splits, mixtures with their running statistics, packed VMM_Thetas, firstFit).  The

@@ -155,6 +155,7 @@ struct oracle_ctx {
     b200pt_push_constants pushC;
     // images (RGBA)
     std::vector<float> image, accumulateImage, estimateImage;
+    std::vector<float> aovImage;        // per pixel: maxReachedDepth, depthSum, depthsCounter, nextSplitSlot (rgen:1653-1655)
     // irradiance cache (bindings 10,12,13)
     b200pt_cache_header header{0, 0, 0};
     std::vector<b200pt_cache_data> cache;
@@ -1084,6 +1085,7 @@ struct Pixel {
             if ((pushC.useADRRS && pushC.adrrsSplit) || pushC.splitOnFirst) return;
         }
         const int numNEE = pushC.numNEE, maxDepth = pushC.maxDepth;
+        int maxReachedDepth = 0, depthSum = 0, depthsCounter = 0;            // rgen:1653-1655
         float firstT;
         if (pushC.visualizeMode == 0 || pushC.storeEstimate) {
             const int samplesPerPixel = pushC.isIrradiancePrepareFrame ? 1 : pushC.samplesPerPixel;
@@ -1097,6 +1099,7 @@ struct Pixel {
                 int currentDepth = 0;
                 result += raytrace(origin, direction, v3(1.0f), currentDepth, maxDepth, maxFollowDiscrete, addDirectLights, true, useNEE, numNEE,
                                    useIC, true, pushC.useADRRS != 0, pushC.updateGuiding != 0, firstT);
+                maxReachedDepth = std::max(maxReachedDepth, currentDepth); depthSum += currentDepth; depthsCounter++;      // rgen:1677-1679
             }
             for (int iSplit = 0; iSplit < nextSplitSlot; iSplit++) {
                 SplitInfo sp = splits[iSplit];
@@ -1108,9 +1111,11 @@ struct Pixel {
                 v3 throughput = sp.throughput * evalBsdf(mat, sp.u, sp.v, sp.normal, sp.wi, direction, sp.isFrontFace) / pdf;
                 result += raytrace(sp.origin, direction, throughput, sp.currentDepth, maxDepth, maxFollowDiscrete, addDirectLights, false, useNEE,
                                    numNEE, useIC, true, pushC.useADRRS != 0, pushC.updateGuiding != 0, firstT);
+                maxReachedDepth = std::max(maxReachedDepth, sp.currentDepth); depthSum += sp.currentDepth; depthsCounter++;  // rgen:1705-1707
             }
             result /= float(samplesPerPixel);
         }
+        { float *a = &C.aovImage[(size_t(py) * C.width + px) * 4]; a[0] = float(maxReachedDepth); a[1] = float(depthSum); a[2] = float(depthsCounter); a[3] = float(nextSplitSlot); }
         if (pushC.storeEstimate) { float *e = &C.estimateImage[(size_t(py) * C.width + px) * 4]; st3(e, result); e[3] = 1; }
         if (pushC.visualizeMode == 0) saveResult(result);
         for (int i = 0; i < nextNewIrradianceCacheSlot; i++) {
@@ -1158,7 +1163,7 @@ oracle_ctx *oracle_create(int width, int height, int ic_size, int use_accel) {
     oracle_ctx *C = new oracle_ctx();
     C->width = width; C->height = height;
     size_t N = size_t(width) * height;
-    C->image.assign(N * 4, 0.0f); C->accumulateImage.assign(N * 4, 0.0f); C->estimateImage.assign(N * 4, 0.0f);
+    C->image.assign(N * 4, 0.0f); C->accumulateImage.assign(N * 4, 0.0f); C->estimateImage.assign(N * 4, 0.0f); C->aovImage.assign(N * 4, 0.0f);
     C->header.maxCaches = uint32_t(ic_size);
     C->cache.assign(size_t(ic_size), b200pt_cache_data{});
     C->cacheSpheres.assign(size_t(ic_size), b200pt_sphere{});
@@ -1360,7 +1365,7 @@ int oracle_trace_rays(oracle_ctx *C, const b200pt_ray *rays, int64_t n, b200pt_h
 uint32_t oracle_tea(uint32_t a, uint32_t b) { return tea(a, b); }
 
 float *oracle_image(oracle_ctx *C, int which) {
-    return which == B200PT_IMAGE_OUTPUT ? C->image.data() : which == B200PT_IMAGE_ACCUM ? C->accumulateImage.data() : C->estimateImage.data();
+    return which == B200PT_IMAGE_OUTPUT ? C->image.data() : which == B200PT_IMAGE_ACCUM ? C->accumulateImage.data() : which == 3 ? C->aovImage.data() : C->estimateImage.data();
 }
 void oracle_get_counters(oracle_ctx *C, uint64_t out[3]) { out[0] = C->extendRays; out[1] = C->shadowRays; out[2] = C->pathVertices; }
 void oracle_reset_counters(oracle_ctx *C) { C->extendRays = C->shadowRays = C->pathVertices = 0; }

@@ -159,7 +159,7 @@ EXPORTS = [
     "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
-    "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks",
+    "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks",
     "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
@@ -224,6 +224,8 @@ def lib():
         L.b200pt_read_exr.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200pt_free.argtypes = [C.c_void_p]
         L.b200pt_read_image_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.b200pt_set_aovs.argtypes = [C.c_void_p, C.c_int]
+        L.b200pt_read_aovs.argtypes = [C.c_void_p, C.c_void_p]
         L.b200pt_save_state.argtypes = [C.c_void_p, C.c_char_p]
         L.b200pt_load_state.argtypes = [C.c_void_p, C.c_char_p]
         L.b200pt_comm_unique_id.argtypes = [C.c_char_p]
@@ -485,6 +487,15 @@ class Renderer:
         a = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty_like(a)
         _check(lib().b200pt_guiding_fastexp(self._h, a.ctypes.data, out.ctypes.data, a.size))
+        return out
+
+    def set_aovs(self, enabled=True):
+        _check(lib().b200pt_set_aovs(self._h, int(enabled)))
+
+    def read_aovs(self):
+        """(H, W, 4): maxReachedDepth, depthSum, depthsCounter, nextSplitSlot of the last frame (rgen:1653-1655, :1722-1741)."""
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _check(lib().b200pt_read_aovs(self._h, out.ctypes.data))
         return out
 
     def save_state(self, path):

@@ -102,7 +102,8 @@ struct b200pt_ctx {
     float view[16], proj[16], viewInv[16], projInv[16];
 
     // images
-    DevBuf<float4> imgOutput, imgAccum, imgEstimate;
+    DevBuf<float4> imgOutput, imgAccum, imgEstimate, imgAov;
+    bool aovs = false;
 
     // wavefront
     Wavefront wf{};
@@ -115,6 +116,12 @@ struct b200pt_ctx {
     // pinned ring of queue-counter snapshots: the host looks at iteration i-LAG while iteration i is being issued
     enum { RING = 4, LAG = 2 };
     uint32_t *hostCounters = nullptr;   // pinned, RING x CNT_NUM
+    // default: k_iter_prep stores the queue sizes into this mapped pinned ring and the host polls a sequence number —
+    // no copy-engine operation inside the loop (B200PT_COUNTER_COPY=1 selects the memcpy + event variant)
+    volatile uint32_t *hostRing = nullptr;
+    uint32_t *hostRingDev = nullptr;
+    uint32_t ringSeq = 0;
+    bool counterCopy = false;
     unsigned long long *hostDstats = nullptr;   // pinned, DST_NUM
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
@@ -317,6 +324,14 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostCounters), b200pt_ctx::RING * CNT_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostDstats), DST_NUM * sizeof(unsigned long long)));
     for (auto &e : c->ringEvent) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        void *hp = nullptr, *dp = nullptr;
+        CUDA_TRY(cudaHostAlloc(&hp, b200pt_ctx::RING * 8 * sizeof(uint32_t), cudaHostAllocMapped));
+        memset(hp, 0, b200pt_ctx::RING * 8 * sizeof(uint32_t));
+        CUDA_TRY(cudaHostGetDevicePointer(&dp, hp, 0));
+        c->hostRing = static_cast<volatile uint32_t *>(hp); c->hostRingDev = static_cast<uint32_t *>(dp);
+        if (const char *e = getenv("B200PT_COUNTER_COPY")) c->counterCopy = atoi(e) != 0;
+    }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
     cudaDeviceProp prop;
@@ -376,7 +391,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->modelVertexOffset.release(); c->modelIndexOffset.release(); c->randomLightIndex.release(); c->primVerts.release();
     c->materials.release(); c->instances.release(); c->lights.release(); c->randomTriIndex.release(); c->spheres.release(); c->textures.release();
     c->alphaTextures.release(); c->alphaMaterialTexture.release(); c->alphaScene.release();
-    c->imgOutput.release(); c->imgAccum.release(); c->imgEstimate.release();
+    c->imgOutput.release(); c->imgAccum.release(); c->imgEstimate.release(); c->imgAov.release();
     for (int i = 0; i < 2; i++) { c->pathRayO[i].release(); c->pathRayD[i].release(); }
     c->pathHit.release(); c->probeRayO.release(); c->probeRayD.release(); c->probeHit.release(); c->probeA.release(); c->probeB.release();
     c->shRayO.release(); c->shRayD.release(); c->shC.release(); c->thr.release(); c->pixelSum.release();
@@ -398,6 +413,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     c->guiding.release();
     for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
+    if (c->hostRing) cudaFreeHost(const_cast<uint32_t *>(c->hostRing));
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
     if (c->evTimer0) cudaEventDestroy(c->evTimer0);
@@ -602,6 +618,8 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             w.rec.state = c->recState.p; w.rec.distanceFactor = c->recDistanceFactor.p; w.rec.pathSum = c->recPathSum.p;
             w.shG = c->shG.p;
         }
+        w.aov = nullptr;
+        if (c->aovs) { CUDA_TRY(c->imgAov.alloc(size_t(c->numPixels))); w.aov = c->imgAov.p; }
         w.ic = ICState{};
         if (useCache) {
             w.ic.view = c->icGrid;
@@ -670,6 +688,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     const uint64_t pathsPerPixel = uint64_t(fp.samplesPerPixel) + (splitMode ? IC_MAX_SPLITS : 0);
     const uint64_t maxIter = pathsPerPixel * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
     bool drained = earlyReturn;
+    const uint32_t seqBase = c->ringSeq;          // sequence numbers never repeat across frames
     for (uint64_t iter = 0; !drained; iter++) {
         if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
         {
@@ -684,7 +703,9 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             }
         }
         if ((pc->enableNEE || useCache) && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
-        k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur);
+        const int slot = int(iter % b200pt_ctx::RING);
+        if (c->counterCopy) k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, nullptr, 0u);
+        else k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, c->hostRingDev + slot * 8, seqBase + uint32_t(iter) + 1u);
         c->stats.kernel_launches++;
         if (useCache) { StageTimer t(c, KIND_SHADE); k_ic_query<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur); }
         {
@@ -695,21 +716,46 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             else k_shade<false, false><<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
         }
         cur = 1 - cur;
-        const int slot = int(iter % b200pt_ctx::RING);
-        CUDA_TRY(cudaMemcpyAsync(c->hostCounters + slot * CNT_NUM, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(c->ringEvent[slot], st));
-        if (iter >= b200pt_ctx::LAG) {
-            const int old = int((iter - b200pt_ctx::LAG) % b200pt_ctx::RING);
-            CUDA_TRY(cudaEventSynchronize(c->ringEvent[old]));
-            const uint32_t *hc = c->hostCounters + old * CNT_NUM;
-            // after iteration j the live path queue is PATH[(j+1)&1]; all three empty => every later iteration is a no-op
-            const int liveQ = int((iter - b200pt_ctx::LAG + 1) & 1);
-            if (hc[CNT_PATH0 + liveQ] > N || hc[CNT_PROBE] > N * uint32_t(c->queueNEE) || hc[CNT_SHADOW] > N * uint32_t(c->queueNEE))
+        uint32_t qPath = 1, qProbe = 0, qShadow = 0;
+        bool have = false;
+        if (c->counterCopy) {
+            CUDA_TRY(cudaMemcpyAsync(c->hostCounters + slot * CNT_NUM, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(c->ringEvent[slot], st));
+            if (iter >= b200pt_ctx::LAG) {
+                const int old = int((iter - b200pt_ctx::LAG) % b200pt_ctx::RING);
+                CUDA_TRY(cudaEventSynchronize(c->ringEvent[old]));
+                const uint32_t *hc = c->hostCounters + old * CNT_NUM;
+                // after iteration j the live path queue is PATH[(j+1)&1]; all three empty => every later iteration is a no-op
+                const int liveQ = int((iter - b200pt_ctx::LAG + 1) & 1);
+                qPath = hc[CNT_PATH0 + liveQ]; qProbe = hc[CNT_PROBE]; qShadow = hc[CNT_SHADOW];
+                have = true;
+            }
+        } else if (iter >= b200pt_ctx::LAG) {
+            // queue sizes iteration j = iter - LAG STARTED with (= what the shade pass of j - 1 left), published by its k_iter_prep
+            const uint64_t j = iter - b200pt_ctx::LAG;
+            volatile uint32_t *hs = c->hostRing + (j % b200pt_ctx::RING) * 8;
+            const uint32_t want = seqBase + uint32_t(j) + 1u;
+            for (uint64_t spins = 0; hs[7] != want; spins++) {
+                if ((spins & 0x3ff) == 0x3ff) {      // a faulted stream would never publish: do not spin forever
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q != cudaErrorNotReady && hs[7] != want) {
+                        if (q == cudaSuccess) return setError(B200PT_E_STATE, "b200pt_render_frame: iteration counters were not published (internal error)");
+                        return setError(B200PT_E_CUDA, std::string("b200pt_render_frame: ") + cudaGetErrorString(q));
+                    }
+                }
+            }
+            __sync_synchronize();
+            qPath = hs[0]; qProbe = hs[1]; qShadow = hs[2];
+            have = true;
+        }
+        if (have) {
+            if (qPath > N || qProbe > N * uint32_t(c->queueNEE) || qShadow > N * uint32_t(c->queueNEE))
                 return setError(B200PT_E_STATE, "b200pt_render_frame: queue overflow (internal error)");
-            drained = hc[CNT_PATH0 + liveQ] == 0 && hc[CNT_PROBE] == 0 && hc[CNT_SHADOW] == 0;
-            if (c->dumpIters) fprintf(c->dumpIters, "%llu %u %u %u\n", (unsigned long long)(iter - b200pt_ctx::LAG), hc[CNT_PATH0 + liveQ], hc[CNT_PROBE], hc[CNT_SHADOW]);
+            drained = qPath == 0 && qProbe == 0 && qShadow == 0;
+            if (c->dumpIters) fprintf(c->dumpIters, "%llu %u %u %u\n", (unsigned long long)(iter - b200pt_ctx::LAG), qPath, qProbe, qShadow);
         }
     }
+    c->ringSeq = seqBase + uint32_t(maxIter) + 8u;
     if (!earlyReturn) {
         StageTimer t(c, KIND_SHADE);
         k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec);
@@ -965,6 +1011,20 @@ int b200pt_guiding_put_samples(b200pt_ctx *c, const b200pt_directional_data *in,
     if (!c || !in || n < 0 || n > b200pt_guiding_sample_capacity(c)) return setError(B200PT_E_INVALID, "b200pt_guiding_put_samples: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(c->samples.p, in, size_t(n) * sizeof(b200pt_directional_data), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_set_aovs(b200pt_ctx *c, int enabled) {
+    if (!c) return setError(B200PT_E_INVALID, "b200pt_set_aovs: null argument");
+    c->aovs = enabled != 0;
+    return B200PT_OK;
+}
+int b200pt_read_aovs(b200pt_ctx *c, float *rgba) {
+    if (!c || !rgba) return setError(B200PT_E_INVALID, "b200pt_read_aovs: null argument");
+    if (!c->aovs || !c->imgAov.p) return setError(B200PT_E_STATE, "b200pt_read_aovs: enable AOVs (b200pt_set_aovs) and render a frame first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(rgba, c->imgAov.p, size_t(c->numPixels) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return B200PT_OK;
 }

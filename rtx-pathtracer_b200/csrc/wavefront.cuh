@@ -51,6 +51,7 @@ struct Wavefront {
     GuidingView guide;       // region tree + mixtures (useGuiding / updateGuiding)
     GuidingRecord rec;       // sample-recording state (updateGuiding); rec.samples == nullptr when not recording
     ICState ic;              // irradiance cache / ADRRS state (useIrradianceCache / useADRRS / splitOnFirst frames)
+    float4 *aov;             // optional per-pixel layer: max depth, depth sum, path count, split count (b200pt_set_aovs)
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
     if (fp.pc.useIrradianceCache) {      // rgen:1639-1641: the update draw; k_ic_update has advanced the stream of the selected pixels
         if (rnd(seed) < fp.pc.irradianceUpdateProb) seed = wf.seed[p];
     }
+    if (wf.aov) wf.aov[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (wf.ic.newCount) wf.ic.newCount[p] = 0u;
     if (wf.ic.splitState) wf.ic.splitState[p] = 0u;
     const int px = p % fp.width, py = p / fp.width;
@@ -185,10 +187,17 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, c
 
 // between trace and shade of one iteration: fold the queue sizes into the 64-bit statistics, publish the shade count
 // and reset the counters the shade kernel is about to fill
-__global__ void k_iter_prep(Wavefront wf, int cur) {
+// hostSlot (optional): 8 words of mapped pinned host memory — the queue sizes this iteration started with go straight to
+// the host (no copy-engine operation between the kernels of the loop), followed by a sequence number the host polls
+__global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t *c = wf.counters;
     const uint32_t nPath = c[CNT_PATH0 + cur], nProbe = c[CNT_PROBE], nShadow = c[CNT_SHADOW];
+    if (hostSlot) {
+        hostSlot[0] = nPath; hostSlot[1] = nProbe; hostSlot[2] = nShadow;
+        __threadfence_system();
+        hostSlot[7] = seq;
+    }
     wf.dstats[DST_EXTEND] += (unsigned long long)nPath + nProbe;
     wf.dstats[DST_SHADOW] += (unsigned long long)nShadow + c[CNT_INLINE_SHADOW];
     wf.dstats[DST_VERTICES] += nPath;
@@ -498,6 +507,12 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
         }
 
         if (terminated) {
+            if (wf.aov) {           // maxReachedDepth / depthSum / depthsCounter (rgen:1677-1679, :1705-1707), nextSplitSlot
+                float4 a = wf.aov[pid];
+                a.x = fmaxf(a.x, float(depth)); a.y += float(depth); a.z += 1.0f;
+                if (IC && wf.ic.splitState) a.w = float(wf.ic.splitState[pid] & 0xffffu);
+                wf.aov[pid] = a;
+            }
             // next sample of this pixel (rgen:1668-1681): same RNG stream, fresh path state
             const uint32_t s = wf.sampleIdx[pid] + 1;
             wf.sampleIdx[pid] = s;

@@ -193,6 +193,28 @@ def test_radiance_parity_reference_envmap_scenes(scene_name):
     assert c.mean() > 0.05
 
 
+def test_aov_layer_depth_and_split_statistics():
+    """b200pt_read_aovs: maxReachedDepth / depthSum / depthsCounter / nextSplitSlot per pixel (rgen:1653-1655, :1677-1679,
+    :1705-1707) — the data of the reference's depth and split debug views — against the oracle."""
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair("cornell-dielectric", 128, 72)
+    with pytest.raises(P.B200ptError):
+        r.read_aovs()
+    r.set_aovs(True)
+    pc = P.default_push_constants(randomUInt=P.tea(2, 0xC0FFEE), previousFrames=0, samplesPerPixel=4, enableMIS=1, splitOnFirst=1)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    g, c = r.read_aovs(), o.image(3)
+    assert np.array_equal(g[..., 2], c[..., 2])                    # paths per pixel: 4 samples + the drained splits
+    assert (g[..., 2] > 4).mean() > 0.5 and np.array_equal(g[..., 3], c[..., 3]) and g[..., 3].max() >= 4
+    assert (g[..., 0] == c[..., 0]).mean() >= 0.995 and (g[..., 1] == c[..., 1]).mean() >= 0.995
+    assert c[..., 0].max() > 5 and c[..., 1].mean() > c[..., 2].mean()      # depths are real
+    r.set_aovs(False)
+    r.render_frame(pc)
+    with pytest.raises(P.B200ptError):
+        r.read_aovs()
+
+
 def test_accumulation_over_frames_matches_oracle():
     """previousFrames > 0: running mean mix(prev, x, 1/(n+1)) (rgen:1476-1483), and the sum/divide variant."""
     r, o, g, c = _render_both("veachMIS", 96, 54, frames=3, samplesPerPixel=1, enableMIS=1)
