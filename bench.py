@@ -302,7 +302,7 @@ def main():
         traffic = None
         try:
             rd = wr = None
-            for l in open(os.path.join(ROOT, "profiles", "r01b_ncu_trace.txt")):
+            for l in open(os.path.join(ROOT, "profiles", "r01c_ncu_trace.txt")):
                 f = l.split()
                 if l.startswith("dram__bytes_read.sum") and rd is None:
                     rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -359,7 +359,7 @@ def main():
             line["em"] = em
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            w, h, spp = 320, 180, 4
+            w, h, spp = 640, 360, 8          # ~10 s of CPU work on 16 threads
             times, crays = cpu_oracle_run(P, w, h, spp, 2, threads)
             line["cpu_baseline"] = {"value": crays[-1] / times[-1] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%dx%d view of the same scene/camera, %d spp, 1 warm-up + 1 timed frame of oracle/tracer_oracle.cpp (own BVH)" % (w, h, spp)}
