@@ -1,4 +1,5 @@
 #include "bvh.h"
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -32,6 +33,8 @@ struct Builder {
     std::vector<float> centroid;   // 3 per tri
     std::vector<uint32_t> order;
     std::vector<Node2> nodes;
+    uint32_t maxLeaf = 3;
+    float travCost = 0.5f;
 
     int build(uint32_t first, uint32_t count) {
         int idx = int(nodes.size());
@@ -68,10 +71,11 @@ struct Builder {
                 if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
             }
         }
-        // leaves hold at most 3 triangles (unary count in 3 bits of the node meta byte)
-        if (count <= 3) {
+        // leaves hold at most 3 triangles (unary count in 3 bits of the node meta byte); travCost = cost of one more
+        // node visit in units of a triangle test (B200PT_BVH_MAX_LEAF / B200PT_BVH_TRAV_COST override for tuning)
+        if (count <= maxLeaf) {
             float leafCost = box.halfArea() * count;
-            if (bestAxis < 0 || bestCost + box.halfArea() * 0.5f >= leafCost) return idx;
+            if (bestAxis < 0 || bestCost + box.halfArea() * travCost >= leafCost) return idx;
         }
         uint32_t mid;
         if (bestAxis >= 0) {
@@ -105,6 +109,8 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
     out.pad = pad;
 
     Builder b;
+    if (const char *e = getenv("B200PT_BVH_MAX_LEAF")) b.maxLeaf = uint32_t(std::max(1, std::min(3, atoi(e))));
+    if (const char *e = getenv("B200PT_BVH_TRAV_COST")) b.travCost = float(atof(e));
     b.verts = verts;
     b.triBox.resize(numTris); b.centroid.resize(size_t(numTris) * 3); b.order.resize(numTris);
     std::iota(b.order.begin(), b.order.end(), 0u);
