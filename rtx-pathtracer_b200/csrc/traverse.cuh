@@ -39,6 +39,9 @@ struct HitRec { float t; uint32_t prim; float u, v; };
 #define PT_STACK_SMEM 8       // entries per thread kept in shared memory
 #define PT_STACK_LOCAL 24     // overflow entries in local memory
 #define PT_TRACE_BLOCK 128
+#ifndef PT_TRACE_MIN_BLOCKS
+#define PT_TRACE_MIN_BLOCKS 7   // __launch_bounds__ minimum CTAs per SM of the trace kernels (register cap)
+#endif
 
 // exact (non-contracted) Möller–Trumbore; returns true and t,u,v when the ray hits the triangle's plane inside it
 __device__ __forceinline__ bool intersectTriExact(const float4 a, const float4 b, const float4 c, const vec3 o, const vec3 d,
@@ -155,6 +158,65 @@ __device__ __forceinline__ bool travInit(Trav &s, const TraceScene &sc, const ve
 #ifndef PT_TRI_CAP
 #define PT_TRI_CAP 0          // compile-time: 0 = no cap (test every triangle of the group in this step)
 #endif
+// node half of a step: pops the next child of the current node group (pushing the rest of the group), fetches that
+// node, slab-tests its 8 children and returns the new node group in `cur` and the hit leaf triangles in `triGroup`
+__device__ __forceinline__ void travNode(Trav &s, const TraceScene &sc, uint2 &cur, uint2 &triGroup, uint2 *smemStack, uint2 *localStack, const int stride) {
+    const vec3 o = s.o, d = s.d;
+    const uint32_t hits = cur.y;
+    const int bit = 31 - __clz(hits);
+    cur.y &= ~(1u << bit);
+    if (cur.y & 0xff000000u) {   // push the rest of the group
+        if (s.sp < PT_STACK_SMEM) smemStack[s.sp * stride] = cur;
+        else localStack[s.sp - PT_STACK_SMEM] = cur;
+        s.sp++;
+    }
+    const uint32_t octInv = s.octInv;
+    const uint32_t octInv4 = octInv * 0x01010101u;
+    const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
+    const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));   // low byte of hits = imask
+    const uint32_t nodeIdx = cur.x + rel;
+
+    const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
+    const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
+    const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
+    const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
+    const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
+    const uint32_t e = __float_as_uint(n0.w);
+    const float ax = __uint_as_float((e & 0xffu) << 23) * s.idx;
+    const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * s.idy;
+    const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
+    const float ox = (n0.x - o.x) * s.idx, oy = (n0.y - o.y) * s.idy, oz = (n0.z - o.z) * s.idz;
+    const float best = s.best;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+        const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+        const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+        const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+        const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
+        const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
+        const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
+            const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
+            const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
+            const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+            const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
+            if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
+        }
+    }
+    cur.x = __float_as_uint(n1.x);
+    cur.y = (hitmask & 0xff000000u) | (e >> 24);
+    triGroup.x = __float_as_uint(n1.y);
+    triGroup.y = hitmask & 0x00ffffffu;
+}
+
 // ALPHA compiles the alpha test of textured triangles in (scenes without a transparent texel run the plain kernel):
 // 0 = none, 1 = out-of-line call (the trace kernels: keeps their register count), 2 = in line (callers that must not
 // contain an ABI call: a CALL anywhere in the shade kernel costs it 7 % even when it is never executed)
@@ -164,59 +226,7 @@ __device__ __forceinline__ bool travStep(Trav &s, const TraceScene &sc, uint2 *s
     uint2 cur = s.cur;
     uint2 triGroup;
     if (cur.y & 0xff000000u) {
-        const uint32_t hits = cur.y;
-        const int bit = 31 - __clz(hits);
-        cur.y &= ~(1u << bit);
-        if (cur.y & 0xff000000u) {   // push the rest of the group
-            if (s.sp < PT_STACK_SMEM) smemStack[s.sp * stride] = cur;
-            else localStack[s.sp - PT_STACK_SMEM] = cur;
-            s.sp++;
-        }
-        const uint32_t octInv = s.octInv;
-        const uint32_t octInv4 = octInv * 0x01010101u;
-        const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
-        const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));   // low byte of hits = imask
-        const uint32_t nodeIdx = cur.x + rel;
-
-        const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
-        const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
-        const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
-        const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
-        const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
-        const uint32_t e = __float_as_uint(n0.w);
-        const float ax = __uint_as_float((e & 0xffu) << 23) * s.idx;
-        const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * s.idy;
-        const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
-        const float ox = (n0.x - o.x) * s.idx, oy = (n0.y - o.y) * s.idy, oz = (n0.z - o.z) * s.idz;
-        const float best = s.best;
-        uint32_t hitmask = 0;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-            const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-            const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
-            const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-            const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
-            const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
-            const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
-            const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
-            const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
-            const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
-                const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
-                const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
-                const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
-                if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
-            }
-        }
-        cur.x = __float_as_uint(n1.x);
-        cur.y = (hitmask & 0xff000000u) | (e >> 24);
-        triGroup.x = __float_as_uint(n1.y);
-        triGroup.y = hitmask & 0x00ffffffu;
+        travNode(s, sc, cur, triGroup, smemStack, localStack, stride);
     } else {
         triGroup = cur;
         cur = make_uint2(0u, 0u);
@@ -337,6 +347,171 @@ __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &
                 io.store(rayIdx, s.hit, any);
                 active = false;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative triangle phase.  In the per-lane loop above a node step hands a lane 0..24 leaf triangles (0.8 on
+// average) and the warp sits through the longest lane's loop: on cornell-dielectric the triangle loop ran 4.4
+// iterations per step with 6 -> 2 of 32 lanes active and took 55 % of the kernel's issue slots
+// (profiles/r01c_ncu_trace_sass.txt).  Here the lanes of a warp pool the triangles their node steps produced into a
+// shared-memory work list and every lane — including lanes without a ray — tests list entry `lane`, `lane + 32`, ...
+// against the OWNER's ray (kept in shared memory).  Candidates are merged per owner with a 64-bit atomicMin on
+// (ordered bits of t) << 32 | primitive id, which IS the closest-hit rule (lexicographic minimum of (t, id)), so the
+// result does not depend on which lane tested what; the winner's u,v follow after a warp barrier.
+#ifndef PT_COOP
+#define PT_COOP 1
+#endif
+#ifndef PT_COOP_CAP
+#define PT_COOP_CAP 128       // work-list entries per warp and round (a warp can produce up to 32 x 24)
+#endif
+struct CoopSmem {
+    float4 rayO[PT_TRACE_BLOCK];                 // origin, tmin of the lane's current ray
+    float4 rayD[PT_TRACE_BLOCK];                 // direction
+    unsigned long long key[PT_TRACE_BLOCK];      // best (t, id) of the lane's ray during a triangle phase
+    float2 uv[PT_TRACE_BLOCK];
+    uint32_t base[PT_TRACE_BLOCK];               // first packed triangle of the lane's triangle group
+    uint16_t items[PT_TRACE_BLOCK / 32][PT_COOP_CAP];   // owner lane << 5 | triangle offset
+};
+
+// order-preserving map float -> uint32 (and back); -0 is folded onto +0 first
+__device__ __forceinline__ uint32_t orderedBits(float f) {
+    const uint32_t b = __float_as_uint(__fadd_rn(f, 0.0f));
+    return b ^ (uint32_t(int32_t(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float fromOrderedBits(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+// must be called by all 32 lanes; `triGroup.y` = 0 for lanes that bring no triangles
+template <int ALPHA>
+__device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, const uint2 triGroup, CoopSmem &sm, const unsigned lane, const unsigned tid) {
+    uint32_t bits = triGroup.y;
+    if (!__any_sync(0xffffffffu, bits != 0u)) return;
+    const unsigned wl = tid & ~31u, warp = tid >> 5;
+    const bool mine = bits != 0u;
+    unsigned long long initKey = 0ull;
+    if (mine) {
+        initKey = ((unsigned long long)orderedBits(s.best) << 32) | (s.hit.prim == PT_MISS ? 0u : s.hit.prim);
+        sm.key[tid] = initKey;
+        sm.base[tid] = triGroup.x;
+    }
+    volatile unsigned long long *vkey = sm.key;
+    for (;;) {
+        const uint32_t cnt = __popc(bits);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, dlt);
+            if (int(lane) >= dlt) incl += nb;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t pos = incl - cnt;
+        while (bits && pos < PT_COOP_CAP) {
+            const uint32_t ti = uint32_t(__ffs(bits) - 1);
+            bits &= bits - 1u;
+            sm.items[warp][pos++] = uint16_t((lane << 5) | ti);
+        }
+        __syncwarp();
+        const uint32_t n = min(total, uint32_t(PT_COOP_CAP));
+        for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            bool won = false;
+            unsigned long long cand = 0ull;
+            float u = 0.0f, v = 0.0f;
+            uint32_t ol = 0u;
+            if (i < n) {
+                const uint32_t it = sm.items[warp][i];
+                ol = wl + (it >> 5);
+                const float4 ro = sm.rayO[ol], rd = sm.rayD[ol];
+                const uint32_t tb = (sm.base[ol] + (it & 31u)) * 3u;
+                const float4 a = __ldg(&sc.tris[tb + 0]);
+                const float4 b = __ldg(&sc.tris[tb + 1]);
+                const float4 c = __ldg(&sc.tris[tb + 2]);
+                float t;
+                if (intersectTriExact(a, b, c, make_vec3(ro), make_vec3(rd), t, u, v) && t > ro.w) {
+                    const uint32_t id = __float_as_uint(a.w);
+                    cand = ((unsigned long long)orderedBits(t) << 32) | id;
+                    if (cand < vkey[ol]) {
+                        if (!ALPHA || __float_as_uint(b.w) == 0u || !(ALPHA == 2 ? alphaRejectsInline(sc, id, u, v, ro.x, t) : alphaRejects(sc, id, u, v, ro.x, t)))
+                            won = cand < atomicMin(&sm.key[ol], cand);
+                    }
+                }
+            }
+            __syncwarp();
+            if (won && vkey[ol] == cand) sm.uv[ol] = make_float2(u, v);
+        }
+        if (total <= uint32_t(PT_COOP_CAP)) break;
+        __syncwarp();            // the next round rewrites the work list
+    }
+    __syncwarp();
+    if (mine) {
+        const unsigned long long k = sm.key[tid];
+        if (k != initKey) {
+            const float2 uv = sm.uv[tid];
+            s.best = s.hit.t = fromOrderedBits(uint32_t(k >> 32));
+            s.hit.prim = uint32_t(k);
+            s.hit.u = uv.x; s.hit.v = uv.y;
+        }
+    }
+}
+
+// tracePersistent with the cooperative triangle phase: a step = node half for every lane with a ray, then ONE pooled
+// triangle phase for the warp, then the stack pop.
+template <int ALPHA, typename IO>
+__device__ __forceinline__ void tracePersistentCoop(const TraceScene &sc, const IO &io, const uint32_t total, uint32_t *workCounter,
+                                                    const uint32_t chunk, const int refillMin, uint2 *smemStack, CoopSmem &sm) {
+    const unsigned tid = threadIdx.x;
+    const unsigned lane = tid & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int stride = blockDim.x;
+    uint2 localStack[PT_STACK_LOCAL];
+    Trav s;
+    uint32_t rayIdx = 0, wBase = 0, wEnd = 0;
+    bool active = false, any = false, exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refillMin)) {
+            if (wBase >= wEnd) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(workCounter, chunk);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= total) { exhausted = true; wBase = wEnd = 0; }
+                else { wBase = b; wEnd = min(b + chunk, total); }
+            }
+            if (!active) {
+                const uint32_t idx = wBase + __popc(idle & ltMask);
+                if (idx < wEnd) {
+                    vec3 o, d; float tmin, tmax;
+                    io.load(idx, o, d, tmin, tmax, any);
+                    rayIdx = idx;
+                    active = !travInit(s, sc, o, d, tmin, tmax, any);
+                    if (!active) io.store(idx, s.hit, any);
+                    else { sm.rayO[tid] = make_float4(o.x, o.y, o.z, tmin); sm.rayD[tid] = make_float4(d.x, d.y, d.z, 0.0f); }
+                }
+            }
+            wBase = min(wEnd, wBase + uint32_t(__popc(idle)));
+        }
+        uint2 cur = make_uint2(0u, 0u), triGroup = make_uint2(0u, 0u);
+        if (active) {
+            cur = s.cur;
+            travNode(s, sc, cur, triGroup, smemStack, localStack, stride);
+        }
+        coopTriangles<ALPHA>(s, sc, triGroup, sm, lane, tid);
+        if (active) {
+            bool done = any && s.hit.prim != PT_MISS;
+            if (!done && (cur.y & 0xff000000u) == 0u) {
+                if (s.sp == 0) done = true;
+                else {
+                    s.sp--;
+                    if (s.sp < PT_STACK_SMEM) cur = smemStack[s.sp * stride];
+                    else cur = localStack[s.sp - PT_STACK_SMEM];
+                }
+            }
+            s.cur = cur;
+            if (done) { io.store(rayIdx, s.hit, any); active = false; }
         }
     }
 }

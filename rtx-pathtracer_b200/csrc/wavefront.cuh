@@ -148,7 +148,7 @@ struct WavefrontRayIO {
 };
 
 template <bool REC, int ALPHA>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefront wf, int cur, TraceTuning tune) {
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MIN_BLOCKS) k_trace(TraceScene sc, Wavefront wf, int cur, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
     WavefrontRayIO<REC> io;
     io.nPath = wf.counters[CNT_PATH0 + cur]; io.nProbe = wf.counters[CNT_PROBE];
@@ -162,7 +162,12 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(TraceScene sc, Wavefro
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
     while (chunk > 32 && total / chunk < warps) chunk >>= 1;
+#if PT_COOP
+    __shared__ CoopSmem coop;
+    tracePersistentCoop<ALPHA>(sc, io, total, &wf.counters[CNT_WORK_TRACE], chunk, tune.refillMin, stack + threadIdx.x, coop);
+#else
     tracePersistent<ALPHA>(sc, io, total, &wf.counters[CNT_WORK_TRACE], chunk, tune.refillMin, stack + threadIdx.x);
+#endif
 }
 
 // generic ray batch for the traversal-only parity hook (b200pt_trace_rays): same persistent loop
@@ -175,14 +180,19 @@ struct BatchRayIO {
     __device__ __forceinline__ void store(uint32_t idx, const HitRec &h, bool) const { hits[idx] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v); }
 };
 template <int ALPHA>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, uint32_t n,
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MIN_BLOCKS) k_trace_batch(TraceScene sc, const float4 *__restrict__ rays, float4 *__restrict__ hits, uint32_t n,
                                                                 int any, uint32_t *workCounter, TraceTuning tune) {
     __shared__ uint2 stack[PT_STACK_SMEM * PT_TRACE_BLOCK];
     BatchRayIO io; io.rays = rays; io.hits = hits; io.any = any != 0;
     const uint32_t warps = gridDim.x * (PT_TRACE_BLOCK / 32);
     uint32_t chunk = tune.chunk;
     while (chunk > 32 && n / chunk < warps) chunk >>= 1;
+#if PT_COOP
+    __shared__ CoopSmem coop;
+    tracePersistentCoop<ALPHA>(sc, io, n, workCounter, chunk, tune.refillMin, stack + threadIdx.x, coop);
+#else
     tracePersistent<ALPHA>(sc, io, n, workCounter, chunk, tune.refillMin, stack + threadIdx.x);
+#endif
 }
 
 // between trace and shade of one iteration: fold the queue sizes into the 64-bit statistics, publish the shade count
