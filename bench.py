@@ -22,7 +22,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-WIDTH, HEIGHT, SPP = 1280, 720, 16
+WIDTH, HEIGHT, SPP = 1280, 720, int(os.environ.get("B200PT_BENCH_SPP", "16"))   # the override is a tuning aid (tail analysis), not a bench mode
 SCENE = os.path.join(ROOT, "scenes", "cornell-dielectric", "cornell-dielectric.xml")
 SEED = 0xC0FFEE
 BYTES_PER_RAY = 152          # algorithmic wavefront-state bytes per extend/shadow ray
