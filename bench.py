@@ -214,7 +214,6 @@ def main():
     r = P.Renderer(WIDTH, HEIGHT, 0, 0, device=local_rank)
     r.set_scene(scene)
     r.set_camera(view, proj)
-    r.set_stage_timing(True)
     accum = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda:%d" % local_rank)
     host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
 
@@ -231,6 +230,10 @@ def main():
 
     for i in range(args.warmup):
         step(i)
+    # one more untimed pass through the call the timed region makes, so that the library's one-time work for a batch
+    # of K frames (second half of the per-pixel sums, the pool of CUDA events) is not inside the timed region
+    r.set_stage_timing(2)            # CUDA events around the trace kernel only (every stage kernel: ~10 % slower frames)
+    r.render_frames([push_constants(P, S.frame_seed(i, rank, world, SEED), i) for i in range(args.steps)])
     if world > 1:   # warm the collective
         r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
         S.combine_images(accum, args.warmup)
@@ -242,8 +245,9 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     r.timer_start()                  # CUDA event on the library's stream (the one every kernel is launched on)
-    for i in range(args.steps):
-        step(i)
+    # the K frames go to the library in ONE call (b200pt_render_frames): same images as K calls of render_frame, but a
+    # pixel that has finished frame i starts frame i + 1 without waiting for the frame's slowest pixels
+    r.render_frames([push_constants(P, S.frame_seed(i, rank, world, SEED), i) for i in range(args.steps)])
     r.read_image_device(P.IMAGE_OUTPUT, accum.data_ptr())
     dev_ms = r.timer_stop()
     final = S.combine_images(accum, args.steps)      # N > 1: one NCCL all-reduce of the image (+ a scalar); N = 1: no-op
@@ -259,6 +263,7 @@ def main():
                                          "launches_shade", "ms_extend", "ms_shadow", "ms_shade", "ms_total")}
 
     # ---- timed region 2: `e2e` through the C ABI with HOST buffers (camera + push constants in, image out) ---------
+    r.set_stage_timing(0)
     barrier()
     r.stats_reset()
     t1 = time.perf_counter()
@@ -272,6 +277,16 @@ def main():
     e2e_elapsed = e2e_dev_ms * 1e-3 if world == 1 else time.perf_counter() - t1
     st2 = r.stats()
     e2e_rays = int(st2.extend_rays) + int(st2.shadow_rays)
+
+    # ---- untimed: two frames with CUDA events around EVERY stage kernel -> the trace / shade split of a frame ---------
+    r.set_stage_timing(1)
+    r.stats_reset()
+    for i in range(2):
+        step(i)
+    st3 = r.stats()
+    split = {"trace": st3.ms_extend, "shade": st3.ms_shade, "frame_total": st3.ms_total, "frames": 2,
+             "note": "separate pass of 2 single frames with events around every kernel (slows a frame by ~10 %); shares, not absolutes"}
+    r.set_stage_timing(0)
 
     # max over ranks, totals over ranks
     if world > 1:
@@ -319,6 +334,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cornell-dielectric 1280x720 NEE+MIS (power heuristic), maxDepth 30, 16 spp per step, stand-in shell.obj",
                        "spp_per_step": SPP, "frames_per_rank": args.steps, "parallelism": "spp-sharded x%d" % world,
+                       "frames": "value: the K frames of a rank in one b200pt_render_frames call (pixels walk from frame to frame; images identical to K single calls, tests/test_frame_batch_gpu.py); e2e: one b200pt_render_frame + image read-back per step",
                        "l2": "no flush: the wavefront queues touched per iteration (~230 MB at 921600 paths) exceed the 126 MB L2"},
             "spp_per_s": SPP * args.steps * world / elapsed,
             "e2e": {"value": total_e2e_rays / e2e_elapsed / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 + 192, "d2h_bytes_per_step": WIDTH * HEIGHT * 16},
@@ -328,8 +344,8 @@ def main():
                          "trace_Mrays_per_s": (stats["extend_rays"] + stats["shadow_rays"]) / max(stats["ms_extend"], 1e-9) / 1e3, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": ext_bytes, "peak_source": peak_src,
                          "note": "152 algorithmic bytes/ray of wavefront state (SURVEY 8d); the kernel is latency/issue bound, see profiles/"},
-            "stage_ms": {"trace": stats["ms_extend"], "shade": stats["ms_shade"], "frame_total": stats["ms_total"],
-                         "device": dev_ms, "wall": 1e3 * wall},
+            "stage_ms": {"trace": stats["ms_extend"], "frame_total": stats["ms_total"], "device": dev_ms, "wall": 1e3 * wall},
+            "stage_split": split,
             "rays": {"extend": stats["extend_rays"], "shadow": stats["shadow_rays"], "iterations": stats["iterations"]},
         }
         if world == 1 and not args.no_em:

@@ -308,6 +308,15 @@ int b200pt_set_camera(b200pt_ctx *ctx, const float view[16], const float proj[16
  * pc->randomUInt is the frame seed (the reference draws it from glm::linearRand, quirk 10). */
 int b200pt_render_frame(b200pt_ctx *ctx, const b200pt_push_constants *pc);
 
+/* `count` consecutive frames in one call: the accumulation loop of the evaluation modes ("N samples -> time -> EXR",
+ * src/RayTracingApp.cpp:93-97 and :159-215, where drawCallback runs frame after frame with a fresh randomUInt and
+ * previousFrames + 1).  The images after the call are IDENTICAL to `count` calls of b200pt_render_frame.  When the
+ * frames are plain path-tracing frames that differ only in randomUInt / previousFrames (no irradiance cache, ADRRS,
+ * guiding, estimate, AOVs or alpha-tested textures) a pixel that has finished frame f starts frame f + 1 without
+ * waiting for the other pixels, which removes the drain tail of every frame but the last; otherwise the frames run
+ * one after the other. */
+int b200pt_render_frames(b200pt_ctx *ctx, const b200pt_push_constants *pcs, int count);
+
 /* replaces PostProcessing::saveOffscreenImage read-back (src/PostProcessing.cpp:310-338): W*H RGBA32F */
 int b200pt_read_image(b200pt_ctx *ctx, int which, float *rgba_host);
 int b200pt_write_image(b200pt_ctx *ctx, int which, const float *rgba_host);
@@ -322,7 +331,9 @@ int b200pt_trace_rays(b200pt_ctx *ctx, const b200pt_ray *rays, int64_t n, b200pt
 int b200pt_trace_rays_device(b200pt_ctx *ctx, const void *rays_device, int64_t n, void *hits_device, int any_hit);
 
 int b200pt_stats_get(b200pt_ctx *ctx, b200pt_stats *out);
-/* per-kernel CUDA-event timing of the wavefront stages (replaces the reference's std::chrono prints) */
+/* per-kernel CUDA-event timing of the wavefront stages (replaces the reference's std::chrono prints):
+ * 0 = off, 1 = every stage kernel (costs ~10 % of a frame: ~8 event records per wavefront iteration), 2 = only the
+ * trace kernel (b200pt_stats.ms_extend / launches_extend stay valid, the other stage times read 0) */
 int b200pt_set_stage_timing(b200pt_ctx *ctx, int enabled);
 int b200pt_stats_reset(b200pt_ctx *ctx);
 int b200pt_synchronize(b200pt_ctx *ctx);

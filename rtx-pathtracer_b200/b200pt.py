@@ -150,7 +150,7 @@ assert C.sizeof(Vertex) == 48 and C.sizeof(Material) == 96 and C.sizeof(Instance
 # every symbol include/b200pt.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
     "b200pt_last_error", "b200pt_device_count", "b200pt_create", "b200pt_destroy", "b200pt_set_scene", "b200pt_set_camera",
-    "b200pt_render_frame", "b200pt_read_image", "b200pt_write_image", "b200pt_read_image_device", "b200pt_write_image_device",
+    "b200pt_render_frame", "b200pt_render_frames", "b200pt_read_image", "b200pt_write_image", "b200pt_read_image_device", "b200pt_write_image_device",
     "b200pt_trace_rays", "b200pt_trace_rays_device", "b200pt_stats_get", "b200pt_set_stage_timing", "b200pt_stats_reset", "b200pt_synchronize",
     "b200pt_timer_start", "b200pt_timer_stop",
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
@@ -184,6 +184,7 @@ def lib():
         L.b200pt_set_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
         L.b200pt_set_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.b200pt_render_frame.argtypes = [C.c_void_p, C.POINTER(PushConstants)]
+        L.b200pt_render_frames.argtypes = [C.c_void_p, C.POINTER(PushConstants), C.c_int]
         L.b200pt_read_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b200pt_write_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b200pt_read_image_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -360,6 +361,11 @@ class Renderer:
 
     def render_frame(self, pc):
         _check(lib().b200pt_render_frame(self._h, C.byref(pc)))
+
+    def render_frames(self, pcs):
+        """`len(pcs)` consecutive frames in one call (b200pt_render_frames): same images as render_frame in a loop."""
+        arr = (PushConstants * len(pcs))(*pcs)
+        _check(lib().b200pt_render_frames(self._h, arr, len(pcs)))
 
     def read_image(self, which=IMAGE_OUTPUT, out=None):
         if out is None:

@@ -126,7 +126,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
-    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, resolveGrid = 0, icQueryGrid = 0;
+    int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, shadeGridBatch = 0, resolveGrid = 0, icQueryGrid = 0;
     TraceTuning tune{64u, 8};
 
     // guiding / IC state
@@ -158,7 +158,9 @@ struct b200pt_ctx {
     FILE *dumpIters = nullptr;          // B200PT_DUMP_ITERS=file: queue sizes after every wavefront iteration (tuning aid)
 
     // optional per-kernel timing: (kind, start event, stop event) triples resolved at the end of a frame
-    bool stageTiming = false;
+    int stageTiming = 0;             // 0 off, 1 every stage kernel, 2 the trace kernel only
+    bool timed(int kind) const { return stageTiming == 1 || (stageTiming == 2 && kind == 0 /* KIND_EXTEND */); }
+    DevBuf<uint32_t> batchSeeds, batchPrev;      // b200pt_render_frames: per-frame randomUInt / previousFrames
     std::vector<cudaEvent_t> eventPool;
     size_t eventsUsed = 0;
     struct Span { int kind; size_t a, b; };
@@ -173,10 +175,10 @@ enum { KIND_EXTEND = 0, KIND_SHADOW = 1, KIND_SHADE = 2 };
 struct StageTimer {   // records start/stop events around one launch when stage timing is on
     b200pt_ctx *c; int kind; size_t a = 0;
     StageTimer(b200pt_ctx *ctx, int k) : c(ctx), kind(k) {
-        if (c->stageTiming) { a = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); }
+        if (c->timed(kind)) { a = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); }
     }
     ~StageTimer() {
-        if (c->stageTiming) { size_t b = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); c->spans.push_back({kind, a, b}); }
+        if (c->timed(kind)) { size_t b = c->eventsUsed; cudaEventRecord(c->nextEvent(), c->stream); c->spans.push_back({kind, a, b}); }
         c->stats.kernel_launches++;
         if (kind == KIND_EXTEND) c->stats.launches_extend++; else if (kind == KIND_SHADOW) c->stats.launches_shadow++; else c->stats.launches_shade++;
     }
@@ -355,6 +357,9 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->icQueryGrid = c->numSMs * std::max(1, occQuery);
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostIcHdr), ICH_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
+    int occShadeBatch = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occShadeBatch, k_shade<false, false, true>, 128, 0));
+    c->shadeGridBatch = c->numSMs * std::max(1, occShadeBatch);
     c->traceGrid = c->numSMs * std::max(1, occTrace);
     c->shadeGrid = c->numSMs * std::max(1, occShade);
     c->resolveGrid = c->numSMs * std::max(1, occResolve);
@@ -577,8 +582,35 @@ int b200pt_set_camera(b200pt_ctx *c, const float view[16], const float proj[16])
     return B200PT_OK;
 }
 
+// one frame (batchCount <= 1) or a batch of plain frames that differ only in seed and previousFrames (pc = the first)
+static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b200pt_push_constants *batchPcs, int batchCount);
+
 int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     if (!c || !pc) return setError(B200PT_E_INVALID, "b200pt_render_frame: null argument");
+    return renderFrames(c, pc, nullptr, 0);
+}
+
+int b200pt_render_frames(b200pt_ctx *c, const b200pt_push_constants *pcs, int count) {
+    if (!c || !pcs || count < 1) return setError(B200PT_E_INVALID, "b200pt_render_frames: bad argument");
+    // the frame walk needs frames that are independent of each other and identical up to the seed and the frame counter
+    bool walk = count > 1 && count < 65536 && pcs[0].samplesPerPixel < 65536 && !c->aovs && c->hasScene && c->dscene.trace.alpha == nullptr &&
+                !getenv("B200PT_NO_FRAME_WALK");
+    const b200pt_push_constants &a = pcs[0];
+    if (a.useIrradianceCache || a.useADRRS || a.splitOnFirst || a.useGuiding || a.updateGuiding || a.storeEstimate || a.isIrradiancePrepareFrame ||
+        a.visualizeMode != 0 || a.showIrradianceCacheOnly) walk = false;
+    for (int i = 1; walk && i < count; i++) {
+        b200pt_push_constants b = pcs[i];
+        b.randomUInt = a.randomUInt; b.previousFrames = a.previousFrames;
+        if (memcmp(&a, &b, sizeof(b)) != 0) walk = false;
+    }
+    if (!walk) {
+        for (int i = 0; i < count; i++) { const int rc = renderFrames(c, &pcs[i], nullptr, 0); if (rc != B200PT_OK) return rc; }
+        return B200PT_OK;
+    }
+    return renderFrames(c, &pcs[0], pcs, count);
+}
+
+static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b200pt_push_constants *batchPcs, int batchCount) {
     if (!c->hasScene || !c->hasCamera) return setError(B200PT_E_STATE, "b200pt_render_frame: set_scene and set_camera must be called first");
     if (pc->showIrradianceCacheOnly || pc->visualizeMode != 0)
         return setError(B200PT_E_STATE, "b200pt_render_frame: the debug views (visualizeMode, showIrradianceCacheOnly) are not part of this library");
@@ -598,6 +630,19 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     int rc = ensureQueues(c, (pc->enableNEE || useCache ? pc->numNEE : 1) * (splitMode ? 2 : 1));
     if (rc != B200PT_OK) return rc;
     if (icMode) { rc = ensureIC(c, useCache, splitMode); if (rc != B200PT_OK) return rc; }
+    const bool batch = batchCount > 1;
+    c->wf.batch = FrameBatch{};
+    if (batch) {
+        CUDA_TRY(c->pixelSum.alloc(size_t(c->numPixels) * 2));      // one half per frame parity
+        c->wf.pixelSum = c->pixelSum.p;
+        std::vector<uint32_t> seeds(size_t(batchCount), 0u), prevs(size_t(batchCount), 0u);
+        for (int i = 0; i < batchCount; i++) { seeds[size_t(i)] = batchPcs[i].randomUInt; prevs[size_t(i)] = batchPcs[i].previousFrames; }
+        CUDA_TRY(c->batchSeeds.upload(seeds.data(), seeds.size(), c->stream));
+        CUDA_TRY(c->batchPrev.upload(prevs.data(), prevs.size(), c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));                 // the staging vectors go out of scope
+        c->wf.batch.frameSeed = c->batchSeeds.p; c->wf.batch.framePrev = c->batchPrev.p; c->wf.batch.numFrames = batchCount;
+        c->wf.batch.image = c->imgOutput.p; c->wf.batch.accum = c->imgAccum.p;
+    }
     // samples are not collected while splitting: the raygen returns right after resetting them (rgen:1643-1650)
     const bool earlyReturn = pc->updateGuiding && splitMode;
 
@@ -679,14 +724,14 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     }
 
     { StageTimer t(c, KIND_SHADE); k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf); }
-    c->stats.samples += N;
+    c->stats.samples += uint64_t(N) * uint64_t(batch ? batchCount : 1);
     uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     // Wavefront loop.  Every kernel reads its queue sizes from device memory, so iterations are issued back-to-back;
     // the host only peeks at the counters of iteration i-LAG to learn when the queues have drained.
     int cur = 0;
     const uint64_t pathsPerPixel = uint64_t(fp.samplesPerPixel) + (splitMode ? IC_MAX_SPLITS : 0);
-    const uint64_t maxIter = pathsPerPixel * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
+    const uint64_t maxIter = uint64_t(batch ? batchCount : 1) * pathsPerPixel * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
     bool drained = earlyReturn;
     const uint32_t seqBase = c->ringSeq;          // sequence numbers never repeat across frames
     for (uint64_t iter = 0; !drained; iter++) {
@@ -713,6 +758,7 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
             if (guided && icMode) k_shade<true, true><<<c->shadeGridGuidedIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
             else if (icMode) k_shade<false, true><<<c->shadeGridIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
             else if (guided) k_shade<true, false><<<c->shadeGridGuided, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            else if (batch) k_shade<false, false, true><<<c->shadeGridBatch, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
             else k_shade<false, false><<<c->shadeGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
         }
         cur = 1 - cur;
@@ -758,6 +804,10 @@ int b200pt_render_frame(b200pt_ctx *c, const b200pt_push_constants *pc) {
     c->ringSeq = seqBase + uint32_t(maxIter) + 8u;
     if (!earlyReturn) {
         StageTimer t(c, KIND_SHADE);
+        if (batch) {      // the last frame of the batch (every earlier one was folded in by the pixels themselves)
+            fp.pc.previousFrames = batchPcs[batchCount - 1].previousFrames;
+            k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum + ((batchCount - 1) & 1) * size_t(N), c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec);
+        } else
         k_accumulate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf.pixelSum, c->imgOutput.p, c->imgAccum.p, c->imgEstimate.p, c->wf.rec);
     }
     if (useCache && !earlyReturn) {
@@ -877,7 +927,7 @@ int b200pt_stats_reset(b200pt_ctx *c) {
 }
 int b200pt_set_stage_timing(b200pt_ctx *c, int enabled) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_set_stage_timing: null argument");
-    c->stageTiming = enabled != 0;
+    c->stageTiming = enabled < 0 || enabled > 2 ? 1 : enabled;
     return B200PT_OK;
 }
 int b200pt_timer_start(b200pt_ctx *c) {

@@ -28,6 +28,22 @@ enum { DST_EXTEND = 0, DST_SHADOW = 1, DST_VERTICES = 2, DST_ITERATIONS = 3, DST
 
 struct TraceTuning { uint32_t chunk; int refillMin; };
 
+// Frame batch (b200pt_render_frames).  Every pixel runs its samples one after the other, so a frame ends with a long
+// tail of iterations in which only the pixels with long paths are alive (cornell-dielectric: 405 iterations per
+// 16-spp frame, half of them with < 25 % of the paths; ~9 % of the frame time).  In a batch a pixel that has finished
+// frame f starts frame f + 1 at once: it re-seeds with tea(pixel, frameSeed[f + 1]) exactly like k_generate and sums
+// into the other half of the doubled pixelSum buffer (parity = f & 1), because the last light samples of frame f are
+// still in the shadow / probe queues.  Frame f - 1 is folded into the image (accumulatePixel = k_accumulate's
+// arithmetic) when the pixel finishes frame f, the last frame by k_accumulate after the queues have drained — per
+// pixel the same operations in the same order as `count` calls of b200pt_render_frame, so the images are identical.
+struct FrameBatch {
+    const uint32_t *frameSeed;       // pushC.randomUInt of every frame
+    const uint32_t *framePrev;       // pushC.previousFrames of every frame
+    int numFrames;                   // 0 = no batch
+    float4 *image, *accum;
+};
+#define ST_FRAME_SHIFT 16            // sampleIdx word: sample of the frame (low 16 bits) | frame of the batch
+
 struct Wavefront {
     float4 *pathRayO[2];     // xyz origin, w = path id bits
     float4 *pathRayD[2];     // xyz direction
@@ -52,10 +68,12 @@ struct Wavefront {
     GuidingRecord rec;       // sample-recording state (updateGuiding); rec.samples == nullptr when not recording
     ICState ic;              // irradiance cache / ADRRS state (useIrradianceCache / useADRRS / splitOnFirst frames)
     float4 *aov;             // optional per-pixel layer: max depth, depth sum, path count, split count (b200pt_set_aovs)
+    FrameBatch batch;        // b200pt_render_frames: the frames a pixel walks through without waiting for the other pixels
 };
 
 #define ST_ADDNEXT (1u << 24)
 #define ST_FOLLOW  (1u << 25)
+#define ST_ODDFRAME (1u << 26)   // frame batches: the path belongs to an odd frame of the batch
 
 // warp-aggregated queue append: the lanes that are converged at the call share ONE atomic and get consecutive slots
 // (keeps the queues roughly path-ordered and the counter traffic 32x lower than per-thread atomics)
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
     wf.state[p] = ST_ADDNEXT;     // depth 0, addNextDirectLights = addFirstHitLight = true (rgen:995,1676)
     wf.sampleIdx[p] = 0;
     wf.pixelSum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (wf.batch.numFrames) wf.pixelSum[p + fp.numPixels] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (fp.pc.updateGuiding) {           // resetSamplesToInvalid (rgen:1615-1621, :1642-1643) + fresh recording state
         for (int i = 0; i < B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL; i++) wf.rec.samples[p * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL + i].flags = B200PT_INVALID_REGION;
         wf.rec.state[p] = make_int4(0, 0, -1, -1);
@@ -342,6 +361,27 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
     }
 }
 
+// saveResult (rgen:1459-1485): fold one frame's per-pixel sum into the output / accumulation images
+__device__ __forceinline__ void accumulatePixel(const b200pt_push_constants &pc, const int samplesPerPixel, const uint32_t prev, const float4 s,
+                                                float4 *image, float4 *accum, float4 *estimate, const int p) {
+    vec3 result = V3(s.x, s.y, s.z) / float(samplesPerPixel);
+    if (pc.storeEstimate) estimate[p] = make_f4(result, 1.0f);
+    if (pc.visualizeMode != 0) return;   // debug views are out of scope
+    if (pc.enableAverageInsteadOfMix) {
+        if (prev > 0) {
+            vec3 a = make_vec3(accum[p]) + result;
+            image[p] = make_f4(a / float(prev + 1u), 1.0f);
+            accum[p] = make_f4(a, 1.0f);
+        } else {
+            accum[p] = make_f4(result, 1.0f);
+            image[p] = make_f4(result, 1.0f);
+        }
+    } else {
+        if (prev > 0) result = mix(make_vec3(image[p]), result, 1.0f / float(prev + 1u));
+        image[p] = make_f4(result, 1.0f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // shade: one bounce of rgen raytrace() (:1025-1215) for every path in the current queue
 // GUIDE compiles in guided sampling (pc.useGuiding) and sample recording (pc.updateGuiding);
@@ -349,7 +389,8 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 5        // 96 registers, ~200 B of spills: 5 CTAs per SM beat 4 without spills by 5 % (tools/tune_variants.sh)
 #endif
-template <bool GUIDE, bool IC>
+// BATCH compiles in the frame walk of b200pt_render_frames (plain frames only)
+template <bool GUIDE, bool IC, bool BATCH = false>
 __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = wf.counters[CNT_SHADE_N];
@@ -367,6 +408,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
         uint32_t st = wf.state[pid];
         uint32_t depth = st & 0xffffu, followCount = (st >> 16) & 0xffu;
         bool addNext = (st & ST_ADDNEXT) != 0, follow = (st & ST_FOLLOW) != 0;
+        bool oddFrame = BATCH && (st & ST_ODDFRAME) != 0;
+        // where this path's radiance is summed: the pixel, or the pixel in the second half of pixelSum for odd frames of a batch
+        const int sumIdx = oddFrame ? pid + fp.numPixels : pid;
         vec3 add = V3(0.0f);
 
         const b200pt_push_constants &pc = fp.pc;
@@ -462,7 +506,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
                         if (!isMatAlmostDiscrete(mat)) gst.z = -1;
                     }
                     if (useNEE && neeSupported(mat.type))                 // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
-                        neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
+                        neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, BATCH ? sumIdx : pid, saveSamples, gst.y, stack + threadIdx.x);
                 }
             }
 
@@ -501,9 +545,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
         if (!terminated && !(int(depth) <= pc.maxDepth || (follow && int(followCount) <= pc.maxFollowDiscrete))) terminated = true;
 
         if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f || isnan(add.x + add.y + add.z)) {
-            float4 ps = wf.pixelSum[pid];
+            float4 ps = wf.pixelSum[BATCH ? sumIdx : pid];
             ps.x += add.x; ps.y += add.y; ps.z += add.z;
-            wf.pixelSum[pid] = ps;
+            wf.pixelSum[BATCH ? sumIdx : pid] = ps;
             if (saveSamples) {
                 float4 pp = wf.rec.pathSum[pid];
                 pp.x += add.x; pp.y += add.y; pp.z += add.z;
@@ -524,9 +568,24 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
                 wf.aov[pid] = a;
             }
             // next sample of this pixel (rgen:1668-1681): same RNG stream, fresh path state
-            const uint32_t s = wf.sampleIdx[pid] + 1;
+            uint32_t s = wf.sampleIdx[pid] + 1;
+            if (BATCH && int(s & 0xffffu) >= fp.samplesPerPixel) {
+                // frame f of the batch is finished for this pixel (its last light samples are still queued): fold frame
+                // f - 1 into the image, hand its half of pixelSum to frame f + 1 and start that frame like k_generate
+                const uint32_t f = s >> ST_FRAME_SHIFT;
+                const int otherIdx = oddFrame ? pid : pid + fp.numPixels;
+                if (f >= 1u) {
+                    accumulatePixel(pc, fp.samplesPerPixel, wf.batch.framePrev[f - 1u], wf.pixelSum[otherIdx], wf.batch.image, wf.batch.accum, nullptr, pid);
+                    wf.pixelSum[otherIdx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                if (int(f) + 1 < wf.batch.numFrames) {
+                    s = (f + 1u) << ST_FRAME_SHIFT;
+                    seed = tea(uint32_t(pid), wf.batch.frameSeed[f + 1u]);
+                    oddFrame = !oddFrame;
+                }
+            }
             wf.sampleIdx[pid] = s;
-            if (int(s) < fp.samplesPerPixel) {
+            if (int(BATCH ? (s & 0xffffu) : s) < fp.samplesPerPixel) {
                 cameraRay(fp, seed, pid % fp.width, pid / fp.width, outO, outD);
                 T = V3(1.0f);
                 depth = 0; followCount = 0; addNext = true; follow = false;
@@ -565,7 +624,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
         }
         wf.seed[pid] = seed;
         wf.thr[pid] = make_f4(T, 0.0f);
-        wf.state[pid] = (depth & 0xffffu) | ((followCount & 0xffu) << 16) | (addNext ? ST_ADDNEXT : 0u) | (follow ? ST_FOLLOW : 0u);
+        wf.state[pid] = (depth & 0xffffu) | ((followCount & 0xffu) << 16) | (addNext ? ST_ADDNEXT : 0u) | (follow ? ST_FOLLOW : 0u) | (oddFrame ? ST_ODDFRAME : 0u);
     }
     if (pushPath) {
         const uint32_t slot = queuePush(&wf.counters[CNT_PATH0 + (1 - cur)]);
@@ -585,24 +644,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams fp, const float4
         int4 gst = rec.state[p];
         if (gst.w >= 0) { commitSamples(rec, p, gst); rec.state[p] = gst; }
     }
-    const float4 s = pixelSum[p];
-    vec3 result = V3(s.x, s.y, s.z) / float(fp.samplesPerPixel);
-    if (fp.pc.storeEstimate) estimate[p] = make_f4(result, 1.0f);
-    if (fp.pc.visualizeMode != 0) return;   // debug views are out of scope
-    const uint32_t prev = fp.pc.previousFrames;
-    if (fp.pc.enableAverageInsteadOfMix) {
-        if (prev > 0) {
-            vec3 a = make_vec3(accum[p]) + result;
-            image[p] = make_f4(a / float(prev + 1u), 1.0f);
-            accum[p] = make_f4(a, 1.0f);
-        } else {
-            accum[p] = make_f4(result, 1.0f);
-            image[p] = make_f4(result, 1.0f);
-        }
-    } else {
-        if (prev > 0) result = mix(make_vec3(image[p]), result, 1.0f / float(prev + 1u));
-        image[p] = make_f4(result, 1.0f);
-    }
+    accumulatePixel(fp.pc, fp.samplesPerPixel, fp.pc.previousFrames, pixelSum[p], image, accum, estimate, p);
 }
 
 }  // namespace b200pt

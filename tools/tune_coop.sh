@@ -2,7 +2,7 @@
 # Run under gpurun: knobs of the cooperative-triangle trace kernel (refill threshold, chunk, CTAs/SM) and the BVH leaf policy
 mkdir -p gpurun_out; out=gpurun_out/tune_coop.txt; : > $out
 run() { line=$(env "$@" python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-em 2>&1 | tail -1)
-  echo "$* $(echo "$line" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("Mrays/s=%.1f trace_Mrays/s=%.1f trace_ms=%.2f shade_ms=%.2f frame_ms=%.2f dev_ms=%.2f" % (d["value"], d["roofline"]["trace_Mrays_per_s"], d["stage_ms"]["trace"], d["stage_ms"]["shade"], d["stage_ms"]["frame_total"], d["stage_ms"]["device"]))' 2>&1 | tail -1)" >> $out; }
+  echo "$* $(echo "$line" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("Mrays/s=%.1f trace_Mrays/s=%.1f trace_ms=%.2f shade_ms=%.2f frame_ms=%.2f dev_ms=%.2f" % (d["value"], d["roofline"]["trace_Mrays_per_s"], d["stage_ms"]["trace"], d["stage_split"]["shade"], d["stage_ms"]["frame_total"], d["stage_ms"]["device"]))' 2>&1 | tail -1)" >> $out; }
 run X=1
 run B200PT_TRACE_REFILL=4
 run B200PT_TRACE_REFILL=12
