@@ -26,6 +26,7 @@ WIDTH, HEIGHT, SPP = 1280, 720, int(os.environ.get("B200PT_BENCH_SPP", "16"))   
 SCENE = os.path.join(ROOT, "scenes", "cornell-dielectric", "cornell-dielectric.xml")
 SEED = 0xC0FFEE
 BYTES_PER_RAY = 152          # algorithmic wavefront-state bytes per extend/shadow ray
+WORKLOAD = "cornell-dielectric 1280x720 NEE+MIS (power heuristic), maxDepth 30, 16 spp per step, stand-in shell.obj"
 METRIC, UNIT = "Mrays/s (extend+shadow) cornell-dielectric 1280x720 NEE+MIS", "Mrays/s"
 
 
@@ -166,7 +167,7 @@ def run_reference(args, rank, world):
     value = r / t / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "cornell-dielectric 1280x720 NEE+MIS 16 spp/frame (stand-in shell)"},
+            "data": "synthetic", "config": {"workload": WORKLOAD, "spp_per_step": SPP},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%dx%d view of the same scene/camera, %d spp per step, oracle/tracer_oracle.cpp with its own BVH" % (w, h, spp)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -332,7 +333,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cornell-dielectric 1280x720 NEE+MIS (power heuristic), maxDepth 30, 16 spp per step, stand-in shell.obj",
+            "config": {"workload": WORKLOAD,
                        "spp_per_step": SPP, "frames_per_rank": args.steps, "parallelism": "spp-sharded x%d" % world,
                        "frames": "value: the K frames of a rank in one b200pt_render_frames call (pixels walk from frame to frame; images identical to K single calls, tests/test_frame_batch_gpu.py); e2e: one b200pt_render_frame + image read-back per step",
                        "l2": "no flush: the wavefront queues touched per iteration (~230 MB at 921600 paths) exceed the 126 MB L2"},
