@@ -1,4 +1,5 @@
 #include "bvh.h"
+#include <cstdio>
 #include <cstdlib>
 #include <algorithm>
 #include <cmath>
@@ -35,6 +36,58 @@ struct Builder {
     std::vector<Node2> nodes;
     uint32_t maxLeaf = 3;
     float travCost = 0.5f;
+    float nodeCost = 2.0f;         // cost of visiting one 8-wide node, in triangle tests (the collapse below)
+
+    // Collapse of the binary tree into 8-wide nodes by dynamic programming over the SAH cost (Ylitie, Karras, Laine
+    // 2017, section 3.1): cost[n][i-1] = cheapest way to represent the subtree of n as at most i roots, each root a
+    // leaf (<= maxLeaf triangles) or an 8-wide node whose children are again such a forest of the two subtrees.
+    // The greedy "open the largest child" collapse left half of the nodes of cornell-dielectric with two children
+    // (4.0 children per node on average); every node visit costs the same 5 x 128-bit loads and 8 slab tests.
+    std::vector<float> cost;       // 7 per node
+    std::vector<float> costInner, costLeaf;
+    std::vector<uint8_t> splitK;   // 9 per node: roots given to the left subtree when j roots are distributed (j = 2..8)
+    float distribute(int n, int j, int &bestK) const {
+        const int l = nodes[n].left, r = nodes[n].right;
+        float best = std::numeric_limits<float>::infinity(); bestK = 1;
+        for (int k = std::max(1, j - 7); k <= std::min(7, j - 1); k++) {
+            const float c = cost[size_t(l) * 7 + (k - 1)] + cost[size_t(r) * 7 + (j - k - 1)];
+            if (c < best) { best = c; bestK = k; }
+        }
+        return best;
+    }
+    void solve(int n) {
+        const Node2 &nd = nodes[n];
+        const float area = nd.box.halfArea();
+        costLeaf[n] = nd.count <= maxLeaf ? area * float(nd.count) : std::numeric_limits<float>::infinity();
+        if (nd.left < 0) {
+            costInner[n] = std::numeric_limits<float>::infinity();
+            for (int i = 0; i < 7; i++) cost[size_t(n) * 7 + i] = costLeaf[n];
+            return;
+        }
+        solve(nd.left); solve(nd.right);
+        float dist[9];
+        for (int j = 2; j <= 8; j++) { int k; dist[j] = distribute(n, j, k); splitK[size_t(n) * 9 + j] = uint8_t(k); }
+        costInner[n] = dist[8] + area * nodeCost;
+        cost[size_t(n) * 7] = std::min(costLeaf[n], costInner[n]);
+        for (int i = 2; i <= 7; i++) cost[size_t(n) * 7 + (i - 1)] = std::min(dist[i], cost[size_t(n) * 7 + (i - 2)]);
+    }
+    struct Kid { int node; bool leaf; };
+    // the (at most i) roots that represent the subtree of n
+    void collect(int n, int i, std::vector<Kid> &out) const {
+        const Node2 &nd = nodes[n];
+        if (nd.left < 0) { out.push_back({n, true}); return; }
+        if (i == 1) { out.push_back({n, costLeaf[n] <= costInner[n]}); return; }
+        int k; const float d = distribute(n, i, k);
+        if (cost[size_t(n) * 7 + (i - 2)] <= d) { collect(n, i - 1, out); return; }
+        collect(nd.left, k, out); collect(nd.right, i - k, out);
+    }
+    // children of the 8-wide node that n becomes
+    void children(int n, std::vector<Kid> &out) const {
+        const Node2 &nd = nodes[n];
+        if (nd.left < 0) { out.push_back({n, true}); return; }
+        const int k = splitK[size_t(n) * 9 + 8];
+        collect(nd.left, k, out); collect(nd.right, 8 - k, out);
+    }
 
     int build(uint32_t first, uint32_t count) {
         int idx = int(nodes.size());
@@ -128,6 +181,14 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
     }
     b.nodes.reserve(size_t(numTris) * 2);
     int root2 = b.build(0, numTris);
+    if (const char *e = getenv("B200PT_BVH_NODE_COST")) b.nodeCost = float(atof(e));
+    const bool greedy = getenv("B200PT_BVH_GREEDY") != nullptr;
+    std::vector<Builder::Kid> kidList;
+    if (!greedy) {
+        b.cost.assign(b.nodes.size() * 7, 0.0f); b.costInner.assign(b.nodes.size(), 0.0f); b.costLeaf.assign(b.nodes.size(), 0.0f);
+        b.splitK.assign(b.nodes.size() * 9, 0);
+        b.solve(root2);
+    }
 
     struct Work { int node2; uint32_t node8; int depth; };
     std::vector<Work> queue;
@@ -137,22 +198,29 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
         Work w = queue[qi];
         out.maxDepth = std::max(out.maxDepth, w.depth);
         const Node2 &n2 = b.nodes[w.node2];
-        // gather up to 8 children by repeatedly opening the inner child with the largest area
-        int kids[8]; int nk = 0;
-        if (n2.left < 0) kids[nk++] = w.node2;   // the whole (sub)tree is a single leaf
-        else { kids[nk++] = n2.left; kids[nk++] = n2.right; }
-        for (;;) {
-            if (nk == 8) break;
-            int best = -1; float bestArea = -1;
-            for (int k = 0; k < nk; k++) {
-                const Node2 &c = b.nodes[kids[k]];
-                if (c.left < 0) continue;
-                float a = c.box.halfArea();
-                if (a > bestArea) { bestArea = a; best = k; }
+        // children of this 8-wide node: the DP's choice (B200PT_BVH_GREEDY=1: open the largest inner child until 8)
+        int kids[8]; bool kidLeaf[8]; int nk = 0;
+        if (!greedy) {
+            kidList.clear();
+            b.children(w.node2, kidList);
+            for (const Builder::Kid &k : kidList) { kids[nk] = k.node; kidLeaf[nk] = k.leaf; nk++; }
+        } else {
+            if (n2.left < 0) kids[nk++] = w.node2;   // the whole (sub)tree is a single leaf
+            else { kids[nk++] = n2.left; kids[nk++] = n2.right; }
+            for (;;) {
+                if (nk == 8) break;
+                int best = -1; float bestArea = -1;
+                for (int k = 0; k < nk; k++) {
+                    const Node2 &c = b.nodes[kids[k]];
+                    if (c.left < 0) continue;
+                    float a = c.box.halfArea();
+                    if (a > bestArea) { bestArea = a; best = k; }
+                }
+                if (best < 0) break;
+                const Node2 &c = b.nodes[kids[best]];
+                kids[best] = c.left; kids[nk++] = c.right;
             }
-            if (best < 0) break;
-            const Node2 &c = b.nodes[kids[best]];
-            kids[best] = c.left; kids[nk++] = c.right;
+            for (int k = 0; k < nk; k++) kidLeaf[k] = b.nodes[kids[k]].left < 0;
         }
         // slot assignment: greedy matching of children to octant directions (slot bit set = high side of the axis)
         float nc[3];
@@ -177,9 +245,9 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
                 for (int s = 0; s < 8; s++) if (!slotUsed[s] && cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
             kidDone[bk] = true; slotUsed[bs] = true; slotOf[bk] = bs;
         }
-        int kidInSlot[8];
-        for (int s = 0; s < 8; s++) kidInSlot[s] = -1;
-        for (int k = 0; k < nk; k++) kidInSlot[slotOf[k]] = kids[k];
+        int kidInSlot[8]; bool leafInSlot[8];
+        for (int s = 0; s < 8; s++) { kidInSlot[s] = -1; leafInSlot[s] = false; }
+        for (int k = 0; k < nk; k++) { kidInSlot[slotOf[k]] = kids[k]; leafInSlot[slotOf[k]] = kidLeaf[k]; }
 
         Bvh8Node n; memset(&n, 0, sizeof(n));
         for (int a = 0; a < 3; a++) {
@@ -205,7 +273,7 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
                 n.qlo[a][s] = uint8_t(std::max(0.0, std::min(255.0, lo)));
                 n.qhi[a][s] = uint8_t(std::max(0.0, std::min(255.0, hi)));
             }
-            if (c.left >= 0) {
+            if (!leafInSlot[s]) {
                 n.imask |= uint8_t(1u << s);
                 n.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
                 out.nodes.emplace_back();
@@ -225,6 +293,24 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
             }
         }
         out.nodes[w.node8] = n;
+    }
+    if (getenv("B200PT_BVH_STATS")) {     // tuning aid: fill of the 8-wide nodes and the SAH cost of the collapsed tree
+        size_t inner = 0, leafKids = 0, leafTris = 0, hist[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (const Bvh8Node &n : out.nodes) {
+            int kids = 0;
+            for (int s = 0; s < 8; s++) {
+                if (n.meta[s] == 0) continue;
+                kids++;
+                if (n.imask & (1u << s)) inner++;
+                else { leafKids++; uint32_t u = n.meta[s] >> 5; leafTris += u == 1 ? 1 : u == 3 ? 2 : 3; }
+            }
+            hist[kids]++;
+        }
+        fprintf(stderr, "[bvh8] tris %u nodes %zu depth %d inner children %zu leaf children %zu (%.2f tris each) children/node %.2f  hist",
+                numTris, out.nodes.size(), out.maxDepth, inner, leafKids, leafKids ? double(leafTris) / leafKids : 0.0,
+                double(inner + leafKids) / out.nodes.size());
+        for (int k = 1; k <= 8; k++) fprintf(stderr, " %d:%zu", k, hist[k]);
+        fprintf(stderr, "\n");
     }
 }
 
