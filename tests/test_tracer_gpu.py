@@ -13,7 +13,7 @@ MISS = 0xFFFFFFFF
 NT = os.cpu_count() or 1
 
 
-@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML", "test-scene", "envSynthetic", "envMap", "testSpheres"])
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong", "sponzaXML", "test-scene", "envSynthetic", "envMap", "testSpheres", "stackedCards"])
 def test_closest_hit_bit_exact(scene_name):
     w, h = 256, 144
     scene, r, o = helpers.make_pair(scene_name, w, h, accel=True)
@@ -43,7 +43,7 @@ def test_closest_hit_vs_pure_brute_force_subset():
     assert np.array_equal(g["t"][hit], c["t"][hit])
 
 
-@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS"])
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "stackedCards"])
 def test_any_hit_matches_oracle(scene_name):
     w, h = 256, 144
     scene, r, o = helpers.make_pair(scene_name, w, h)
@@ -241,3 +241,19 @@ def test_converges_to_reference_image():
     assert abs(img.mean() - gold.mean()) < 0.05 * gold.mean()
     rel = ((img - gold) ** 2 / (gold ** 2 + 1e-2)).mean()
     assert rel < 0.05
+
+
+def test_tie_in_t_resolves_to_lowest_primitive_id():
+    """stackedCards: 150 coincident quads (a 300-way tie in t on every hit) — the closest-hit rule is the lexicographic
+    minimum of (t, primitive id), whatever order the warp's pooled triangle tests finish in; every node visit hands a ray
+    24 leaf triangles, so a warp's candidate list (768) needs several rounds of the cooperative triangle phase."""
+    w, h = 192, 108
+    scene, r, o = helpers.make_pair("stackedCards", w, h)
+    prim = helpers.camera_rays(scene, w, h, seed=5)
+    g = r.trace_rays(prim)
+    stack = g["prim"] < 300
+    assert stack.mean() > 0.15 and set(np.unique(g["prim"][stack])) <= {0, 1}
+    c = o.trace_rays(prim, threads=NT)
+    assert np.array_equal(g["prim"], c["prim"])
+    for f in ("t", "u", "v"):
+        assert np.array_equal(g[f][stack].view(np.uint32), c[f][stack].view(np.uint32)), f
