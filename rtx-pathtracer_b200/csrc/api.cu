@@ -455,6 +455,8 @@ int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
             int m = inst.modelIndex;
             if (m < 0 || m >= s->num_models) return setError(B200PT_E_INVALID, "b200pt_set_scene: instance model index out of range");
             int nt = s->num_indices[m] / 3;
+            bool identity = true;
+            for (int k = 0; k < 16; k++) identity = identity && inst.transform[k] == (k % 5 == 0 ? 1.0f : 0.0f) && inst.normalTransform[k] == (k % 5 == 0 ? 1.0f : 0.0f);
             for (int t = 0; t < nt; t++) {
                 int4 pv;
                 int *pvp = &pv.x;
@@ -465,7 +467,7 @@ int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
                     world.insert(world.end(), w, w + 3);
                     pvp[k] = vOff[m] + int(li);
                 }
-                pv.w = i;
+                pv.w = int(uint32_t(i) | (identity ? PT_INSTANCE_IDENTITY : 0u));
                 primVerts.push_back(pv);
             }
         }
@@ -513,7 +515,14 @@ int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
         CUDA_TRY(c->modelIndexOffset.upload(iOff.data(), iOff.size(), st));
         CUDA_TRY(c->primVerts.upload(primVerts.data(), primVerts.size(), st));
         CUDA_TRY(c->materials.upload(s->materials, size_t(s->num_materials), st));
-        CUDA_TRY(c->instances.upload(s->instances, size_t(s->num_instances), st));
+        // device copy of the instance records: the std140 padding word carries "both matrices are exactly the identity"
+        std::vector<b200pt_instance> devInstances(s->instances, s->instances + s->num_instances);
+        for (b200pt_instance &di : devInstances) {
+            bool identity = true;
+            for (int k = 0; k < 16; k++) identity = identity && di.transform[k] == (k % 5 == 0 ? 1.0f : 0.0f) && di.normalTransform[k] == (k % 5 == 0 ? 1.0f : 0.0f);
+            di._pad[0] = identity ? 1 : 0;
+        }
+        CUDA_TRY(c->instances.upload(devInstances.data(), devInstances.size(), st));
         CUDA_TRY(c->lights.upload(s->lights, size_t(s->num_lights), st));
         CUDA_TRY(c->randomLightIndex.upload(s->random_light_index, B200PT_SIZE_LIGHT_RANDOM, st));
         CUDA_TRY(c->randomTriIndex.upload(s->random_tri_index, size_t(std::max(1, s->num_face_tables)) * B200PT_SIZE_TRI_RANDOM, st));
