@@ -364,15 +364,18 @@ __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &
 #define PT_COOP 1
 #endif
 #ifndef PT_COOP_CAP
-#define PT_COOP_CAP 128       // work-list entries per warp and round (a warp can produce up to 32 x 24)
+#define PT_COOP_CAP 128       // work-list entries per warp and round (a warp can produce up to 32 x 24 per node step)
+#endif
+#ifndef PT_COOP_STEPS
+#define PT_COOP_STEPS 2       // node steps per pooled triangle phase, 1..4 (more: fewer phases, but `best` shrinks later)
 #endif
 struct CoopSmem {
     float4 rayO[PT_TRACE_BLOCK];                 // origin, tmin of the lane's current ray
     float4 rayD[PT_TRACE_BLOCK];                 // direction
     unsigned long long key[PT_TRACE_BLOCK];      // best (t, id) of the lane's ray during a triangle phase
     float2 uv[PT_TRACE_BLOCK];
-    uint32_t base[PT_TRACE_BLOCK];               // first packed triangle of the lane's triangle group
-    uint16_t items[PT_TRACE_BLOCK / 32][PT_COOP_CAP];   // owner lane << 5 | triangle offset
+    uint32_t base[PT_COOP_STEPS][PT_TRACE_BLOCK];   // first packed triangle of the lane's triangle group(s)
+    uint16_t items[PT_TRACE_BLOCK / 32][PT_COOP_CAP];   // (owner lane << 2 | group) << 5 | triangle offset (one step: lane << 5 | offset)
 };
 
 // order-preserving map float -> uint32 (and back); -0 is folded onto +0 first
@@ -384,22 +387,28 @@ __device__ __forceinline__ float fromOrderedBits(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
 
-// must be called by all 32 lanes; `triGroup.y` = 0 for lanes that bring no triangles
+// must be called by all 32 lanes; `tg[g].y` = 0 for lanes that bring no triangles in group g
 template <int ALPHA>
-__device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, const uint2 triGroup, CoopSmem &sm, const unsigned lane, const unsigned tid) {
-    uint32_t bits = triGroup.y;
-    if (!__any_sync(0xffffffffu, bits != 0u)) return;
+__device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, const uint2 (&tg)[PT_COOP_STEPS], CoopSmem &sm, const unsigned lane, const unsigned tid) {
+    uint32_t bits[PT_COOP_STEPS];
+    uint32_t anyBits = 0u;
+#pragma unroll
+    for (int g = 0; g < PT_COOP_STEPS; g++) { bits[g] = tg[g].y; anyBits |= bits[g]; }
+    if (!__any_sync(0xffffffffu, anyBits != 0u)) return;
     const unsigned wl = tid & ~31u, warp = tid >> 5;
-    const bool mine = bits != 0u;
+    const bool mine = anyBits != 0u;
     unsigned long long initKey = 0ull;
     if (mine) {
         initKey = ((unsigned long long)orderedBits(s.best) << 32) | (s.hit.prim == PT_MISS ? 0u : s.hit.prim);
         sm.key[tid] = initKey;
-        sm.base[tid] = triGroup.x;
+#pragma unroll
+        for (int g = 0; g < PT_COOP_STEPS; g++) sm.base[g][tid] = tg[g].x;
     }
     volatile unsigned long long *vkey = sm.key;
     for (;;) {
-        const uint32_t cnt = __popc(bits);
+        uint32_t cnt = 0u;
+#pragma unroll
+        for (int g = 0; g < PT_COOP_STEPS; g++) cnt += __popc(bits[g]);
         uint32_t incl = cnt;
 #pragma unroll
         for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -408,10 +417,24 @@ __device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, con
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t pos = incl - cnt;
-        while (bits && pos < PT_COOP_CAP) {
-            const uint32_t ti = uint32_t(__ffs(bits) - 1);
-            bits &= bits - 1u;
-            sm.items[warp][pos++] = uint16_t((lane << 5) | ti);
+        if (PT_COOP_STEPS == 1) {
+            while (bits[0] && pos < PT_COOP_CAP) {
+                const uint32_t ti = uint32_t(__ffs(bits[0]) - 1);
+                bits[0] &= bits[0] - 1u;
+                sm.items[warp][pos++] = uint16_t((lane << 5) | ti);
+            }
+        } else {
+            while (pos < PT_COOP_CAP) {
+                uint32_t g = 0u, b = bits[0];
+#pragma unroll
+                for (int k = 1; k < PT_COOP_STEPS; k++) if (b == 0u) { g = uint32_t(k); b = bits[k]; }
+                if (b == 0u) break;
+                const uint32_t ti = uint32_t(__ffs(b) - 1);
+                b &= b - 1u;
+#pragma unroll
+                for (int k = 0; k < PT_COOP_STEPS; k++) if (g == uint32_t(k)) bits[k] = b;
+                sm.items[warp][pos++] = uint16_t((((lane << 2) | g) << 5) | ti);
+            }
         }
         __syncwarp();
         const uint32_t n = min(total, uint32_t(PT_COOP_CAP));
@@ -423,9 +446,10 @@ __device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, con
             uint32_t ol = 0u;
             if (i < n) {
                 const uint32_t it = sm.items[warp][i];
-                ol = wl + (it >> 5);
+                uint32_t tb;
+                if (PT_COOP_STEPS == 1) { ol = wl + (it >> 5); tb = (sm.base[0][ol] + (it & 31u)) * 3u; }
+                else { ol = wl + (it >> 7); tb = (sm.base[(it >> 5) & 3u][ol] + (it & 31u)) * 3u; }
                 const float4 ro = sm.rayO[ol], rd = sm.rayD[ol];
-                const uint32_t tb = (sm.base[ol] + (it & 31u)) * 3u;
                 const float4 a = __ldg(&sc.tris[tb + 0]);
                 const float4 b = __ldg(&sc.tris[tb + 1]);
                 const float4 c = __ldg(&sc.tris[tb + 2]);
@@ -494,24 +518,30 @@ __device__ __forceinline__ void tracePersistentCoop(const TraceScene &sc, const 
             }
             wBase = min(wEnd, wBase + uint32_t(__popc(idle)));
         }
-        uint2 cur = make_uint2(0u, 0u), triGroup = make_uint2(0u, 0u);
-        if (active) {
-            cur = s.cur;
-            travNode(s, sc, cur, triGroup, smemStack, localStack, stride);
-        }
-        coopTriangles<ALPHA>(s, sc, triGroup, sm, lane, tid);
-        if (active) {
-            bool done = any && s.hit.prim != PT_MISS;
-            if (!done && (cur.y & 0xff000000u) == 0u) {
-                if (s.sp == 0) done = true;
-                else {
-                    s.sp--;
-                    if (s.sp < PT_STACK_SMEM) cur = smemStack[s.sp * stride];
-                    else cur = localStack[s.sp - PT_STACK_SMEM];
+        // PT_COOP_STEPS node steps (each followed by its stack pop), then one pooled triangle phase for the warp
+        uint2 tg[PT_COOP_STEPS];
+        bool stackEmpty = false;
+        uint2 cur = make_uint2(0u, 0u);
+        if (active) cur = s.cur;
+#pragma unroll
+        for (int g = 0; g < PT_COOP_STEPS; g++) {
+            tg[g] = make_uint2(0u, 0u);
+            if (active && !stackEmpty) {
+                travNode(s, sc, cur, tg[g], smemStack, localStack, stride);
+                if ((cur.y & 0xff000000u) == 0u) {
+                    if (s.sp == 0) stackEmpty = true;
+                    else {
+                        s.sp--;
+                        if (s.sp < PT_STACK_SMEM) cur = smemStack[s.sp * stride];
+                        else cur = localStack[s.sp - PT_STACK_SMEM];
+                    }
                 }
             }
+        }
+        coopTriangles<ALPHA>(s, sc, tg, sm, lane, tid);
+        if (active) {
             s.cur = cur;
-            if (done) { io.store(rayIdx, s.hit, any); active = false; }
+            if (stackEmpty || (any && s.hit.prim != PT_MISS)) { io.store(rayIdx, s.hit, any); active = false; }
         }
     }
 }
