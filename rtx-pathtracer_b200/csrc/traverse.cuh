@@ -80,6 +80,33 @@ __device__ __forceinline__ bool intersectSphereExact(const float4 s, const vec3 
 
 __device__ __forceinline__ uint32_t byteOf(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
 
+// Slab arithmetic of the node step: bit-identical variants, measured in profiles/r01e_slab_variants.txt — both lose.
+// ncu names ALU the busiest pipe of k_trace (48.6 %), so the I2F.U8 conversions (conversion pipe) and the scalar FFMAs
+// (FMA pipe) are already off the critical pipe; FFMA2 halves the FMA issue slots but costs registers (28 B of spills at 72).
+//   PT_SLAB_F2  1 = the six fmaf of a child as three packed fma.rn.f32x2 (Blackwell FFMA2): trace -2.4 %
+//   PT_SLAB_CVT 0 = I2F.U8 with byte select, 1 = PRMT into 0x4B0000qq (= 2^23 + q) and an exact FADD of -2^23: trace -4.9 %
+#ifndef PT_SLAB_F2
+#define PT_SLAB_F2 0
+#endif
+#ifndef PT_SLAB_CVT
+#define PT_SLAB_CVT 0
+#endif
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ void ffma2(float &rlo, float &rhi, unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    rlo = __uint_as_float(uint32_t(d)); rhi = __uint_as_float(uint32_t(d >> 32));
+}
+__device__ __forceinline__ float byteToFloat(uint32_t x, int i) {
+#if PT_SLAB_CVT == 1
+    return __fadd_rn(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540u + uint32_t(i))), -8388608.0f);
+#else
+    return float(byteOf(x, i));
+#endif
+}
+
 // raytrace.rahit:22-46 — any-hit shader of the (non-opaque) triangle geometry: a hit on a textured material is ignored
 // when rnd(seed) > alpha, seed = tea(uint(uv.x * 1e8 + rayOrigin.x * t), pushC.randomUInt).  Runs for closest-hit and
 // shadow rays alike.  Out of line: only scenes with a non-opaque texel ever get here.
@@ -187,6 +214,9 @@ __device__ __forceinline__ void travNode(Trav &s, const TraceScene &sc, uint2 &c
     const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
     const float ox = (n0.x - o.x) * s.idx, oy = (n0.y - o.y) * s.idy, oz = (n0.z - o.z) * s.idz;
     const float best = s.best;
+#if PT_SLAB_F2
+    const unsigned long long axy = pack2(ax, ay), oxy = pack2(ox, oy), azz = pack2(az, az), ozz = pack2(oz, oz);
+#endif
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -203,9 +233,16 @@ __device__ __forceinline__ void travNode(Trav &s, const TraceScene &sc, uint2 &c
         const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
-            const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
-            const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
+#if PT_SLAB_F2
+            float t0x, t0y, t1x, t1y, t0z, t1z;
+            ffma2(t0x, t0y, pack2(byteToFloat(xn, j), byteToFloat(yn, j)), axy, oxy);
+            ffma2(t1x, t1y, pack2(byteToFloat(xf, j), byteToFloat(yf, j)), axy, oxy);
+            ffma2(t0z, t1z, pack2(byteToFloat(zn, j), byteToFloat(zf, j)), azz, ozz);
+#else
+            const float t0x = fmaf(byteToFloat(xn, j), ax, ox), t1x = fmaf(byteToFloat(xf, j), ax, ox);
+            const float t0y = fmaf(byteToFloat(yn, j), ay, oy), t1y = fmaf(byteToFloat(yf, j), ay, oy);
+            const float t0z = fmaf(byteToFloat(zn, j), az, oz), t1z = fmaf(byteToFloat(zf, j), az, oz);
+#endif
             const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
             const float tf = fminf(fminf(t1x, t1y), fminf(t1z, best));
             if (tn <= tf) hitmask |= byteOf(childBits4, j) << byteOf(bitIndex4, j);
