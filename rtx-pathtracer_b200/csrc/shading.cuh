@@ -60,7 +60,7 @@ __device__ __forceinline__ vec3 envColor(const DeviceScene &sc, vec3 dir, bool r
     vec3 udir = renormalize ? normalize(dir) : dir;
     float at = atan2f(udir.x, -udir.z);
     float u = at * 1.0f / (2.0f * PT_PI);      // `atan * M_INV_2PI` with the unparenthesised macro
-    float v = acosf(udir.y) / PT_PI;
+    float v = PT_ACOSF(udir.y) / PT_PI;
     float4 c = sampleTexture(sc, 0, u, v);
     return V3(c.x, c.y, c.z);
 }
@@ -137,19 +137,19 @@ __device__ __forceinline__ float fresnelConductor(float cosThetaI, float eta, fl
 __device__ __forceinline__ float beckmannD(const b200pt_material &mat, vec3 n, vec3 m) {   // rgen:179-202
     float cosTheta = dot(n, m);
     if (cosTheta <= 0) return 0.0f;
-    float theta = acosf(cosTheta);
+    float theta = PT_ACOSF(cosTheta);
     if (isnan(theta) || isinf(theta)) theta = 0;
-    float tanTheta = tanf(theta);
+    float tanTheta = PT_TANF(theta);
     if (isnan(tanTheta) || isinf(tanTheta)) tanTheta = 0;
     float alphaSqr = mat.roughness * mat.roughness;
-    return powf(PT_E, -tanTheta * tanTheta / alphaSqr) / (PT_PI * alphaSqr * powf(cosTheta, 4.0f));
+    return PT_POWF(PT_E, -tanTheta * tanTheta / alphaSqr) / (PT_PI * alphaSqr * PT_POWF(cosTheta, 4.0f));
 }
 
 __device__ __forceinline__ float smithG1(const b200pt_material &mat, vec3 n, vec3 m, vec3 v) {   // rgen:204-222 (quirk 1 kept)
     float thetaV = dot(v, n);
     float c = dot(v, m) / thetaV;
     if (c <= 0) return 0;
-    float a = 1.0f / (mat.roughness * tanf(thetaV));
+    float a = 1.0f / (mat.roughness * PT_TANF(thetaV));
     if (a >= 1.6f) return 1.0f;
     float a2 = a * a;
     return (3.535f * a + 2.181f * a2) / (1 + 2.276f * a + 2.577f * a);
@@ -178,7 +178,7 @@ __device__ __forceinline__ vec3 phongBsdf(const DeviceScene &sc, const b200pt_ma
         float dotReflDir = dot(reflect(-wo, normal), wi);
         if (dotReflDir > 0) {
             vec3 ks = V3(mat.specular[0], mat.specular[1], mat.specular[2]);
-            vec3 s = (mat.specularHighlight + 2) / (2 * PT_PI) * ks * powf(dotReflDir, mat.specularHighlight);
+            vec3 s = (mat.specularHighlight + 2) / (2 * PT_PI) * ks * PT_POWF(dotReflDir, mat.specularHighlight);
             if (mat.textureIdSpecular != -1) {
                 float4 t = sampleTexture(sc, mat.textureIdSpecular, u, v);
                 s = s * V3(t.x, t.y, t.z);
@@ -199,7 +199,7 @@ __device__ __forceinline__ vec3 roughConductorBsdf(const b200pt_material &mat, v
     return V3(f);
 }
 
-__device__ __forceinline__ float pdfBSDF(const b200pt_material &mat, vec3 normal, vec3 wi, vec3 wo) {   // rgen:284-332
+PT_NI2 float pdfBSDF(const b200pt_material &mat, vec3 normal, vec3 wi, vec3 wo) {   // rgen:284-332
     switch (mat.type) {
         case B200PT_MAT_ROUGH_CONDUCTOR: {
             vec3 hr = normalize(wi + wo);
@@ -217,7 +217,7 @@ __device__ __forceinline__ float pdfBSDF(const b200pt_material &mat, vec3 normal
             float highlight = mat.specularHighlight;
             float pdf = 0;
             if (dot(reflected, wo) > 0) {
-                pdf = (highlight + 1) * powf(dot(reflected, wo), highlight) / (2 * PT_PI);
+                pdf = (highlight + 1) * PT_POWF(dot(reflected, wo), highlight) / (2 * PT_PI);
                 pdf *= lSpecular / sumSpecDiff;
             }
             pdf += dot(wo, normal) / PT_PI * lDiffuse / sumSpecDiff;
@@ -229,7 +229,7 @@ __device__ __forceinline__ float pdfBSDF(const b200pt_material &mat, vec3 normal
 }
 
 // rgen:483-552. Returns the pdf (or the discrete probability); consumes RNG draws exactly like the shader.
-__device__ __forceinline__ float sampleBSDF(uint32_t &seed, const b200pt_material &mat, vec3 wi, vec3 normal, bool frontFace, vec3 &newDirection) {
+PT_NI2 float sampleBSDF(uint32_t &seed, const b200pt_material &mat, vec3 wi, vec3 normal, bool frontFace, vec3 &newDirection) {
     switch (mat.type) {
         case B200PT_MAT_ROUGH_CONDUCTOR: {
             vec3 worldM = randomBeckmannNormal(seed, mat.roughness, normal);
@@ -269,7 +269,7 @@ __device__ __forceinline__ float sampleBSDF(uint32_t &seed, const b200pt_materia
 }
 
 // rgen:557-599 — returns f * cos(theta_o)
-__device__ __forceinline__ vec3 evalBsdf(const DeviceScene &sc, const b200pt_material &mat, float u, float v, vec3 normal, vec3 wi, vec3 wo, bool frontFace) {
+PT_NI1 vec3 evalBsdf(const DeviceScene &sc, const b200pt_material &mat, float u, float v, vec3 normal, vec3 wi, vec3 wo, bool frontFace) {
     switch (mat.type) {
         case B200PT_MAT_DIFFUSE:
         case B200PT_MAT_LIGHT:
@@ -314,7 +314,7 @@ __device__ __forceinline__ float pdfLight(const b200pt_light &light, vec3 lightD
 }
 
 // rgen:358-473 — picks a light from the pre-drawn table and a point on it; returns the pdf
-__device__ __forceinline__ float sampleLights(const DeviceScene &sc, uint32_t &seed, bool useVisibleSphereSampling, vec3 origin, vec3 normal,
+PT_NI3 float sampleLights(const DeviceScene &sc, uint32_t &seed, bool useVisibleSphereSampling, vec3 origin, vec3 normal,
                                               vec3 &lightDir, vec3 &lightColor, float &lightDistance) {
     int iRandomLight = rndInteger(seed, B200PT_SIZE_LIGHT_RANDOM - 1);
     int iLight = __ldg(&sc.randomLightIndex[iRandomLight]);

@@ -364,6 +364,28 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
     }
 }
 
+// Out-of-line copies for the big shade variants (IC / guided).  Fully inlined, k_shade<0,1> is 40 640 SASS instructions
+// (650 KB; the guided IC variant 55 296) — neeQueued alone is expanded three times, each with its own sampleLights,
+// evalBsdf x2, pdfBSDF, sampleBSDF and the in-line visibility traversal — and ncu attributes 81 % of that kernel's warp
+// stall cycles to "no instruction" (instruction-cache misses; issue slots 9.9 % busy, profiles/r01e_ncu_shade_ic.txt).
+// One shared copy of the three heavy callees keeps the hot code inside the instruction cache.  The plain kernel (15 464
+// instructions, 12 % no-instruction stalls) keeps everything in line: an ABI call costs it more than it saves.
+__device__ __noinline__ void neeQueuedNI(const FrameParams &fp, const DeviceScene &sc, const Wavefront &wf, uint32_t &seed, const b200pt_material &mat,
+                                         const HitInfo &info, vec3 origin, vec3 normal, vec3 wi, vec3 T, int pid, bool saveSamples, int cso, uint2 *stack) {
+    neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, cso, stack);
+}
+template <bool GUIDE>
+__device__ __noinline__ float getNewDirectionNI(const b200pt_push_constants &pc, const GuidingView &guide, uint32_t &seed, const b200pt_material &mat,
+                                                vec3 origin, vec3 normal, vec3 wi, bool frontFace, vec3 &newDirection) {
+    return getNewDirection<GUIDE>(pc, guide, seed, mat, origin, normal, wi, frontFace, newDirection);
+}
+__device__ __noinline__ vec3 evalBsdfNI(const DeviceScene &sc, const b200pt_material &mat, float u, float v, vec3 normal, vec3 wi, vec3 wo, bool frontFace) {
+    return evalBsdf(sc, mat, u, v, normal, wi, wo, frontFace);
+}
+#ifndef PT_SHADE_NI
+#define PT_SHADE_NI 1         // 0: everything in line in every variant (the state before round 1e)
+#endif
+
 // saveResult (rgen:1459-1485): fold one frame's per-pixel sum into the output / accumulation images
 __device__ __forceinline__ void accumulatePixel(const b200pt_push_constants &pc, const int samplesPerPixel, const uint32_t prev, const float4 s,
                                                 float4 *image, float4 *accum, float4 *estimate, const int p) {
@@ -394,8 +416,13 @@ __device__ __forceinline__ void accumulatePixel(const b200pt_push_constants &pc,
 #endif
 // BATCH compiles in the frame walk of b200pt_render_frames (plain frames only)
 template <bool GUIDE, bool IC, bool BATCH = false>
-__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
+__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const __grid_constant__ DeviceScene sc,
+                                                                    const __grid_constant__ Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
+    constexpr bool NI = PT_SHADE_NI && IC;      // heavy callees out of line (see neeQueuedNI); guided-only: one expansion each, nothing to share
+    #define NEE_QUEUED(...) do { if (NI) neeQueuedNI(__VA_ARGS__); else neeQueued(__VA_ARGS__); } while (0)
+    #define GET_NEW_DIRECTION(...) (NI ? getNewDirectionNI<GUIDE>(__VA_ARGS__) : getNewDirection<GUIDE>(__VA_ARGS__))
+    #define EVAL_BSDF(...) (NI ? evalBsdfNI(__VA_ARGS__) : evalBsdf(__VA_ARGS__))
     const uint32_t n = wf.counters[CNT_SHADE_N];
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
     bool pushPath = false;
@@ -488,7 +515,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
                             }
                         } else {
                             add += T * approxDiffuse(sc, mat, normal, wi, info.u, info.v) * irradianceColor;
-                            if (neeSupported(mat.type)) neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
+                            if (neeSupported(mat.type)) NEE_QUEUED(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
                             terminated = true;
                         }
                     } else if (rnd(seed) < pc.irradianceCreateProb) {                  // createIC is true on every path of main()
@@ -509,17 +536,17 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
                         if (!isMatAlmostDiscrete(mat)) gst.z = -1;
                     }
                     if (useNEE && neeSupported(mat.type))                 // multipleNEE, rgen:871-877 / nextEventEstimation :601-731
-                        neeQueued(fp, sc, wf, seed, mat, info, origin, normal, wi, T, BATCH ? sumIdx : pid, saveSamples, gst.y, stack + threadIdx.x);
+                        NEE_QUEUED(fp, sc, wf, seed, mat, info, origin, normal, wi, T, BATCH ? sumIdx : pid, saveSamples, gst.y, stack + threadIdx.x);
                 }
             }
 
             // getNewDirection (rgen:923-960) + throughput update (:1169-1177) + sample recording (:1179-1212)
             if (!terminated) {
                 vec3 newDirection = V3(0.0f);
-                const float pdf = getNewDirection<GUIDE>(pc, wf.guide, seed, mat, origin, normal, wi, info.isFrontFace, newDirection);
+                const float pdf = GET_NEW_DIRECTION(pc, wf.guide, seed, mat, origin, normal, wi, info.isFrontFace, newDirection);
                 if (pdf <= 0.0f) terminated = true;
                 else {
-                    const vec3 change = evalBsdf(sc, mat, info.u, info.v, normal, wi, newDirection, info.isFrontFace) / pdf;
+                    const vec3 change = EVAL_BSDF(sc, mat, info.u, info.v, normal, wi, newDirection, info.isFrontFace) / pdf;
                     T *= change;
                     if (saveSamples && gst.y < B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL) {
                         b200pt_directional_data &sd = wf.rec.samples[sbase + gst.y];
@@ -608,12 +635,12 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
                     const vec3 swi = make_vec3(s2), sT = make_vec3(s3);
                     const b200pt_material smat = sc.materials[sinfo.matIndex];
                     if (useNEE && neeSupported(smat.type))      // the split happened before NEE: do it for the split's origin
-                        neeQueued(fp, sc, wf, seed, smat, sinfo, sinfo.worldPos, sinfo.normal, swi, sT, pid, false, 0, stack + threadIdx.x);
+                        NEE_QUEUED(fp, sc, wf, seed, smat, sinfo, sinfo.worldPos, sinfo.normal, swi, sT, pid, false, 0, stack + threadIdx.x);
                     vec3 newDirection = V3(0.0f);
-                    const float pdf = getNewDirection<GUIDE>(pc, wf.guide, seed, smat, sinfo.worldPos, sinfo.normal, swi, sinfo.isFrontFace, newDirection);
+                    const float pdf = GET_NEW_DIRECTION(pc, wf.guide, seed, smat, sinfo.worldPos, sinfo.normal, swi, sinfo.isFrontFace, newDirection);
                     if (pdf <= 0.0f) iSplit = nextSlot;      // `break`: the remaining splits are dropped
                     else {
-                        T = sT * evalBsdf(sc, smat, sinfo.u, sinfo.v, sinfo.normal, swi, newDirection, sinfo.isFrontFace) / pdf;
+                        T = sT * EVAL_BSDF(sc, smat, sinfo.u, sinfo.v, sinfo.normal, swi, newDirection, sinfo.isFrontFace) / pdf;
                         outO = sinfo.worldPos; outD = newDirection;
                         depth = uint32_t(__float_as_int(s3.w)); followCount = 0; addNext = false; follow = true;
                         pushPath = true;
@@ -635,6 +662,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(FrameParams 
         wf.pathRayD[1 - cur][slot] = make_f4(outD, 0.0f);
     }
   }
+#undef NEE_QUEUED
+#undef GET_NEW_DIRECTION
+#undef EVAL_BSDF
 }
 
 // ---------------------------------------------------------------------------------------------------------------

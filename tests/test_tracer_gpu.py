@@ -243,6 +243,37 @@ def test_converges_to_reference_image():
     assert rel < 0.05
 
 
+@pytest.mark.parametrize("scene_name", ["cornell-dielectric", "veachMIS", "miPhong"])
+def test_converged_4096spp_independent_streams(scene_name):
+    """Level 3 proper (north_star: converged 4096-spp images reach relMSE < 1e-3).  Device and oracle render 4096 spp with
+    INDEPENDENT random streams, so nothing but the expectation can make them agree: relMSE(device, oracle) has to sit
+    at the Monte-Carlo noise floor, measured as relMSE(device, device with other seeds).  cornell-dielectric is the
+    config-2 scene and meets the absolute 1e-3; the rough-conductor / Phong plates of veachMIS and miPhong are noisier
+    at 4096 spp (floor ~1.3e-3 at 64x36), there the bound is relative to the floor (tools/converged_check.py)."""
+    P = helpers.pt()
+    w, h, spp, per = 64, 36, 4096, 64
+    scene, r, o = helpers.make_pair(scene_name, w, h)
+    over = dict(enableNEE=1, enableMIS=1, samplesPerPixel=per)
+
+    def device(seed):
+        for f in range(spp // per):
+            r.render_frame(P.default_push_constants(randomUInt=P.tea(f, seed), previousFrames=f, **over))
+        return r.read_image()[..., :3].astype(np.float64)
+
+    def rel_mse(a, b):
+        return float(((a - b) ** 2 / (b ** 2 + 1e-2)).mean())
+
+    ga, gb = device(0xA11CE), device(0xB0B)
+    for f in range(spp // per):
+        o.render_region(P.default_push_constants(randomUInt=P.tea(f, 0xC0FFEE), previousFrames=f, **over), threads=NT)
+    c = o.image()[..., :3].astype(np.float64)
+    floor, err = rel_mse(ga, gb), rel_mse(ga, c)
+    assert err < 1.6 * floor + 1e-4, (err, floor)
+    assert abs(ga.mean() - c.mean()) < 0.03 * c.mean()
+    if scene_name == "cornell-dielectric":
+        assert err < 1e-3, err
+
+
 def test_tie_in_t_resolves_to_lowest_primitive_id():
     """stackedCards: 150 coincident quads (a 300-way tie in t on every hit) — the closest-hit rule is the lexicographic
     minimum of (t, primitive id), whatever order the warp's pooled triangle tests finish in; every node visit hands a ray
