@@ -122,6 +122,7 @@ struct b200pt_ctx {
     uint32_t *hostRingDev = nullptr;
     uint32_t ringSeq = 0;
     bool counterCopy = false;
+    bool fusePrep = true;         // k_iter_prep folded into k_probe_resolve (B200PT_FUSE_PREP=0: separate launch, for A/B)
     unsigned long long *hostDstats = nullptr;   // pinned, DST_NUM
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
@@ -333,6 +334,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
         CUDA_TRY(cudaHostGetDevicePointer(&dp, hp, 0));
         c->hostRing = static_cast<volatile uint32_t *>(hp); c->hostRingDev = static_cast<uint32_t *>(dp);
         if (const char *e = getenv("B200PT_COUNTER_COPY")) c->counterCopy = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_FUSE_PREP")) c->fusePrep = atoi(e) != 0;
     }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
@@ -756,11 +758,18 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
                 else k_trace<false, 0><<<c->traceGrid, PT_TRACE_BLOCK, 0, st>>>(c->dscene.trace, c->wf, cur, c->tune);
             }
         }
-        if ((pc->enableNEE || useCache) && pc->enableMIS) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
         const int slot = int(iter % b200pt_ctx::RING);
-        if (c->counterCopy) k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, nullptr, 0u);
-        else k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, c->hostRingDev + slot * 8, seqBase + uint32_t(iter) + 1u);
-        c->stats.kernel_launches++;
+        const bool probes = (pc->enableNEE || useCache) && pc->enableMIS;
+        volatile uint32_t *prepSlot = c->counterCopy ? nullptr : c->hostRingDev + slot * 8;
+        const uint32_t prepSeq = c->counterCopy ? 0u : seqBase + uint32_t(iter) + 1u;
+        if (probes && c->fusePrep) {
+            StageTimer t(c, KIND_SHADE);
+            k_probe_resolve_prep<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur, prepSlot, prepSeq);
+        } else {
+            if (probes) { StageTimer t(c, KIND_SHADE); k_probe_resolve<<<c->resolveGrid, 256, 0, st>>>(fp, c->dscene, c->wf); }
+            k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, prepSlot, prepSeq);
+            c->stats.kernel_launches++;
+        }
         if (useCache) { StageTimer t(c, KIND_SHADE); k_ic_query<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur); }
         {
             StageTimer t(c, KIND_SHADE);

@@ -22,6 +22,7 @@ struct FrameParams {
 // queue counters (device).  The host never needs them to size a launch: every stage kernel is persistent / grid-stride
 // and reads its own element count from here, so a frame's iterations are issued back-to-back without host round trips.
 enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_INLINE_SHADOW = 4, CNT_WORK_TRACE = 5, CNT_SHADE_N = 6,
+       CNT_TICKET = 7,      // k_probe_resolve_prep: blocks that have finished (the last one does the iteration bookkeeping)
        CNT_NUM = 8 };
 // 64-bit statistics accumulated on the device by k_iter_prep
 enum { DST_EXTEND = 0, DST_SHADOW = 1, DST_VERTICES = 2, DST_ITERATIONS = 3, DST_NUM = 4 };
@@ -221,8 +222,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MIN_BLOCKS) k_trace_b
 // and reset the counters the shade kernel is about to fill
 // hostSlot (optional): 8 words of mapped pinned host memory — the queue sizes this iteration started with go straight to
 // the host (no copy-engine operation between the kernels of the loop), followed by a sequence number the host polls
-__global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void iterPrep(const Wavefront &wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
     uint32_t *c = wf.counters;
     const uint32_t nPath = c[CNT_PATH0 + cur], nProbe = c[CNT_PROBE], nShadow = c[CNT_SHADOW];
     if (hostSlot) {
@@ -236,6 +236,10 @@ __global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, 
     if (nPath + nProbe + nShadow) wf.dstats[DST_ITERATIONS] += 1;
     c[CNT_SHADE_N] = nPath;
     c[CNT_PATH0 + (1 - cur)] = 0; c[CNT_PROBE] = 0; c[CNT_SHADOW] = 0; c[CNT_INLINE_SHADOW] = 0; c[CNT_WORK_TRACE] = 0;
+}
+__global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    iterPrep(wf, cur, hostSlot, seq);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -277,6 +281,20 @@ __device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const Dev
 __global__ void __launch_bounds__(256) k_probe_resolve(FrameParams fp, DeviceScene sc, Wavefront wf) {
     const uint32_t n = wf.counters[CNT_PROBE];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) probeResolveOne(fp, sc, wf, k);
+}
+// the same with k_iter_prep folded in: the block that finishes last (ticket counter) does the iteration bookkeeping, one
+// launch and one launch gap less per wavefront iteration.  Every block has read CNT_PROBE before it takes its ticket.
+__global__ void __launch_bounds__(256) k_probe_resolve_prep(FrameParams fp, DeviceScene sc, Wavefront wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
+    const uint32_t n = wf.counters[CNT_PROBE];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) probeResolveOne(fp, sc, wf, k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&wf.counters[CNT_TICKET], 1u) == gridDim.x - 1u) {
+            wf.counters[CNT_TICKET] = 0u;
+            iterPrep(wf, cur, hostSlot, seq);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
