@@ -318,7 +318,7 @@ def main():
         traffic = None
         try:
             rd = wr = None
-            for l in open(os.path.join(ROOT, "profiles", "r01c_ncu_trace.txt")):
+            for l in open(os.path.join(ROOT, "profiles", "r01e_ncu_trace.txt")):
                 f = l.split()
                 if l.startswith("dram__bytes_read.sum") and rd is None:
                     rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
