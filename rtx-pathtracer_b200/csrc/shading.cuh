@@ -116,7 +116,7 @@ __device__ __forceinline__ void computeHitInfo(const DeviceScene &sc, const HitR
 }
 
 // --- BSDF kit ------------------------------------------------------------------------------------------------
-PT_NI_M2 float fresnelDielectric(float eta, float cosThetaI) {   // rgen:145-160
+PT_NI_M3 float fresnelDielectric(float eta, float cosThetaI) {   // rgen:145-160
     float sinThetaSqr = eta * eta * (1 - cosThetaI * cosThetaI);
     if (sinThetaSqr > 1.0f) return 1.0f;
     float cosThetaT = sqrtf(1.0f - sinThetaSqr);
@@ -125,7 +125,7 @@ PT_NI_M2 float fresnelDielectric(float eta, float cosThetaI) {   // rgen:145-160
     return (Rs * Rs + Rp * Rp) / 2.0f;
 }
 
-PT_NI_M2 float fresnelConductor(float cosThetaI, float eta, float k) {   // rgen:163-175
+PT_NI_M3 float fresnelConductor(float cosThetaI, float eta, float k) {   // rgen:163-175
     if (cosThetaI < 0.0f) cosThetaI = -cosThetaI;
     float Rs2 = ((eta * eta + k * k) * cosThetaI * cosThetaI - 2 * eta * cosThetaI + 1)
               / ((eta * eta + k * k) * cosThetaI * cosThetaI + 2 * eta * cosThetaI + 1);
