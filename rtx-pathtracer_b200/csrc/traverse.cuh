@@ -406,6 +406,9 @@ __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &
 #ifndef PT_COOP_STEPS
 #define PT_COOP_STEPS 2       // node steps per pooled triangle phase, 1..4 (more: fewer phases, but `best` shrinks later)
 #endif
+#ifndef PT_COOP_LIST
+#define PT_COOP_LIST 0        // work-list construction: 0 = one merged loop over the groups, 1 = one loop per group
+#endif
 struct CoopSmem {
     float4 rayO[PT_TRACE_BLOCK];                 // origin, tmin of the lane's current ray
     float4 rayD[PT_TRACE_BLOCK];                 // direction
@@ -459,6 +462,19 @@ __device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, con
                 const uint32_t ti = uint32_t(__ffs(bits[0]) - 1);
                 bits[0] &= bits[0] - 1u;
                 sm.items[warp][pos++] = uint16_t((lane << 5) | ti);
+            }
+        } else if (PT_COOP_LIST == 1) {
+            // one plain loop per group: half the instructions per entry of the merged loop below
+#pragma unroll
+            for (int g = 0; g < PT_COOP_STEPS; g++) {
+                uint32_t b = bits[g];
+                const uint32_t tag = ((lane << 2) | uint32_t(g)) << 5;
+                while (b && pos < PT_COOP_CAP) {
+                    const uint32_t ti = uint32_t(__ffs(b) - 1);
+                    b &= b - 1u;
+                    sm.items[warp][pos++] = uint16_t(tag | ti);
+                }
+                bits[g] = b;
             }
         } else {
             while (pos < PT_COOP_CAP) {
