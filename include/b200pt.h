@@ -279,6 +279,11 @@ typedef struct b200pt_stats {
     uint64_t launches_guiding;              /* sort + fit kernels launched */
     float ms_guiding_sort;                  /* device time: sort by region + preFit + SoA conversion */
     float ms_guiding_fit;                   /* device time: per-region EM / merge / split / statistics / pack */
+    /* region-sharded refit across ranks (b200pt_guiding_update_all_ranks); single GPU: all_ranks == samples, rest 0 */
+    uint64_t guiding_samples_all_ranks;     /* valid records of all ranks that took part in the updates */
+    uint64_t guiding_bytes_received;        /* sample bytes this rank fetched from its peers' HBM (24 B per record) */
+    float ms_guiding_exchange;              /* device time: barrier + record exchange into region-contiguous order */
+    float ms_guiding_gather;                /* device time: all-gather of the fitted mixtures */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
@@ -422,7 +427,7 @@ int b200pt_load_state(b200pt_ctx *ctx, const char *path);
 /* ---- multi-GPU (ours: the reference is single-GPU) -----------------------------------------------
  * One context per GPU and per process; the image shards by sample index: every rank renders disjoint
  * frames of the full image, the running means are combined with one NCCL all-reduce, and guiding training frames
- * all-gather their DirectionalData buffers so that every rank refits on the identical concatenation.  NCCL is loaded
+ * exchange their compacted DirectionalData so that every region is refitted once, by one rank, on all ranks' records.  NCCL is loaded
  * with dlopen("libnccl.so.2") on first use; B200PT_E_STATE when it is not installed. */
 #define B200PT_COMM_ID_BYTES 128
 int b200pt_comm_unique_id(char id[B200PT_COMM_ID_BYTES]);      /* ncclGetUniqueId: call on one rank, hand the bytes to the others */
@@ -430,10 +435,27 @@ int b200pt_comm_init(b200pt_ctx *ctx, const char id[B200PT_COMM_ID_BYTES], int r
 int b200pt_comm_destroy(b200pt_ctx *ctx);
 /* image `which` of every rank becomes sum_r(frames_r * image_r) / sum_r(frames_r): the mean over all frames of all ranks */
 int b200pt_reduce_image(b200pt_ctx *ctx, int which, int frames_local);
-/* all-gather of the ranks' DirectionalData buffers (rank order) into the context; *total_out = records gathered */
+/* all-gather of the ranks' whole DirectionalData buffers (rank order) into the context; *total_out = records gathered.
+ * Parity hook: the concatenation is what a single-GPU update would see (b200pt_guiding_update_device on it must give the
+ * mixtures of b200pt_guiding_update_all_ranks bit for bit); the product path below never moves INVALID records. */
 int b200pt_allgather_samples(b200pt_ctx *ctx, int64_t *total_out);
-/* b200pt_allgather_samples + b200pt_guiding_update on the gathered records: identical mixtures on every rank, no broadcast */
+/* PathGuiding::update (src/PathGuiding.cpp:276-312) across the ranks of a spp-sharded training run, region-sharded:
+ *   1. every rank sorts + compacts ITS records by region on the device (SampleCollector::getSortedData, :76-131);
+ *   2. the per-region counts are all-gathered (regions x 4 B) and every rank derives the same plan: regions are dealt
+ *      to ranks longest-first by total count, so each rank fits about 1/N of the samples;
+ *   3. the owner of a region collects that region's valid records (24 B each) from the other ranks — one kernel that
+ *      reads the peers' HBM over NVLink through CUDA-IPC mappings and writes them region-contiguous in rank order
+ *      (fallback when IPC is unavailable or B200PT_EXCHANGE=nccl: grouped ncclSend / ncclRecv + the same kernel);
+ *   4. every rank fits only its regions (updateRegion, :350-451);
+ *   5. the fitted mixtures + packed VMM_Thetas are all-gathered (1.8 KB per region).
+ * Result: bit-identical mixtures on every rank, equal to a single-GPU update on the concatenation of the ranks'
+ * buffers in rank order.  Collective: every rank must call it, with the same params and the same buffer size. */
 int b200pt_guiding_update_all_ranks(b200pt_ctx *ctx, const b200pt_guiding_params *params);
+/* same on `n` caller-provided records in device memory per rank (n equal on all ranks; INVALID records allowed) */
+int b200pt_guiding_update_all_ranks_device(b200pt_ctx *ctx, const b200pt_guiding_params *params, const void *samples_device, int64_t n);
+/* 0 = no communicator, 1 = records travel by ncclSend/ncclRecv, 2 = peers' buffers are read directly (CUDA IPC over NVLink);
+ * decided collectively by the first b200pt_guiding_update_all_ranks */
+int b200pt_comm_exchange_mode(b200pt_ctx *ctx);
 
 /* ---- irradiance cache parity hooks (bindings 10,12,13) ---------------------------------------- */
 int b200pt_ic_get(b200pt_ctx *ctx, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n);

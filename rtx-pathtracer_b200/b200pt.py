@@ -128,7 +128,9 @@ class Stats(C.Structure):
                 ("launches_shadow", C.c_uint64), ("launches_shade", C.c_uint64), ("ms_extend", C.c_float), ("ms_shadow", C.c_float),
                 ("ms_shade", C.c_float), ("ms_total", C.c_float),
                 ("guiding_samples", C.c_uint64), ("guiding_em_sample_iterations", C.c_uint64), ("guiding_regions_fit", C.c_uint64),
-                ("launches_guiding", C.c_uint64), ("ms_guiding_sort", C.c_float), ("ms_guiding_fit", C.c_float)]
+                ("launches_guiding", C.c_uint64), ("ms_guiding_sort", C.c_float), ("ms_guiding_fit", C.c_float),
+                ("guiding_samples_all_ranks", C.c_uint64), ("guiding_bytes_received", C.c_uint64), ("ms_guiding_exchange", C.c_float),
+                ("ms_guiding_gather", C.c_float)]
 
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
@@ -159,7 +161,7 @@ EXPORTS = [
     "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
-    "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks",
+    "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_comm_exchange_mode",
     "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
@@ -235,6 +237,8 @@ def lib():
         L.b200pt_reduce_image.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b200pt_allgather_samples.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.b200pt_guiding_update_all_ranks.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
+        L.b200pt_guiding_update_all_ranks_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
+        L.b200pt_comm_exchange_mode.argtypes = [C.c_void_p]
         L.b200pt_app_init.restype = None
         L.b200pt_app_init.argtypes = [C.POINTER(AppState)]
         L.b200pt_app_scene_switched.restype = None
@@ -528,6 +532,14 @@ class Renderer:
     def guiding_update_all_ranks(self, params=None):
         p = params if params is not None else default_guiding_params()
         _check(lib().b200pt_guiding_update_all_ranks(self._h, C.byref(p)))
+
+    def guiding_update_all_ranks_device(self, device_ptr, n, params=None):
+        p = params if params is not None else default_guiding_params()
+        _check(lib().b200pt_guiding_update_all_ranks_device(self._h, C.byref(p), C.c_void_p(device_ptr), n))
+
+    def comm_exchange_mode(self):
+        """0 no communicator, 1 ncclSend/ncclRecv, 2 CUDA-IPC peer reads (decided by the first all-ranks update)"""
+        return lib().b200pt_comm_exchange_mode(self._h)
 
     # irradiance cache
     def ic_get(self):

@@ -12,8 +12,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
-#include <dlfcn.h>
-#include <nccl.h>
+#include "comm.cuh"
 
 using namespace b200pt;
 
@@ -27,32 +26,9 @@ static int setError(int code, const std::string &msg) { g_lastError = msg; retur
             return setError(B200PT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
     } while (0)
 
+namespace b200pt { NcclApi g_nccl; }
+
 namespace {
-// NCCL entry points, resolved at run time so that the library loads on machines without NCCL
-struct NcclApi {
-    void *handle = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-    bool load() {
-        if (handle) return true;
-        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!handle) return false;
-#define B200PT_NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(handle, name)); if (!field) { dlclose(handle); handle = nullptr; return false; }
-        B200PT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") B200PT_NCCL_SYM(CommInitRank, "ncclCommInitRank") B200PT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
-        B200PT_NCCL_SYM(AllReduce, "ncclAllReduce") B200PT_NCCL_SYM(AllGather, "ncclAllGather") B200PT_NCCL_SYM(GroupStart, "ncclGroupStart")
-        B200PT_NCCL_SYM(GroupEnd, "ncclGroupEnd") B200PT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
-#undef B200PT_NCCL_SYM
-        return true;
-    }
-};
-NcclApi g_nccl;
 
 template <typename T>
 struct DevBuf {
@@ -149,8 +125,7 @@ struct b200pt_ctx {
     DevBuf<float4> batchRays, batchHits;
 
     // multi-GPU
-    ncclComm_t comm = nullptr;
-    int commRank = 0, commRanks = 1;
+    RankComm rc;
     DevBuf<float4> commImage;
     DevBuf<float> commCount;
     DevBuf<b200pt_directional_data> commSamples;
@@ -407,7 +382,7 @@ int b200pt_destroy(b200pt_ctx *c) {
     for (auto &e : c->ringEvent) if (e) cudaEventDestroy(e);
     if (c->hostDstats) cudaFreeHost(c->hostDstats);
     if (c->dumpIters) fclose(c->dumpIters);
-    if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
+    if (c->rc.comm && g_nccl.handle) g_nccl.CommDestroy(c->rc.comm);
     c->commImage.release(); c->commCount.release(); c->commSamples.release();
     c->samples.release(); c->hostSamples.release(); c->icData.release(); c->icSpheres.release(); c->icHeader.release();
     c->batchRays.release(); c->batchHits.release();
@@ -1175,18 +1150,22 @@ int b200pt_comm_unique_id(char id[B200PT_COMM_ID_BYTES]) {
 int b200pt_comm_init(b200pt_ctx *c, const char id[B200PT_COMM_ID_BYTES], int rank, int nranks) {
     if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return setError(B200PT_E_INVALID, "b200pt_comm_init: bad argument");
     if (!g_nccl.load()) return setError(B200PT_E_STATE, "b200pt_comm_init: libnccl.so.2 not found");
-    if (c->comm) return setError(B200PT_E_STATE, "b200pt_comm_init: communicator already initialised");
+    if (c->rc.comm) return setError(B200PT_E_STATE, "b200pt_comm_init: communicator already initialised");
     CUDA_TRY(cudaSetDevice(c->device));
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
-    NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
-    c->commRank = rank; c->commRanks = nranks;
+    NCCL_TRY(g_nccl.CommInitRank(&c->rc.comm, nranks, uid, rank));
+    c->rc.rank = rank; c->rc.nranks = nranks;
     return B200PT_OK;
 }
 int b200pt_comm_destroy(b200pt_ctx *c) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_comm_destroy: null argument");
-    if (c->comm) { CUDA_TRY(cudaSetDevice(c->device)); CUDA_TRY(cudaStreamSynchronize(c->stream)); NCCL_TRY(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; }
-    c->commRank = 0; c->commRanks = 1;
+    if (c->rc.comm) {
+        CUDA_TRY(cudaSetDevice(c->device)); CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->guiding.closePeers(); c->guiding.peerTried = false; c->rc.peerMode = false;
+        NCCL_TRY(g_nccl.CommDestroy(c->rc.comm)); c->rc.comm = nullptr;
+    }
+    c->rc.rank = 0; c->rc.nranks = 1;
     return B200PT_OK;
 }
 
@@ -1205,14 +1184,14 @@ extern "C" {
 
 int b200pt_reduce_image(b200pt_ctx *c, int which, int frames_local) {
     if (!c || !imagePtr(c, which) || frames_local < 0) return setError(B200PT_E_INVALID, "b200pt_reduce_image: bad argument");
-    if (!c->comm) return setError(B200PT_E_STATE, "b200pt_reduce_image: b200pt_comm_init must be called first");
+    if (!c->rc.comm) return setError(B200PT_E_STATE, "b200pt_reduce_image: b200pt_comm_init must be called first");
     CUDA_TRY(cudaSetDevice(c->device));
     const int n = c->numPixels;
     CUDA_TRY(c->commImage.alloc(size_t(n))); CUDA_TRY(c->commCount.alloc(1));
     k_comm_scale<<<gridFor(uint64_t(n), 256), 256, 0, c->stream>>>(imagePtr(c, which), c->commImage.p, n, float(frames_local), c->commCount.p);
     NCCL_TRY(g_nccl.GroupStart());
-    NCCL_TRY(g_nccl.AllReduce(c->commImage.p, c->commImage.p, size_t(n) * 4, ncclFloat, ncclSum, c->comm, c->stream));
-    NCCL_TRY(g_nccl.AllReduce(c->commCount.p, c->commCount.p, 1, ncclFloat, ncclSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(c->commImage.p, c->commImage.p, size_t(n) * 4, ncclFloat, ncclSum, c->rc.comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(c->commCount.p, c->commCount.p, 1, ncclFloat, ncclSum, c->rc.comm, c->stream));
     NCCL_TRY(g_nccl.GroupEnd());
     k_comm_normalise<<<gridFor(uint64_t(n), 256), 256, 0, c->stream>>>(c->commImage.p, imagePtr(c, which), n, c->commCount.p);
     c->stats.kernel_launches += 2;
@@ -1222,25 +1201,34 @@ int b200pt_reduce_image(b200pt_ctx *c, int which, int frames_local) {
 }
 int b200pt_allgather_samples(b200pt_ctx *c, int64_t *total_out) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_allgather_samples: null argument");
-    if (!c->comm) return setError(B200PT_E_STATE, "b200pt_allgather_samples: b200pt_comm_init must be called first");
+    if (!c->rc.comm) return setError(B200PT_E_STATE, "b200pt_allgather_samples: b200pt_comm_init must be called first");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t per = size_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL;      // every rank renders the same resolution
-    CUDA_TRY(c->commSamples.alloc(per * size_t(c->commRanks)));
-    NCCL_TRY(g_nccl.AllGather(c->samples.p, c->commSamples.p, per * sizeof(b200pt_directional_data), ncclChar, c->comm, c->stream));
+    CUDA_TRY(c->commSamples.alloc(per * size_t(c->rc.nranks)));
+    NCCL_TRY(g_nccl.AllGather(c->samples.p, c->commSamples.p, per * sizeof(b200pt_directional_data), ncclChar, c->rc.comm, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (total_out) *total_out = int64_t(per * size_t(c->commRanks));
+    if (total_out) *total_out = int64_t(per * size_t(c->rc.nranks));
     return B200PT_OK;
 }
 int b200pt_guiding_update_all_ranks(b200pt_ctx *c, const b200pt_guiding_params *params) {
     if (!c || !params) return setError(B200PT_E_INVALID, "b200pt_guiding_update_all_ranks: null argument");
     if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update_all_ranks: set_scene must be called first");
-    int64_t total = 0;
-    int rc = b200pt_allgather_samples(c, &total);
-    if (rc != B200PT_OK) return rc;
-    rc = c->guiding.update(c->commSamples.p, total, *params, c->stream, &c->stats);
+    if (!c->rc.comm) return setError(B200PT_E_STATE, "b200pt_guiding_update_all_ranks: b200pt_comm_init must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.update(c->samples.p, int64_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL, *params, c->stream, &c->stats, &c->rc);
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_all_ranks: " + c->guiding.error);
     return B200PT_OK;
 }
+int b200pt_guiding_update_all_ranks_device(b200pt_ctx *c, const b200pt_guiding_params *params, const void *samples_device, int64_t n) {
+    if (!c || !params || n < 0 || (n > 0 && !samples_device)) return setError(B200PT_E_INVALID, "b200pt_guiding_update_all_ranks_device: bad argument");
+    if (!c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_guiding_update_all_ranks_device: set_scene must be called first");
+    if (!c->rc.comm) return setError(B200PT_E_STATE, "b200pt_guiding_update_all_ranks_device: b200pt_comm_init must be called first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.update(static_cast<b200pt_directional_data *>(const_cast<void *>(samples_device)), n, *params, c->stream, &c->stats, &c->rc);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_all_ranks_device: " + c->guiding.error);
+    return B200PT_OK;
+}
+int b200pt_comm_exchange_mode(b200pt_ctx *c) { return c && c->rc.comm ? (c->rc.peerMode ? 2 : 1) : 0; }
 
 // ---- irradiance cache parity hooks -------------------------------------------------------------------------------
 int b200pt_ic_get(b200pt_ctx *c, b200pt_cache_header *hdr, b200pt_cache_data *data, b200pt_sphere *spheres, int n) {

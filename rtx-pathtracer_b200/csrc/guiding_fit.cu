@@ -15,6 +15,7 @@
 // (src/Shapes.h:32-53).
 #include "guiding_fit.cuh"
 #include "guiding_math.cuh"
+#include "comm.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 #include <cstring>
@@ -103,41 +104,178 @@ __global__ void __launch_bounds__(256) k_sort_scan_tiles(uint32_t *tileCounts, u
     if (threadIdx.x == 0) regionTotal[r] = running;
 }
 
-// exclusive scan of the region totals -> regionOffset[R + 1]; also the list of non-empty regions for the fit launch
-__global__ void __launch_bounds__(1024) k_sort_scan_regions(const uint32_t *__restrict__ regionTotal, uint32_t R, uint32_t *regionOffset,
-                                                            uint32_t *activeRegions, uint32_t *numActive) {
-    __shared__ uint32_t warpSum[32];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t v = threadIdx.x < R ? regionTotal[threadIdx.x] : 0u;
-    uint32_t incl = v;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += u; }
-    if (lane == 31) warpSum[warp] = incl;
+// ---- plan: who fits which region, and where every record goes -------------------------------------------------------
+// One block.  Input: the per-region counts of every rank (allCounts[s][g]; a single-GPU update is the case N = 1).
+//   * owner[g]: longest-processing-time-first over the regions sorted by total count (ties: lower region id), so every
+//     rank fits about total/N samples whatever the distribution over regions; deterministic, and identical on every
+//     rank because all of them see the same counts.
+//   * every rank sorts its own records by (owner, region): the records for rank d are ONE contiguous slice of its
+//     buffer (srcStart[s][g] = where region g starts in rank s's sorted buffer).
+//   * the owner lays its regions out contiguously, each region as the concatenation of the ranks' records in rank
+//     order (= the order of a single-GPU sort of the concatenated buffers): regionBegin / regionCount, and one copy
+//     segment per (owned region, source rank) for k_pull.
+//   * activeRegions: the owned non-empty regions, LARGEST FIRST, so the longest fits start in the first wave.
+// (replaces SampleCollector::getSortedData's offset computation, src/SampleCollector.cpp:100-126)
+struct GSegment { uint32_t src, srcOff, dstOff, len; };
+struct GPlanSummary {
+    uint32_t numActive, numOwned, numSegments, localValid;
+    unsigned long long ownedSamples, totalSamples;
+    uint32_t sendStart[B200PT_MAX_RANKS + 1];    // slice of rank d inside this rank's sorted buffer
+    uint32_t recvCount[B200PT_MAX_RANKS];        // records of rank s that belong to regions owned here
+    uint32_t stageStart[B200PT_MAX_RANKS];       // NCCL mode: where rank s's slice is staged
+};
+
+__global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allCounts, int N, int me, uint32_t R, uint32_t stride, int peerMode,
+                                               uint32_t *srcStart, uint32_t *regionBegin, uint32_t *regionCount, uint32_t *regionOffset,
+                                               uint32_t *activeRegions, uint32_t *totalAll, uint8_t *ownerOut, GSegment *segments, GPlanSummary *summary) {
+    __shared__ uint32_t total[1024];
+    __shared__ uint16_t order[1024], binOf[1024], regionOfBin[1024];
+    __shared__ uint8_t own[1024];
+    __shared__ uint32_t firstBin[B200PT_MAX_RANKS + 1], sliceStart[B200PT_MAX_RANKS], stageStart[B200PT_MAX_RANKS], recvCount[B200PT_MAX_RANKS];
+    const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    uint32_t v = 0;
+    if (t < R) for (int s = 0; s < N; s++) v += allCounts[size_t(s) * stride + t];
+    total[t] = v;
     __syncthreads();
-    uint32_t before = 0;
-    for (unsigned w = 0; w < warp; w++) before += warpSum[w];
-    if (threadIdx.x < R) regionOffset[threadIdx.x] = before + incl - v;
-    if (threadIdx.x == R - 1) regionOffset[R] = before + incl;
-    // compact the non-empty regions (ascending region id)
-    const unsigned has = __ballot_sync(0xffffffffu, v > 0);
+    if (t < R) {                                   // position in the order (total descending, region id ascending)
+        uint32_t rk = 0;
+        for (uint32_t u = 0; u < R; u++) rk += (total[u] > v) || (total[u] == v && u < t);
+        order[rk] = uint16_t(t);
+        totalAll[t] = v;
+    }
     __syncthreads();
-    if (lane == 0) warpSum[warp] = __popc(has);
+    if (t == 0) {
+        unsigned long long loads[B200PT_MAX_RANKS];
+        for (int d = 0; d < N; d++) loads[d] = 0ull;
+        uint32_t numActive = 0;
+        unsigned long long tot = 0ull;
+        for (uint32_t i = 0; i < R; i++) {
+            const uint32_t g = order[i];
+            if (total[g] == 0u) { own[g] = uint8_t(g % uint32_t(N)); continue; }
+            int d = 0;
+            for (int k = 1; k < N; k++) if (loads[k] < loads[d]) d = k;
+            own[g] = uint8_t(d); loads[d] += total[g]; tot += total[g];
+            if (d == me) activeRegions[numActive++] = g;
+        }
+        summary->numActive = numActive; summary->ownedSamples = loads[me]; summary->totalSamples = tot;
+    }
     __syncthreads();
-    uint32_t pos = 0;
-    for (unsigned w = 0; w < warp; w++) pos += warpSum[w];
-    if (v > 0) activeRegions[pos + __popc(has & ((1u << lane) - 1u))] = threadIdx.x;
-    if (threadIdx.x == 1023) { uint32_t tot = 0; for (int w = 0; w < 32; w++) tot += warpSum[w]; *numActive = tot; }
+    if (t < R) {                                   // bins: regions ordered by (owner, region id)
+        uint32_t b = 0;
+        for (uint32_t u = 0; u < R; u++) b += (own[u] < own[t]) || (own[u] == own[t] && u < t);
+        binOf[t] = uint16_t(b); regionOfBin[b] = uint16_t(t);
+        ownerOut[t] = own[t];
+        regionCount[t] = own[t] == me ? total[t] : 0u;
+    }
+    if (t <= unsigned(N)) { uint32_t c = 0; for (uint32_t u = 0; u < R; u++) c += own[u] < t; firstBin[t] = c; }
+    __syncthreads();
+    for (int s = int(warp); s < N; s += 32) {      // every rank's sorted layout: exclusive scan of its counts over the bins
+        uint32_t run = 0;
+        for (uint32_t base = 0; base < R; base += 32) {
+            const uint32_t b = base + lane;
+            const uint32_t g = b < R ? regionOfBin[b] : 0u;
+            const uint32_t c = b < R ? allCounts[size_t(s) * stride + g] : 0u;
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += u; }
+            if (b < R) srcStart[size_t(s) * stride + g] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (s == me && lane == 0) summary->localValid = run;
+    }
+    if (t >= 32u * 16u && t < 32u * 16u + unsigned(N)) {        // my slice inside rank s's buffer
+        const int s = int(t) - 32 * 16;
+        uint32_t before = 0, mine = 0;
+        for (uint32_t g = 0; g < R; g++) { const uint32_t c = allCounts[size_t(s) * stride + g]; before += own[g] < me ? c : 0u; mine += own[g] == me ? c : 0u; }
+        sliceStart[s] = before; recvCount[s] = mine; summary->recvCount[s] = mine;
+    }
+    if (t >= 32u * 17u && t <= 32u * 17u + unsigned(N)) {       // rank d's slice inside my buffer
+        const unsigned d = t - 32u * 17u;
+        uint32_t before = 0;
+        for (uint32_t g = 0; g < R; g++) before += own[g] < d ? allCounts[size_t(me) * stride + g] : 0u;
+        summary->sendStart[d] = before;
+    }
+    if (warp == 18) {                              // my fit layout: owned regions in bin order, each one contiguous
+        uint32_t run = 0;
+        for (uint32_t base = firstBin[me]; base < firstBin[me + 1]; base += 32) {
+            const uint32_t b = base + lane;
+            const bool in = b < firstBin[me + 1];
+            const uint32_t g = in ? regionOfBin[b] : 0u;
+            const uint32_t c = in ? total[g] : 0u;
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += u; }
+            if (in) regionBegin[g] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t run = 0;
+        for (int s = 0; s < N; s++) { stageStart[s] = run; summary->stageStart[s] = run; if (s != me) run += recvCount[s]; }
+        summary->numOwned = firstBin[me + 1] - firstBin[me];
+        summary->numSegments = (firstBin[me + 1] - firstBin[me]) * uint32_t(N);
+    }
+    __syncthreads();
+    if (t < R && own[t] == me) {
+        const uint32_t idx = binOf[t] - firstBin[me];
+        uint32_t dst = regionBegin[t];
+        for (int s = 0; s < N; s++) {
+            const uint32_t len = allCounts[size_t(s) * stride + t];
+            uint32_t off = srcStart[size_t(s) * stride + t];
+            if (!peerMode && s != me) off = stageStart[s] + (off - sliceStart[s]);
+            segments[size_t(idx) * N + s] = GSegment{uint32_t(s), off, dst, len};
+            dst += len;
+        }
+    }
+    if (N == 1) {                                  // region-order offsets of the sorted buffer (parity hook b200pt_guiding_get_sorted)
+        if (t < R) regionOffset[t] = regionBegin[t];
+        if (t == 0) regionOffset[R] = uint32_t(summary->totalSamples);
+    }
+}
+
+// the exchange: every block copies (part of) one segment — the records of one owned region that rank `src` holds — from
+// that rank's sorted buffer (a CUDA-IPC mapping of its HBM, read over NVLink; or the local staging buffer in NCCL mode)
+// to the region's place in the fit buffer.  Four independent 16-byte + 8-byte loads in flight per thread.
+struct GPeerPtrs { const float4 *dirw[B200PT_MAX_RANKS]; const float2 *pd[B200PT_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) k_pull(const GSegment *__restrict__ segs, GPeerPtrs peers, float4 *__restrict__ dstDirw, float2 *__restrict__ dstPd) {
+    const GSegment sg = segs[blockIdx.x];
+    const float4 *__restrict__ sd = peers.dirw[sg.src] + sg.srcOff;
+    const float2 *__restrict__ sp = peers.pd[sg.src] + sg.srcOff;
+    float4 *dd = dstDirw + sg.dstOff;
+    float2 *dp = dstPd + sg.dstOff;
+    const uint32_t step = gridDim.y * 256u;
+    uint32_t i = blockIdx.y * 256u + threadIdx.x;
+    for (; i + 3u * step < sg.len; i += 4u * step) {
+        const float4 a0 = sd[i], a1 = sd[i + step], a2 = sd[i + 2u * step], a3 = sd[i + 3u * step];
+        const float2 b0 = sp[i], b1 = sp[i + step], b2 = sp[i + 2u * step], b3 = sp[i + 3u * step];
+        dd[i] = a0; dd[i + step] = a1; dd[i + 2u * step] = a2; dd[i + 3u * step] = a3;
+        dp[i] = b0; dp[i + step] = b1; dp[i + 2u * step] = b2; dp[i + 3u * step] = b3;
+    }
+    for (; i < sg.len; i += step) { dd[i] = sd[i]; dp[i] = sp[i]; }
+}
+
+// after the fit: every rank holds all ranks' mixture arrays (all-gather); a region that received samples takes its
+// owner's result
+__global__ void __launch_bounds__(128) k_pick_results(GMix *mixes, b200pt_vmm_theta *vmms, const GMix *__restrict__ gatherMix,
+                                                       const b200pt_vmm_theta *__restrict__ gatherVmm, const uint8_t *__restrict__ owner,
+                                                       const uint32_t *__restrict__ totalAll, uint32_t stride, int me) {
+    const uint32_t g = blockIdx.x;
+    if (totalAll[g] == 0u || owner[g] == me) return;
+    const uint32_t *ms = reinterpret_cast<const uint32_t *>(gatherMix + size_t(owner[g]) * stride + g); uint32_t *md = reinterpret_cast<uint32_t *>(mixes + g);
+    for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += blockDim.x) md[i] = ms[i];
+    const uint32_t *vs = reinterpret_cast<const uint32_t *>(gatherVmm + size_t(owner[g]) * stride + g); uint32_t *vd = reinterpret_cast<uint32_t *>(vmms + g);
+    for (uint32_t i = threadIdx.x; i < sizeof(b200pt_vmm_theta) / 4; i += blockDim.x) vd[i] = vs[i];
 }
 
 __global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_scatter(const b200pt_directional_data *__restrict__ recs, uint64_t n, uint32_t R,
                                                                   const uint32_t *__restrict__ tileOffsets, uint32_t numTiles,
-                                                                  const uint32_t *__restrict__ regionOffset, const b200pt_aabb *__restrict__ aabbs,
+                                                                  const uint32_t *__restrict__ regionStart, const b200pt_aabb *__restrict__ aabbs,
                                                                   int parallax, float4 *__restrict__ dirw, float2 *__restrict__ pdfDist,
                                                                   uint32_t *__restrict__ srcIndex) {
     extern __shared__ uint32_t hist[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x * SORT_WARPS + warp;
     uint32_t *h = hist + warp * R;
-    if (tile < numTiles) for (uint32_t i = lane; i < R; i += 32) h[i] = regionOffset[i] + tileOffsets[uint64_t(tile) * R + i];
+    if (tile < numTiles) for (uint32_t i = lane; i < R; i += 32) h[i] = regionStart[i] + tileOffsets[uint64_t(tile) * R + i];
     __syncwarp();
     if (tile >= numTiles) return;
     const uint64_t begin = uint64_t(tile) * SORT_TILE;
@@ -351,15 +489,17 @@ struct BlockExec {
 };
 
 __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
-                                                              const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ regionOffset,
+                                                              const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ numActive,
+                                                              const uint32_t *__restrict__ regionBegin, const uint32_t *__restrict__ regionCount,
                                                               const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist,
                                                               b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
     __shared__ BlockShared sh;
     const long long t0 = clock64();
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t csize = cluster.num_blocks(), crank = cluster.block_rank();
+    if (blockIdx.x / csize >= *numActive) return;      // the grid is sized for every region; the whole cluster leaves together
     const uint32_t region = activeRegions[blockIdx.x / csize];
-    const uint32_t begin = regionOffset[region], end = regionOffset[region + 1];
+    const uint32_t begin = regionBegin[region], end = begin + regionCount[region];
     {   // mixture -> shared
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&mixes[region]);
         uint32_t *dstw = reinterpret_cast<uint32_t *>(&sh.mix);
@@ -474,6 +614,17 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
     G_TRY(cudaMemsetAsync(spawnFirst, 0xff, size_t(maxRegions) * sizeof(int32_t), stream));
     G_TRY(cudaMemsetAsync(spawnNext, 0xff, size_t(maxRegions) * sizeof(int32_t), stream));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&activeRegions), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionBegin), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionLen), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&totalAll), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&owner), size_t(maxRegions)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&planDev), sizeof(GPlanSummary)));
+    G_TRY(cudaMemsetAsync(planDev, 0, sizeof(GPlanSummary), stream));
+    G_TRY(cudaMallocHost(reinterpret_cast<void **>(&planHost), sizeof(GPlanSummary)));
+    memset(planHost, 0, sizeof(GPlanSummary));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&barrierWord), sizeof(float)));
+    G_TRY(cudaMemsetAsync(barrierWord, 0, sizeof(float), stream));
+    for (auto &e : ev) G_TRY(cudaEventCreate(&e));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&devScalars), 4 * sizeof(unsigned long long)));
     G_TRY(cudaMallocHost(reinterpret_cast<void **>(&hostScalars), 4 * sizeof(unsigned long long)));
     G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
@@ -514,50 +665,203 @@ int GuidingState::ensureCapacity(int64_t numSamples) {
     return B200PT_OK;
 }
 
+int GuidingState::ensurePlan(int ranks) {
+    if (ranks <= planRanks) return B200PT_OK;
+    if (allCounts) cudaFree(allCounts);
+    if (srcStart) cudaFree(srcStart);
+    if (segments) cudaFree(segments);
+    if (gatherMix) cudaFree(gatherMix);
+    if (gatherVmm) cudaFree(gatherVmm);
+    allCounts = nullptr; srcStart = nullptr; segments = nullptr; gatherMix = nullptr; gatherVmm = nullptr; planRanks = 0;
+    const size_t n = size_t(ranks) * size_t(maxRegions);
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&allCounts), n * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&srcStart), n * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&segments), n * sizeof(GSegment)));
+    if (ranks > 1) {
+        G_TRY(cudaMalloc(reinterpret_cast<void **>(&gatherMix), n * sizeof(GMix)));
+        G_TRY(cudaMalloc(reinterpret_cast<void **>(&gatherVmm), n * sizeof(b200pt_vmm_theta)));
+    }
+    planRanks = ranks;
+    return B200PT_OK;
+}
+
+#define G_NCCL(expr)                                                                             \
+    do {                                                                                         \
+        ncclResult_t _r = (expr);                                                                \
+        if (_r != ncclSuccess) { error = std::string(#expr) + ": " + g_nccl.GetErrorString(_r); return B200PT_E_CUDA; } \
+    } while (0)
+
+// Map every rank's sorted-sample buffers (dirw, pdfDist) into this process with CUDA IPC: the handles travel through the
+// communicator, and the decision to use them is taken collectively (a rank that cannot open a peer's handle makes all
+// ranks fall back to ncclSend / ncclRecv).  B200PT_EXCHANGE=nccl forces the fallback.
+int GuidingState::setupPeers(RankComm &rc, cudaStream_t stream) {
+    closePeers();
+    peerSelf = rc.rank;
+    peerTried = true; peerCapacity = capacity; rc.peerMode = false;
+    struct Handles { cudaIpcMemHandle_t dirw, pd; };
+    Handles mine{};
+    float ok = 1.0f;
+    if (const char *e = getenv("B200PT_EXCHANGE")) if (!strcmp(e, "nccl")) ok = 0.0f;
+    if (ok != 0.0f && (cudaIpcGetMemHandle(&mine.dirw, dirw) != cudaSuccess || cudaIpcGetMemHandle(&mine.pd, pdfDist) != cudaSuccess)) { cudaGetLastError(); ok = 0.0f; }
+    Handles *devAll = nullptr;
+    std::vector<Handles> all(size_t(rc.nranks));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&devAll), sizeof(Handles) * size_t(rc.nranks)));
+    G_TRY(cudaMemcpyAsync(devAll + rc.rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, stream));
+    G_NCCL(g_nccl.AllGather(devAll + rc.rank, devAll, sizeof(Handles), ncclChar, rc.comm, stream));
+    G_TRY(cudaMemcpyAsync(all.data(), devAll, sizeof(Handles) * size_t(rc.nranks), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    if (ok != 0.0f)
+        for (int s = 0; s < rc.nranks; s++) {
+            if (s == rc.rank) { peerDirw[s] = dirw; peerPdfDist[s] = pdfDist; continue; }
+            void *a = nullptr, *b = nullptr;
+            if (cudaIpcOpenMemHandle(&a, all[size_t(s)].dirw, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&b, all[size_t(s)].pd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError(); if (a) cudaIpcCloseMemHandle(a); ok = 0.0f; break;
+            }
+            peerDirw[s] = static_cast<const float4 *>(a); peerPdfDist[s] = static_cast<const float2 *>(b);
+        }
+    // collective decision: min over ranks
+    G_TRY(cudaMemcpyAsync(barrierWord, &ok, sizeof(float), cudaMemcpyHostToDevice, stream));
+    G_NCCL(g_nccl.AllReduce(barrierWord, barrierWord, 1, ncclFloat, ncclMin, rc.comm, stream));
+    G_TRY(cudaMemcpyAsync(&ok, barrierWord, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    cudaFree(devAll);
+    if (ok == 0.0f) closePeers();
+    rc.peerMode = ok != 0.0f;
+    if (getenv("B200PT_COMM_DEBUG")) fprintf(stderr, "[b200pt rank %d] sample exchange: %s\n", rc.rank, rc.peerMode ? "CUDA-IPC peer reads over NVLink" : "ncclSend/ncclRecv");
+    return B200PT_OK;
+}
+
+void GuidingState::closePeers() {
+    const int me = peerSelf;
+    for (int s = 0; s < B200PT_MAX_RANKS; s++) {
+        if (s != me && peerDirw[s]) cudaIpcCloseMemHandle(const_cast<float4 *>(peerDirw[s]));
+        if (s != me && peerPdfDist[s]) cudaIpcCloseMemHandle(const_cast<float2 *>(peerPdfDist[s]));
+        peerDirw[s] = nullptr; peerPdfDist[s] = nullptr;
+    }
+}
+
 int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream,
-                         b200pt_stats *stats) {
+                         b200pt_stats *stats, RankComm *rc) {
     if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
     if (regionCount > 1024) { error = "the device sort supports at most 1024 guiding regions (GUIDING_SPLITS <= 10)"; return B200PT_E_INVALID; }
     if (numSamples < 0 || numSamples > int64_t(0xfffffff0u)) { error = "bad sample count"; return B200PT_E_INVALID; }
     if (params.numInitialComponents < 1 || params.numInitialComponents > G_MAXK || params.maxItr < 0 || params.minItr < 0) {
         error = "bad guiding parameters"; return B200PT_E_INVALID;
     }
+    const int N = (rc && rc->comm) ? rc->nranks : 1, me = N > 1 ? rc->rank : 0;
+    if (N > B200PT_MAX_RANKS) { error = "too many ranks"; return B200PT_E_INVALID; }
     if (firstFit && memcmp(&params, &lastParams, sizeof(params)) != 0) {   // factory properties changed before the first fit: re-initialise
-        int rc = reset(params, stream);
-        if (rc != B200PT_OK) return rc;
+        int r0 = reset(params, stream);
+        if (r0 != B200PT_OK) return r0;
     }
     lastParams = params;
-    int rc = ensureCapacity(numSamples);
-    if (rc != B200PT_OK) return rc;
-    const uint32_t R = uint32_t(regionCount);
+    int rcode = ensureCapacity(numSamples);
+    if (rcode != B200PT_OK) return rcode;
+    rcode = ensurePlan(N);
+    if (rcode != B200PT_OK) return rcode;
+    if (N > 1 && (!peerTried || peerCapacity != capacity)) {               // (re)map the peers' buffers: collective, same condition on every rank
+        rcode = setupPeers(*rc, stream);
+        if (rcode != B200PT_OK) return rcode;
+    }
+    const bool peerMode = N > 1 && rc->peerMode;
+    const uint32_t R = uint32_t(regionCount), stride = uint32_t(maxRegions);
     const uint32_t numTiles = uint32_t((uint64_t(numSamples) + SORT_TILE - 1) / SORT_TILE);
     const uint32_t sortBlocks = (numTiles + SORT_WARPS - 1) / SORT_WARPS;
     const size_t sortSmem = size_t(SORT_WARPS) * R * sizeof(uint32_t);
-    cudaEvent_t e0, e1, e2;
-    G_TRY(cudaEventCreate(&e0)); G_TRY(cudaEventCreate(&e1)); G_TRY(cudaEventCreate(&e2));
-    G_TRY(cudaEventRecord(e0, stream));
+    unsigned launches = 0;
+    G_TRY(cudaEventRecord(ev[0], stream));
     G_TRY(cudaMemsetAsync(devScalars, 0, 2 * sizeof(unsigned long long), stream));
+    // ---- count (local), exchange the counts, plan
+    uint32_t *myCounts = allCounts + size_t(me) * stride;
     if (numTiles) {
         k_sort_count<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles);
-        k_sort_scan_tiles<<<R, 256, 0, stream>>>(tileCounts, numTiles, R, regionTotal);
+        k_sort_scan_tiles<<<R, 256, 0, stream>>>(tileCounts, numTiles, R, myCounts);
+        launches += 2;
     } else {
-        G_TRY(cudaMemsetAsync(regionTotal, 0, R * sizeof(uint32_t), stream));
+        G_TRY(cudaMemsetAsync(myCounts, 0, R * sizeof(uint32_t), stream));
     }
-    uint32_t *numActiveDev = reinterpret_cast<uint32_t *>(devScalars + 1);
-    k_sort_scan_regions<<<1, 1024, 0, stream>>>(regionTotal, R, regionOffset, activeRegions, numActiveDev);
-    if (numTiles)
-        k_sort_scatter<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles, regionOffset, aabbs,
+    if (N > 1) G_NCCL(g_nccl.AllGather(myCounts, allCounts, size_t(stride) * sizeof(uint32_t), ncclChar, rc->comm, stream));
+    k_plan<<<1, 1024, 0, stream>>>(allCounts, N, me, R, stride, peerMode ? 1 : 0, srcStart, regionBegin, regionLen, regionOffset, activeRegions, totalAll,
+                                   owner, segments, planDev);
+    launches++;
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaMemcpyAsync(planHost, planDev, sizeof(GPlanSummary), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaEventRecord(ev[2], stream));
+    // ---- scatter (sorted by (owner, region); preFit applied), while the host waits for the plan
+    if (numTiles) {
+        k_sort_scatter<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles, srcStart + size_t(me) * stride, aabbs,
                                                                           params.useParallaxCompensation, dirw, pdfDist, srcIndex);
-    G_TRY(cudaEventRecord(e1, stream));
-    G_TRY(cudaMemcpyAsync(hostScalars + 1, devScalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    G_TRY(cudaStreamSynchronize(stream));
-    const uint32_t numActive = uint32_t(hostScalars[1] & 0xffffffffu);
-    if (numActive) {
+        launches++;
+    }
+    G_TRY(cudaEventRecord(ev[1], stream));
+    const float4 *fitD = dirw;
+    const float2 *fitP = pdfDist;
+    uint32_t fitRegions = R;                     // single GPU: the grid covers every region, empty ones leave at once (no host round trip)
+    uint64_t bytesReceived = 0;
+    if (N > 1) {
+        G_TRY(cudaEventSynchronize(ev[2]));      // the only host wait inside the update; the scatter is running meanwhile
+        const GPlanSummary &ps = *planHost;
+        fitRegions = ps.numActive;
+        if (int64_t(ps.ownedSamples) > fitCapacity) {
+            if (fitDirw) cudaFree(fitDirw);
+            if (fitPdfDist) cudaFree(fitPdfDist);
+            fitDirw = nullptr; fitPdfDist = nullptr; fitCapacity = 0;
+            const size_t n = size_t(ps.ownedSamples) + size_t(ps.ownedSamples) / 8 + 1024;      // head room: the shares move a little from update to update
+            G_TRY(cudaMalloc(reinterpret_cast<void **>(&fitDirw), n * sizeof(float4)));
+            G_TRY(cudaMalloc(reinterpret_cast<void **>(&fitPdfDist), n * sizeof(float2)));
+            fitCapacity = int64_t(n);
+        }
+        GPeerPtrs peers{};
+        uint64_t fromPeers = 0;
+        for (int s = 0; s < N; s++) if (s != me) fromPeers += ps.recvCount[s];
+        bytesReceived = fromPeers * (sizeof(float4) + sizeof(float2));
+        if (peerMode) {
+            for (int s = 0; s < N; s++) { peers.dirw[s] = peerDirw[s]; peers.pd[s] = peerPdfDist[s]; }
+            // every rank's scatter must have finished before anybody reads its buffer: a one-word all-reduce is the barrier
+            G_NCCL(g_nccl.AllReduce(barrierWord, barrierWord, 1, ncclFloat, ncclMin, rc->comm, stream));
+        } else {
+            if (int64_t(fromPeers) > stageCapacity) {
+                if (stageDirw) cudaFree(stageDirw);
+                if (stagePdfDist) cudaFree(stagePdfDist);
+                stageDirw = nullptr; stagePdfDist = nullptr; stageCapacity = 0;
+                const size_t n = size_t(fromPeers) + size_t(fromPeers) / 8 + 1024;
+                G_TRY(cudaMalloc(reinterpret_cast<void **>(&stageDirw), n * sizeof(float4)));
+                G_TRY(cudaMalloc(reinterpret_cast<void **>(&stagePdfDist), n * sizeof(float2)));
+                stageCapacity = int64_t(n);
+            }
+            for (int s = 0; s < N; s++) { peers.dirw[s] = s == me ? dirw : stageDirw; peers.pd[s] = s == me ? pdfDist : stagePdfDist; }
+            G_NCCL(g_nccl.GroupStart());
+            for (int d = 0; d < N; d++) {
+                const size_t cnt = size_t(ps.sendStart[d + 1] - ps.sendStart[d]);
+                if (d == me || !cnt) continue;
+                G_NCCL(g_nccl.Send(dirw + ps.sendStart[d], cnt * sizeof(float4), ncclChar, d, rc->comm, stream));
+                G_NCCL(g_nccl.Send(pdfDist + ps.sendStart[d], cnt * sizeof(float2), ncclChar, d, rc->comm, stream));
+            }
+            for (int s = 0; s < N; s++) {
+                const size_t cnt = size_t(ps.recvCount[s]);
+                if (s == me || !cnt) continue;
+                G_NCCL(g_nccl.Recv(stageDirw + ps.stageStart[s], cnt * sizeof(float4), ncclChar, s, rc->comm, stream));
+                G_NCCL(g_nccl.Recv(stagePdfDist + ps.stageStart[s], cnt * sizeof(float2), ncclChar, s, rc->comm, stream));
+            }
+            G_NCCL(g_nccl.GroupEnd());
+        }
+        if (ps.numSegments) {
+            // blocks per segment: enough to keep ~8 blocks per SM busy on the average segment
+            const uint64_t avg = ps.ownedSamples / ps.numSegments + 1;
+            const unsigned perSeg = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(64, avg / 2048 + 1)));
+            k_pull<<<dim3(ps.numSegments, perSeg, 1), 256, 0, stream>>>(segments, peers, fitDirw, fitPdfDist);
+            launches++;
+        }
+        fitD = fitDirw; fitP = fitPdfDist;
+    }
+    G_TRY(cudaEventRecord(ev[3], stream));
+    if (fitRegions) {
         // one cluster of `clusterSize` CTAs per region (portable maximum 8); B200PT_GUIDING_CLUSTER overrides
         int clusterSize = 4;
         if (const char *e = getenv("B200PT_GUIDING_CLUSTER")) clusterSize = std::max(1, std::min(8, atoi(e)));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(numActive * clusterSize, 1, 1);
+        cfg.gridDim = dim3(fitRegions * clusterSize, 1, 1);
         cfg.blockDim = dim3(G_BLOCK, 1, 1);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = stream;
@@ -565,23 +869,34 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = clusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const uint32_t *activePtr = activeRegions, *offPtr = regionOffset;
+        const uint32_t *activePtr = activeRegions, *numActivePtr = &planDev->numActive, *beginPtr = regionBegin, *countPtr = regionLen;
         const b200pt_aabb *aabbPtr = aabbs;
-        const float4 *dirwPtr = dirw; const float2 *pdPtr = pdfDist;
-        G_TRY(cudaLaunchKernelEx(&cfg, k_guiding_update, mixes, vmms, aabbPtr, activePtr, offPtr, dirwPtr, pdPtr, params, firstFit ? 1 : 0, devScalars));
+        G_TRY(cudaLaunchKernelEx(&cfg, k_guiding_update, mixes, vmms, aabbPtr, activePtr, numActivePtr, beginPtr, countPtr, fitD, fitP, params, firstFit ? 1 : 0, devScalars));
+        launches++;
     }
     G_TRY(cudaGetLastError());
-    G_TRY(cudaEventRecord(e2, stream));
+    G_TRY(cudaEventRecord(ev[4], stream));
+    if (N > 1) {
+        // results: all-gather of the mixture arrays, then every region takes its owner's copy.  This also is the barrier
+        // that keeps a rank from overwriting its sorted buffer (next update) while a peer still reads it.
+        G_NCCL(g_nccl.GroupStart());
+        G_NCCL(g_nccl.AllGather(mixes, gatherMix, size_t(stride) * sizeof(GMix), ncclChar, rc->comm, stream));
+        G_NCCL(g_nccl.AllGather(vmms, gatherVmm, size_t(stride) * sizeof(b200pt_vmm_theta), ncclChar, rc->comm, stream));
+        G_NCCL(g_nccl.GroupEnd());
+        k_pick_results<<<R, 128, 0, stream>>>(mixes, vmms, gatherMix, gatherVmm, owner, totalAll, stride, me);
+        launches++;
+    }
+    G_TRY(cudaEventRecord(ev[5], stream));
     G_TRY(cudaMemcpyAsync(hostScalars, devScalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    uint32_t validCount = 0;
-    G_TRY(cudaMemcpyAsync(&validCount, regionOffset + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    G_TRY(cudaStreamSynchronize(stream));
-    float msSort = 0, msFit = 0;
-    cudaEventElapsedTime(&msSort, e0, e1);
-    cudaEventElapsedTime(&msFit, e1, e2);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (N == 1) G_TRY(cudaMemcpyAsync(planHost, planDev, sizeof(GPlanSummary), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));        // the one synchronisation of a single-GPU update
+    float msSort = 0, msExchange = 0, msFit = 0, msGather = 0;
+    cudaEventElapsedTime(&msSort, ev[0], ev[1]);
+    cudaEventElapsedTime(&msExchange, ev[1], ev[3]);
+    cudaEventElapsedTime(&msFit, ev[3], ev[4]);
+    cudaEventElapsedTime(&msGather, ev[4], ev[5]);
     firstFit = false;
-    lastValidSamples = validCount;
+    lastValidSamples = planHost->localValid;
     if (params.splitRegions) { int rcs = splitRegions(params, stream); if (rcs != B200PT_OK) return rcs; }
     if (getenv("B200PT_GUIDING_PROFILE")) {   // per-region cost distribution (development aid)
         std::vector<GMix> hm;
@@ -596,13 +911,17 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
                 it.front(), it[it.size() / 2], it.back());
     }
     if (stats) {
-        stats->guiding_samples += validCount;
+        stats->guiding_samples += planHost->ownedSamples;
+        stats->guiding_samples_all_ranks += planHost->totalSamples;
+        stats->guiding_bytes_received += bytesReceived;
         stats->guiding_em_sample_iterations += hostScalars[0];
-        stats->guiding_regions_fit += numActive;
+        stats->guiding_regions_fit += planHost->numActive;
         stats->ms_guiding_sort += msSort;
+        stats->ms_guiding_exchange += msExchange;
         stats->ms_guiding_fit += msFit;
-        stats->kernel_launches += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
-        stats->launches_guiding += (numTiles ? 3 : 0) + 1 + (numActive ? 1 : 0);
+        stats->ms_guiding_gather += msGather;
+        stats->kernel_launches += launches;
+        stats->launches_guiding += launches;
     }
     return B200PT_OK;
 }
@@ -725,6 +1044,17 @@ int GuidingState::getSorted(b200pt_directional_data *out, uint32_t *offsets, con
 }
 
 void GuidingState::release() {
+    closePeers();
+    peerTried = false; peerCapacity = -1;
+    for (void *p : {(void *)allCounts, (void *)srcStart, (void *)segments, (void *)gatherMix, (void *)gatherVmm, (void *)regionBegin, (void *)regionLen,
+                    (void *)totalAll, (void *)owner, (void *)planDev, (void *)fitDirw, (void *)fitPdfDist, (void *)stageDirw, (void *)stagePdfDist, (void *)barrierWord})
+        if (p) cudaFree(p);
+    allCounts = nullptr; srcStart = nullptr; segments = nullptr; gatherMix = nullptr; gatherVmm = nullptr; regionBegin = nullptr; regionLen = nullptr;
+    totalAll = nullptr; owner = nullptr; planDev = nullptr; fitDirw = nullptr; fitPdfDist = nullptr; stageDirw = nullptr; stagePdfDist = nullptr; barrierWord = nullptr;
+    fitCapacity = 0; stageCapacity = 0; planRanks = 0;
+    if (planHost) cudaFreeHost(planHost);
+    planHost = nullptr;
+    for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (aabbs) cudaFree(aabbs);
     if (levelAabbs) cudaFree(levelAabbs);
     levelAabbs = nullptr;

@@ -6,10 +6,13 @@
 #include <string>
 #include <vector>
 #include "../../include/b200pt.h"
+#include "comm.cuh"
 
 namespace b200pt {
 
 struct GMix;
+struct GSegment;
+struct GPlanSummary;
 
 struct GuidingState {
     bool ready = false;
@@ -32,14 +35,41 @@ struct GuidingState {
     float2 *pdfDist = nullptr;             // sorted samples: pdf, distance (after preFit)
     int64_t capacity = 0;
     uint32_t lastValidSamples = 0;
-    unsigned long long *devScalars = nullptr, *hostScalars = nullptr;   // [0] EM sample-iterations, [1] active regions
+    unsigned long long *devScalars = nullptr, *hostScalars = nullptr;   // [0] EM sample-iterations
+    // plan of an update (k_plan): ownership, layouts, copy segments; see guiding_fit.cu
+    uint32_t *allCounts = nullptr, *srcStart = nullptr;                 // [ranks][maxRegions]
+    uint32_t *regionBegin = nullptr, *regionLen = nullptr, *totalAll = nullptr;
+    uint8_t *owner = nullptr;
+    GSegment *segments = nullptr;                                       // [maxRegions * ranks]
+    GPlanSummary *planDev = nullptr, *planHost = nullptr;               // device / pinned host copy
+    int planRanks = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, sorted, planned, exchanged, fitted, gathered
+    // region-sharded refit across ranks
+    float4 *fitDirw = nullptr, *stageDirw = nullptr;                    // owned regions, contiguous / NCCL staging
+    float2 *fitPdfDist = nullptr, *stagePdfDist = nullptr;
+    int64_t fitCapacity = 0, stageCapacity = 0;
+    GMix *gatherMix = nullptr;
+    b200pt_vmm_theta *gatherVmm = nullptr;
+    float *barrierWord = nullptr;
+    const float4 *peerDirw[B200PT_MAX_RANKS] = {};
+    const float2 *peerPdfDist[B200PT_MAX_RANKS] = {};
+    int64_t peerCapacity = -1;                                          // capacity the peer mappings were made for
+    bool peerTried = false;
+    int peerSelf = -1;                                                  // own entries alias dirw / pdfDist: never IPC-closed
     b200pt_guiding_params lastParams{};
     std::string error;
 
     int init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream);
     int reset(const b200pt_guiding_params &params, cudaStream_t stream);
     int ensureCapacity(int64_t numSamples);
-    int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats);
+    // rc == nullptr or one rank: PathGuiding::update on this GPU's records.  Several ranks: every rank passes its own
+    // records; regions are fitted by their owner on the records of ALL ranks and the results are shared (identical
+    // mixtures everywhere, equal to a single-GPU update on the concatenation of the ranks' buffers in rank order).
+    int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats,
+               RankComm *rc = nullptr);
+    int ensurePlan(int ranks);
+    int setupPeers(RankComm &rc, cudaStream_t stream);
+    void closePeers();
     int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);
     int save(FILE *f, cudaStream_t stream);          // checkpoint: regions, spawn chains, mixtures, packed VMMs
     int load(FILE *f, cudaStream_t stream);      // PathGuiding.cpp:291-300, :328-348
