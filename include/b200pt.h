@@ -395,6 +395,15 @@ int b200pt_guiding_reset(b200pt_ctx *ctx, const b200pt_guiding_params *params);
 int b200pt_guiding_update_host(b200pt_ctx *ctx, const b200pt_guiding_params *params, const b200pt_directional_data *samples, int64_t n);
 /* same with `n` records already resident in DEVICE memory (no copy) */
 int b200pt_guiding_update_device(b200pt_ctx *ctx, const b200pt_guiding_params *params, const void *samples_device, int64_t n);
+/* Summation order of the per-region sample sums.  lightpmm adds the sufficient statistics sample after sample in float
+ * (VMMFactory.h:497-536, incremental*.h); STRICT (default) keeps exactly that order on the device (parallel over the
+ * 4K+2 running sums instead of over the samples), so a refit on the same records in the same order reproduces the
+ * reference's mixtures to float rounding of the per-sample terms (1e-4, same EM iteration counts).  REORDERED sums
+ * per-thread partitions block-parallel (thread-block cluster per region): results differ from the reference's like
+ * the reference's differ from itself under its unstable sample sort (weights ~1e-4, kappa ~2e-3, rare iteration flips).
+ * Env B200PT_GUIDING_ORDER=strict|reordered overrides. */
+enum { B200PT_GUIDING_ORDER_STRICT = 0, B200PT_GUIDING_ORDER_REORDERED = 1 };
+int b200pt_guiding_set_order(b200pt_ctx *ctx, int order);
 /* parity hooks: the sorted + pre-fitted samples of the last update (what SampleCollector::getSortedData + preFit
  * produce; positions are the region's parallax mean) with region offsets [regions + 1]; either pointer may be NULL */
 int64_t b200pt_guiding_sorted_count(b200pt_ctx *ctx);

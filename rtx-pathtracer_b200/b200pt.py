@@ -133,6 +133,8 @@ class Stats(C.Structure):
                 ("ms_guiding_gather", C.c_float)]
 
 
+GUIDING_ORDER_STRICT, GUIDING_ORDER_REORDERED = 0, 1      # b200pt_guiding_set_order
+
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("u", "<f4"), ("v", "<f4")])
 DIRECTIONAL_DATA_DTYPE = np.dtype([("position", "<f4", 3), ("direction", "<f4", 3), ("weight", "<f4"), ("pdf", "<f4"),
@@ -158,7 +160,7 @@ EXPORTS = [
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
     "b200pt_guiding_sample_capacity", "b200pt_guiding_get_samples_device", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
-    "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
+    "b200pt_guiding_set_order", "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
     "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_comm_exchange_mode",
@@ -239,6 +241,7 @@ def lib():
         L.b200pt_guiding_update_all_ranks.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_guiding_update_all_ranks_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
         L.b200pt_comm_exchange_mode.argtypes = [C.c_void_p]
+        L.b200pt_guiding_set_order.argtypes = [C.c_void_p, C.c_int]
         L.b200pt_app_init.restype = None
         L.b200pt_app_init.argtypes = [C.POINTER(AppState)]
         L.b200pt_app_scene_switched.restype = None
@@ -483,6 +486,10 @@ class Renderer:
         return out, off
 
     GUIDING_STATE_FIELDS = ("weight", "kappa", "r", "mux", "muy", "muz", "distance", "distSumW", "chi", "chiN", "covxx", "covyy", "covxy", "covSumW")
+
+    def guiding_set_order(self, order):
+        """0 = strict (the reference's sequential float sums, default), 1 = reordered (block-parallel sums)"""
+        _check(lib().b200pt_guiding_set_order(self._h, int(order)))
 
     def guiding_state(self, region):
         sc = np.empty(5, dtype=np.float32)

@@ -988,6 +988,11 @@ int b200pt_guiding_update_host(b200pt_ctx *c, const b200pt_guiding_params *param
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_host: " + c->guiding.error);
     return B200PT_OK;
 }
+int b200pt_guiding_set_order(b200pt_ctx *c, int order) {
+    if (!c || (order != B200PT_GUIDING_ORDER_STRICT && order != B200PT_GUIDING_ORDER_REORDERED)) return setError(B200PT_E_INVALID, "b200pt_guiding_set_order: bad argument");
+    c->guiding.summationOrder = order;
+    return B200PT_OK;
+}
 int64_t b200pt_guiding_sorted_count(b200pt_ctx *c) { return c ? int64_t(c->guiding.lastValidSamples) : 0; }
 int b200pt_guiding_get_sorted(b200pt_ctx *c, b200pt_directional_data *out, uint32_t *region_offsets) {
     if (!c) return setError(B200PT_E_INVALID, "b200pt_guiding_get_sorted: null argument");

@@ -527,14 +527,290 @@ __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMi
     }
 }
 
-// PathGuiding::createPMMs + syncPMMsToVMM_Thetas at construction (src/PathGuiding.cpp:42-51, 101-103)
-__global__ void k_guiding_init(GMix *mixes, b200pt_vmm_theta *vmms, uint32_t R, b200pt_guiding_params gp) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- strict-order executor ---------------------------------------------------------------------------------------------
+// lightpmm sums the sufficient statistics sample after sample in float (VMMFactory.h:497-536): float addition does not
+// commute with regrouping, so any parallel partition of a region's samples changes the last bits of the sums, and the EM
+// iteration amplifies that (weights ~1e-4, kappa ~1e-3, now and then one EM iteration more or less).  This executor keeps
+// the reference's order exactly and is still parallel — over the ACCUMULATORS instead of the samples:
+//   * producer warps evaluate the per-sample terms (soft assignment, 4K+2 values per sample for an EM pass) for a tile of
+//     GC_TILE consecutive samples, one sample per thread, and store them value-major in shared memory;
+//   * consumer thread v owns running sum v and adds its row of the tile in sample order: a dependent FADD chain
+//     (4 cycles per sample), 4K+2 chains side by side, fed by LDS.128 (row stride = 41 x 16 B: conflict-free);
+//   * the two tile buffers alternate: the consumers add tile j while the producers compute tile j + 1.
+// A skipped sample (mixture pdf <= 1e-8) contributes +0 to every sum, which leaves a float sum unchanged.  The result
+// is the serial sum, bit for bit the one the host build of guiding_math.cuh (tests/harness) produces.
+#define GC_CONSUMERS 96
+#define GC_TILE 160
+#define GC_BLOCK (GC_CONSUMERS + GC_TILE)
+#define GC_STRIDE (GC_TILE + 4)
+#define GC_ROWS G_STATACC_FLOATS
+#define GC_SMEM_BYTES (2 * GC_ROWS * GC_STRIDE * sizeof(float))
+
+struct ChainShared {
+    GMix mix;
+    GPacked packed;
+    GFrames frames;
+    GFitState fitState;
+    union { EmAcc em; StatAcc stat; DistAcc dist; float raw[G_STATACC_FLOATS]; } acc;
+    float metric[G_MAXK * (G_MAXK - 1) / 2];
+    float staged[G_STATACC_FLOATS];
+    int bc;
+};
+
+struct ChainExec {
+    ChainShared &sh;
+    float *tiles;               // dynamic shared memory: [2][GC_ROWS][GC_STRIDE]
+    const float4 *dirw;
+    const float2 *pdfDist;
+    uint32_t N;
+
+    __device__ bool leader() const { return threadIdx.x == 0; }
+    __device__ int bcast(int v) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.bc = v;
+        __syncthreads();
+        return sh.bc;
+    }
+    __device__ EmAcc &em() { return sh.acc.em; }
+    __device__ StatAcc &stat() { return sh.acc.stat; }
+    __device__ DistAcc &dst() { return sh.acc.dist; }
+    __device__ GFrames &frames() { return sh.frames; }
+    __device__ float *metric() { return sh.metric; }
+    __device__ GFitState &fit() { return sh.fitState; }
+
+    __device__ void publish(const GMix &m) {
+        __syncthreads();
+        if (threadIdx.x < G_MAXK) {
+            const int c = threadIdx.x;
+            sh.packed.a[c].mx = m.mux[c]; sh.packed.a[c].my = m.muy[c]; sh.packed.a[c].mz = m.muz[c]; sh.packed.a[c].kappa = m.kappa[c];
+            sh.packed.b[c].norm = m.norm[c]; sh.packed.b[c].w = m.w[c];
+        }
+        __syncthreads();
+    }
+
+    // One pass over the region's samples.  produce(i, col): thread-local evaluation of sample i, stores NV values at
+    // col[v * GC_STRIDE].  Afterwards sh.staged[0..NV) holds the sequential sums.
+    template <int NV, class Produce>
+    __device__ __forceinline__ void chainPass(Produce produce) {
+        const unsigned tid = threadIdx.x;
+        const bool consumer = tid < GC_CONSUMERS;
+        const uint32_t numTiles = (N + GC_TILE - 1) / GC_TILE;
+        float acc = 0.0f;
+        if (!consumer) {
+            const uint32_t i = tid - GC_CONSUMERS;
+            if (i < N) produce(i, tiles + i);
+        }
+        __syncthreads();
+        for (uint32_t j = 0; j < numTiles; j++) {
+            if (consumer) {
+                if (tid < unsigned(NV)) {
+                    const float *row = tiles + (j & 1u) * (GC_ROWS * GC_STRIDE) + tid * GC_STRIDE;
+                    const uint32_t count = min(uint32_t(GC_TILE), N - j * GC_TILE);
+                    uint32_t sIdx = 0;
+                    if (count == GC_TILE) {
+#pragma unroll 8
+                        for (; sIdx < GC_TILE; sIdx += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(row + sIdx);
+                            acc += t4.x; acc += t4.y; acc += t4.z; acc += t4.w;
+                        }
+                    } else {
+                        for (; sIdx < count; sIdx++) acc += row[sIdx];
+                    }
+                }
+            } else if (j + 1 < numTiles) {
+                const uint32_t p = tid - GC_CONSUMERS;
+                const uint32_t i = (j + 1) * GC_TILE + p;
+                if (i < N) produce(i, tiles + ((j + 1) & 1u) * (GC_ROWS * GC_STRIDE) + p);
+            }
+            __syncthreads();
+        }
+        if (tid < unsigned(NV)) sh.staged[tid] = acc;
+        __syncthreads();
+    }
+
+    template <int KPAD> __device__ void emPassT(EmAcc &out) {
+        const GPacked &pk = sh.packed;
+        const float4 *d = dirw;
+        chainPass<4 * KPAD + 2>([&](uint32_t i, float *col) {
+            G_NO_HOIST();
+            const float4 s = d[i];
+            float sw[KPAD], ll;
+            const bool ok = gEmTerms<KPAD>(pk, s.x, s.y, s.z, s.w, sw, ll);
+#pragma unroll
+            for (int c = 0; c < KPAD; c++) {
+                const float w = ok ? sw[c] : 0.0f;
+                col[c * GC_STRIDE] = w;
+                col[(KPAD + c) * GC_STRIDE] = s.x * w;
+                col[(2 * KPAD + c) * GC_STRIDE] = s.y * w;
+                col[(3 * KPAD + c) * GC_STRIDE] = s.z * w;
+            }
+            col[(4 * KPAD) * GC_STRIDE] = ok ? s.w : 0.0f;
+            col[(4 * KPAD + 1) * GC_STRIDE] = ok ? ll : 0.0f;
+        });
+        const float *staged = sh.staged;
+        if (threadIdx.x < KPAD) {
+            const int c = threadIdx.x;
+            out.W[c] = staged[c]; out.Rx[c] = staged[KPAD + c]; out.Ry[c] = staged[2 * KPAD + c]; out.Rz[c] = staged[3 * KPAD + c];
+        }
+        if (threadIdx.x == 0) { out.sumWeight = staged[4 * KPAD]; out.logLikelihood = staged[4 * KPAD + 1]; }
+        __syncthreads();
+    }
+    __device__ void emPass(const GMix &m, EmAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: emPassT<4>(out); break;
+            case 8: emPassT<8>(out); break;
+            case 12: emPassT<12>(out); break;
+            default: emPassT<16>(out); break;
+        }
+    }
+
+    template <int KPAD> __device__ void statPassT(const GFrames &f, StatAcc &out) {
+        const GPacked &pk = sh.packed;
+        const float4 *d = dirw;
+        const float2 *pd2 = pdfDist;
+        chainPass<5 * KPAD>([&](uint32_t i, float *col) {
+            const float4 s = d[i];
+            const float2 pd = pd2[i];
+            G_NO_HOIST();
+            float chi[KPAD], covW[KPAD], covXX[KPAD], covYY[KPAD], covXY[KPAD];
+            const bool ok = gStatTerms<KPAD>(pk, f, s.x, s.y, s.z, s.w, pd.x, chi, covW, covXX, covYY, covXY);
+#pragma unroll
+            for (int c = 0; c < KPAD; c++) {
+                col[c * GC_STRIDE] = ok ? chi[c] : 0.0f;
+                col[(KPAD + c) * GC_STRIDE] = ok ? covW[c] : 0.0f;
+                col[(2 * KPAD + c) * GC_STRIDE] = ok ? covXX[c] : 0.0f;
+                col[(3 * KPAD + c) * GC_STRIDE] = ok ? covYY[c] : 0.0f;
+                col[(4 * KPAD + c) * GC_STRIDE] = ok ? covXY[c] : 0.0f;
+            }
+        });
+        const float *staged = sh.staged;
+        if (threadIdx.x < KPAD) {
+            const int c = threadIdx.x;
+            out.chi[c] = staged[c]; out.covW[c] = staged[KPAD + c]; out.covXX[c] = staged[2 * KPAD + c]; out.covYY[c] = staged[3 * KPAD + c]; out.covXY[c] = staged[4 * KPAD + c];
+        }
+        __syncthreads();
+    }
+    __device__ void statPass(const GMix &m, const GFrames &f, StatAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: statPassT<4>(f, out); break;
+            case 8: statPassT<8>(f, out); break;
+            case 12: statPassT<12>(f, out); break;
+            default: statPassT<16>(f, out); break;
+        }
+    }
+
+    template <int KPAD> __device__ void distPassT(DistAcc &out) {
+        const GPacked &pk = sh.packed;
+        const float4 *d = dirw;
+        const float2 *pd2 = pdfDist;
+        chainPass<2 * KPAD>([&](uint32_t i, float *col) {
+            const float4 s = d[i];
+            const float2 pd = pd2[i];
+            G_NO_HOIST();
+            float w[KPAD], wd[KPAD];
+            const bool ok = gDistTerms<KPAD>(pk, s.x, s.y, s.z, s.w, pd.y, w, wd);
+#pragma unroll
+            for (int c = 0; c < KPAD; c++) {
+                col[c * GC_STRIDE] = ok ? w[c] : 0.0f;
+                col[(KPAD + c) * GC_STRIDE] = ok ? wd[c] : 0.0f;
+            }
+        });
+        const float *staged = sh.staged;
+        if (threadIdx.x < KPAD) { const int c = threadIdx.x; out.w[c] = staged[c]; out.wd[c] = staged[KPAD + c]; }
+        __syncthreads();
+    }
+    __device__ void distPass(const GMix &m, DistAcc &out) {
+        publish(m);
+        switch (gKpad(m.K)) {
+            case 4: distPassT<4>(out); break;
+            case 8: distPassT<8>(out); break;
+            case 12: distPassT<12>(out); break;
+            default: distPassT<16>(out); break;
+        }
+    }
+
+    __device__ void metricPass(const GMix &m, float *metric) {
+        __syncthreads();
+        const int K = m.K, numPairs = K * (K - 1) / 2;
+        for (int p = threadIdx.x; p < numPairs; p += GC_BLOCK) {
+            int idx = p, a = 0;
+            while (idx >= K - 1 - a) { idx -= K - 1 - a; a++; }
+            metric[p] = gMergeMetricPair(m, a, a + 1 + idx);
+        }
+        __syncthreads();
+    }
+};
+
+__global__ void __launch_bounds__(GC_BLOCK, 2) k_guiding_update_strict(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
+                                                                     const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ numActive,
+                                                                     const uint32_t *__restrict__ regionBegin, const uint32_t *__restrict__ regionCount,
+                                                                     const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist,
+                                                                     b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
+    __shared__ ChainShared sh;
+    extern __shared__ __align__(16) float gcTiles[];
+    if (blockIdx.x >= *numActive) return;
+    const long long t0 = clock64();
+    const uint32_t region = activeRegions[blockIdx.x];
+    const uint32_t begin = regionBegin[region], count = regionCount[region];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&mixes[region]);
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(&sh.mix);
+        for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += GC_BLOCK) dstw[i] = src[i];
+    }
+    __syncthreads();
+    ChainExec x{sh, gcTiles, dirw + begin, pdfDist + begin, count};
+    const b200pt_aabb bb = aabbs[region];
+    float mean[3];
+    for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
+    uint64_t iters = 0;
+    gUpdateRegion(x, sh.mix, gp, count, firstFit != 0, mean, &iters);
+    if (threadIdx.x == 0) sh.mix.lastUpdateKCycles = uint32_t((clock64() - t0) >> 10);
+    __syncthreads();
+    {
+        uint32_t *dstw = reinterpret_cast<uint32_t *>(&mixes[region]);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&sh.mix);
+        for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += GC_BLOCK) dstw[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        gPackTheta(sh.mix, gp.useParallaxCompensation != 0, vmms[region]);
+        atomicAdd(emSampleIterations, (unsigned long long)iters);
+    }
+}
+
+#define G_TRY(expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) { error = std::string(#expr) + ": " + cudaGetErrorString(_e); return B200PT_E_CUDA; } \
+    } while (0)
+
+// PathGuiding::createPMMs + syncPMMsToVMM_Thetas at construction (src/PathGuiding.cpp:42-51, 101-103).  The initial
+// mixture is evaluated on the HOST (VMMFactory::initialize uses acos / sin / cos: the C library's floats are the
+// reference's, CUDA's differ in the last bit, and a kappa = 50000 lobe turns one ulp of mu into 0.5 % of pdf) and
+// replicated to every region on the device.
+__global__ void k_guiding_init(GMix *mixes, b200pt_vmm_theta *vmms, uint32_t R, const GMix *__restrict__ mix0, const b200pt_vmm_theta *__restrict__ vmm0) {
+    const uint32_t r = blockIdx.x;
     if (r >= R) return;
+    const uint32_t *ms = reinterpret_cast<const uint32_t *>(mix0); uint32_t *md = reinterpret_cast<uint32_t *>(mixes + r);
+    for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += blockDim.x) md[i] = ms[i];
+    const uint32_t *vs = reinterpret_cast<const uint32_t *>(vmm0); uint32_t *vd = reinterpret_cast<uint32_t *>(vmms + r);
+    for (uint32_t i = threadIdx.x; i < sizeof(b200pt_vmm_theta) / 4; i += blockDim.x) vd[i] = vs[i];
+}
+static int launchGuidingInit(GMix *mixes, b200pt_vmm_theta *vmms, int regions, const b200pt_guiding_params &gp, cudaStream_t stream, std::string &error) {
     GMix m;
+    b200pt_vmm_theta v;
     gInitialize(m, gp);
-    mixes[r] = m;
-    gPackTheta(m, gp.useParallaxCompensation != 0, vmms[r]);
+    gPackTheta(m, gp.useParallaxCompensation != 0, v);
+    char *d = nullptr;
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&d), sizeof(GMix) + sizeof(b200pt_vmm_theta)));
+    G_TRY(cudaMemcpyAsync(d, &m, sizeof(GMix), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(d + sizeof(GMix), &v, sizeof(v), cudaMemcpyHostToDevice, stream));
+    k_guiding_init<<<unsigned(regions), 128, 0, stream>>>(mixes, vmms, uint32_t(regions), reinterpret_cast<const GMix *>(d), reinterpret_cast<const b200pt_vmm_theta *>(d + sizeof(GMix)));
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d);
+    return B200PT_OK;
 }
 
 // known-answer hook: the device build of lightpmm's approximate exp on an array
@@ -556,12 +832,6 @@ int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stre
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
-#define G_TRY(expr)                                                                              \
-    do {                                                                                         \
-        cudaError_t _e = (expr);                                                                 \
-        if (_e != cudaSuccess) { error = std::string(#expr) + ": " + cudaGetErrorString(_e); return B200PT_E_CUDA; } \
-    } while (0)
-
 // PathGuiding::splitRegion (src/PathGuiding.cpp:328-348), device half: decay the split mixture's sample counters, then the
 // new region starts as a copy of it (mixture, extra statistics, packed VMM_Theta)
 __global__ void __launch_bounds__(128) k_guiding_split_regions(GMix *mixes, b200pt_vmm_theta *vmms, const int2 *pairs) {
@@ -630,9 +900,7 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
     G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(regionCount) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
     G_TRY(cudaMemsetAsync(devScalars, 0, 4 * sizeof(unsigned long long), stream));
     b200pt_default_guiding_params(&lastParams);
-    k_guiding_init<<<(regionCount + 127) / 128, 128, 0, stream>>>(mixes, vmms, uint32_t(regionCount), lastParams);
-    G_TRY(cudaGetLastError());
-    G_TRY(cudaStreamSynchronize(stream));
+    { int rci = launchGuidingInit(mixes, vmms, regionCount, lastParams, stream, error); if (rci != B200PT_OK) return rci; }
     firstFit = true;
     ready = true;
     return B200PT_OK;
@@ -641,9 +909,7 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
 int GuidingState::reset(const b200pt_guiding_params &params, cudaStream_t stream) {
     if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
     lastParams = params;
-    k_guiding_init<<<(regionCount + 127) / 128, 128, 0, stream>>>(mixes, vmms, uint32_t(regionCount), params);
-    G_TRY(cudaGetLastError());
-    G_TRY(cudaStreamSynchronize(stream));
+    { int rci = launchGuidingInit(mixes, vmms, regionCount, params, stream, error); if (rci != B200PT_OK) return rci; }
     firstFit = true;
     return B200PT_OK;
 }
@@ -856,8 +1122,18 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
         fitD = fitDirw; fitP = fitPdfDist;
     }
     G_TRY(cudaEventRecord(ev[3], stream));
-    if (fitRegions) {
-        // one cluster of `clusterSize` CTAs per region (portable maximum 8); B200PT_GUIDING_CLUSTER overrides
+    int order = summationOrder;
+    if (const char *e = getenv("B200PT_GUIDING_ORDER")) order = !strcmp(e, "reordered") ? 1 : 0;
+    if (fitRegions && order == 0) {
+        // strict order: one CTA per region, 2 CTAs per SM, regions largest first
+        static bool attrSet = false;
+        if (!attrSet) { G_TRY(cudaFuncSetAttribute(k_guiding_update_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GC_SMEM_BYTES))); attrSet = true; }
+        k_guiding_update_strict<<<fitRegions, GC_BLOCK, GC_SMEM_BYTES, stream>>>(mixes, vmms, aabbs, activeRegions, &planDev->numActive, regionBegin, regionLen, fitD, fitP,
+                                                                                 params, firstFit ? 1 : 0, devScalars);
+        launches++;
+    } else if (fitRegions) {
+        // block-parallel sums (a different float summation order than the reference's): one cluster of `clusterSize` CTAs
+        // per region (portable maximum 8); B200PT_GUIDING_CLUSTER overrides
         int clusterSize = 4;
         if (const char *e = getenv("B200PT_GUIDING_CLUSTER")) clusterSize = std::max(1, std::min(8, atoi(e)));
         cudaLaunchConfig_t cfg = {};

@@ -57,6 +57,7 @@ struct GuidingState {
     bool peerTried = false;
     int peerSelf = -1;                                                  // own entries alias dirw / pdfDist: never IPC-closed
     b200pt_guiding_params lastParams{};
+    int summationOrder = 0;                // 0: the reference's sequential float sums (strict), 1: block-parallel sums (reordered)
     std::string error;
 
     int init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream);

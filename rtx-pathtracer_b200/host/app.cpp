@@ -106,7 +106,8 @@ int b200pt_app_draw_frame(b200pt_app *app, b200pt_ctx *ctx, uint32_t frame_seed,
     if (b200pt_app_end_frame(app)) {
         b200pt_guiding_params gp;
         if (!guiding_params) { b200pt_default_guiding_params(&gp); gp.useParallaxCompensation = pc.useParallaxCompensation; guiding_params = &gp; }
-        rc = b200pt_guiding_update(ctx, guiding_params);
+        // spp-sharded training run (b200pt_comm_init was called): the ranks' samples are refitted together, region-sharded
+        rc = b200pt_comm_exchange_mode(ctx) > 0 ? b200pt_guiding_update_all_ranks(ctx, guiding_params) : b200pt_guiding_update(ctx, guiding_params);
     }
     return rc;
 }

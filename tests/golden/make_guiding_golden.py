@@ -27,7 +27,10 @@ SPLITS, PER_REGION, SEEDS = 2, 3000, (11, 12, 13)
 def main():
     P, O = helpers.pt(), helpers.oracle()
     out = {}
-    x = np.concatenate([np.linspace(-180.0, 2.0, 4001), -np.logspace(-7, 2, 2000), [0.0, -0.0, -87.0, -88.5, -126.0, -1e30]]).astype(np.float32)
+    x = np.concatenate([np.linspace(-180.0, 2.0, 4001), -np.logspace(-7, 2, 2000), [0.0, -0.0, -87.0, -88.5, -126.0, -1e30],
+                        # overflow / NaN / infinities: cvtps2dq returns the "integer indefinite" 0x80000000 (= -0.0f), _mm_max_ps passes a NaN
+                        # in its second operand through — both reachable from the merge metric (VMFKernel::division with kappa = 50000)
+                        np.linspace(60.0, 120.0, 241), [1e4, 1e30, np.inf, -np.inf, np.nan]]).astype(np.float32)
     out["fastexp_in"] = x
     out["fastexp_out"] = O.ref_fastexp(x).view(np.uint32)
     gp = P.default_guiding_params()
