@@ -414,6 +414,10 @@ int b200pt_guiding_get_sorted(b200pt_ctx *ctx, b200pt_directional_data *out, uin
 int b200pt_guiding_get_state(b200pt_ctx *ctx, int region, float scalars5[5], float per_component[224]);
 /* known-answer hook: lightpmm::exp (PMM_APPROX_EXP fastexp, pmm-vcl.h:157-184) as evaluated by the device code */
 int b200pt_guiding_fastexp(b200pt_ctx *ctx, const float *in_host, float *out_host, int n);
+/* self-test hook: the division inside fastexp (pmm-vcl.h:171, 27.7280233 / (4.84252568 - z)) is evaluated on the device
+ * by a reciprocal + Newton + Markstein sequence instead of nvcc's guarded `/`; compares it bit for bit with IEEE division
+ * for EVERY float divisor in [lo, hi] (fastexp reaches 2.84 < d < 4.85) */
+int b200pt_guiding_selftest_division(b200pt_ctx *ctx, float lo, float hi, uint64_t *mismatches, uint64_t *tested);
 
 /* ---- AOVs ---------------------------------------------------------------
  * The quantities behind the reference's depth / split debug views (shaders/raytrace.rgen:1653-1655, :1677-1679,

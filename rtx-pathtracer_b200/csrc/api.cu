@@ -1016,6 +1016,16 @@ int b200pt_guiding_fastexp(b200pt_ctx *c, const float *in, float *out, int n) {
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_fastexp: " + err);
     return B200PT_OK;
 }
+int b200pt_guiding_selftest_division(b200pt_ctx *c, float lo, float hi, uint64_t *mismatches, uint64_t *tested) {
+    if (!c || !mismatches || !tested) return setError(B200PT_E_INVALID, "b200pt_guiding_selftest_division: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::string err;
+    unsigned long long m = 0, t = 0;
+    int rc = guidingDivisionSelfTest(lo, hi, &m, &t, c->stream, err);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_selftest_division: " + err);
+    *mismatches = m; *tested = t;
+    return B200PT_OK;
+}
 int b200pt_guiding_region_count(b200pt_ctx *c, int *count) {
     if (!c || !count) return setError(B200PT_E_INVALID, "b200pt_guiding_region_count: null argument");
     *count = c->guiding.regionCount;

@@ -127,7 +127,7 @@ struct GPlanSummary {
 
 __global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allCounts, int N, int me, uint32_t R, uint32_t stride, int peerMode,
                                                uint32_t *srcStart, uint32_t *regionBegin, uint32_t *regionCount, uint32_t *regionOffset,
-                                               uint32_t *activeRegions, uint32_t *totalAll, uint8_t *ownerOut, GSegment *segments, GPlanSummary *summary) {
+                                               uint32_t *activeRegions, uint32_t *totalAll, uint8_t *ownerOut, uint32_t *regionSlot, GSegment *segments, GPlanSummary *summary) {
     __shared__ uint32_t total[1024];
     __shared__ uint16_t order[1024], binOf[1024], regionOfBin[1024];
     __shared__ uint8_t own[1024];
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allC
     }
     if (t <= unsigned(N)) { uint32_t c = 0; for (uint32_t u = 0; u < R; u++) c += own[u] < t; firstBin[t] = c; }
     __syncthreads();
+    if (t < R) regionSlot[t] = own[t] == me ? uint32_t(binOf[t]) - firstBin[me] : 0u;      // position among this rank's regions
     for (int s = int(warp); s < N; s += 32) {      // every rank's sorted layout: exclusive scan of its counts over the bins
         uint32_t run = 0;
         for (uint32_t base = 0; base < R; base += 32) {
@@ -527,6 +528,471 @@ __global__ void __launch_bounds__(G_BLOCK, G_BLOCKS_PER_SM) k_guiding_update(GMi
     }
 }
 
+// ---- work-sharing executor (block-parallel sums, the fast path) --------------------------------------------------------
+// One thread block per region ("owner") runs the updateRegion sequence; every pass over the region's samples is cut
+// into fixed chunks of GS_CHUNK samples that are handed out through one atomic word — to the owner itself and to every
+// block that has no region of its own left ("helper").  The whole machine therefore works on whatever pass is open:
+// a region that needs 100 EM iterations, or that holds a third of all samples, no longer sets the kernel time.
+//   * a sample is evaluated by FOUR threads, thread q taking the components q, q+4, q+8, q+12 — lightpmm's SSE lanes:
+//     the lane sums of the mixture pdf are combined as (l0+l2)+(l1+l3) with two shuffles, the values are the reference's;
+//     18 accumulators per thread instead of 66 (registers for 3-4 resident blocks per SM instead of 1);
+//   * partial sums: thread -> warp (shuffles) -> block (shared memory, warp order) -> one row per chunk in global memory;
+//     the owner adds the rows in chunk order.  Sample -> thread, chunk boundaries and all summation orders are fixed, so
+//     the result does not depend on which block computed which chunk (bit-identical from run to run and across ranks).
+#define GS_BLOCK 256
+#define GS_QUADS (GS_BLOCK / 4)
+#define GS_WARPS (GS_BLOCK / 32)
+#define GS_CHUNK_MAX 2048            // 32 samples per quad
+#define GS_ROWS_PER_REGION 66        // a region's passes have at most max(65, N_r / 2048 + 1) chunks
+enum { GS_PASS_EM = 0, GS_PASS_STAT = 1, GS_PASS_DIST = 2 };
+// Chunk size of a region's passes: a function of the region's sample count only (so the summation order is fixed):
+// about 64 chunks per pass for mid-size regions — enough for the whole machine to finish the last regions' iterations
+// together — between 4 and 32 samples per quad.
+__host__ __device__ __forceinline__ uint32_t gsChunkSamples(uint32_t count) {
+    uint32_t perQuad = (count + 4095u) / 4096u;
+    perQuad = perQuad < 4u ? 4u : (perQuad > 32u ? 32u : perQuad);
+    return perQuad * 64u;
+}
+
+struct alignas(16) GPass {           // one per region, global memory
+    unsigned long long word;         // number of chunks << 32 | next chunk; atomicAdd(word, 1) hands out a chunk
+    uint32_t done;                   // chunks finished
+    uint32_t type;                   // GS_PASS_* | KPAD << 8
+    uint32_t begin, count, chunkBase, passCount;   // passCount: passes this region has opened in this update (helpers prefer long runners)
+    GPacked packed;
+    GFrames frames;
+};
+
+struct SharedShared {
+    GMix mix;
+    GPacked packed;                  // lobes of the pass being processed (own region's or a helped one's)
+    GFrames frames;
+    GFitState fitState;
+    union { EmAcc em; StatAcc stat; DistAcc dist; float raw[G_STATACC_FLOATS]; } acc;
+    float metric[G_MAXK * (G_MAXK - 1) / 2];
+    float staged[G_STATACC_FLOATS];
+    float red[GS_WARPS][G_STATACC_FLOATS];
+    int bc;
+    unsigned long long grab;
+    uint32_t hType, hBegin, hCount, hChunkBase, hSlot;
+};
+
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// (l0 + l2) + (l1 + l3) over the four threads of a quad; every thread gets the same float (addition commutes)
+__device__ __forceinline__ float quadLaneSum(float lane) {
+    const float a = lane + __shfl_xor_sync(0xffffffffu, lane, 2);
+    return a + __shfl_xor_sync(0xffffffffu, a, 1);
+}
+// weighted component pdfs of this thread's components (gMixturePdf restricted to lane q) and the mixture pdf
+template <int KQ, bool WANT_PDF>
+__device__ __forceinline__ float quadMixturePdf(const GPacked &m, unsigned q, float dx, float dy, float dz, float *wpdf, float *pdf) {
+    float lane = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KQ; k++) {
+        const GPacked::A a = m.a[4 * k + q];
+        const GPacked::B b = m.b[4 * k + q];
+        const float cosTheta = a.mx * dx + a.my * dy + a.mz * dz;
+        const float t = gSseMin(cosTheta - 1.0f, 0.0f);
+        const float p = b.norm * gFastExp(a.kappa * t);
+        if (WANT_PDF) pdf[k] = p;
+        wpdf[k] = b.w * p;
+        lane += wpdf[k];
+    }
+    return quadLaneSum(lane);
+}
+
+// sum NA per-thread accumulators over the block: threads with the same quad lane q hold the same components.
+// value index of accumulator j of lane q: idx(j, q).  Result rows -> out[0..NV) (global), fixed order.
+template <int NA, class Idx>
+__device__ __forceinline__ void quadBlockReduce(float (&v)[NA], Idx idx, int NV, float (*red)[G_STATACC_FLOATS], float *out) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, q = threadIdx.x & 3u;
+#pragma unroll
+    for (int j = 0; j < NA; j++) {
+        float x = v[j];
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        const int i = idx(j, q);
+        if (lane < 4 && i >= 0) red[warp][i] = x;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += GS_BLOCK) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < GS_WARPS; w++) s += red[w][i];
+        out[i] = s;
+    }
+}
+
+template <int KQ>
+__device__ void chunkEm(const GPacked &pk, const float4 *__restrict__ dirw, uint32_t first, uint32_t end, float (*red)[G_STATACC_FLOATS], float *out) {
+    constexpr int KPAD = 4 * KQ;
+    const unsigned q = threadIdx.x & 3u, quad = threadIdx.x >> 2;
+    float acc[4 * KQ + 2];
+#pragma unroll
+    for (int j = 0; j < 4 * KQ + 2; j++) acc[j] = 0.0f;
+    // the log-likelihood term needs one logf per SAMPLE, not per thread: lane (it & 3) of the quad keeps the sample's
+    // (weight, mixture pdf) and every fourth iteration each lane takes the logarithm of the one it holds
+    float pendW = 0.0f, pendPdf = 1.0f;
+    const float4 idle = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+    uint32_t i = first + quad, it = 0;
+    bool valid = i < end;
+    float4 s = valid ? dirw[i] : idle;
+    for (uint32_t base = first; base < end; base += GS_QUADS, it++) {
+        G_NO_HOIST();
+        const uint32_t in = i + GS_QUADS;
+        const bool validNext = in < end;
+        const float4 sn = validNext ? dirw[in] : idle;          // next sample: in flight while this one is evaluated
+        float sw[KQ];
+        const float mixturePDF = quadMixturePdf<KQ, false>(pk, q, s.x, s.y, s.z, sw, (float *)0);
+        const bool ok = valid && mixturePDF > G_PMM_EPSILON;
+        if (ok) {
+            const float inv = 1.0f / mixturePDF;
+#pragma unroll
+            for (int k = 0; k < KQ; k++) {
+                const float w = (sw[k] * inv) * s.w;
+                acc[KQ + k] += s.x * w; acc[2 * KQ + k] += s.y * w; acc[3 * KQ + k] += s.z * w;
+                acc[k] += w;
+            }
+            acc[4 * KQ] += s.w;
+        }
+        if ((it & 3u) == q) { pendW = ok ? s.w : 0.0f; pendPdf = ok ? mixturePDF : 1.0f; }
+        if ((it & 3u) == 3u) { acc[4 * KQ + 1] += pendW * logf(pendPdf); pendW = 0.0f; pendPdf = 1.0f; }
+        s = sn; valid = validNext; i = in;
+    }
+    float ll = acc[4 * KQ + 1] + pendW * logf(pendPdf);
+    ll += __shfl_xor_sync(0xffffffffu, ll, 1);
+    ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+    acc[4 * KQ + 1] = ll;
+    // EmAcc layout of the partial row: W[c] | Rx[c] | Ry[c] | Rz[c] | sumWeight | logLikelihood, c = 4k + q
+    quadBlockReduce<4 * KQ + 2>(acc, [](int j, unsigned q) -> int {
+        if (j < 4 * KQ) return (j / KQ) * KPAD + 4 * (j % KQ) + int(q);
+        return q == 0 ? 4 * KPAD + (j - 4 * KQ) : -1;
+    }, 4 * KPAD + 2, red, out);
+}
+
+template <int KQ>
+__device__ void chunkStat(const GPacked &pk, const GFrames &f, const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist, uint32_t first, uint32_t end,
+                          float (*red)[G_STATACC_FLOATS], float *out) {
+    constexpr int KPAD = 4 * KQ;
+    const unsigned q = threadIdx.x & 3u, quad = threadIdx.x >> 2;
+    float acc[5 * KQ];
+#pragma unroll
+    for (int j = 0; j < 5 * KQ; j++) acc[j] = 0.0f;
+    const float4 idle = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+    uint32_t i = first + quad;
+    bool valid = i < end;
+    float4 s = valid ? dirw[i] : idle;
+    float2 pd = valid ? pdfDist[i] : make_float2(1.0f, 0.0f);
+    for (uint32_t base = first; base < end; base += GS_QUADS) {
+        G_NO_HOIST();
+        const uint32_t in = i + GS_QUADS;
+        const bool validNext = in < end;
+        const float4 sn = validNext ? dirw[in] : idle;
+        const float2 pdn = validNext ? pdfDist[in] : make_float2(1.0f, 0.0f);
+        float wpdf[KQ], pdf[KQ];
+        const float mixturePDF = quadMixturePdf<KQ, true>(pk, q, s.x, s.y, s.z, wpdf, pdf);
+        if (valid && mixturePDF > G_PMM_EPSILON) {
+            const float mixturePDFSqr = mixturePDF * mixturePDF;
+            const float ideal = s.w * s.w * pd.x / mixturePDFSqr;
+            const float inv = 1.0f / mixturePDF;
+#pragma unroll
+            for (int k = 0; k < KQ; k++) {
+                const int c = 4 * k + int(q);
+                acc[k] += pdf[k] * ideal;
+                const float ws = s.w * (wpdf[k] * inv);
+                acc[KQ + k] += ws;
+                const float lx = f.sx[c] * s.x + f.sy[c] * s.y + f.sz[c] * s.z;
+                const float ly = f.tx[c] * s.x + f.ty[c] * s.y + f.tz[c] * s.z;
+                acc[2 * KQ + k] += lx * lx * ws;
+                acc[3 * KQ + k] += ly * ly * ws;
+                acc[4 * KQ + k] += lx * ly * ws;
+            }
+        }
+        s = sn; pd = pdn; valid = validNext; i = in;
+    }
+    quadBlockReduce<5 * KQ>(acc, [](int j, unsigned q) -> int { return (j / KQ) * KPAD + 4 * (j % KQ) + int(q); }, 5 * KPAD, red, out);
+}
+
+template <int KQ>
+__device__ void chunkDist(const GPacked &pk, const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist, uint32_t first, uint32_t end,
+                          float (*red)[G_STATACC_FLOATS], float *out) {
+    constexpr int KPAD = 4 * KQ;
+    const unsigned q = threadIdx.x & 3u, quad = threadIdx.x >> 2;
+    float acc[2 * KQ];
+#pragma unroll
+    for (int j = 0; j < 2 * KQ; j++) acc[j] = 0.0f;
+    const float4 idle = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+    uint32_t i = first + quad;
+    bool valid = i < end;
+    float4 s = valid ? dirw[i] : idle;
+    float2 pd = valid ? pdfDist[i] : make_float2(1.0f, 0.0f);
+    for (uint32_t base = first; base < end; base += GS_QUADS) {
+        G_NO_HOIST();
+        const uint32_t in = i + GS_QUADS;
+        const bool validNext = in < end;
+        const float4 sn = validNext ? dirw[in] : idle;
+        const float2 pdn = validNext ? pdfDist[in] : make_float2(1.0f, 0.0f);
+        float wpdf[KQ], pdf[KQ];
+        const float mixturePDF = quadMixturePdf<KQ, true>(pk, q, s.x, s.y, s.z, wpdf, pdf);
+        if (valid && pd.y > 0.0f && mixturePDF > G_PMM_EPSILON) {
+            const float sw = s.w / mixturePDF;
+#pragma unroll
+            for (int k = 0; k < KQ; k++) {
+                const float v = wpdf[k] * pdf[k] * sw;
+                acc[k] += v;
+                acc[KQ + k] += v / pd.y;
+            }
+        }
+        s = sn; pd = pdn; valid = validNext; i = in;
+    }
+    quadBlockReduce<2 * KQ>(acc, [](int j, unsigned q) -> int { return (j / KQ) * KPAD + 4 * (j % KQ) + int(q); }, 2 * KPAD, red, out);
+}
+
+// one chunk of one pass; lobes (and frames) are in shared memory
+__device__ void processChunk(SharedShared &sh, uint32_t type, uint32_t begin, uint32_t count, uint32_t chunk, const float4 *__restrict__ dirw,
+                             const float2 *__restrict__ pdfDist, float *out) {
+    const uint32_t cs = gsChunkSamples(count);
+    const uint32_t first = begin + chunk * cs, end = begin + min(count, (chunk + 1) * cs);
+    const uint32_t kq = (type >> 8) / 4, pass = type & 0xffu;
+#define GS_DISPATCH(FN, ...)                                                   \
+    switch (kq) {                                                              \
+        case 1: FN<1>(__VA_ARGS__); break;                                     \
+        case 2: FN<2>(__VA_ARGS__); break;                                     \
+        case 3: FN<3>(__VA_ARGS__); break;                                     \
+        default: FN<4>(__VA_ARGS__); break;                                    \
+    }
+    if (pass == GS_PASS_EM) { GS_DISPATCH(chunkEm, sh.packed, dirw, first, end, sh.red, out) }
+    else if (pass == GS_PASS_STAT) { GS_DISPATCH(chunkStat, sh.packed, sh.frames, dirw, pdfDist, first, end, sh.red, out) }
+    else { GS_DISPATCH(chunkDist, sh.packed, dirw, pdfDist, first, end, sh.red, out) }
+#undef GS_DISPATCH
+}
+
+struct SharedExec {
+    SharedShared &sh;
+    GPass *pass;                // this region's pass descriptor (global)
+    float *partials;            // [chunks][G_STATACC_FLOATS] (global)
+    const float4 *dirw;         // whole sorted buffer
+    const float2 *pdfDist;
+    uint32_t begin, N, chunkBase;
+    uint32_t passCount;         // thread 0 only
+
+    __device__ bool leader() const { return threadIdx.x == 0; }
+    __device__ int bcast(int v) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.bc = v;
+        __syncthreads();
+        return sh.bc;
+    }
+    __device__ EmAcc &em() { return sh.acc.em; }
+    __device__ StatAcc &stat() { return sh.acc.stat; }
+    __device__ DistAcc &dst() { return sh.acc.dist; }
+    __device__ GFrames &frames() { return sh.frames; }
+    __device__ float *metric() { return sh.metric; }
+    __device__ GFitState &fit() { return sh.fitState; }
+
+    // open a pass: lobes (+ frames) to shared AND global memory, then the chunk counter; work on it until no chunk is
+    // left; wait for the helpers' chunks; add the partial rows in chunk order -> sh.staged[0..nv)
+    __device__ void runPass(const GMix &m, uint32_t passType, int nv) {
+        __syncthreads();
+        const uint32_t kpad = uint32_t(gKpad(m.K)), type = passType | (kpad << 8);
+        if (threadIdx.x < G_MAXK) {
+            const int c = threadIdx.x;
+            GPacked::A a; a.mx = m.mux[c]; a.my = m.muy[c]; a.mz = m.muz[c]; a.kappa = m.kappa[c];
+            GPacked::B b; b.norm = m.norm[c]; b.w = m.w[c];
+            sh.packed.a[c] = a; sh.packed.b[c] = b;
+            pass->packed.a[c] = a; pass->packed.b[c] = b;
+            if (passType == GS_PASS_STAT) {
+                pass->frames.sx[c] = sh.frames.sx[c]; pass->frames.sy[c] = sh.frames.sy[c]; pass->frames.sz[c] = sh.frames.sz[c];
+                pass->frames.tx[c] = sh.frames.tx[c]; pass->frames.ty[c] = sh.frames.ty[c]; pass->frames.tz[c] = sh.frames.tz[c];
+            }
+            __threadfence();
+        }
+        const uint32_t cs = gsChunkSamples(N), numChunks = (N + cs - 1) / cs;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            pass->type = type; pass->done = 0u; pass->passCount = ++passCount;
+            __threadfence();
+            atomicExch(&pass->word, (unsigned long long)numChunks << 32);
+        }
+        for (;;) {
+            if (threadIdx.x == 0) sh.grab = atomicAdd(&pass->word, 1ull);
+            __syncthreads();
+            const unsigned long long g = sh.grab;
+            const uint32_t c = uint32_t(g & 0xffffffffull);
+            if (c >= uint32_t(g >> 32)) break;
+            processChunk(sh, type, begin, N, c, dirw, pdfDist, partials + size_t(chunkBase + c) * G_STATACC_FLOATS);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&pass->done, 1u);
+        }
+        if (threadIdx.x == 0) while (ldAcquire(&pass->done) < numChunks) __nanosleep(100);
+        __syncthreads();
+        if (int(threadIdx.x) < nv) {      // rows in chunk order; eight loads in flight
+            float sum = 0.0f;
+            const float *row = partials + size_t(chunkBase) * G_STATACC_FLOATS + threadIdx.x;
+            uint32_t c = 0;
+            for (; c + 8 <= numChunks; c += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __ldcg(row + size_t(c + j) * G_STATACC_FLOATS);
+#pragma unroll
+                for (int j = 0; j < 8; j++) sum += v[j];
+            }
+            for (; c < numChunks; c++) sum += __ldcg(row + size_t(c) * G_STATACC_FLOATS);
+            sh.staged[threadIdx.x] = sum;
+        }
+        __syncthreads();
+    }
+
+    __device__ void emPass(const GMix &m, EmAcc &out) {
+        const int KPAD = gKpad(m.K);
+        runPass(m, GS_PASS_EM, 4 * KPAD + 2);
+        const float *staged = sh.staged;
+        if (int(threadIdx.x) < KPAD) {
+            const int c = threadIdx.x;
+            out.W[c] = staged[c]; out.Rx[c] = staged[KPAD + c]; out.Ry[c] = staged[2 * KPAD + c]; out.Rz[c] = staged[3 * KPAD + c];
+        }
+        if (threadIdx.x == 0) { out.sumWeight = staged[4 * KPAD]; out.logLikelihood = staged[4 * KPAD + 1]; }
+        __syncthreads();
+    }
+    __device__ void statPass(const GMix &m, const GFrames &f, StatAcc &out) {
+        (void)f;    // == sh.frames
+        const int KPAD = gKpad(m.K);
+        runPass(m, GS_PASS_STAT, 5 * KPAD);
+        const float *staged = sh.staged;
+        if (int(threadIdx.x) < KPAD) {
+            const int c = threadIdx.x;
+            out.chi[c] = staged[c]; out.covW[c] = staged[KPAD + c]; out.covXX[c] = staged[2 * KPAD + c]; out.covYY[c] = staged[3 * KPAD + c]; out.covXY[c] = staged[4 * KPAD + c];
+        }
+        __syncthreads();
+    }
+    __device__ void distPass(const GMix &m, DistAcc &out) {
+        const int KPAD = gKpad(m.K);
+        runPass(m, GS_PASS_DIST, 2 * KPAD);
+        const float *staged = sh.staged;
+        if (int(threadIdx.x) < KPAD) { const int c = threadIdx.x; out.w[c] = staged[c]; out.wd[c] = staged[KPAD + c]; }
+        __syncthreads();
+    }
+    __device__ void metricPass(const GMix &m, float *metric) {
+        __syncthreads();
+        const int K = m.K, numPairs = K * (K - 1) / 2;
+        for (int p = threadIdx.x; p < numPairs; p += GS_BLOCK) {
+            int idx = p, a = 0;
+            while (idx >= K - 1 - a) { idx -= K - 1 - a; a++; }
+            metric[p] = gMergeMetricPair(m, a, a + 1 + idx);
+        }
+        __syncthreads();
+    }
+};
+
+// persistent: every block first takes regions to own (largest first), then helps until all regions are done.
+// control[0] = next region to hand out, control[1] = regions finished
+#ifndef GS_MIN_BLOCKS
+#define GS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS) k_guiding_update_shared(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
+                                                                     const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ numActivePtr,
+                                                                     const uint32_t *__restrict__ regionBegin, const uint32_t *__restrict__ regionCount,
+                                                                     const uint32_t *__restrict__ regionSlot, const float4 *__restrict__ dirw,
+                                                                     const float2 *__restrict__ pdfDist, GPass *passes, float *partials, uint32_t *control,
+                                                                     b200pt_guiding_params gp, int firstFit, unsigned long long *emSampleIterations) {
+    __shared__ SharedShared sh;
+    const uint32_t numActive = *numActivePtr;
+    for (;;) {      // ---- owner phase
+        if (threadIdx.x == 0) sh.hSlot = atomicAdd(&control[0], 1u);
+        __syncthreads();
+        const uint32_t slot = sh.hSlot;
+        __syncthreads();
+        if (slot >= numActive) break;
+        const long long t0 = clock64();
+        const uint32_t region = activeRegions[slot];
+        const uint32_t begin = regionBegin[region], count = regionCount[region];
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&mixes[region]);
+            uint32_t *dstw = reinterpret_cast<uint32_t *>(&sh.mix);
+            for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += GS_BLOCK) dstw[i] = src[i];
+        }
+        __syncthreads();
+        GPass *pass = passes + region;
+        const uint32_t chunkBase = begin / GS_CHUNK_MAX + regionSlot[region] * GS_ROWS_PER_REGION;
+        if (threadIdx.x == 0) { pass->begin = begin; pass->count = count; pass->chunkBase = chunkBase; }
+        SharedExec x{sh, pass, partials, dirw, pdfDist, begin, count, chunkBase, 0u};
+        const b200pt_aabb bb = aabbs[region];
+        float mean[3];
+        for (int a = 0; a < 3; a++) mean[a] = bb.min[a] + 0.5f * (bb.max[a] - bb.min[a]);
+        uint64_t iters = 0;
+        gUpdateRegion(x, sh.mix, gp, count, firstFit != 0, mean, &iters);
+        if (threadIdx.x == 0) sh.mix.lastUpdateKCycles = uint32_t((clock64() - t0) >> 10);
+        __syncthreads();
+        {
+            uint32_t *dstw = reinterpret_cast<uint32_t *>(&mixes[region]);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&sh.mix);
+            for (uint32_t i = threadIdx.x; i < sizeof(GMix) / 4; i += GS_BLOCK) dstw[i] = src[i];
+        }
+        if (threadIdx.x == 0) {
+            gPackTheta(sh.mix, gp.useParallaxCompensation != 0, vmms[region]);
+            atomicAdd(emSampleIterations, (unsigned long long)iters);
+            __threadfence();
+            atomicAdd(&control[1], 1u);
+        }
+        __syncthreads();
+    }
+    // ---- helper phase: look for the open pass with the most chunks left, take one chunk, repeat
+    for (;;) {
+        if (threadIdx.x < 32) {      // one warp looks at the open passes; the others wait at the barrier (no issue slots)
+            uint32_t best = 0u, bestSlot = 0xffffffffu;
+            for (uint32_t sl = threadIdx.x; sl < numActive; sl += 32) {
+                const GPass *ps = passes + activeRegions[sl];
+                const unsigned long long w = __ldcg(&ps->word);
+                const uint32_t next = uint32_t(w & 0xffffffffull), n = uint32_t(w >> 32);
+                if (next >= n) continue;
+                // prefer the region that has run the most passes (it is the one the kernel will end up waiting for), then the fullest pass
+                const uint32_t key32 = (min(__ldcg(&ps->passCount), 0xffffu) << 16) | min(n - next, 0xffffu);
+                if (key32 > best) { best = key32; bestSlot = sl; }
+            }
+            unsigned long long key = (unsigned long long)best << 32 | (0xffffffffu - bestSlot);
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
+            if (threadIdx.x == 0) {
+                sh.hSlot = (key >> 32) ? 0xffffffffu - uint32_t(key & 0xffffffffull) : 0xffffffffu;
+                sh.grab = ~0ull;
+                if (sh.hSlot != 0xffffffffu) sh.grab = atomicAdd(&passes[activeRegions[sh.hSlot]].word, 1ull);
+                else if (ldAcquire(&control[1]) >= numActive) sh.hSlot = 0xfffffffeu;      // nothing open and every region finished: leave
+                else __nanosleep(1000);
+            }
+        }
+        __syncthreads();
+        const uint32_t sl = sh.hSlot;
+        const unsigned long long g = sh.grab;
+        const uint32_t c = uint32_t(g & 0xffffffffull);
+        if (sl == 0xfffffffeu) break;
+        if (sl == 0xffffffffu || c >= uint32_t(g >> 32)) { __syncthreads(); continue; }
+        // a chunk of a foreign pass is ours: its parameters were published before the counter was opened
+        GPass *pass = passes + activeRegions[sl];
+        __threadfence();
+        if (threadIdx.x < G_MAXK) {
+            const int cc = threadIdx.x;
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(&pass->packed.a[cc]));
+            const float2 b = __ldcg(reinterpret_cast<const float2 *>(&pass->packed.b[cc]));
+            sh.packed.a[cc].mx = a.x; sh.packed.a[cc].my = a.y; sh.packed.a[cc].mz = a.z; sh.packed.a[cc].kappa = a.w;
+            sh.packed.b[cc].norm = b.x; sh.packed.b[cc].w = b.y;
+            sh.frames.sx[cc] = __ldcg(&pass->frames.sx[cc]); sh.frames.sy[cc] = __ldcg(&pass->frames.sy[cc]); sh.frames.sz[cc] = __ldcg(&pass->frames.sz[cc]);
+            sh.frames.tx[cc] = __ldcg(&pass->frames.tx[cc]); sh.frames.ty[cc] = __ldcg(&pass->frames.ty[cc]); sh.frames.tz[cc] = __ldcg(&pass->frames.tz[cc]);
+        }
+        if (threadIdx.x == 32) { sh.hType = __ldcg(&pass->type); sh.hBegin = __ldcg(&pass->begin); sh.hCount = __ldcg(&pass->count); sh.hChunkBase = __ldcg(&pass->chunkBase); }
+        __syncthreads();
+        processChunk(sh, sh.hType, sh.hBegin, sh.hCount, c, dirw, pdfDist, partials + size_t(sh.hChunkBase + c) * G_STATACC_FLOATS);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&pass->done, 1u);
+    }
+}
+
 // ---- strict-order executor ---------------------------------------------------------------------------------------------
 // lightpmm sums the sufficient statistics sample after sample in float (VMMFactory.h:497-536): float addition does not
 // commute with regrouping, so any parallel partition of a region's samples changes the last bits of the sums, and the EM
@@ -818,6 +1284,29 @@ __global__ void k_fastexp(const float *__restrict__ in, float *__restrict__ out,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = gFastExp(in[i]);
 }
+// exhaustive check of gFastExpDiv against the IEEE division it replaces: every float bit pattern in [lo, hi]
+__global__ void k_fastexp_div_check(uint32_t loBits, uint32_t count, unsigned long long *mismatches) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float d = __uint_as_float(loBits + i);
+    if (__float_as_uint(gFastExpDiv(d)) != __float_as_uint(__fdiv_rn(27.7280233f, d))) atomicAdd(mismatches, 1ull);
+}
+int guidingDivisionSelfTest(float lo, float hi, unsigned long long *mismatchesOut, unsigned long long *testedOut, cudaStream_t stream, std::string &error) {
+    uint32_t a, b;
+    memcpy(&a, &lo, 4); memcpy(&b, &hi, 4);
+    if (!(lo > 0.0f) || !(hi >= lo)) { error = "bad range"; return B200PT_E_INVALID; }
+    const uint32_t count = b - a + 1;
+    unsigned long long *d = nullptr, h = 0;
+    if (cudaMalloc(reinterpret_cast<void **>(&d), sizeof(h)) != cudaSuccess) { error = "cudaMalloc failed"; return B200PT_E_CUDA; }
+    cudaMemsetAsync(d, 0, sizeof(h), stream);
+    k_fastexp_div_check<<<(count + 255) / 256, 256, 0, stream>>>(a, count, d);
+    cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { error = cudaGetErrorString(e); return B200PT_E_CUDA; }
+    *mismatchesOut = h; *testedOut = count;
+    return B200PT_OK;
+}
 int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stream, std::string &error) {
     if (n <= 0) return B200PT_OK;
     float *d = nullptr;
@@ -888,6 +1377,17 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionLen), size_t(maxRegions) * sizeof(uint32_t)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&totalAll), size_t(maxRegions) * sizeof(uint32_t)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&owner), size_t(maxRegions)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&regionSlot), size_t(maxRegions) * sizeof(uint32_t)));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&passes), size_t(maxRegions) * sizeof(GPass)));
+    G_TRY(cudaMemsetAsync(passes, 0, size_t(maxRegions) * sizeof(GPass), stream));
+    G_TRY(cudaMalloc(reinterpret_cast<void **>(&fitControl), 2 * sizeof(uint32_t)));
+    {
+        int dev = 0, sms = 0, occ = 0;
+        G_TRY(cudaGetDevice(&dev));
+        G_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        G_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_guiding_update_shared, GS_BLOCK, 0));
+        sharedGrid = sms * std::max(1, occ);
+    }
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&planDev), sizeof(GPlanSummary)));
     G_TRY(cudaMemsetAsync(planDev, 0, sizeof(GPlanSummary), stream));
     G_TRY(cudaMallocHost(reinterpret_cast<void **>(&planHost), sizeof(GPlanSummary)));
@@ -1049,7 +1549,7 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     }
     if (N > 1) G_NCCL(g_nccl.AllGather(myCounts, allCounts, size_t(stride) * sizeof(uint32_t), ncclChar, rc->comm, stream));
     k_plan<<<1, 1024, 0, stream>>>(allCounts, N, me, R, stride, peerMode ? 1 : 0, srcStart, regionBegin, regionLen, regionOffset, activeRegions, totalAll,
-                                   owner, segments, planDev);
+                                   owner, regionSlot, segments, planDev);
     launches++;
     G_TRY(cudaGetLastError());
     G_TRY(cudaMemcpyAsync(planHost, planDev, sizeof(GPlanSummary), cudaMemcpyDeviceToHost, stream));
@@ -1131,8 +1631,21 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
         k_guiding_update_strict<<<fitRegions, GC_BLOCK, GC_SMEM_BYTES, stream>>>(mixes, vmms, aabbs, activeRegions, &planDev->numActive, regionBegin, regionLen, fitD, fitP,
                                                                                  params, firstFit ? 1 : 0, devScalars);
         launches++;
+    } else if (fitRegions && !getenv("B200PT_GUIDING_CLUSTER")) {
+        // block-parallel sums (a different float summation order than the reference's), work shared between all blocks
+        const int64_t rows = (fitD == dirw ? capacity : fitCapacity) / GS_CHUNK_MAX + int64_t(maxRegions) * GS_ROWS_PER_REGION + 2;
+        if (rows > partialRows) {
+            if (partials) cudaFree(partials);
+            partials = nullptr; partialRows = 0;
+            G_TRY(cudaMalloc(reinterpret_cast<void **>(&partials), size_t(rows) * G_STATACC_FLOATS * sizeof(float)));
+            partialRows = rows;
+        }
+        G_TRY(cudaMemsetAsync(fitControl, 0, 2 * sizeof(uint32_t), stream));
+        k_guiding_update_shared<<<sharedGrid, GS_BLOCK, 0, stream>>>(mixes, vmms, aabbs, activeRegions, &planDev->numActive, regionBegin, regionLen, regionSlot, fitD, fitP,
+                                                                     passes, partials, fitControl, params, firstFit ? 1 : 0, devScalars);
+        launches++;
     } else if (fitRegions) {
-        // block-parallel sums (a different float summation order than the reference's): one cluster of `clusterSize` CTAs
+        // the round-1 kernel, kept for A/B (B200PT_GUIDING_CLUSTER=<size>): one cluster of CTAs per region
         // per region (portable maximum 8); B200PT_GUIDING_CLUSTER overrides
         int clusterSize = 4;
         if (const char *e = getenv("B200PT_GUIDING_CLUSTER")) clusterSize = std::max(1, std::min(8, atoi(e)));
@@ -1323,10 +1836,10 @@ void GuidingState::release() {
     closePeers();
     peerTried = false; peerCapacity = -1;
     for (void *p : {(void *)allCounts, (void *)srcStart, (void *)segments, (void *)gatherMix, (void *)gatherVmm, (void *)regionBegin, (void *)regionLen,
-                    (void *)totalAll, (void *)owner, (void *)planDev, (void *)fitDirw, (void *)fitPdfDist, (void *)stageDirw, (void *)stagePdfDist, (void *)barrierWord})
+                    (void *)totalAll, (void *)owner, (void *)regionSlot, (void *)passes, (void *)partials, (void *)fitControl, (void *)planDev, (void *)fitDirw, (void *)fitPdfDist, (void *)stageDirw, (void *)stagePdfDist, (void *)barrierWord})
         if (p) cudaFree(p);
     allCounts = nullptr; srcStart = nullptr; segments = nullptr; gatherMix = nullptr; gatherVmm = nullptr; regionBegin = nullptr; regionLen = nullptr;
-    totalAll = nullptr; owner = nullptr; planDev = nullptr; fitDirw = nullptr; fitPdfDist = nullptr; stageDirw = nullptr; stagePdfDist = nullptr; barrierWord = nullptr;
+    totalAll = nullptr; owner = nullptr; regionSlot = nullptr; passes = nullptr; partials = nullptr; fitControl = nullptr; partialRows = 0; planDev = nullptr; fitDirw = nullptr; fitPdfDist = nullptr; stageDirw = nullptr; stagePdfDist = nullptr; barrierWord = nullptr;
     fitCapacity = 0; stageCapacity = 0; planRanks = 0;
     if (planHost) cudaFreeHost(planHost);
     planHost = nullptr;

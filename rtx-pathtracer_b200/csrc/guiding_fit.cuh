@@ -13,6 +13,7 @@ namespace b200pt {
 struct GMix;
 struct GSegment;
 struct GPlanSummary;
+struct GPass;
 
 struct GuidingState {
     bool ready = false;
@@ -40,6 +41,13 @@ struct GuidingState {
     uint32_t *allCounts = nullptr, *srcStart = nullptr;                 // [ranks][maxRegions]
     uint32_t *regionBegin = nullptr, *regionLen = nullptr, *totalAll = nullptr;
     uint8_t *owner = nullptr;
+    uint32_t *regionSlot = nullptr;                                     // position of a region among this rank's regions
+    // work-sharing fit kernel: pass descriptors, per-chunk partial sums, {next region, regions finished}
+    GPass *passes = nullptr;
+    float *partials = nullptr;
+    int64_t partialRows = 0;
+    uint32_t *fitControl = nullptr;
+    int sharedGrid = 0;
     GSegment *segments = nullptr;                                       // [maxRegions * ranks]
     GPlanSummary *planDev = nullptr, *planHost = nullptr;               // device / pinned host copy
     int planRanks = 0;
@@ -57,7 +65,7 @@ struct GuidingState {
     bool peerTried = false;
     int peerSelf = -1;                                                  // own entries alias dirw / pdfDist: never IPC-closed
     b200pt_guiding_params lastParams{};
-    int summationOrder = 0;                // 0: the reference's sequential float sums (strict), 1: block-parallel sums (reordered)
+    int summationOrder = 1;                // 0: the reference's sequential float sums (strict), 1: block-parallel sums (reordered, the fast default)
     std::string error;
 
     int init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream);
@@ -79,6 +87,7 @@ struct GuidingState {
     void release();
 };
 
+int guidingDivisionSelfTest(float lo, float hi, unsigned long long *mismatchesOut, unsigned long long *testedOut, cudaStream_t stream, std::string &error);
 int guidingFastExp(const float *hostIn, float *hostOut, int n, cudaStream_t stream, std::string &error);
 
 }  // namespace b200pt
