@@ -14,7 +14,7 @@ CU_SRCS   := $(PKG)/csrc/api.cu $(PKG)/csrc/guiding_fit.cu
 HOST_SRCS := $(PKG)/host/scene.cpp $(PKG)/host/bvh.cpp $(PKG)/host/exr.cpp $(PKG)/host/app.cpp $(PKG)/host/image_decode.cpp
 CU_OBJS   := $(patsubst $(PKG)/csrc/%.cu,$(BUILD)/%.o,$(CU_SRCS))
 HOST_OBJS := $(patsubst $(PKG)/host/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
-HEADERS   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/host/*.h) include/b200pt.h
+HEADERS   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/host/*.h) include/b200pt.h include/b200pt_detmath.h
 
 all: $(LIB) $(CLI)
 

@@ -419,6 +419,16 @@ int b200pt_guiding_fastexp(b200pt_ctx *ctx, const float *in_host, float *out_hos
  * for EVERY float divisor in [lo, hi] (fastexp reaches 2.84 < d < 4.85) */
 int b200pt_guiding_selftest_division(b200pt_ctx *ctx, float lo, float hi, uint64_t *mismatches, uint64_t *tested);
 
+/* ---- deterministic elementary functions (include/b200pt_detmath.h) --------------------------------
+ * The kernels evaluate sin / cos / tan / asin / acos / atan / atan2 / pow / log / exp with double-precision kernels made of
+ * IEEE add / mul / div / sqrt only (GLSL's results are the hardware's; CUDA's and glibc's libm differ from each other in the
+ * last bit, which used to make 0.5-15 % of same-seed pixels differ between this library and its CPU checker).  Parity
+ * hooks: `fn` over n inputs on the device / by the host compilation of the same header; b may be NULL for unary functions. */
+enum { B200PT_DM_SIN = 0, B200PT_DM_COS, B200PT_DM_TAN, B200PT_DM_ASIN, B200PT_DM_ACOS, B200PT_DM_ATAN, B200PT_DM_ATAN2, B200PT_DM_POW,
+       B200PT_DM_LOG, B200PT_DM_EXP };
+int b200pt_detmath_eval(b200pt_ctx *ctx, int fn, const float *a, const float *b, float *out, int n);
+int b200pt_detmath_eval_host(int fn, const float *a, const float *b, float *out, int n);
+
 /* ---- AOVs ---------------------------------------------------------------
  * The quantities behind the reference's depth / split debug views (shaders/raytrace.rgen:1653-1655, :1677-1679,
  * :1705-1707, :1722-1741) as a per-pixel RGBA32F layer of the LAST rendered frame instead of a view mode:

@@ -24,6 +24,8 @@
 // slots (header.nextCacheSlot++) are handed out in pixel order, and the results are committed in that order after the
 // last pixel: that is what the reference does when its invocations happen to run one after the other.
 #include <cmath>
+#include "../include/b200pt_detmath.h"   // sin / cos / pow / ...: the same deterministic kernels the device code uses (see the header)
+namespace dm = b200pt_dm;
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
@@ -230,19 +232,19 @@ struct Pixel {
         x = cross(y, z);
     }
     static v3 toWorld(v3 v, v3 n) { v3 x, y; coordinateAxis(n, x, y); return v.x * x + v.y * y + v.z * n; }
-    static v3 sphericalToCartesian(float theta, float phi) { return v3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta)); }
+    static v3 sphericalToCartesian(float theta, float phi) { return v3(dm::sinF(theta) * dm::cosF(phi), dm::sinF(theta) * dm::sinF(phi), dm::cosF(theta)); }
     v3 randomInHemisphereCosine(v3 normal) {                             // random.glsl:86-94
         float u = rnd();
         float sqrt_u = sqrtf(u);
         float phi = 2 * kPi * rnd();
-        return toWorld(v3(sqrt_u * cosf(phi), sqrt_u * sinf(phi), sqrtf(1 - u)), normal);
+        return toWorld(v3(sqrt_u * dm::cosF(phi), sqrt_u * dm::sinF(phi), sqrtf(1 - u)), normal);
     }
     v3 randomInHemisphereCosinePower(v3 reflected, float p) {            // :97-106
         float u = rnd();
-        float cosTheta = powf(u, 1.0f / (p + 1));
+        float cosTheta = dm::powF(u, 1.0f / (p + 1));
         float phi = 2 * kPi * rnd();
         float sinTheta = sqrtf(1 - cosTheta * cosTheta);
-        return toWorld(v3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta), reflected);
+        return toWorld(v3(sinTheta * dm::cosF(phi), sinTheta * dm::sinF(phi), cosTheta), reflected);
     }
     v3 randomOnSphere(const b200pt_sphere &s, v3 &normal) {              // :108-115
         normal = randomOnUnitSphere();
@@ -254,10 +256,10 @@ struct Pixel {
         return v3(s.center) + sphereNormal * s.radius;
     }
     v3 randomBeckmannNormal(const b200pt_material &mat, v3 normal) {     // :126-136
-        float thetaM = atanf(sqrtf(-mat.roughness * mat.roughness * logf(1 - rnd())));
+        float thetaM = dm::atanF(sqrtf(-mat.roughness * mat.roughness * dm::logF(1 - rnd())));
         float phiM = 2 * kPi * rnd();
-        float cosThetaNM = cosf(thetaM);
-        return toWorld(v3(sinf(thetaM) * cosf(phiM), sinf(thetaM) * sinf(phiM), cosThetaNM), normal);
+        float cosThetaNM = dm::cosF(thetaM);
+        return toWorld(v3(dm::sinF(thetaM) * dm::cosF(phiM), dm::sinF(thetaM) * dm::sinF(phiM), cosThetaNM), normal);
     }
 
     // ---- texture(): linear filter, repeat addressing -------------------------------------------------------------
@@ -372,9 +374,9 @@ struct Pixel {
     // texture 0 lat-long lookup — raytrace.rmiss:21-28
     v3 missColor(v3 dir) const {
         v3 udir = normalize(dir);
-        float at = atan2f(udir.x, -udir.z);
+        float at = dm::atan2F(udir.x, -udir.z);
         float u = at * 1.0f / (2 * kPi);
-        float v = acosf(udir.y) / kPi;
+        float v = dm::acosF(udir.y) / kPi;
         return textureRGB(0, u, v);
     }
 
@@ -455,18 +457,18 @@ struct Pixel {
     static float D(const b200pt_material &mat, v3 n, v3 m) {              // rgen:179-202
         float cosTheta = dot(n, m);
         if (cosTheta <= 0) return 0.0f;
-        float theta = acosf(cosTheta);
+        float theta = dm::acosF(cosTheta);
         if (isnanf_(theta) || isinff_(theta)) theta = 0;
-        float tanTheta = tanf(theta);
+        float tanTheta = dm::tanF(theta);
         if (isnanf_(tanTheta) || isinff_(tanTheta)) tanTheta = 0;
         float alphaSqr = mat.roughness * mat.roughness;
-        return powf(kE, -tanTheta * tanTheta / alphaSqr) / (kPi * alphaSqr * powf(cosTheta, 4));
+        return dm::powF(kE, -tanTheta * tanTheta / alphaSqr) / (kPi * alphaSqr * dm::powF(cosTheta, 4));
     }
     static float G1(const b200pt_material &mat, v3 n, v3 m, v3 v) {       // rgen:204-222
         float thetaV = dot(v, n);
         float c = dot(v, m) / thetaV;
         if (c <= 0) return 0;
-        float a = 1.0f / (mat.roughness * tanf(thetaV));
+        float a = 1.0f / (mat.roughness * dm::tanF(thetaV));
         if (a >= 1.6f) return 1.0f;
         float a2 = a * a;
         return (3.535f * a + 2.181f * a2) / (1 + 2.276f * a + 2.577f * a);
@@ -486,7 +488,7 @@ struct Pixel {
             res += diffuse(mat, u, v);
             float dotReflDir = dot(reflect(-wo, normal), wi);
             if (dotReflDir > 0) {
-                v3 s = (mat.specularHighlight + 2) / (2 * kPi) * v3(mat.specular) * powf(dotReflDir, mat.specularHighlight);
+                v3 s = (mat.specularHighlight + 2) / (2 * kPi) * v3(mat.specular) * dm::powF(dotReflDir, mat.specularHighlight);
                 if (mat.textureIdSpecular != -1) s = s * textureRGB(mat.textureIdSpecular, u, v);
                 res += s;
             }
@@ -516,7 +518,7 @@ struct Pixel {
                 float highlight = mat.specularHighlight;
                 float pdf = 0;
                 if (dot(reflected, wo) > 0) {
-                    pdf = (highlight + 1) * powf(dot(reflected, wo), highlight) / (2 * kPi);
+                    pdf = (highlight + 1) * dm::powF(dot(reflected, wo), highlight) / (2 * kPi);
                     pdf *= lSpecular / sumSpecDiff;
                 }
                 pdf += dot(wo, normal) / kPi * lDiffuse / sumSpecDiff;
@@ -560,9 +562,9 @@ struct Pixel {
             return light.sampleProb * lightDistance * lightDistance / (cosThetaLight * area);
         } else if (light.type == B200PT_LIGHT_ENV_MAP) {
             lightDir = randomInHemisphere(normal);
-            float at = atan2f(lightDir.x, -lightDir.z);
+            float at = dm::atan2F(lightDir.x, -lightDir.z);
             float u = at * 1.0f / (2 * kPi);
-            float v = acosf(lightDir.y) / kPi;
+            float v = dm::acosF(lightDir.y) / kPi;
             lightColor = textureRGB(0, u, v);
             lightDistance = tMax;
             return light.sampleProb * 1.0f / (2 * kPi);
@@ -786,7 +788,7 @@ struct Pixel {
         if (th.k == 0.0f) return 0.07957747155f;
         v3 mu(th.mu);
         if (parallax && th.distance > 0) mu = normalize(v3(th.target) - worldPos);
-        return th.norm * expf(th.k * (dot(mu, wo) - 1));
+        return th.norm * dm::expF(th.k * (dot(mu, wo) - 1));
     }
     static float VMM(v3 wo, const b200pt_vmm_theta &vmm, v3 worldPos, bool parallax) {   // guiding.glsl:53-60
         float res = 0;
@@ -797,10 +799,10 @@ struct Pixel {
         if (th.k > 0.0f) {
             const float r1 = rnd();
             const float r2 = rnd();
-            const float cosTheta = 1.0f + logf(1 + th.eMin2K * r1 - r1) / th.k;
+            const float cosTheta = 1.0f + dm::logF(1 + th.eMin2K * r1 - r1) / th.k;
             const float sinTheta = 1.0f - cosTheta * cosTheta <= 0.0f ? 0.0f : sqrtf(1.0f - cosTheta * cosTheta);
             const float phi = 2.f * kPi * r2;
-            const float cosPhi = cosf(phi), sinPhi = sinf(phi);
+            const float cosPhi = dm::cosF(phi), sinPhi = dm::sinF(phi);
             v3 mu(th.mu);
             if (parallax && th.distance > 0) mu = normalize(v3(th.target) - worldPos);
             return toWorld(v3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta), mu);
@@ -989,7 +991,7 @@ struct Pixel {
             v3 previousVk = toWorld(sphericalToCartesian(M_HALF_PI, 2 * kPi * k / N + M_HALF_PI), normal);
             float previousJR = 0, previousJL = 0;
             for (int j = 0; j < M; j++) {
-                float theta = asinf(sqrtf((j + rnd()) / M));
+                float theta = dm::asinF(sqrtf((j + rnd()) / M));
                 v3 direction = toWorld(sphericalToCartesian(theta, phi), normal);
                 float r = tMax;
                 int currentDepth = 0;
@@ -998,16 +1000,16 @@ struct Pixel {
                 color += sampleColor;
                 if (r < tMax) { invDistanceSum += 1.0f / r; numDistances++; }
                 float L = length(sampleColor);
-                float previousJTheta = asinf(sqrtf(j / float(M)));
-                float nextJTheta = asinf(sqrtf((j + 1) / float(M)));
-                float tanTheta = tanf(theta);
+                float previousJTheta = dm::asinF(sqrtf(j / float(M)));
+                float nextJTheta = dm::asinF(sqrtf((j + 1) / float(M)));
+                float tanTheta = dm::tanF(theta);
                 if (isinff_(tanTheta) || isnanf_(tanTheta)) tanTheta = 0;
                 rotGrad -= tanTheta * L * vk;
                 if (j > 0) {
-                    float cosPreviousTheta = cosf(previousJTheta);
-                    transGrad += uk * 2 * kPi / N * sinf(previousJTheta) * cosPreviousTheta * cosPreviousTheta / std::min(r, previousJR) * (L - previousJL);
+                    float cosPreviousTheta = dm::cosF(previousJTheta);
+                    transGrad += uk * 2 * kPi / N * dm::sinF(previousJTheta) * cosPreviousTheta * cosPreviousTheta / std::min(r, previousJR) * (L - previousJL);
                 }
-                if (k > 0) transGrad += previousVk * (sinf(nextJTheta) - sinf(previousJTheta)) / std::min(r, previousKRs[j]) * (L - previousKLs[j]);
+                if (k > 0) transGrad += previousVk * (dm::sinF(nextJTheta) - dm::sinF(previousJTheta)) / std::min(r, previousKRs[j]) * (L - previousKLs[j]);
                 previousKLs[j] = L; previousKRs[j] = r; previousJL = L; previousJR = r;
             }
         }
@@ -1127,7 +1129,7 @@ struct Pixel {
 
 float srgbToLinear(uint8_t v) {
     float c = float(v) / 255.0f;
-    return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+    return c <= 0.04045f ? c / 12.92f : dm::powF((c + 0.055f) / 1.055f, 2.4f);
 }
 
 int buildAccel(oracle_ctx &C, uint32_t first, uint32_t count, const std::vector<float> &lo, const std::vector<float> &hi, float pad, int depth) {

@@ -134,6 +134,16 @@ class Stats(C.Structure):
 
 
 GUIDING_ORDER_STRICT, GUIDING_ORDER_REORDERED = 0, 1      # b200pt_guiding_set_order
+DM_FUNCTIONS = ("sin", "cos", "tan", "asin", "acos", "atan", "atan2", "pow", "log", "exp")      # B200PT_DM_*
+
+
+def detmath_host(fn, a, b=None):
+    """include/b200pt_detmath.h as compiled for the host (inside libb200pt.so): fn in DM_FUNCTIONS over float32 arrays"""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+    out = np.empty_like(a)
+    _check(lib().b200pt_detmath_eval_host(DM_FUNCTIONS.index(fn), a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.size))
+    return out
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("u", "<f4"), ("v", "<f4")])
@@ -160,7 +170,7 @@ EXPORTS = [
     "b200pt_default_guiding_params", "b200pt_guiding_update", "b200pt_guiding_region_count", "b200pt_guiding_get_aabbs",
     "b200pt_guiding_get_vmms", "b200pt_guiding_put_vmms", "b200pt_guiding_get_samples", "b200pt_guiding_put_samples",
     "b200pt_guiding_sample_capacity", "b200pt_guiding_get_samples_device", "b200pt_guiding_reset", "b200pt_guiding_update_host", "b200pt_guiding_update_device",
-    "b200pt_guiding_set_order", "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_guiding_selftest_division", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
+    "b200pt_guiding_set_order", "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_guiding_selftest_division", "b200pt_detmath_eval", "b200pt_detmath_eval_host", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
     "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_comm_exchange_mode",
@@ -242,6 +252,8 @@ def lib():
         L.b200pt_guiding_update_all_ranks_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
         L.b200pt_comm_exchange_mode.argtypes = [C.c_void_p]
         L.b200pt_guiding_set_order.argtypes = [C.c_void_p, C.c_int]
+        L.b200pt_detmath_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b200pt_detmath_eval_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_guiding_selftest_division.argtypes = [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.b200pt_app_init.restype = None
         L.b200pt_app_init.argtypes = [C.POINTER(AppState)]
@@ -487,6 +499,14 @@ class Renderer:
         return out, off
 
     GUIDING_STATE_FIELDS = ("weight", "kappa", "r", "mux", "muy", "muz", "distance", "distSumW", "chi", "chiN", "covxx", "covyy", "covxy", "covSumW")
+
+    def detmath(self, fn, a, b=None):
+        """the same functions evaluated by a kernel on this context's device"""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        out = np.empty_like(a)
+        _check(lib().b200pt_detmath_eval(self._h, DM_FUNCTIONS.index(fn), a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.size))
+        return out
 
     def guiding_selftest_division(self, lo, hi):
         """(mismatches, tested) of the device's fastexp division vs IEEE division over every float in [lo, hi]"""

@@ -407,7 +407,7 @@ int b200pt_destroy(b200pt_ctx *c) {
 
 static float srgbToLinear(uint8_t v) {
     float c = float(v) / 255.0f;
-    return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+    return c <= 0.04045f ? c / 12.92f : b200pt_dm::powF((c + 0.055f) / 1.055f, 2.4f);
 }
 
 int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
@@ -1014,6 +1014,47 @@ int b200pt_guiding_fastexp(b200pt_ctx *c, const float *in, float *out, int n) {
     std::string err;
     int rc = guidingFastExp(in, out, n, c->stream, err);
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_fastexp: " + err);
+    return B200PT_OK;
+}
+}  // extern "C"
+__host__ __device__ static inline float detmathApply(int fn, float a, float b) {
+    switch (fn) {
+        case B200PT_DM_SIN: return b200pt_dm::sinF(a);
+        case B200PT_DM_COS: return b200pt_dm::cosF(a);
+        case B200PT_DM_TAN: return b200pt_dm::tanF(a);
+        case B200PT_DM_ASIN: return b200pt_dm::asinF(a);
+        case B200PT_DM_ACOS: return b200pt_dm::acosF(a);
+        case B200PT_DM_ATAN: return b200pt_dm::atanF(a);
+        case B200PT_DM_ATAN2: return b200pt_dm::atan2F(a, b);
+        case B200PT_DM_POW: return b200pt_dm::powF(a, b);
+        case B200PT_DM_LOG: return b200pt_dm::logF(a);
+        default: return b200pt_dm::expF(a);
+    }
+}
+__global__ void __launch_bounds__(256) k_detmath(int fn, const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = detmathApply(fn, a[i], b ? b[i] : 0.0f);
+}
+extern "C" {
+int b200pt_detmath_eval(b200pt_ctx *c, int fn, const float *a, const float *b, float *out, int n) {
+    if (!c || fn < 0 || fn > B200PT_DM_EXP || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval: bad argument");
+    if (n == 0) return B200PT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    DevBuf<float> da, db, dout;
+    CUDA_TRY(da.upload(a, size_t(n), c->stream));
+    if (b) CUDA_TRY(db.upload(b, size_t(n), c->stream));
+    CUDA_TRY(dout.alloc(size_t(n)));
+    k_detmath<<<gridFor(uint64_t(n), 256), 256, 0, c->stream>>>(fn, da.p, b ? db.p : nullptr, dout.p, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    da.release(); db.release(); dout.release();
+    return B200PT_OK;
+}
+/* the same functions evaluated by the host compilation of the header (no device involved) */
+int b200pt_detmath_eval_host(int fn, const float *a, const float *b, float *out, int n) {
+    if (fn < 0 || fn > B200PT_DM_EXP || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval_host: bad argument");
+    for (int i = 0; i < n; i++) out[i] = detmathApply(fn, a[i], b ? b[i] : 0.0f);
     return B200PT_OK;
 }
 int b200pt_guiding_selftest_division(b200pt_ctx *c, float lo, float hi, uint64_t *mismatches, uint64_t *tested) {

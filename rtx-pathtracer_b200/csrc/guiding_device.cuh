@@ -81,7 +81,7 @@ __device__ __forceinline__ float vmfPdf(vec3 wo, const b200pt_vmf_theta &th, vec
     if (th.k == 0.0f) return 0.07957747155f;
     vec3 mu = V3(th.mu[0], th.mu[1], th.mu[2]);
     if (parallax && th.distance > 0.0f) mu = normalize(V3(th.target[0], th.target[1], th.target[2]) - worldPos);
-    return th.norm * expf(th.k * (dot(mu, wo) - 1.0f));
+    return th.norm * ptExpf(th.k * (dot(mu, wo) - 1.0f));
 }
 __device__ __forceinline__ float vmmPdf(vec3 wo, const b200pt_vmm_theta &vmm, vec3 worldPos, bool parallax) {   // guiding.glsl:53-60
     float res = 0.0f;
@@ -92,10 +92,10 @@ __device__ __forceinline__ vec3 sampleVmf(uint32_t &seed, const b200pt_vmf_theta
     if (th.k > 0.0f) {
         const float r1 = rnd(seed);
         const float r2 = rnd(seed);
-        const float cosTheta = 1.0f + logf(1.0f + th.eMin2K * r1 - r1) / th.k;
+        const float cosTheta = 1.0f + ptLogf(1.0f + th.eMin2K * r1 - r1) / th.k;
         const float sinTheta = 1.0f - cosTheta * cosTheta <= 0.0f ? 0.0f : sqrtf(1.0f - cosTheta * cosTheta);
         const float phi = 2.f * PT_PI * r2;
-        const float cosPhi = cosf(phi), sinPhi = sinf(phi);
+        const float cosPhi = ptCosf(phi), sinPhi = ptSinf(phi);
         vec3 mu = V3(th.mu[0], th.mu[1], th.mu[2]);
         if (parallax && th.distance > 0.0f) mu = normalize(V3(th.target[0], th.target[1], th.target[2]) - worldPos);
         return toWorld(V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta), mu);

@@ -316,23 +316,23 @@ struct InlineTracer {
             const vec3 previousVk = toWorld(sphericalToCartesian(M_HALF_PI, 2.0f * PT_PI * float(k) / float(N) + M_HALF_PI), normal);
             float previousJR = 0.0f, previousJL = 0.0f;
             for (int j = 0; j < M; j++) {
-                const float theta = asinf(sqrtf((float(j) + rnd(seed)) / float(M)));
+                const float theta = ptAsinf(sqrtf((float(j) + rnd(seed)) / float(M)));
                 const vec3 direction = toWorld(sphericalToCartesian(theta, phi), normal);
                 float r = PT_TMAX;
                 const vec3 sampleColor = raytrace(origin, direction, 1, maxFollowDiscrete, pc.irradianceNumNEE, r);
                 color += sampleColor;
                 if (r < PT_TMAX) { invDistanceSum += 1.0f / r; numDistances++; }
                 const float L = length(sampleColor);
-                const float previousJTheta = asinf(sqrtf(float(j) / float(M)));
-                const float nextJTheta = asinf(sqrtf(float(j + 1) / float(M)));
-                float tanTheta = tanf(theta);
+                const float previousJTheta = ptAsinf(sqrtf(float(j) / float(M)));
+                const float nextJTheta = ptAsinf(sqrtf(float(j + 1) / float(M)));
+                float tanTheta = ptTanf(theta);
                 if (isinf(tanTheta) || isnan(tanTheta)) tanTheta = 0.0f;
                 rotGrad = rotGrad - tanTheta * L * vk;
                 if (j > 0) {
-                    const float cosPreviousTheta = cosf(previousJTheta);
-                    transGrad += uk * 2.0f * PT_PI / float(N) * sinf(previousJTheta) * cosPreviousTheta * cosPreviousTheta / fminf(r, previousJR) * (L - previousJL);
+                    const float cosPreviousTheta = ptCosf(previousJTheta);
+                    transGrad += uk * 2.0f * PT_PI / float(N) * ptSinf(previousJTheta) * cosPreviousTheta * cosPreviousTheta / fminf(r, previousJR) * (L - previousJL);
                 }
-                if (k > 0) transGrad += previousVk * (sinf(nextJTheta) - sinf(previousJTheta)) / fminf(r, previousKRs[j]) * (L - previousKLs[j]);
+                if (k > 0) transGrad += previousVk * (ptSinf(nextJTheta) - ptSinf(previousJTheta)) / fminf(r, previousKRs[j]) * (L - previousKLs[j]);
                 previousKLs[j] = L; previousKRs[j] = r; previousJL = L; previousJR = r;
             }
         }

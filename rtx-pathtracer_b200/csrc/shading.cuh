@@ -58,7 +58,7 @@ __device__ __forceinline__ float4 sampleTexture(const DeviceScene &sc, int id, f
 // raytrace.rmiss:17-29 — lat-long lookup into texture 0 (1x1 black when the scene has no env map)
 __device__ __forceinline__ vec3 envColor(const DeviceScene &sc, vec3 dir, bool renormalize = true) {
     vec3 udir = renormalize ? normalize(dir) : dir;
-    float at = atan2f(udir.x, -udir.z);
+    float at = ptAtan2f(udir.x, -udir.z);
     float u = at * 1.0f / (2.0f * PT_PI);      // `atan * M_INV_2PI` with the unparenthesised macro
     float v = PT_ACOSF(udir.y) / PT_PI;
     float4 c = sampleTexture(sc, 0, u, v);
