@@ -9,7 +9,10 @@ import numpy as np
 
 REF = "/root/reference/scenes"
 HERE = os.path.dirname(os.path.abspath(__file__))
-IMAGES = {"cornell-dielectric": "cornell-dielectric/cornell-dielectric.exr", "veachMIS": "veachMIS/veachMIS.exr", "miPhong": "miPhong/miPhong.exr"}
+IMAGES = {"cornell-dielectric": "cornell-dielectric/cornell-dielectric.exr", "veachMIS": "veachMIS/veachMIS.exr", "miPhong": "miPhong/miPhong.exr",
+          "envMap": "envMap/envMap.exr", "testSpheres": "testSpheres/testSpheres.exr", "irradianceCache": "irradianceCache/irradianceCache.exr",
+          "sponzaXML": "sponzaXML/sponzaXML_360spp_10m40.exr"}
+# (roughConductor/roughConductor.exr is not usable: the rough-conductor object of that scene is shell.obj, a missing blob of the checkout)
 
 for name, rel in IMAGES.items():
     img = cv2.imread(os.path.join(REF, rel), cv2.IMREAD_UNCHANGED)[..., :3][..., ::-1].astype(np.float64)

@@ -2,8 +2,8 @@
 
 Both sides use the race-free frame semantic described in oracle/tracer_oracle.cpp: lookups read the frame-start cache,
 update / create slots are handed out in pixel order.  Cache entries are matched by their position (a hit point; the
-traversal is bit-exact), values compared within 1e-3 relative: one entry sums 200 paths whose transcendental functions
-differ in the last bit between CUDA and glibc."""
+traversal is bit-exact) and line up slot by slot; values are compared within 1e-4 relative (one entry sums 200 paths; both
+sides use the elementary functions of include/b200pt_detmath.h, so the paths are the same and only summation order differs)."""
 import os
 
 import numpy as np
@@ -37,34 +37,31 @@ def _estimate_pc(P, frame):
 
 
 def _compare_caches(P, dev, ref, what):
+    _compare_caches_sized(P, dev, ref, IC_SIZE, what)
+
+
+def _compare_caches_sized(P, dev, ref, ic_size, what):
     (hd, dd, sd), (hr, dr, sr) = dev, ref
-    nd, nr = min(hd.nextCacheSlot, IC_SIZE), min(hr.nextCacheSlot, IC_SIZE)
+    nd, nr = min(hd.nextCacheSlot, ic_size), min(hr.nextCacheSlot, ic_size)
     assert nr > 20, what
     assert abs(int(nd) - int(nr)) <= max(2, nr // 50), (what, nd, nr)
-    # entries created at the first path vertex have bit-identical positions (traversal is bit-exact); deeper vertices
-    # inherit the last-bit differences of CUDA's and glibc's sin/cos, so match by nearest centre
-    cd = sd["center"][:nd].astype(np.float64)
-    matched = bad = 0
-    for i in range(nr):
-        dist = np.linalg.norm(cd - sr["center"][i].astype(np.float64), axis=1)
-        j = int(np.argmin(dist))
-        if dist[j] > 1e-3:
-            continue
-        matched += 1
-        ok = np.abs(dd["normal"][j] - dr["normal"][i]).max() <= 1e-4 and dd["numUpdates"][j] == dr["numUpdates"][i]
-        scale = max(float(np.abs(dr["color"][i]).max()), 1e-6)
-        ok = ok and np.abs(dd["color"][j] - dr["color"][i]).max() <= 1e-3 * scale
-        ok = ok and abs(dd["harmonicR"][j] - dr["harmonicR"][i]) <= 1e-3 * dr["harmonicR"][i]
-        ok = ok and abs(sd["radius"][j] - sr["radius"][i]) <= 1e-3 * sr["radius"][i]
-        for g in ("rotGrad", "transGrad"):
-            gs = max(float(np.abs(dr[g][i]).max()), 1e-2 * scale, 1e-6)
-            ok = ok and np.abs(dd[g][j] - dr[g][i]).max() <= 5e-3 * gs
-        bad += not ok
-    assert matched >= 0.98 * nr, (what, matched, nr)
-    assert bad <= max(1, matched // 50), (what, bad, matched)
+    # Slots are handed out in pixel order on both sides and the elementary functions are shared (b200pt_detmath.h), so the
+    # caches line up entry by entry: same count, bit-identical centres and normals, and the values (sums over the 200 paths
+    # of an entry) within the north-star 1e-4 — gradients within 1e-3 of the entry's scale (differences of nearly equal sums).
+    assert nd == nr, (what, nd, nr)
+    n = nr
+    assert np.array_equal(sd["center"][:n], sr["center"][:n]) and np.array_equal(dd["normal"][:n], dr["normal"][:n]), what
+    assert np.array_equal(dd["numUpdates"][:n], dr["numUpdates"][:n]), what
+    scale = np.maximum(np.abs(dr["color"][:n]).max(axis=1), 1e-6)
+    assert (np.abs(dd["color"][:n] - dr["color"][:n]).max(axis=1) <= 1e-4 * scale).all(), what
+    assert (np.abs(dd["harmonicR"][:n] - dr["harmonicR"][:n]) <= 1e-4 * dr["harmonicR"][:n]).all(), what
+    assert (np.abs(sd["radius"][:n] - sr["radius"][:n]) <= 1e-4 * sr["radius"][:n]).all(), what
+    for g in ("rotGrad", "transGrad"):
+        gs = np.maximum(np.maximum(np.abs(dr[g][:n]).max(axis=1), 1e-2 * scale), 1e-6)
+        assert (np.abs(dd[g][:n] - dr[g][:n]).max(axis=1) <= 1e-3 * gs).all(), (what, g)
 
 
-def _images_close(img, ref, what, frac_needed=0.99, mean_tol=5e-3):
+def _images_close(img, ref, what, frac_needed=1.0, mean_tol=1e-4):
     img, ref = img[..., :3].astype(np.float64), ref[..., :3].astype(np.float64)
     assert np.isfinite(img).all(), what
     rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
@@ -122,13 +119,13 @@ def test_estimate_frame_and_adrrs_match_oracle():
     r.render_frame(pc)
     o.render_region(pc, threads=NT)
     est_ref = o.image(P.IMAGE_ESTIMATE)
-    _images_close(r.read_image(P.IMAGE_ESTIMATE), est_ref, "estimate frame", frac_needed=0.97)
+    _images_close(r.read_image(P.IMAGE_ESTIMATE), est_ref, "estimate frame")
     r.write_image(P.IMAGE_ESTIMATE, est_ref)      # identical adjoint inputs for the ADRRS frames
     for f, kw in enumerate([dict(adrrsSplit=1), dict(adrrsSplit=0), dict(adrrsSplit=1, enableMIS=0, numNEE=2)]):
         pc = _pc(P, 30 + f, samplesPerPixel=2, useADRRS=1, adrrsS=5.0, irradianceCreateProb=0.0, irradianceUpdateProb=0.0, **kw)
         r.render_frame(pc)
         o.render_region(pc, threads=NT)
-        _images_close(r.read_image(), o.image(), "ADRRS %r" % (kw,), frac_needed=0.985)
+        _images_close(r.read_image(), o.image(), "ADRRS %r" % (kw,))
 
 
 def test_adrrs_frames_keep_creating_cache_entries():
