@@ -6,13 +6,14 @@
  * a sampled direction decides stochastic branches further down a path (rejection loops, Fresnel coin, an ill-conditioned
  * silhouette test), so 0.5-15 % of the pixels of a same-seed render used to differ between the kernels and the oracle.
  *
- * These versions use only IEEE-754 double add / sub / mul / div / sqrt and integer operations on the bits — no fused
- * multiply-add (compile with contraction off: nvcc -fmad=false, gcc -ffp-contract=off), no libm — in a fixed order, and
- * round the double result to float once.  They are therefore (a) bit-identical between the sm_100a kernels and any
- * host compiler, and (b) correctly rounded floats except for ~1e-6 of the inputs (double evaluation error 1e-15
- * against the float rounding boundary), i.e. at least as faithful to the mathematical function as any libm.
- * B200 issues FP64 at half the FP32 rate, so a 30-operation double kernel costs about what CUDA's accurate float
- * sinf / powf expansions cost.  tests/test_detmath.py measures the error against mpmath-grade references.
+ * These versions use only IEEE-754 add / sub / mul / div / sqrt and integer operations on the bits — no fused
+ * multiply-add (compile with contraction off: nvcc -fmad=false, gcc -ffp-contract=off), no libm — in a fixed order.
+ * They are therefore bit-identical between the sm_100a kernels and any host compiler.  The hot functions (sin, cos,
+ * tan, asin, acos, atan, atan2, log, exp) are single-precision kernels of ~20 operations, accurate to 1-3 ulp; pow
+ * carries log x as a sum of two floats (exp(y log x) needs the extra bits).  A first version evaluated everything in
+ * double: bit-identical too, but B200's FP64 pipe made sponzaXML frames 1.4-2x slower (profiles/r02_detmath.txt); the
+ * only double code left is the range reduction of sin / cos for |x| >= 1e4, which the tracer never reaches.
+ * tests/test_detmath.py measures the errors against float64 references.
  *
  * Included by the device code (rtx-pathtracer_b200/csrc/device_math.cuh) and by the CPU oracle (oracle/): the same
  * source, so the two sides of every parity test agree on these functions by construction, and disagree only where
@@ -69,98 +70,193 @@ DM_HD void sincosD(double x, double *s, double *c) {
     }
 }
 
-/* atan for x >= 0 */
-DM_HD double atanPos(double ax) {
-    const bool inv = ax > 1.0;
-    if (inv) ax = 1.0 / ax;
-    ax = ax / (1.0 + sqrt(1.0 + ax * ax));       /* two angle halvings: argument <= tan(pi/16) */
-    ax = ax / (1.0 + sqrt(1.0 + ax * ax));
-    const double t2 = ax * ax;
-    const double p = -0.3333333333333333 + t2 * (0.2 + t2 * (-0.14285714285714285 + t2 * (0.1111111111111111 + t2 * (-0.09090909090909091 + t2 * (0.07692307692307693 +
-                     t2 * (-0.06666666666666667 + t2 * (0.058823529411764705 + t2 * (-0.05263157894736842 + t2 * (0.047619047619047616 + t2 * (-0.043478260869565216 +
-                     t2 * (0.04 + t2 * -0.037037037037037035)))))))))));
-    const double a = 4.0 * (ax + ax * t2 * p);
-    return inv ? 1.5707963267948966 - a : a;
+/* ---- single-precision kernels: the hot functions (one per bounce and per vMF lobe) ------------------------------------
+ * Same rules — IEEE float add / sub / mul / div / sqrt and bit operations only, fixed order — at about 20 FP32 operations
+ * each (CUDA's accurate sinf / expf / logf are 40-100, the double kernels above ~100 issue slots).  Accuracy 1-3 ulp
+ * (tests/test_detmath.py), which is what GLSL implementations deliver at best; bit-identity between device and host is
+ * what matters here and holds by construction. */
+DM_HD uint32_t fBits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t b; memcpy(&b, &f, 4); return b;
+#endif
 }
-DM_HD double atanD(double x) {
+DM_HD float bitsF(uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+DM_HD float rnef(float x) { const float big = 12582912.0f; return (x + big) - big; }      /* |x| < 2^22 */
+
+DM_HD void sincosF(float x, float *s, float *c) {
+    if (!(fabsf(x) < 1.0e4f)) { double ds, dc; sincosD((double)x, &ds, &dc); *s = (float)ds; *c = (float)dc; return; }
+    const float kf = rnef(x * 0.636619747f);
+    /* pi/2 = 1.5703125 + 4.837512969970703125e-4 + 7.54978995489188216e-8 (Cody-Waite: the first two products are exact) */
+    float r = x - kf * 1.5703125f;
+    r = r - kf * 4.837512969970703125e-4f;
+    r = r - kf * 7.54978995489188216e-8f;
+    const float r2 = r * r;
+    const float sp = -0.166666672f + r2 * (0.00833333377f + r2 * (-0.000198412701f + r2 * 2.75573188e-06f));
+    const float sr = r + r * r2 * sp;
+    const float cp = 0.0416666679f + r2 * (-0.00138888892f + r2 * (2.48015876e-05f + r2 * -2.75573199e-07f));
+    const float cr = (1.0f - 0.5f * r2) + r2 * r2 * cp;
+    switch (((int)kf) & 3) {
+        case 0: *s = sr; *c = cr; break;
+        case 1: *s = cr; *c = -sr; break;
+        case 2: *s = -sr; *c = -cr; break;
+        default: *s = -cr; *c = sr; break;
+    }
+}
+DM_HD float sinF(float x) { float s, c; sincosF(x, &s, &c); return s; }
+DM_HD float cosF(float x) { float s, c; sincosF(x, &s, &c); return c; }
+DM_HD float tanF(float x) { float s, c; sincosF(x, &s, &c); return s / c; }
+
+/* atan on [0, inf): reduce to |t| <= tan(pi/8) with one division (x > tan(3pi/8): -1/x, x > tan(pi/8): (x-1)/(x+1)), then
+ * t + t^3 P(t^2), P = degree-4 Chebyshev fit of (atan(t)/t - 1)/t^2 on [0, tan^2(pi/8)] (own fit, |error| 1.6e-8) */
+DM_HD float atanPosF(float ax) {
+    float y0, t;
+    if (ax > 2.41421366f) { y0 = 1.57079637f; t = -1.0f / ax; }
+    else if (ax > 0.414213568f) { y0 = 0.785398185f; t = (ax - 1.0f) / (ax + 1.0f); }
+    else { y0 = 0.0f; t = ax; }
+    const float z = t * t;
+    const float p = -0.333333318f + z * (0.199995399f + z * (-0.142639562f + z * (0.107437313f + z * -0.0645192862f)));
+    return y0 + (t + t * z * p);
+}
+DM_HD float atanF(float x) {
     if (x != x) return x;
-    const double a = atanPos(fabs(x));
-    return x < 0.0 ? -a : a;
+    const float a = atanPosF(fabsf(x));
+    return x < 0.0f ? -a : a;
 }
-DM_HD double atan2D(double y, double x) {
+DM_HD float atan2F(float y, float x) {
     if (x != x || y != y) return x + y;
-    if (x == 0.0) return y > 0.0 ? 1.5707963267948966 : (y < 0.0 ? -1.5707963267948966 : 0.0);
-    const double a = atanPos(fabs(y / x));                     /* in [0, pi/2] */
-    const double q = x > 0.0 ? a : 3.141592653589793 - a;      /* angle of (|y|, x) */
-    return y < 0.0 ? -q : q;
+    if (x == 0.0f) return y > 0.0f ? 1.57079637f : (y < 0.0f ? -1.57079637f : 0.0f);
+    const float a = atanPosF(fabsf(y / x));
+    const float q = x > 0.0f ? a : 3.14159274f - a;
+    return y < 0.0f ? -q : q;
 }
-
-/* natural logarithm of a positive finite double that came from a float (so never subnormal as a double) */
-DM_HD double logD(double x) {
-    if (x != x || x < 0.0) return x - x + (x != x ? x : bitsD(0x7ff8000000000000ull));
-    if (x == 0.0) return -bitsD(0x7ff0000000000000ull);
-    const uint64_t b = dBits(x);
-    if ((b >> 52) == 0x7ffull) return x;                       /* +inf */
-    int e = (int)((b >> 52) & 0x7ffull) - 1023;
-    double m = bitsD((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);     /* [1, 2) */
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    const double s = (m - 1.0) / (m + 1.0);
-    const double s2 = s * s;
-    const double p = 0.3333333333333333 + s2 * (0.2 + s2 * (0.14285714285714285 + s2 * (0.1111111111111111 + s2 * (0.09090909090909091 + s2 * (0.07692307692307693 +
-                     s2 * (0.06666666666666667 + s2 * (0.058823529411764705 + s2 * (0.05263157894736842 + s2 * (0.047619047619047616 + s2 * 0.043478260869565216)))))))));
-    const double lm = 2.0 * (s + s * s2 * p);
-    const double ed = (double)e;
-    return ed * 0.6931471801362932 + (ed * 4.236521365809284e-10 + lm);
-}
-
-DM_HD double expD(double x) {
-    if (x != x) return x;
-    if (x > 709.0) return bitsD(0x7ff0000000000000ull);
-    if (x < -745.0) return 0.0;
-    const double kd = rne(x * 1.4426950408889634);
-    const double r = (x - kd * 0.6931471801362932) - kd * 4.236521365809284e-10;
-    const double p = 0.5 + r * (0.16666666666666666 + r * (0.041666666666666664 + r * (0.008333333333333333 + r * (0.001388888888888889 + r * (0.0001984126984126984 +
-                     r * (2.48015873015873e-05 + r * (2.7557319223985893e-06 + r * (2.755731922398589e-07 + r * (2.505210838544172e-08 + r * (2.08767569878681e-09 +
-                     r * (1.6059043836821613e-10 + r * 1.1470745597729725e-11)))))))))));
-    const double er = 1.0 + (r + r * r * p);
-    long long k = (long long)kd;
-    /* 2^k in two factors so that results in the subnormal range of double (never reached from float use) stay finite */
-    const long long k1 = k / 2, k2 = k - k1;
-    return er * bitsD((uint64_t)(k1 + 1023) << 52) * bitsD((uint64_t)(k2 + 1023) << 52);
-}
-
-/* ---- float front ends: one rounding at the end ---- */
-DM_HD float sinF(float x) { double s, c; sincosD((double)x, &s, &c); return (float)s; }
-DM_HD float cosF(float x) { double s, c; sincosD((double)x, &s, &c); return (float)c; }
-DM_HD float tanF(float x) { double s, c; sincosD((double)x, &s, &c); return (float)(s / c); }
-DM_HD float atanF(float x) { return (float)atanD((double)x); }
-DM_HD float atan2F(float y, float x) { return (float)atan2D((double)y, (double)x); }
 DM_HD float asinF(float x) {
-    const double d = (double)x;
-    if (!(fabs(d) <= 1.0)) return (float)(d - d + bitsD(0x7ff8000000000000ull));
-    return (float)atan2D(d, sqrt((1.0 - d) * (1.0 + d)));
+    if (!(fabsf(x) <= 1.0f)) return bitsF(0x7fc00000u);
+    return atan2F(x, sqrtf((1.0f - x) * (1.0f + x)));
 }
 DM_HD float acosF(float x) {
-    const double d = (double)x;
-    if (!(fabs(d) <= 1.0)) return (float)(d - d + bitsD(0x7ff8000000000000ull));
-    return (float)atan2D(sqrt((1.0 - d) * (1.0 + d)), d);
+    if (!(fabsf(x) <= 1.0f)) return bitsF(0x7fc00000u);
+    return atan2F(sqrtf((1.0f - x) * (1.0f + x)), x);
 }
-DM_HD float logF(float x) { return (float)logD((double)x); }
-DM_HD float expF(float x) { return (float)expD((double)x); }
+
+DM_HD float logF(float x) {
+    if (x != x || x < 0.0f) return bitsF(0x7fc00000u);
+    if (x == 0.0f) return bitsF(0xff800000u);
+    uint32_t b = fBits(x);
+    if ((b >> 23) == 0xffu) return x;                           /* +inf */
+    int e = 0;
+    if ((b >> 23) == 0u) { x = x * 8388608.0f; b = fBits(x); e = -23; }      /* subnormal */
+    e += (int)(b >> 23) - 127;
+    float m = bitsF((b & 0x007fffffu) | 0x3f800000u);           /* [1, 2) */
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    const float s = (m - 1.0f) / (m + 1.0f);
+    const float s2 = s * s;
+    const float p = s2 * (0.333333343f + s2 * (0.2f + s2 * (0.142857149f + s2 * 0.111111112f)));
+    const float lm = 2.0f * (s + s * p);
+    const float ef = (float)e;
+    return ef * 0.693359375f + (ef * -2.12194440e-4f + lm);      /* ln 2 in two pieces; ef * hi is exact */
+}
+
+DM_HD float expF(float x) {
+    if (!(fabsf(x) <= 87.0f)) {                                 /* NaN, overflow, underflow and subnormal results: off the fast path */
+        if (x != x) return x;
+        if (x > 88.8f) return bitsF(0x7f800000u);
+        if (x < -104.0f) return 0.0f;
+    }
+    const float kf = rnef(x * 1.44269502f);
+    const float r = (x - kf * 0.693359375f) - kf * -2.12194440e-4f;
+    const float p = r * r * (0.5f + r * (0.166666672f + r * (0.0416666679f + r * (0.00833333377f + r * (0.00138888892f + r * 0.000198412701f)))));
+    const float er = 1.0f + (r + p);                            /* in (0.70, 1.42) */
+    const int k = (int)kf;
+    if (k >= -125 && k <= 126) return bitsF(fBits(er) + ((uint32_t)k << 23));      /* er * 2^k: exact, the result is normal */
+    const int k1 = k / 2, k2 = k - k1;                          /* 2^k in two normal factors (the result may be subnormal) */
+    return er * bitsF((uint32_t)(k1 + 127) << 23) * bitsF((uint32_t)(k2 + 127) << 23);
+}
+
+/* ---- pow in single precision with double-float steps -------------------------------------------------------------------
+ * exp(y log x) needs log x to ~2^-32 (Phong exponents in the thousands); the first version ran it in double and the
+ * FP64 pipe cost sponzaXML 30-50 % of its frame rate (one Phong material is enough: a warp with one such lane takes the
+ * path).  Here log x is carried as an unevaluated sum of two floats (Dekker / Veltkamp error-free transformations — no
+ * fused multiply-add), multiplied by y with an exact product, and the exponential takes the low part as a correction. */
+DM_HD void twoSumF(float a, float b, float *s, float *e) { const float t = a + b, bb = t - a; *e = (a - (t - bb)) + (b - bb); *s = t; }
+DM_HD void splitF(float a, float *hi, float *lo) { const float c = 4097.0f * a, h = c - (c - a); *hi = h; *lo = a - h; }
+DM_HD void twoProdF(float a, float b, float *p, float *e) {
+    float ah, al, bh, bl;
+    splitF(a, &ah, &al); splitF(b, &bh, &bl);
+    const float pp = a * b;
+    *e = (((ah * bh - pp) + ah * bl) + al * bh) + al * bl;
+    *p = pp;
+}
+/* x > 0 finite, y finite non-zero */
+DM_HD float powPosF(float x, float y) {
+    uint32_t b = fBits(x);
+    int e = 0;
+    if ((b >> 23) == 0u) { x = x * 8388608.0f; b = fBits(x); e = -23; }
+    e += (int)(b >> 23) - 127;
+    float m = bitsF((b & 0x007fffffu) | 0x3f800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    /* s = (m - 1) / (m + 1) as sh + sl */
+    const float u = m - 1.0f;                                   /* exact */
+    float dh, dl; twoSumF(m, 1.0f, &dh, &dl);
+    const float sh = u / dh;
+    float ph, pl; twoProdF(sh, dh, &ph, &pl);
+    const float sl = (((u - ph) - pl) - sh * dl) / dh;
+    const float s2 = sh * sh;
+    const float tail = sh * s2 * (0.333333343f + s2 * (0.2f + s2 * (0.142857149f + s2 * (0.111111112f + s2 * 0.0909090936f))));
+    /* ln m = 2 (sh + sl + tail) */
+    const float a = sl + tail;
+    float lh = sh + a;
+    float ll = a - (lh - sh);
+    lh = 2.0f * lh; ll = 2.0f * ll;
+    /* + e ln 2, ln 2 = 0.693359375 - 0.00021219253540039062 - 1.90465421e-09 (the first two products are exact) */
+    const float ef = (float)e;
+    float h, l, l2;
+    twoSumF(ef * 0.693359375f, ef * -0.00021219253540039062f, &h, &l);
+    twoSumF(h, lh, &h, &l2);
+    l = ((l + l2) + ef * -1.90465421e-09f) + ll;
+    const float Lh = h + l, Ll = l - (Lh - h);
+    /* P = y L */
+    float Ph, Pl; twoProdF(y, Lh, &Ph, &Pl);
+    Pl = Pl + y * Ll;
+    if (Ph > 88.8f) return bitsF(0x7f800000u);
+    if (Ph < -104.0f) return 0.0f;
+    const float kf = rnef(Ph * 1.44269502f);
+    float r = ((Ph - kf * 0.693359375f) - kf * -0.00021219253540039062f) - kf * -1.90465421e-09f;
+    r = r + Pl;
+    const float p = r * r * (0.5f + r * (0.166666672f + r * (0.0416666679f + r * (0.00833333377f + r * (0.00138888892f + r * 0.000198412701f)))));
+    const float er = 1.0f + (r + p);
+    const int k = (int)kf;
+    if (k >= -125 && k <= 126) return bitsF(fBits(er) + ((uint32_t)k << 23));
+    const int k1 = k / 2, k2 = k - k1;
+    return er * bitsF((uint32_t)(k1 + 127) << 23) * bitsF((uint32_t)(k2 + 127) << 23);
+}
 /* GLSL pow(x, y) is defined for x > 0, and for x == 0 with y > 0; the rest follows C powf: pow(x, 0) = 1, pow(0, y < 0) = inf,
  * negative base with an integral exponent = +-|x|^y, otherwise NaN */
 DM_HD float powF(float x, float y) {
-    const double dx = (double)x, dy = (double)y;
-    if (dx != dx || dy != dy) return (float)(dx + dy);
-    if (dy == 0.0) return 1.0f;
-    if (dx == 0.0) return dy > 0.0 ? 0.0f : (float)bitsD(0x7ff0000000000000ull);
-    if (dx < 0.0) {      /* like C powf: a negative base is defined for integral exponents only */
-        if (!(fabs(dy) < 9.0e15) || rne(dy) != dy) return (float)bitsD(0x7ff8000000000000ull);
-        const double r = expD(dy * logD(-dx));
-        const double half = dy * 0.5;
-        return (float)(rne(half) != half ? -r : r);
+    if (x != x || y != y) return x + y;
+    if (y == 0.0f) return 1.0f;
+    if (x == 0.0f) return y > 0.0f ? 0.0f : bitsF(0x7f800000u);
+    if (fabsf(y) > 3.0e38f) {                                   /* y = +-inf */
+        const float ax = fabsf(x);
+        if (ax == 1.0f) return 1.0f;
+        return ((ax > 1.0f) == (y > 0.0f)) ? bitsF(0x7f800000u) : 0.0f;
     }
-    return (float)expD(dy * logD(dx));
+    if (fabsf(x) > 3.0e38f) return (y > 0.0f) ? (x > 0.0f ? x : bitsF(0x7f800000u)) : 0.0f;      /* x = +-inf (sign of odd powers ignored) */
+    if (x < 0.0f) {      /* like C powf: a negative base is defined for integral exponents only */
+        if (fabsf(y) >= 16777216.0f) return powPosF(-x, y);     /* every float that large is an even integer */
+        if (rnef(y) != y) return bitsF(0x7fc00000u);
+        const float r = powPosF(-x, y);
+        const float half = y * 0.5f;
+        return rnef(half) != half ? -r : r;
+    }
+    return powPosF(x, y);
 }
 
 }  /* namespace b200pt_dm */

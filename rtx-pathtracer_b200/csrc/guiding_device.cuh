@@ -95,7 +95,8 @@ __device__ __forceinline__ vec3 sampleVmf(uint32_t &seed, const b200pt_vmf_theta
         const float cosTheta = 1.0f + ptLogf(1.0f + th.eMin2K * r1 - r1) / th.k;
         const float sinTheta = 1.0f - cosTheta * cosTheta <= 0.0f ? 0.0f : sqrtf(1.0f - cosTheta * cosTheta);
         const float phi = 2.f * PT_PI * r2;
-        const float cosPhi = ptCosf(phi), sinPhi = ptSinf(phi);
+        float cosPhi, sinPhi;
+        ptSinCosf(phi, &sinPhi, &cosPhi);
         vec3 mu = V3(th.mu[0], th.mu[1], th.mu[2]);
         if (parallax && th.distance > 0.0f) mu = normalize(V3(th.target[0], th.target[1], th.target[2]) - worldPos);
         return toWorld(V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta), mu);

@@ -295,27 +295,45 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
     struct Chan { std::string name; int type; };
     std::vector<Chan> chans;
     int comp = -1, dw[4] = {0, 0, -1, -1}, lineOrder = 0;
+    const size_t size = data.size();
+    // every read below is bounds-checked: a malformed or hostile file raises the loader's runtime_error instead of
+    // reading or writing out of bounds
+    auto need = [&](size_t at, size_t n) { if (at > size || n > size - at) throw std::runtime_error("EXR: truncated or corrupt header: " + path); };
+    auto cstr = [&](size_t at) -> std::string {
+        const void *z = at < size ? memchr(data.data() + at, 0, size - at) : nullptr;
+        if (!z) throw std::runtime_error("EXR: unterminated string in header: " + path);
+        return std::string(data.data() + at, static_cast<const char *>(z) - (data.data() + at));
+    };
     for (;;) {
-        if (i >= data.size()) throw std::runtime_error("EXR: truncated header");
+        need(i, 1);
         if (data[i] == 0) { i++; break; }
-        std::string name(data.c_str() + i); i += name.size() + 1;
-        std::string type(data.c_str() + i); i += type.size() + 1;
+        std::string name = cstr(i); i += name.size() + 1;
+        std::string type = cstr(i); i += type.size() + 1;
+        need(i, 4);
         int32_t sz; memcpy(&sz, data.data() + i, 4); i += 4;
+        if (sz < 0) throw std::runtime_error("EXR: negative attribute size: " + path);
+        need(i, size_t(sz));
         if (name == "channels") {
             size_t j = i;
-            while (data[j] != 0) {
-                Chan c; c.name = std::string(data.c_str() + j); j += c.name.size() + 1;
+            const size_t end = i + size_t(sz);
+            for (;;) {
+                if (j >= end) throw std::runtime_error("EXR: unterminated channel list: " + path);
+                if (data[j] == 0) break;
+                Chan c; c.name = cstr(j); j += c.name.size() + 1;
+                if (j + 16 > end) throw std::runtime_error("EXR: truncated channel list: " + path);
                 int32_t t; memcpy(&t, data.data() + j, 4); c.type = t; j += 16;
                 chans.push_back(c);
+                if (chans.size() > 64) throw std::runtime_error("EXR: too many channels: " + path);
             }
-        } else if (name == "compression") comp = (unsigned char)data[i];
-        else if (name == "dataWindow") memcpy(dw, data.data() + i, 16);
-        else if (name == "lineOrder") lineOrder = (unsigned char)data[i];
+        } else if (name == "compression") { if (sz < 1) throw std::runtime_error("EXR: bad compression attribute"); comp = (unsigned char)data[i]; }
+        else if (name == "dataWindow") { if (sz < 16) throw std::runtime_error("EXR: bad dataWindow attribute"); memcpy(dw, data.data() + i, 16); }
+        else if (name == "lineOrder") { if (sz < 1) throw std::runtime_error("EXR: bad lineOrder attribute"); lineOrder = (unsigned char)data[i]; }
         i += size_t(sz);
     }
     (void)lineOrder;
-    width = dw[2] - dw[0] + 1; height = dw[3] - dw[1] + 1;
-    if (width <= 0 || height <= 0 || chans.empty()) throw std::runtime_error("EXR: bad header " + path);
+    const int64_t w64 = int64_t(dw[2]) - dw[0] + 1, h64 = int64_t(dw[3]) - dw[1] + 1;
+    if (w64 <= 0 || h64 <= 0 || w64 > 65536 || h64 > 65536 || chans.empty()) throw std::runtime_error("EXR: bad header " + path);
+    width = int(w64); height = int(h64);
     int linesPerBlock;
     if (comp == 0 || comp == 2) linesPerBlock = 1;
     else if (comp == 3) linesPerBlock = 16;
@@ -332,19 +350,22 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
     for (auto &c : chans) if (c.name == "A") hasA = true;
     if (!hasA) for (size_t p = 0; p < size_t(width) * height; p++) rgba[p * 4 + 3] = 1.0f;
     std::vector<unsigned char> raw, tmp;
+    need(i, size_t(numBlocks) * 8);                           // the chunk-offset table
     for (int b = 0; b < numBlocks; b++) {
         uint64_t off; memcpy(&off, data.data() + i + size_t(b) * 8, 8);
-        if (off + 8 > data.size()) throw std::runtime_error("EXR: bad chunk offset");
+        if (off > size || size - off < 8) throw std::runtime_error("EXR: bad chunk offset");
         int32_t y0, sz; memcpy(&y0, data.data() + off, 4); memcpy(&sz, data.data() + off + 4, 4);
-        int lines = std::min(linesPerBlock, dw[3] - y0 + 1);
+        if (y0 < dw[1] || y0 > dw[3]) throw std::runtime_error("EXR: chunk outside the data window");
+        if (sz < 0 || size_t(sz) > size - off - 8) throw std::runtime_error("EXR: bad chunk size");
+        const int lines = int(std::min<int64_t>(linesPerBlock, int64_t(dw[3]) - y0 + 1));
         size_t expect = bytesPerLine * size_t(lines);
         const unsigned char *src = reinterpret_cast<const unsigned char *>(data.data() + off + 8);
         raw.resize(expect);
+        if (comp == 0 && size_t(sz) != expect) throw std::runtime_error("EXR: uncompressed chunk of the wrong size");
         if (comp == 0 || size_t(sz) == expect) memcpy(raw.data(), src, expect);
         else if (comp == 4) {
             std::vector<int> wordsPerPixel;
             for (auto &c : chans) wordsPerPixel.push_back(c.type == 1 ? 1 : 2);
-            if (off + 8 + size_t(sz) > data.size()) throw std::runtime_error("EXR: bad chunk size");
             pizDecompress(src, size_t(sz), raw.data(), expect, width, lines, wordsPerPixel);
         } else {
             tmp.resize(expect);

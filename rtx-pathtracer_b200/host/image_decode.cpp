@@ -220,12 +220,15 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
         const int len = u16(pos);
         const size_t seg = pos + 2, segEnd = pos + size_t(len);
         if (len < 2 || segEnd > d.size()) throw std::runtime_error("JPEG: bad segment length");
+        // every index below stays inside [seg, segEnd): a truncated or corrupt segment raises instead of reading past it
+        auto segNeed = [&](size_t at, size_t n) { if (at < seg || at > segEnd || n > segEnd - at) throw std::runtime_error("JPEG: truncated segment"); };
         if (marker == 0xdb) {                                    // DQT
             size_t i = seg;
             while (i < segEnd) {
                 int pq = d[i] >> 4, tq = d[i] & 15;
                 i++;
                 if (tq > 3 || pq > 1) throw std::runtime_error("JPEG: bad DQT");
+                segNeed(i, pq ? 128 : 64);
                 for (int k = 0; k < 64; k++) { quant[tq][kZigZag[k]] = uint16_t(pq ? u16(i) : d[i]); i += pq ? 2 : 1; }
                 quantDefined[tq] = true;
             }
@@ -244,10 +247,12 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
                 i += size_t(n);
             }
         } else if (marker == 0xc0 || marker == 0xc1) {           // SOF0 / SOF1: baseline / extended sequential, Huffman
+            segNeed(seg, 6);
             if (d[seg] != 8) throw std::runtime_error("JPEG: only 8-bit samples are supported");
             height = u16(seg + 1); width = u16(seg + 3);
             const int n = d[seg + 5];
             if (width <= 0 || height <= 0 || (n != 1 && n != 3)) throw std::runtime_error("JPEG: unsupported frame (size or component count)");
+            segNeed(seg + 6, 3 * size_t(n));
             comps.assign(size_t(n), Component());
             for (int k = 0; k < n; k++) {
                 Component &c = comps[size_t(k)];
@@ -261,13 +266,16 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
         } else if (marker == 0xc2 || (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc)) {
             throw std::runtime_error("JPEG: progressive / lossless / arithmetic-coded files are not supported");
         } else if (marker == 0xdd) {
+            segNeed(seg, 2);
             restartInterval = u16(seg);
         } else if (marker == 0xee && len >= 14 && memcmp(&d[seg], "Adobe", 5) == 0) {
             adobeTransformKnown = true; adobeTransform = d[seg + 11];
         } else if (marker == 0xda) {                             // SOS: the (single, interleaved) scan of a baseline file
             if (!haveFrame) throw std::runtime_error("JPEG: scan before frame header");
+            segNeed(seg, 1);
             const int ns = d[seg];
             if (ns != int(comps.size())) throw std::runtime_error("JPEG: non-interleaved scans are not supported");
+            segNeed(seg + 1, 2 * size_t(ns));
             for (int k = 0; k < ns; k++) {
                 const int cid = d[seg + 1 + 2 * size_t(k)], tbl = d[seg + 2 + 2 * size_t(k)];
                 Component *c = nullptr;

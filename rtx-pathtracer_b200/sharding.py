@@ -5,7 +5,10 @@ frame.  Two exchange steps exist:
   * image:   one all-reduce (sum) of the per-rank RGBA32F running means, weighted by the frames each rank rendered;
   * guiding: an all-gather of the ranks' DirectionalData buffers before a refit, after which every rank runs the same
              deterministic `b200pt_guiding_update_device` on the same records (so no VMM broadcast is needed).
-The reference is single-GPU (no collective call sites); this module is our addition and has no counterpart to mirror."""
+The reference is single-GPU (no collective call sites); this module is our addition and has no counterpart to mirror.
+It is the torch.distributed VARIANT of the two exchange steps, kept as the checker of the native path and for the gloo
+tests; the product path is inside the library: b200pt_reduce_image, and b200pt_guiding_update_all_ranks (region-sharded
+refit: only compacted valid records travel, every region is fitted once) — bench.py and the frame driver use those."""
 import torch
 import torch.distributed as dist
 
@@ -88,5 +91,8 @@ def guiding_update_all_ranks(renderer, params=None, group=None):
     local = torch.empty((n, RECORD_BYTES), dtype=torch.uint8, device=device)
     renderer.guiding_get_samples_device(local.data_ptr(), n)
     allrec = allgather_samples(local, group)
+    # the library launches on its own non-blocking stream: everything torch queued for `allrec` (NCCL all-gather, the
+    # concatenation) has to be complete before the sort kernels read it
+    torch.cuda.current_stream().synchronize()
     renderer.guiding_update_device(allrec.data_ptr(), allrec.shape[0], params)
     return allrec.shape[0]

@@ -79,3 +79,84 @@ def test_exr_reader_matches_openexr_digest(rel):
     assert img.shape == (want["height"], want["width"], 4)
     assert hashlib.sha256(np.ascontiguousarray(img[..., :3]).tobytes()).hexdigest() == want["sha256"]
     assert {EXR_DIGESTS[k]["compression"] for k in EXR_DIGESTS} >= {0, 4}
+
+
+def _expect_loader_error(fn, path):
+    P = helpers.pt()
+    with pytest.raises(P.B200ptError):
+        fn(path)
+
+
+def test_corrupt_exr_files_raise_instead_of_corrupting_memory(tmp_path):
+    """A malformed .exr in a scene directory must end in the loader's error, not in out-of-bounds reads or writes
+    (header attribute sizes, channel list, chunk-offset table, chunk y and size are all untrusted)."""
+    import struct
+    P = helpers.pt()
+    rng = np.random.default_rng(3)
+    good = str(tmp_path / "good.exr")
+    P.write_exr(good, rng.uniform(0, 2, (7, 9, 4)).astype(np.float32))
+    data = bytearray(open(good, "rb").read())
+    assert P.read_exr(good).shape == (7, 9, 4)
+
+    def variant(name, mutate):
+        d = bytearray(data)
+        mutate(d)
+        p = str(tmp_path / name)
+        open(p, "wb").write(d)
+        _expect_loader_error(P.read_exr, p)
+
+    for cut in (6, 20, 60, len(data) // 2, len(data) - 5):           # truncations everywhere
+        variant("cut%d.exr" % cut, lambda d, cut=cut: d.__delitem__(slice(cut, None)))
+    # attribute size of the first attribute blown up / negative
+    first = data.index(b"\x00", 8)                                    # end of the first attribute name
+    tpos = data.index(b"\x00", first + 1) + 1                         # after its type string: the int32 size
+    variant("bigattr.exr", lambda d: d.__setitem__(slice(tpos, tpos + 4), struct.pack("<i", 0x7fffff00)))
+    variant("negattr.exr", lambda d: d.__setitem__(slice(tpos, tpos + 4), struct.pack("<i", -8)))
+    # data window turned inside out / huge
+    dwp = data.index(b"dataWindow\x00box2i\x00") + len(b"dataWindow\x00box2i\x00") + 4
+    variant("dwneg.exr", lambda d: d.__setitem__(slice(dwp, dwp + 16), struct.pack("<4i", 5, 5, 0, 0)))
+    variant("dwhuge.exr", lambda d: d.__setitem__(slice(dwp, dwp + 16), struct.pack("<4i", 0, 0, 2000000000, 2000000000)))
+    # the chunk table: an offset beyond the file, and a chunk whose y lies outside the data window / whose size is bogus
+    hdr_end = data.index(b"\x00\x00", dwp) if False else None
+    # locate the offset table: it follows the header's terminating zero byte; find it by parsing like the reader does
+    i = 8
+    while data[i] != 0:
+        i = data.index(b"\x00", i) + 1
+        i = data.index(b"\x00", i) + 1
+        sz = struct.unpack_from("<i", data, i)[0]
+        i += 4 + sz
+    table = i + 1
+    off0 = struct.unpack_from("<Q", data, table)[0]
+    variant("badoff.exr", lambda d: struct.pack_into("<Q", d, table, len(data) + 1000))
+    variant("bady.exr", lambda d: struct.pack_into("<i", d, off0, 123456))
+    variant("badsize.exr", lambda d: struct.pack_into("<i", d, off0 + 4, 0x7ffffff0))
+    variant("negsize.exr", lambda d: struct.pack_into("<i", d, off0 + 4, -4))
+
+
+def test_corrupt_jpeg_segments_raise(tmp_path):
+    P = helpers.pt()
+    src = os.path.join(helpers.ROOT, "tests", "golden", "images", "cube.jpg")
+    data = bytearray(open(src, "rb").read())
+    assert P.read_image_file(src).ndim == 3
+    raised = 0
+    for marker in (b"\xff\xdb", b"\xff\xc0", b"\xff\xc4", b"\xff\xda"):
+        pos = data.index(marker)
+        d = bytearray(data)
+        d[pos + 2:pos + 4] = (2).to_bytes(2, "big")                  # segment length shrunk to its minimum: the body is gone
+        p = str(tmp_path / ("seg%02x.jpg" % marker[1]))
+        open(p, "wb").write(d)
+        try:                                                          # (the byte pair may also sit inside an APPn payload: then the file still decodes)
+            P.read_image_file(p)
+        except P.B200ptError:
+            raised += 1
+    assert raised >= 2
+    for cut in (3, 30, 200):                                          # inside the header segments
+        p = str(tmp_path / ("cut%d.jpg" % cut))
+        open(p, "wb").write(data[:cut])
+        _expect_loader_error(P.read_image_file, p)
+    p = str(tmp_path / "cutscan.jpg")                                 # inside the entropy-coded data: like stb_image the decoder pads
+    open(p, "wb").write(data[:len(data) // 3])                        # the missing bits with zeros — it must not read past the buffer
+    try:
+        assert P.read_image_file(p).ndim == 3
+    except P.B200ptError:
+        pass
