@@ -9,10 +9,10 @@
  * These versions use only IEEE-754 add / sub / mul / div / sqrt and integer operations on the bits — no fused
  * multiply-add (compile with contraction off: nvcc -fmad=false, gcc -ffp-contract=off), no libm — in a fixed order.
  * They are therefore bit-identical between the sm_100a kernels and any host compiler.  The hot functions (sin, cos,
- * tan, asin, acos, atan, atan2, log, exp) are single-precision kernels of ~20 operations, accurate to 1-3 ulp; pow
- * carries log x as a sum of two floats (exp(y log x) needs the extra bits).  A first version evaluated everything in
- * double: bit-identical too, but B200's FP64 pipe made sponzaXML frames 1.4-2x slower (profiles/r02_detmath.txt); the
- * only double code left is the range reduction of sin / cos for |x| >= 1e4, which the tracer never reaches.
+ * tan, asin, acos, atan, atan2, log, exp) are single-precision kernels of ~20 operations, accurate to 1-3 ulp; pow is
+ * exp(y log x) of those, like GLSL's.  A first version evaluated everything in double: bit-identical too, but B200's
+ * FP64 pipe made sponzaXML frames 1.4-2x slower (profiles/r02_detmath.txt); the only double code left is the range
+ * reduction of sin / cos for |x| >= 1e4, which the tracer never reaches.
  * tests/test_detmath.py measures the errors against float64 references.
  *
  * Included by the device code (rtx-pathtracer_b200/csrc/device_math.cuh) and by the CPU oracle (oracle/): the same
@@ -180,63 +180,13 @@ DM_HD float expF(float x) {
     return er * bitsF((uint32_t)(k1 + 127) << 23) * bitsF((uint32_t)(k2 + 127) << 23);
 }
 
-/* ---- pow in single precision with double-float steps -------------------------------------------------------------------
- * exp(y log x) needs log x to ~2^-32 (Phong exponents in the thousands); the first version ran it in double and the
- * FP64 pipe cost sponzaXML 30-50 % of its frame rate (one Phong material is enough: a warp with one such lane takes the
- * path).  Here log x is carried as an unevaluated sum of two floats (Dekker / Veltkamp error-free transformations — no
- * fused multiply-add), multiplied by y with an exact product, and the exponential takes the low part as a correction. */
-DM_HD void twoSumF(float a, float b, float *s, float *e) { const float t = a + b, bb = t - a; *e = (a - (t - bb)) + (b - bb); *s = t; }
-DM_HD void splitF(float a, float *hi, float *lo) { const float c = 4097.0f * a, h = c - (c - a); *hi = h; *lo = a - h; }
-DM_HD void twoProdF(float a, float b, float *p, float *e) {
-    float ah, al, bh, bl;
-    splitF(a, &ah, &al); splitF(b, &bh, &bl);
-    const float pp = a * b;
-    *e = (((ah * bh - pp) + ah * bl) + al * bh) + al * bl;
-    *p = pp;
-}
-/* x > 0 finite, y finite non-zero */
-DM_HD float powPosF(float x, float y) {
-    uint32_t b = fBits(x);
-    int e = 0;
-    if ((b >> 23) == 0u) { x = x * 8388608.0f; b = fBits(x); e = -23; }
-    e += (int)(b >> 23) - 127;
-    float m = bitsF((b & 0x007fffffu) | 0x3f800000u);
-    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
-    /* s = (m - 1) / (m + 1) as sh + sl */
-    const float u = m - 1.0f;                                   /* exact */
-    float dh, dl; twoSumF(m, 1.0f, &dh, &dl);
-    const float sh = u / dh;
-    float ph, pl; twoProdF(sh, dh, &ph, &pl);
-    const float sl = (((u - ph) - pl) - sh * dl) / dh;
-    const float s2 = sh * sh;
-    const float tail = sh * s2 * (0.333333343f + s2 * (0.2f + s2 * (0.142857149f + s2 * (0.111111112f + s2 * 0.0909090936f))));
-    /* ln m = 2 (sh + sl + tail) */
-    const float a = sl + tail;
-    float lh = sh + a;
-    float ll = a - (lh - sh);
-    lh = 2.0f * lh; ll = 2.0f * ll;
-    /* + e ln 2, ln 2 = 0.693359375 - 0.00021219253540039062 - 1.90465421e-09 (the first two products are exact) */
-    const float ef = (float)e;
-    float h, l, l2;
-    twoSumF(ef * 0.693359375f, ef * -0.00021219253540039062f, &h, &l);
-    twoSumF(h, lh, &h, &l2);
-    l = ((l + l2) + ef * -1.90465421e-09f) + ll;
-    const float Lh = h + l, Ll = l - (Lh - h);
-    /* P = y L */
-    float Ph, Pl; twoProdF(y, Lh, &Ph, &Pl);
-    Pl = Pl + y * Ll;
-    if (Ph > 88.8f) return bitsF(0x7f800000u);
-    if (Ph < -104.0f) return 0.0f;
-    const float kf = rnef(Ph * 1.44269502f);
-    float r = ((Ph - kf * 0.693359375f) - kf * -0.00021219253540039062f) - kf * -1.90465421e-09f;
-    r = r + Pl;
-    const float p = r * r * (0.5f + r * (0.166666672f + r * (0.0416666679f + r * (0.00833333377f + r * (0.00138888892f + r * 0.000198412701f)))));
-    const float er = 1.0f + (r + p);
-    const int k = (int)kf;
-    if (k >= -125 && k <= 126) return bitsF(fBits(er) + ((uint32_t)k << 23));
-    const int k1 = k / 2, k2 = k - k1;
-    return er * bitsF((uint32_t)(k1 + 127) << 23) * bitsF((uint32_t)(k2 + 127) << 23);
-}
+/* ---- pow ------------------------------------------------------------------------------------------------------------------
+ * exp(y log x) in single precision, which is how GLSL defines pow (exp2(y * log2(x)), GLSL 4.60 spec 8.2) and what the
+ * reference's GPU evaluates: the relative error grows with |y ln x| (about (1 + |y ln x|) ulp: 1e-6 for a Phong lobe
+ * of exponent 100 at 25 degrees).  More accurate versions were measured and dropped: log x carried as two floats (<= 4 ulp for
+ * exponents up to 2000) cost sponzaXML — one Phong material — 9 % of its frame rate, a double-precision kernel 30-50 %
+ * (B200's FP64 pipe); bit-identity between device and host, the point of this header, holds for all three. */
+DM_HD float powPosF(float x, float y) { return expF(y * logF(x)); }
 /* GLSL pow(x, y) is defined for x > 0, and for x == 0 with y > 0; the rest follows C powf: pow(x, 0) = 1, pow(0, y < 0) = inf,
  * negative base with an integral exponent = +-|x|^y, otherwise NaN */
 DM_HD float powF(float x, float y) {
