@@ -1212,6 +1212,13 @@ int b200pt_comm_init(b200pt_ctx *c, const char id[B200PT_COMM_ID_BYTES], int ran
     memcpy(&uid, id, sizeof(uid));
     NCCL_TRY(g_nccl.CommInitRank(&c->rc.comm, nranks, uid, rank));
     c->rc.rank = rank; c->rc.nranks = nranks;
+    if (nranks > 1 && c->guiding.ready) {
+        // one-time work of the region-sharded refit, done here instead of inside the first update: the sorted-sample buffers
+        // for this context's W*H*16 records, their CUDA-IPC mappings on every peer (collective), NCCL's lazy connection set-up
+        int rc2 = c->guiding.ensureCapacity(int64_t(c->numPixels) * B200PT_MAX_DIRECTIONAL_DATA_PER_PIXEL);
+        if (rc2 == B200PT_OK) rc2 = c->guiding.setupPeers(c->rc, c->stream);
+        if (rc2 != B200PT_OK) return setError(rc2, "b200pt_comm_init: " + c->guiding.error);
+    }
     return B200PT_OK;
 }
 int b200pt_comm_destroy(b200pt_ctx *c) {
