@@ -286,6 +286,7 @@ typedef struct b200pt_stats {
     float ms_guiding_gather;                /* device time: all-gather of the fitted mixtures */
 } b200pt_stats;
 
+#define B200PT_MAX_GUIDING_SPLITS 9          /* 512 initial regions; adaptive refinement (splitRegions) may grow them to 1024 */
 typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
 typedef struct b200pt_scene b200pt_scene;   /* opaque host-side scene (loader output) */
 

@@ -6,6 +6,7 @@
 #include "../host/scene.h"
 #include "../host/bvh.h"
 #include <cstdio>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -287,8 +288,11 @@ int b200pt_device_count(void) {
 }
 
 int b200pt_create(int device_ordinal, int width, int height, int ic_size, int guiding_splits, b200pt_ctx **out) {
-    if (!out || width <= 0 || height <= 0 || ic_size < 0 || guiding_splits < 0 || guiding_splits > 16)
+    if (!out || width <= 0 || height <= 0 || ic_size < 0 || guiding_splits < 0)
         return setError(B200PT_E_INVALID, "b200pt_create: bad arguments");
+    if (guiding_splits > B200PT_MAX_GUIDING_SPLITS)
+        return setError(B200PT_E_INVALID, "b200pt_create: GUIDING_SPLITS > 9 is not supported (the device sort and plan handle at most 1024 regions, "
+                                          "and adaptive region refinement needs head room above 2^splits)");
     int n = b200pt_device_count();
     if (n <= 0) return setError(B200PT_E_NODEVICE, "b200pt_create: no CUDA device visible (libb200pt has no CPU fallback)");
     if (device_ordinal < 0 || device_ordinal >= n) return setError(B200PT_E_INVALID, "b200pt_create: device ordinal out of range");
@@ -1129,15 +1133,19 @@ int b200pt_read_aovs(b200pt_ctx *c, float *rgba) {
 }
 
 // ---- checkpoint / resume -------------------------------------------------------------------------------------------
-static const char kStateMagic[8] = {'B', '2', 'P', 'T', 'S', 'T', '0', '1'};
+static const char kStateMagic[8] = {'B', '2', 'P', 'T', 'S', 'T', '0', '2'};
+static const int32_t kStateVersion = 2;      // little-endian raw structs; bump on any layout change of GMix / b200pt_vmm_theta / the headers
 
 int b200pt_save_state(b200pt_ctx *c, const char *path) {
     if (!c || !path) return setError(B200PT_E_INVALID, "b200pt_save_state: null argument");
     if (!c->hasScene) return setError(B200PT_E_STATE, "b200pt_save_state: set_scene must be called first");
     CUDA_TRY(cudaSetDevice(c->device));
-    FILE *f = fopen(path, "wb");
-    if (!f) return setError(B200PT_E_IO, std::string("b200pt_save_state: cannot open ") + path);
-    const int32_t hdr[4] = {c->width, c->height, c->icSize, c->guidingSplits};
+    // written to <path>.tmp, flushed to disk and renamed: a crash in the middle leaves the previous checkpoint intact
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return setError(B200PT_E_IO, std::string("b200pt_save_state: cannot open ") + tmp);
+    auto fail = [&](int code, const std::string &msg) { fclose(f); remove(tmp.c_str()); return setError(code, msg); };
+    const int32_t hdr[5] = {kStateVersion, c->width, c->height, c->icSize, c->guidingSplits};
     const size_t N = size_t(c->numPixels), S = size_t(c->icSize);
     std::vector<float4> img(N);
     std::vector<b200pt_cache_data> icd(S);
@@ -1145,15 +1153,17 @@ int b200pt_save_state(b200pt_ctx *c, const char *path) {
     b200pt_cache_header ich;
     bool ok = fwrite(kStateMagic, 8, 1, f) == 1 && fwrite(hdr, sizeof(hdr), 1, f) == 1;
     for (int which = 0; which < 3 && ok; which++) {
-        if (cudaMemcpy(img.data(), imagePtr(c, which), N * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); return setError(B200PT_E_CUDA, "b200pt_save_state: image read-back failed"); }
+        if (cudaMemcpy(img.data(), imagePtr(c, which), N * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(B200PT_E_CUDA, "b200pt_save_state: image read-back failed");
         ok = fwrite(img.data(), sizeof(float4), N, f) == N;
     }
     int rc = b200pt_ic_get(c, &ich, S ? icd.data() : nullptr, S ? ics.data() : nullptr, int(S));
-    if (rc != B200PT_OK) { fclose(f); return rc; }
+    if (rc != B200PT_OK) { fclose(f); remove(tmp.c_str()); return rc; }
     ok = ok && fwrite(&ich, sizeof(ich), 1, f) == 1 && fwrite(icd.data(), sizeof(b200pt_cache_data), S, f) == S && fwrite(ics.data(), sizeof(b200pt_sphere), S, f) == S;
-    if (ok) { rc = c->guiding.save(f, c->stream); if (rc != B200PT_OK) { fclose(f); return setError(rc, "b200pt_save_state: " + c->guiding.error); } }
+    if (ok) { rc = c->guiding.save(f, c->stream); if (rc != B200PT_OK) return fail(rc, "b200pt_save_state: " + c->guiding.error); }
+    ok = ok && fflush(f) == 0 && fsync(fileno(f)) == 0;
     ok = (fclose(f) == 0) && ok;
-    if (!ok) return setError(B200PT_E_IO, std::string("b200pt_save_state: write failed: ") + path);
+    if (!ok) { remove(tmp.c_str()); return setError(B200PT_E_IO, std::string("b200pt_save_state: write failed: ") + tmp); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return setError(B200PT_E_IO, std::string("b200pt_save_state: cannot rename to ") + path); }
     return B200PT_OK;
 }
 
@@ -1163,27 +1173,38 @@ int b200pt_load_state(b200pt_ctx *c, const char *path) {
     CUDA_TRY(cudaSetDevice(c->device));
     FILE *f = fopen(path, "rb");
     if (!f) return setError(B200PT_E_IO, std::string("b200pt_load_state: cannot open ") + path);
-    char magic[8]; int32_t hdr[4];
-    if (fread(magic, 8, 1, f) != 1 || memcmp(magic, kStateMagic, 8) != 0 || fread(hdr, sizeof(hdr), 1, f) != 1) { fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: not a b200pt checkpoint"); }
-    if (hdr[0] != c->width || hdr[1] != c->height || hdr[2] != c->icSize || hdr[3] != c->guidingSplits) {
-        fclose(f); return setError(B200PT_E_INVALID, "b200pt_load_state: the checkpoint was written by a context of a different size (width, height, ic_size, guiding_splits)");
-    }
+    auto fail = [&](int code, const std::string &msg) { fclose(f); return setError(code, msg); };
+    char magic[8]; int32_t hdr[5];
+    if (fread(magic, 8, 1, f) != 1 || memcmp(magic, kStateMagic, 8) != 0 || fread(hdr, sizeof(hdr), 1, f) != 1) return fail(B200PT_E_IO, "b200pt_load_state: not a b200pt checkpoint");
+    if (hdr[0] != kStateVersion) return fail(B200PT_E_INVALID, "b200pt_load_state: checkpoint format version " + std::to_string(hdr[0]) + " is not supported (this build reads version " + std::to_string(kStateVersion) + ")");
+    if (hdr[1] != c->width || hdr[2] != c->height || hdr[3] != c->icSize || hdr[4] != c->guidingSplits)
+        return fail(B200PT_E_INVALID, "b200pt_load_state: the checkpoint was written by a context of a different size (width, height, ic_size, guiding_splits)");
+    // The WHOLE file is read into host memory and validated before anything is uploaded: a truncated or corrupt file
+    // leaves the context untouched, and no out-of-range slot, link or component count ever reaches the device.
     const size_t N = size_t(c->numPixels), S = size_t(c->icSize);
-    std::vector<float4> img(N);
+    std::vector<float4> img[3];
     for (int which = 0; which < 3; which++) {
-        if (fread(img.data(), sizeof(float4), N, f) != N) { fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: truncated checkpoint"); }
-        if (cudaMemcpy(imagePtr(c, which), img.data(), N * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) { fclose(f); return setError(B200PT_E_CUDA, "b200pt_load_state: image upload failed"); }
+        img[which].resize(N);
+        if (fread(img[which].data(), sizeof(float4), N, f) != N) return fail(B200PT_E_IO, "b200pt_load_state: truncated checkpoint");
     }
     std::vector<b200pt_cache_data> icd(S);
     std::vector<b200pt_sphere> ics(S);
     b200pt_cache_header ich;
-    if (fread(&ich, sizeof(ich), 1, f) != 1 || fread(icd.data(), sizeof(b200pt_cache_data), S, f) != S || fread(ics.data(), sizeof(b200pt_sphere), S, f) != S) {
-        fclose(f); return setError(B200PT_E_IO, "b200pt_load_state: truncated checkpoint");
-    }
-    int rc = b200pt_ic_put(c, &ich, S ? icd.data() : nullptr, S ? ics.data() : nullptr, int(S));
-    if (rc == B200PT_OK) { rc = c->guiding.load(f, c->stream); if (rc != B200PT_OK) setError(rc, "b200pt_load_state: " + c->guiding.error); }
+    if (fread(&ich, sizeof(ich), 1, f) != 1 || fread(icd.data(), sizeof(b200pt_cache_data), S, f) != S || fread(ics.data(), sizeof(b200pt_sphere), S, f) != S)
+        return fail(B200PT_E_IO, "b200pt_load_state: truncated checkpoint");
+    if (ich.maxCaches != uint32_t(c->icSize) || ich.nextCacheSlot > uint32_t(c->icSize) + 1u || ich.nextUpdateSlot > uint32_t(c->icSize) + 1u)      // (+1: quirk 11, the reference's off-by-one)
+        return fail(B200PT_E_INVALID, "b200pt_load_state: irradiance-cache header out of range");
+    GuidingCheckpoint gck;
+    int rc = c->guiding.readCheckpoint(f, gck);
+    if (rc != B200PT_OK) return fail(rc, "b200pt_load_state: " + c->guiding.error);
     fclose(f);
-    return rc;
+    for (int which = 0; which < 3; which++)
+        if (cudaMemcpy(imagePtr(c, which), img[which].data(), N * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return setError(B200PT_E_CUDA, "b200pt_load_state: image upload failed");
+    rc = b200pt_ic_put(c, &ich, S ? icd.data() : nullptr, S ? ics.data() : nullptr, int(S));
+    if (rc != B200PT_OK) return rc;
+    rc = c->guiding.applyCheckpoint(gck, c->stream);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_load_state: " + c->guiding.error);
+    return B200PT_OK;
 }
 
 // ---- multi-GPU -----------------------------------------------------------------------------------------------------

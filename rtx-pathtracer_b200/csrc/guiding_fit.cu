@@ -1340,7 +1340,7 @@ __global__ void __launch_bounds__(128) k_guiding_split_regions(GMix *mixes, b200
 int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream) {
     release();
     regionCount = 1 << splits;
-    maxRegions = std::max(regionCount, 1024);       // room for adaptive splits up to what the device sort handles
+    maxRegions = 1024;                              // what the device sort / plan handle; b200pt_create limits splits to 9 so adaptive refinement has room
     b200pt_aabb scene;
     for (int a = 0; a < 3; a++) {   // Aabb::addEpsilon, src/Shapes.h:48-53
         float extent = sceneMax[a] - sceneMin[a];
@@ -1768,7 +1768,8 @@ int GuidingState::save(FILE *f, cudaStream_t stream) {
     if (!ok) { error = "write failed"; return B200PT_E_IO; }
     return B200PT_OK;
 }
-int GuidingState::load(FILE *f, cudaStream_t stream) {
+// checkpoint, part 1: read everything into host memory and validate it (nothing is touched on failure)
+int GuidingState::readCheckpoint(FILE *f, GuidingCheckpoint &ck) {
     if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
     int32_t hdr[6];
     if (fread(hdr, sizeof(hdr), 1, f) != 1) { error = "truncated checkpoint"; return B200PT_E_IO; }
@@ -1776,22 +1777,38 @@ int GuidingState::load(FILE *f, cudaStream_t stream) {
         error = "checkpoint belongs to a different guiding configuration"; return B200PT_E_INVALID;
     }
     const int n = hdr[1];
-    std::vector<b200pt_aabb> ab; ab.resize(size_t(n));
-    std::vector<int32_t> sf(size_t(maxRegions), -1), sn(size_t(maxRegions), -1);
-    std::vector<char> mixBuf(size_t(n) * sizeof(GMix));
-    std::vector<b200pt_vmm_theta> vmmBuf; vmmBuf.resize(size_t(n));
-    b200pt_guiding_params gp;
-    bool ok = fread(&gp, sizeof(gp), 1, f) == 1 && fread(ab.data(), sizeof(b200pt_aabb), size_t(n), f) == size_t(n) &&
-              fread(sf.data(), sizeof(int32_t), size_t(n), f) == size_t(n) && fread(sn.data(), sizeof(int32_t), size_t(n), f) == size_t(n) &&
-              fread(mixBuf.data(), 1, mixBuf.size(), f) == mixBuf.size() && fread(vmmBuf.data(), sizeof(b200pt_vmm_theta), vmmBuf.size(), f) == vmmBuf.size();
+    ck.regionCount = n; ck.firstFit = hdr[3] != 0; ck.hasSpawns = hdr[4] != 0;
+    ck.aabbs.resize(size_t(n));
+    ck.spawnFirst.assign(size_t(maxRegions), -1); ck.spawnNext.assign(size_t(maxRegions), -1);
+    ck.mixes.resize(size_t(n) * sizeof(GMix));
+    ck.vmms.resize(size_t(n));
+    bool ok = fread(&ck.params, sizeof(ck.params), 1, f) == 1 && fread(ck.aabbs.data(), sizeof(b200pt_aabb), size_t(n), f) == size_t(n) &&
+              fread(ck.spawnFirst.data(), sizeof(int32_t), size_t(n), f) == size_t(n) && fread(ck.spawnNext.data(), sizeof(int32_t), size_t(n), f) == size_t(n) &&
+              fread(ck.mixes.data(), 1, ck.mixes.size(), f) == ck.mixes.size() && fread(ck.vmms.data(), sizeof(b200pt_vmm_theta), ck.vmms.size(), f) == ck.vmms.size();
     if (!ok) { error = "truncated checkpoint"; return B200PT_E_IO; }
-    regionCount = n; firstFit = hdr[3] != 0; hasSpawns = hdr[4] != 0; lastParams = gp;
-    hostAabbs = ab; hostSpawnFirst = sf; hostSpawnNext = sn;
+    // what the device code indexes with: spawn links, component counts
+    for (int r = 0; r < n; r++) {
+        const int32_t a = ck.spawnFirst[size_t(r)], b = ck.spawnNext[size_t(r)];
+        if (a < -1 || a >= n || b < -1 || b >= n) { error = "checkpoint: region spawn link out of range"; return B200PT_E_INVALID; }
+        GMix m;
+        memcpy(&m, ck.mixes.data() + size_t(r) * sizeof(GMix), sizeof(GMix));
+        if (m.K < 1 || m.K > G_MAXK) { error = "checkpoint: mixture component count out of range"; return B200PT_E_INVALID; }
+        const int used = ck.vmms[size_t(r)].usedDistributions;
+        if (used < 0 || used > G_MAXK) { error = "checkpoint: VMM_Theta component count out of range"; return B200PT_E_INVALID; }
+    }
+    if (ck.params.numInitialComponents < 1 || ck.params.numInitialComponents > G_MAXK) { error = "checkpoint: bad guiding parameters"; return B200PT_E_INVALID; }
+    return B200PT_OK;
+}
+// checkpoint, part 2: upload validated data
+int GuidingState::applyCheckpoint(const GuidingCheckpoint &ck, cudaStream_t stream) {
+    const int n = ck.regionCount;
+    regionCount = n; firstFit = ck.firstFit; hasSpawns = ck.hasSpawns; lastParams = ck.params;
+    hostAabbs = ck.aabbs; hostSpawnFirst = ck.spawnFirst; hostSpawnNext = ck.spawnNext;
     G_TRY(cudaMemcpyAsync(aabbs, hostAabbs.data(), size_t(n) * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
     G_TRY(cudaMemcpyAsync(spawnFirst, hostSpawnFirst.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     G_TRY(cudaMemcpyAsync(spawnNext, hostSpawnNext.data(), size_t(maxRegions) * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    G_TRY(cudaMemcpyAsync(mixes, mixBuf.data(), mixBuf.size(), cudaMemcpyHostToDevice, stream));
-    G_TRY(cudaMemcpyAsync(vmms, vmmBuf.data(), vmmBuf.size() * sizeof(b200pt_vmm_theta), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(mixes, ck.mixes.data(), ck.mixes.size(), cudaMemcpyHostToDevice, stream));
+    G_TRY(cudaMemcpyAsync(vmms, ck.vmms.data(), ck.vmms.size() * sizeof(b200pt_vmm_theta), cudaMemcpyHostToDevice, stream));
     G_TRY(cudaStreamSynchronize(stream));
     return B200PT_OK;
 }

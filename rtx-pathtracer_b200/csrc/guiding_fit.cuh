@@ -15,6 +15,16 @@ struct GSegment;
 struct GPlanSummary;
 struct GPass;
 
+struct GuidingCheckpoint {             // host copy of a checkpoint's guiding section, validated before it is applied
+    int regionCount = 0;
+    bool firstFit = true, hasSpawns = false;
+    b200pt_guiding_params params{};
+    std::vector<b200pt_aabb> aabbs;
+    std::vector<int32_t> spawnFirst, spawnNext;
+    std::vector<char> mixes;
+    std::vector<b200pt_vmm_theta> vmms;
+};
+
 struct GuidingState {
     bool ready = false;
     bool firstFit = true;                  // PathGuiding::firstFit (global: cleared by the first update)
@@ -81,7 +91,8 @@ struct GuidingState {
     void closePeers();
     int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);
     int save(FILE *f, cudaStream_t stream);          // checkpoint: regions, spawn chains, mixtures, packed VMMs
-    int load(FILE *f, cudaStream_t stream);      // PathGuiding.cpp:291-300, :328-348
+    int readCheckpoint(FILE *f, GuidingCheckpoint &ck);          // read + validate, host only
+    int applyCheckpoint(const GuidingCheckpoint &ck, cudaStream_t stream);
     int getState(int region, float scalars5[5], float perComponent[14 * 16], cudaStream_t stream);
     int getSorted(b200pt_directional_data *out, uint32_t *offsets, const b200pt_directional_data *rawDevice, cudaStream_t stream);
     void release();

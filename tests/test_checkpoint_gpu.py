@@ -1,5 +1,8 @@
 """Checkpoint / resume (b200pt_save_state / b200pt_load_state): a run that is saved, torn down and
 resumed in a fresh context continues bit-identically — images, irradiance cache, guiding mixtures incl. adaptive splits."""
+import ctypes as C
+import os
+
 import numpy as np
 import pytest
 
@@ -80,3 +83,45 @@ def test_checkpoint_errors(tmp_path):
     other = _ctx(P, scene, 0, 2)                           # different guiding_splits
     with pytest.raises(P.B200ptError):
         other.load_state(good)
+
+
+def test_corrupt_checkpoints_are_rejected_and_leave_the_context_untouched(tmp_path):
+    """b200pt_load_state reads and validates the whole file before it uploads anything: a truncated file, a stale format
+    version, or out-of-range slots / spawn links / component counts end in an error and the context keeps rendering the
+    same frames as before.  b200pt_save_state writes <path>.tmp and renames."""
+    import struct
+    P = helpers.pt()
+    scene = P.Scene(helpers.scene_path("cornell-dielectric"))
+    r = _ctx(P, scene, 64, 2)
+    for f in range(2):
+        r.render_frame(P.default_push_constants(randomUInt=P.tea(f, 3), previousFrames=f, samplesPerPixel=1, enableMIS=1, updateGuiding=1))
+        r.guiding_update()
+    good = str(tmp_path / "state.ckpt")
+    r.save_state(good)
+    assert not os.path.exists(good + ".tmp")
+    data = bytearray(open(good, "rb").read())
+    before_img, before_vmm = r.read_image().copy(), r.guiding_get_vmms().copy()
+
+    def rejected(name, mutate):
+        d = bytearray(data)
+        mutate(d)
+        p = str(tmp_path / name)
+        open(p, "wb").write(d)
+        with pytest.raises(P.B200ptError):
+            r.load_state(p)
+        assert np.array_equal(r.read_image(), before_img) and np.array_equal(r.guiding_get_vmms().view(np.uint8), before_vmm.view(np.uint8)), name
+
+    rejected("trunc_images.ckpt", lambda d: d.__delitem__(slice(len(d) // 3, None)))
+    rejected("trunc_tail.ckpt", lambda d: d.__delitem__(slice(len(d) - 100, None)))
+    rejected("version.ckpt", lambda d: struct.pack_into("<i", d, 8, 1))
+    n = r.width * r.height
+    ic_hdr = 8 + 20 + 3 * n * 16
+    rejected("ic_slot.ckpt", lambda d: struct.pack_into("<I", d, ic_hdr, 1 << 30))                     # nextCacheSlot far beyond ic_size
+    g = ic_hdr + 12 + 64 * (56 + 24)                                                                     # guiding section: 6 x int32 header
+    regions = struct.unpack_from("<i", data, g + 4)[0]
+    assert regions == 4
+    spawn = g + 24 + C.sizeof(P.GuidingParams) + regions * 24
+    rejected("spawn.ckpt", lambda d: struct.pack_into("<i", d, spawn, 1000))                            # spawn link out of range
+    mix0 = spawn + 2 * regions * 4
+    rejected("mixK.ckpt", lambda d: struct.pack_into("<i", d, mix0, 99))                                # K = 99 components
+    r.load_state(good)                                                                                    # the intact file still loads
