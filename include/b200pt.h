@@ -477,6 +477,15 @@ int b200pt_allgather_samples(b200pt_ctx *ctx, int64_t *total_out);
 int b200pt_guiding_update_all_ranks(b200pt_ctx *ctx, const b200pt_guiding_params *params);
 /* same on `n` caller-provided records in device memory per rank (n equal on all ranks; INVALID records allowed) */
 int b200pt_guiding_update_all_ranks_device(b200pt_ctx *ctx, const b200pt_guiding_params *params, const void *samples_device, int64_t n);
+/* parity hook: the plan of b200pt_guiding_update_all_ranks (steps 2-3) as rank `rank` of `nranks` would compute it from the
+ * per-rank region counts counts[nranks][regions] — no communicator and no samples involved, so one GPU can check ownership
+ * and layouts for any rank count.  Outputs (regions entries unless noted): owner, region_begin / region_len (this rank's fit
+ * layout; len 0 for regions it does not own), src_start[nranks][regions] (where region g starts in rank s's sorted buffer),
+ * active (this rank's non-empty regions, largest first; summary[0] entries), summary = {numActive, numOwned, numSegments,
+ * localValid, ownedSamples, totalSamples}, segments[numOwned * nranks][4] = {src rank, src offset, dst offset, length}.
+ * peer_mode 1: source offsets address the peers' buffers, 0: the staging buffer of the send/recv fallback. */
+int b200pt_guiding_plan_debug(b200pt_ctx *ctx, const uint32_t *counts, int nranks, int rank, int peer_mode, uint8_t *owner, uint32_t *region_begin,
+                              uint32_t *region_len, uint32_t *src_start, uint32_t *active, uint32_t summary[6], uint32_t *segments);
 /* 0 = no communicator, 1 = records travel by ncclSend/ncclRecv, 2 = peers' buffers are read directly (CUDA IPC over NVLink);
  * decided collectively by the first b200pt_guiding_update_all_ranks */
 int b200pt_comm_exchange_mode(b200pt_ctx *ctx);

@@ -173,7 +173,7 @@ EXPORTS = [
     "b200pt_guiding_set_order", "b200pt_guiding_sorted_count", "b200pt_guiding_get_sorted", "b200pt_guiding_get_state", "b200pt_guiding_fastexp", "b200pt_guiding_selftest_division", "b200pt_detmath_eval", "b200pt_detmath_eval_host", "b200pt_ic_get", "b200pt_ic_put", "b200pt_default_push_constants", "b200pt_scene_load",
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
-    "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_comm_exchange_mode",
+    "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_guiding_plan_debug", "b200pt_comm_exchange_mode",
     "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
@@ -251,6 +251,7 @@ def lib():
         L.b200pt_guiding_update_all_ranks.argtypes = [C.c_void_p, C.POINTER(GuidingParams)]
         L.b200pt_guiding_update_all_ranks_device.argtypes = [C.c_void_p, C.POINTER(GuidingParams), C.c_void_p, C.c_int64]
         L.b200pt_comm_exchange_mode.argtypes = [C.c_void_p]
+        L.b200pt_guiding_plan_debug.argtypes = [C.c_void_p] * 2 + [C.c_int] * 3 + [C.c_void_p] * 7
         L.b200pt_guiding_set_order.argtypes = [C.c_void_p, C.c_int]
         L.b200pt_detmath_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b200pt_detmath_eval_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -570,6 +571,18 @@ class Renderer:
     def guiding_update_all_ranks_device(self, device_ptr, n, params=None):
         p = params if params is not None else default_guiding_params()
         _check(lib().b200pt_guiding_update_all_ranks_device(self._h, C.byref(p), C.c_void_p(device_ptr), n))
+
+    def guiding_plan_debug(self, counts, rank, peer_mode=1):
+        """k_plan as rank `rank` on counts[nranks][regions] (b200pt_guiding_plan_debug); returns a dict of numpy arrays"""
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        n, R = counts.shape
+        assert R == self.guiding_region_count()
+        owner = np.empty(R, np.uint8); begin = np.empty(R, np.uint32); length = np.empty(R, np.uint32)
+        src = np.empty((n, R), np.uint32); active = np.empty(R, np.uint32); summary = np.zeros(6, np.uint32); seg = np.zeros((R * n, 4), np.uint32)
+        _check(lib().b200pt_guiding_plan_debug(self._h, counts.ctypes.data, n, rank, peer_mode, owner.ctypes.data, begin.ctypes.data, length.ctypes.data, src.ctypes.data,
+                                               active.ctypes.data, summary.ctypes.data, seg.ctypes.data))
+        return dict(owner=owner, region_begin=begin, region_len=length, src_start=src, active=active[:summary[0]], num_owned=int(summary[1]),
+                    segments=seg[:summary[2]], local_valid=int(summary[3]), owned_samples=int(summary[4]), total_samples=int(summary[5]))
 
     def comm_exchange_mode(self):
         """0 no communicator, 1 ncclSend/ncclRecv, 2 CUDA-IPC peer reads (decided by the first all-ranks update)"""

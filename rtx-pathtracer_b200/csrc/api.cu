@@ -1312,6 +1312,14 @@ int b200pt_guiding_update_all_ranks_device(b200pt_ctx *c, const b200pt_guiding_p
     if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_update_all_ranks_device: " + c->guiding.error);
     return B200PT_OK;
 }
+int b200pt_guiding_plan_debug(b200pt_ctx *c, const uint32_t *counts, int nranks, int rank, int peer_mode, uint8_t *owner, uint32_t *region_begin, uint32_t *region_len,
+                              uint32_t *src_start, uint32_t *active, uint32_t summary[6], uint32_t *segments) {
+    if (!c || !counts || !owner || !region_begin || !region_len || !src_start || !active || !summary || !segments) return setError(B200PT_E_INVALID, "b200pt_guiding_plan_debug: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = c->guiding.planDebug(counts, nranks, rank, peer_mode, owner, region_begin, region_len, src_start, active, summary, segments, c->stream);
+    if (rc != B200PT_OK) return setError(rc, "b200pt_guiding_plan_debug: " + c->guiding.error);
+    return B200PT_OK;
+}
 int b200pt_comm_exchange_mode(b200pt_ctx *c) { return c && c->rc.comm ? (c->rc.peerMode ? 2 : 1) : 0; }
 
 // ---- irradiance cache parity hooks -------------------------------------------------------------------------------

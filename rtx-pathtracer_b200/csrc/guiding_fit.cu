@@ -1451,6 +1451,32 @@ int GuidingState::ensurePlan(int ranks) {
     return B200PT_OK;
 }
 
+// parity hook of the multi-rank plan: runs k_plan on caller-supplied per-rank counts as rank `me` of `N` and returns what it
+// decided (no communicator, no samples involved) — lets a single-GPU test check ownership and layouts for any rank count
+int GuidingState::planDebug(const uint32_t *counts, int N, int me, int peerMode, uint8_t *ownerOut, uint32_t *regionBeginOut, uint32_t *regionLenOut,
+                            uint32_t *srcStartOut, uint32_t *activeOut, uint32_t *summaryOut /* numActive, numOwned, numSegments, localValid, ownedSamples, totalSamples */,
+                            uint32_t *segmentsOut /* numOwned * N x {src, srcOff, dstOff, len} */, cudaStream_t stream) {
+    if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
+    if (N < 1 || N > B200PT_MAX_RANKS || me < 0 || me >= N) { error = "bad rank arguments"; return B200PT_E_INVALID; }
+    int rcode = ensurePlan(N);
+    if (rcode != B200PT_OK) return rcode;
+    const uint32_t R = uint32_t(regionCount), stride = uint32_t(maxRegions);
+    for (int s = 0; s < N; s++) G_TRY(cudaMemcpyAsync(allCounts + size_t(s) * stride, counts + size_t(s) * R, R * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    k_plan<<<1, 1024, 0, stream>>>(allCounts, N, me, R, stride, peerMode, srcStart, regionBegin, regionLen, regionOffset, activeRegions, totalAll, owner, regionSlot, segments, planDev);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaMemcpyAsync(planHost, planDev, sizeof(GPlanSummary), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaMemcpyAsync(ownerOut, owner, R, cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaMemcpyAsync(regionBeginOut, regionBegin, R * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaMemcpyAsync(regionLenOut, regionLen, R * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    for (int s = 0; s < N; s++) G_TRY(cudaMemcpyAsync(srcStartOut + size_t(s) * R, srcStart + size_t(s) * stride, R * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaMemcpyAsync(activeOut, activeRegions, R * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    G_TRY(cudaStreamSynchronize(stream));
+    summaryOut[0] = planHost->numActive; summaryOut[1] = planHost->numOwned; summaryOut[2] = planHost->numSegments; summaryOut[3] = planHost->localValid;
+    summaryOut[4] = uint32_t(planHost->ownedSamples); summaryOut[5] = uint32_t(planHost->totalSamples);
+    if (planHost->numSegments) G_TRY(cudaMemcpy(segmentsOut, segments, size_t(planHost->numSegments) * sizeof(GSegment), cudaMemcpyDeviceToHost));
+    return B200PT_OK;
+}
+
 #define G_NCCL(expr)                                                                             \
     do {                                                                                         \
         ncclResult_t _r = (expr);                                                                \

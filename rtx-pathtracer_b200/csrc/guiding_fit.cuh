@@ -87,6 +87,8 @@ struct GuidingState {
     int update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream, b200pt_stats *stats,
                RankComm *rc = nullptr);
     int ensurePlan(int ranks);
+    int planDebug(const uint32_t *counts, int N, int me, int peerMode, uint8_t *ownerOut, uint32_t *regionBeginOut, uint32_t *regionLenOut, uint32_t *srcStartOut,
+                  uint32_t *activeOut, uint32_t *summaryOut, uint32_t *segmentsOut, cudaStream_t stream);
     int setupPeers(RankComm &rc, cudaStream_t stream);
     void closePeers();
     int splitRegions(const b200pt_guiding_params &params, cudaStream_t stream);
