@@ -999,7 +999,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS) k_guiding_update_shar
 // iteration amplifies that (weights ~1e-4, kappa ~1e-3, now and then one EM iteration more or less).  This executor keeps
 // the reference's order exactly and is still parallel — over the ACCUMULATORS instead of the samples:
 //   * producer warps evaluate the per-sample terms (soft assignment, 4K+2 values per sample for an EM pass) for a tile of
-//     GC_TILE consecutive samples, one sample per thread, and store them value-major in shared memory;
+//     GC_TILE consecutive samples, four threads per sample (lightpmm's lanes, as in the fast path: with one thread per
+//     sample five warps per region could not hide their own latency — 73 ms for config 1, profiles/r02_ncu_guiding_strict.txt),
+//     and store them value-major in shared memory;
 //   * consumer thread v owns running sum v and adds its row of the tile in sample order: a dependent FADD chain
 //     (4 cycles per sample), 4K+2 chains side by side, fed by LDS.128 (row stride = 41 x 16 B: conflict-free);
 //   * the two tile buffers alternate: the consumers add tile j while the producers compute tile j + 1.
@@ -1007,7 +1009,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS) k_guiding_update_shar
 // is the serial sum, bit for bit the one the host build of guiding_math.cuh (tests/harness) produces.
 #define GC_CONSUMERS 96
 #define GC_TILE 160
-#define GC_BLOCK (GC_CONSUMERS + GC_TILE)
+#define GC_PRODUCERS (4 * GC_TILE)            // four threads per sample, like the fast path (thread q: components q, q+4, q+8, q+12)
+#define GC_BLOCK (GC_CONSUMERS + GC_PRODUCERS)
 #define GC_STRIDE (GC_TILE + 4)
 #define GC_ROWS G_STATACC_FLOATS
 #define GC_SMEM_BYTES (2 * GC_ROWS * GC_STRIDE * sizeof(float))
@@ -1054,17 +1057,30 @@ struct ChainExec {
         __syncthreads();
     }
 
-    // One pass over the region's samples.  produce(i, col): thread-local evaluation of sample i, stores NV values at
-    // col[v * GC_STRIDE].  Afterwards sh.staged[0..NV) holds the sequential sums.
-    template <int NV, class Produce>
+    // One pass over the region's samples.  produce(i, valid, q, col): evaluation of sample i by the four threads q = 0..3 of
+    // a quad (all of them call it, also for i >= N: the mixture pdf is combined with warp shuffles); thread q stores the values
+    // of ITS components at col[row * GC_STRIDE].  Afterwards sh.staged[0..NV) holds the sequential sums.
+    struct Smp { float4 s; float2 pd; };
+    template <bool PD>
+    __device__ __forceinline__ Smp loadSample(uint32_t i) const {
+        Smp r;
+        const bool valid = i < N;
+        r.s = valid ? dirw[i] : make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+        r.pd = (PD && valid) ? pdfDist[i] : make_float2(1.0f, 0.0f);
+        return r;
+    }
+    template <int NV, bool PD, class Produce>
     __device__ __forceinline__ void chainPass(Produce produce) {
         const unsigned tid = threadIdx.x;
         const bool consumer = tid < GC_CONSUMERS;
+        const unsigned p = tid - GC_CONSUMERS, quad = p >> 2, q = p & 3u;
         const uint32_t numTiles = (N + GC_TILE - 1) / GC_TILE;
         float acc = 0.0f;
+        Smp next;
         if (!consumer) {
-            const uint32_t i = tid - GC_CONSUMERS;
-            if (i < N) produce(i, tiles + i);
+            const Smp cur = loadSample<PD>(quad);
+            next = loadSample<PD>(GC_TILE + quad);            // the following tile's sample is in flight while this one is evaluated
+            produce(cur, quad < N, q, tiles + quad);
         }
         __syncthreads();
         for (uint32_t j = 0; j < numTiles; j++) {
@@ -1084,9 +1100,10 @@ struct ChainExec {
                     }
                 }
             } else if (j + 1 < numTiles) {
-                const uint32_t p = tid - GC_CONSUMERS;
-                const uint32_t i = (j + 1) * GC_TILE + p;
-                if (i < N) produce(i, tiles + ((j + 1) & 1u) * (GC_ROWS * GC_STRIDE) + p);
+                const uint32_t i = (j + 1) * GC_TILE + quad;
+                const Smp cur = next;
+                next = loadSample<PD>(i + GC_TILE);
+                produce(cur, i < N, q, tiles + ((j + 1) & 1u) * (GC_ROWS * GC_STRIDE) + quad);
             }
             __syncthreads();
         }
@@ -1097,21 +1114,26 @@ struct ChainExec {
     template <int KPAD> __device__ void emPassT(EmAcc &out) {
         const GPacked &pk = sh.packed;
         const float4 *d = dirw;
-        chainPass<4 * KPAD + 2>([&](uint32_t i, float *col) {
+        constexpr int KQ = KPAD / 4;
+        chainPass<4 * KPAD + 2, false>([&](const Smp &smp, bool valid, unsigned q, float *col) {
             G_NO_HOIST();
-            const float4 s = d[i];
-            float sw[KPAD], ll;
-            const bool ok = gEmTerms<KPAD>(pk, s.x, s.y, s.z, s.w, sw, ll);
+            const float4 s = smp.s;
+            float sw[KQ];
+            const float mixturePDF = quadMixturePdf<KQ, false>(pk, q, s.x, s.y, s.z, sw, (float *)0);
+            if (!valid) return;
+            const bool ok = mixturePDF > G_PMM_EPSILON;
+            const float inv = 1.0f / mixturePDF;
 #pragma unroll
-            for (int c = 0; c < KPAD; c++) {
-                const float w = ok ? sw[c] : 0.0f;
+            for (int k = 0; k < KQ; k++) {
+                const int c = 4 * k + int(q);
+                const float w = ok ? (sw[k] * inv) * s.w : 0.0f;
                 col[c * GC_STRIDE] = w;
                 col[(KPAD + c) * GC_STRIDE] = s.x * w;
                 col[(2 * KPAD + c) * GC_STRIDE] = s.y * w;
                 col[(3 * KPAD + c) * GC_STRIDE] = s.z * w;
             }
-            col[(4 * KPAD) * GC_STRIDE] = ok ? s.w : 0.0f;
-            col[(4 * KPAD + 1) * GC_STRIDE] = ok ? ll : 0.0f;
+            if (q == 0u) col[(4 * KPAD) * GC_STRIDE] = ok ? s.w : 0.0f;
+            if (q == 1u) col[(4 * KPAD + 1) * GC_STRIDE] = ok ? s.w * logf(mixturePDF) : 0.0f;
         });
         const float *staged = sh.staged;
         if (threadIdx.x < KPAD) {
@@ -1135,19 +1157,29 @@ struct ChainExec {
         const GPacked &pk = sh.packed;
         const float4 *d = dirw;
         const float2 *pd2 = pdfDist;
-        chainPass<5 * KPAD>([&](uint32_t i, float *col) {
-            const float4 s = d[i];
-            const float2 pd = pd2[i];
+        constexpr int KQ = KPAD / 4;
+        chainPass<5 * KPAD, true>([&](const Smp &smp, bool valid, unsigned q, float *col) {
+            const float4 s = smp.s;
+            const float2 pd = smp.pd;
             G_NO_HOIST();
-            float chi[KPAD], covW[KPAD], covXX[KPAD], covYY[KPAD], covXY[KPAD];
-            const bool ok = gStatTerms<KPAD>(pk, f, s.x, s.y, s.z, s.w, pd.x, chi, covW, covXX, covYY, covXY);
+            float wpdf[KQ], pdf[KQ];
+            const float mixturePDF = quadMixturePdf<KQ, true>(pk, q, s.x, s.y, s.z, wpdf, pdf);
+            if (!valid) return;
+            const bool ok = mixturePDF > G_PMM_EPSILON;
+            const float mixturePDFSqr = mixturePDF * mixturePDF;
+            const float ideal = s.w * s.w * pd.x / mixturePDFSqr;
+            const float inv = 1.0f / mixturePDF;
 #pragma unroll
-            for (int c = 0; c < KPAD; c++) {
-                col[c * GC_STRIDE] = ok ? chi[c] : 0.0f;
-                col[(KPAD + c) * GC_STRIDE] = ok ? covW[c] : 0.0f;
-                col[(2 * KPAD + c) * GC_STRIDE] = ok ? covXX[c] : 0.0f;
-                col[(3 * KPAD + c) * GC_STRIDE] = ok ? covYY[c] : 0.0f;
-                col[(4 * KPAD + c) * GC_STRIDE] = ok ? covXY[c] : 0.0f;
+            for (int k = 0; k < KQ; k++) {
+                const int c = 4 * k + int(q);
+                const float ws = s.w * (wpdf[k] * inv);
+                const float lx = f.sx[c] * s.x + f.sy[c] * s.y + f.sz[c] * s.z;
+                const float ly = f.tx[c] * s.x + f.ty[c] * s.y + f.tz[c] * s.z;
+                col[c * GC_STRIDE] = ok ? pdf[k] * ideal : 0.0f;
+                col[(KPAD + c) * GC_STRIDE] = ok ? ws : 0.0f;
+                col[(2 * KPAD + c) * GC_STRIDE] = ok ? lx * lx * ws : 0.0f;
+                col[(3 * KPAD + c) * GC_STRIDE] = ok ? ly * ly * ws : 0.0f;
+                col[(4 * KPAD + c) * GC_STRIDE] = ok ? lx * ly * ws : 0.0f;
             }
         });
         const float *staged = sh.staged;
@@ -1171,16 +1203,22 @@ struct ChainExec {
         const GPacked &pk = sh.packed;
         const float4 *d = dirw;
         const float2 *pd2 = pdfDist;
-        chainPass<2 * KPAD>([&](uint32_t i, float *col) {
-            const float4 s = d[i];
-            const float2 pd = pd2[i];
+        constexpr int KQ = KPAD / 4;
+        chainPass<2 * KPAD, true>([&](const Smp &smp, bool valid, unsigned q, float *col) {
+            const float4 s = smp.s;
+            const float2 pd = smp.pd;
             G_NO_HOIST();
-            float w[KPAD], wd[KPAD];
-            const bool ok = gDistTerms<KPAD>(pk, s.x, s.y, s.z, s.w, pd.y, w, wd);
+            float wpdf[KQ], pdf[KQ];
+            const float mixturePDF = quadMixturePdf<KQ, true>(pk, q, s.x, s.y, s.z, wpdf, pdf);
+            if (!valid) return;
+            const bool ok = pd.y > 0.0f && mixturePDF > G_PMM_EPSILON;
+            const float sw = s.w / mixturePDF;
 #pragma unroll
-            for (int c = 0; c < KPAD; c++) {
-                col[c * GC_STRIDE] = ok ? w[c] : 0.0f;
-                col[(KPAD + c) * GC_STRIDE] = ok ? wd[c] : 0.0f;
+            for (int k = 0; k < KQ; k++) {
+                const int c = 4 * k + int(q);
+                const float v = wpdf[k] * pdf[k] * sw;
+                col[c * GC_STRIDE] = ok ? v : 0.0f;
+                col[(KPAD + c) * GC_STRIDE] = ok ? v / pd.y : 0.0f;
             }
         });
         const float *staged = sh.staged;
@@ -1209,7 +1247,7 @@ struct ChainExec {
     }
 };
 
-__global__ void __launch_bounds__(GC_BLOCK, 2) k_guiding_update_strict(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
+__global__ void __launch_bounds__(GC_BLOCK, 1) k_guiding_update_strict(GMix *mixes, b200pt_vmm_theta *vmms, const b200pt_aabb *__restrict__ aabbs,
                                                                      const uint32_t *__restrict__ activeRegions, const uint32_t *__restrict__ numActive,
                                                                      const uint32_t *__restrict__ regionBegin, const uint32_t *__restrict__ regionCount,
                                                                      const float4 *__restrict__ dirw, const float2 *__restrict__ pdfDist,
