@@ -1733,10 +1733,10 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
         // results: all-gather of the mixture arrays, then every region takes its owner's copy.  This also is the barrier
         // that keeps a rank from overwriting its sorted buffer (next update) while a peer still reads it.
         G_NCCL(g_nccl.GroupStart());
-        G_NCCL(g_nccl.AllGather(mixes, gatherMix, size_t(stride) * sizeof(GMix), ncclChar, rc->comm, stream));
-        G_NCCL(g_nccl.AllGather(vmms, gatherVmm, size_t(stride) * sizeof(b200pt_vmm_theta), ncclChar, rc->comm, stream));
+        G_NCCL(g_nccl.AllGather(mixes, gatherMix, size_t(R) * sizeof(GMix), ncclChar, rc->comm, stream));      // only the regions in use
+        G_NCCL(g_nccl.AllGather(vmms, gatherVmm, size_t(R) * sizeof(b200pt_vmm_theta), ncclChar, rc->comm, stream));
         G_NCCL(g_nccl.GroupEnd());
-        k_pick_results<<<R, 128, 0, stream>>>(mixes, vmms, gatherMix, gatherVmm, owner, totalAll, stride, me);
+        k_pick_results<<<R, 128, 0, stream>>>(mixes, vmms, gatherMix, gatherVmm, owner, totalAll, R, me);
         launches++;
     }
     G_TRY(cudaEventRecord(ev[5], stream));

