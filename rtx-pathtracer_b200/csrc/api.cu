@@ -104,6 +104,7 @@ struct b200pt_ctx {
     cudaEvent_t ringEvent[RING] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
+    int icBuildBlocksPerSM = 2;
     int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, shadeGridBatch = 0, resolveGrid = 0, icQueryGrid = 0;
     TraceTuning tune{64u, 8};
 
@@ -270,11 +271,18 @@ static int compactPixels(b200pt_ctx *c, Pred pred) {
     return B200PT_OK;
 }
 
-// launch shape of the cache-build kernels: one entry per warp while the list fits the machine, else one per thread
+// launch shape of the cache-build kernels.  One entry = 200 sequential paths on one lane (the pixel's RNG stream is consumed in
+// order), and the kernels hold 255 registers: 2 blocks of 4 warps per SM are resident.  While the list fits that many warps every
+// entry gets a warp of its own (lane 0 active: no divergence); a longer list — the first prepare frames create thousands of
+// entries — is packed 2 / 4 / ... / 32 entries per warp, the sparsest packing that still runs in ONE wave: a second wave costs a
+// whole entry latency (~10 ms), sharing a warp between a few latency-bound entries costs far less.
 static void buildLaunchShape(const b200pt_ctx *c, uint32_t entries, int &grid, int &stride) {
-    const uint32_t warpSlots = uint32_t(c->numSMs) * 16u * 4u;
-    if (entries <= warpSlots) { stride = 32; grid = int(gridFor(entries, 4)); }
-    else { stride = 1; grid = int(gridFor(entries, 128)); }
+    const uint32_t residentWarps = uint32_t(c->numSMs) * uint32_t(std::max(1, c->icBuildBlocksPerSM)) * 4u;
+    uint32_t lanes = 1;
+    while (lanes < 32u && (entries + lanes - 1) / lanes > residentWarps) lanes *= 2;
+    if (getenv("B200PT_IC_BUILD_LANES")) lanes = uint32_t(std::max(1, std::min(32, atoi(getenv("B200PT_IC_BUILD_LANES")))));
+    stride = int(32u / lanes);
+    grid = int(gridFor(uint64_t(entries) * uint64_t(stride), 128));
 }
 
 extern "C" {
@@ -335,6 +343,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     c->shadeGridGuidedIC = c->numSMs * std::max(1, occShadeGuidedIC);
     int occQuery = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQuery, k_ic_query, 256, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->icBuildBlocksPerSM, k_ic_create, 128, 0));
     c->icQueryGrid = c->numSMs * std::max(1, occQuery);
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostIcHdr), ICH_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
