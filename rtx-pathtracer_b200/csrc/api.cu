@@ -105,6 +105,10 @@ struct b200pt_ctx {
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
     int icBuildBlocksPerSM = 2;
+    // IC / ADRRS frames: lookups in grid-cell order (k_icq_*), next paths of finished pixels in a kernel of their own (k_regen)
+    bool icqSort = true, regenSplit = true;
+    DevBuf<uint32_t> icqKey, icqHist, icqCursor, icqOrder, regenQ;
+    int regenGrid = 0, regenGridGuided = 0, shadeGridICDefer = 0, shadeGridGuidedICDefer = 0;
     int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, shadeGridBatch = 0, resolveGrid = 0, icQueryGrid = 0;
     TraceTuning tune{64u, 8};
 
@@ -202,6 +206,16 @@ static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
     CUDA_TRY(c->icSnapHdr.alloc(ICH_NUM));
     CUDA_TRY(c->icBlockCounts.alloc(N / 256 + 2));
     CUDA_TRY(c->icList.alloc(N));
+    if (c->regenSplit) CUDA_TRY(c->regenQ.alloc(N));
+    if (needCache && c->icqSort) {
+        const size_t cells = size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1;
+        CUDA_TRY(c->icqKey.alloc(N)); CUDA_TRY(c->icqOrder.alloc(N));
+        if (!c->icqHist.p) {        // the histogram is zero between two sorts (k_icq_scan clears what k_icq_count added)
+            CUDA_TRY(c->icqHist.alloc(cells));
+            CUDA_TRY(cudaMemsetAsync(c->icqHist.p, 0, cells * sizeof(uint32_t), c->stream));
+        }
+        CUDA_TRY(c->icqCursor.alloc(cells));
+    }
     if (needCache) {
         const size_t S = size_t(std::max(1, c->icSize));
         CUDA_TRY(c->icSnapSphere.alloc(S)); CUDA_TRY(c->icSnapNormalR.alloc(S)); CUDA_TRY(c->icSnapColor.alloc(S));
@@ -322,6 +336,8 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
         c->hostRing = static_cast<volatile uint32_t *>(hp); c->hostRingDev = static_cast<uint32_t *>(dp);
         if (const char *e = getenv("B200PT_COUNTER_COPY")) c->counterCopy = atoi(e) != 0;
         if (const char *e = getenv("B200PT_FUSE_PREP")) c->fusePrep = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_ICQ_SORT")) c->icqSort = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_REGEN_SPLIT")) c->regenSplit = atoi(e) != 0;
     }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
@@ -344,6 +360,15 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     int occQuery = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQuery, k_ic_query, 256, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->icBuildBlocksPerSM, k_ic_create, 128, 0));
+    {
+        int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_regen<false>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_regen<true>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_shade<false, true, false, true>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k_shade<true, true, false, true>, 128, 0));
+        c->regenGrid = c->numSMs * std::max(1, o1); c->regenGridGuided = c->numSMs * std::max(1, o2);
+        c->shadeGridICDefer = c->numSMs * std::max(1, o3); c->shadeGridGuidedICDefer = c->numSMs * std::max(1, o4);
+    }
     c->icQueryGrid = c->numSMs * std::max(1, occQuery);
     CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->hostIcHdr), ICH_NUM * sizeof(uint32_t)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occResolve, k_probe_resolve, 256, 0));
@@ -671,6 +696,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             w.ic.newCount = c->icNewCount.p; w.ic.newEntries = c->icNewEntries.p; w.ic.queryResult = c->icQueryResult.p;
         }
         if (splitMode) { w.ic.splitState = c->icSplitState.p; w.ic.splitData = c->icSplitData.p; }
+        w.regenQ = (icMode && c->regenSplit) ? c->regenQ.p : nullptr;
     }
     FrameParams fp;
     fp.pc = *pc;
@@ -724,7 +750,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
 
     { StageTimer t(c, KIND_SHADE); k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf); }
     c->stats.samples += uint64_t(N) * uint64_t(batch ? batchCount : 1);
-    uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     // Wavefront loop.  Every kernel reads its queue sizes from device memory, so iterations are issued back-to-back;
     // the host only peeks at the counters of iteration i-LAG to learn when the queues have drained.
@@ -758,8 +784,26 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             k_iter_prep<<<1, 32, 0, st>>>(c->wf, cur, prepSlot, prepSeq);
             c->stats.kernel_launches++;
         }
-        if (useCache) { StageTimer t(c, KIND_SHADE); k_ic_query<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur); }
-        {
+        if (useCache && c->icqSort) {
+            StageTimer t(c, KIND_SHADE);
+            const ICQuerySort qs{c->icqKey.p, c->icqHist.p, c->icqCursor.p, c->icqOrder.p, c->icNumCells};
+            k_icq_count<<<c->icQueryGrid, 256, 0, st>>>(fp, c->wf, qs, cur);
+            k_icq_scan<<<1, 1024, 0, st>>>(qs, c->counters.p);
+            k_icq_scatter<<<c->icQueryGrid, 256, 0, st>>>(c->wf, qs);
+            k_ic_query_sorted<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, qs, cur);
+            c->stats.kernel_launches += 3;
+        } else if (useCache) { StageTimer t(c, KIND_SHADE); k_ic_query<<<c->icQueryGrid, 256, 0, st>>>(fp, c->dscene, c->wf, cur); }
+        if (icMode && c->regenSplit) {
+            StageTimer t(c, KIND_SHADE);
+            if (guided) {
+                k_shade<true, true, false, true><<<c->shadeGridGuidedICDefer, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+                k_regen<true><<<c->regenGridGuided, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            } else {
+                k_shade<false, true, false, true><<<c->shadeGridICDefer, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+                k_regen<false><<<c->regenGrid, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
+            }
+            c->stats.kernel_launches++;
+        } else {
             StageTimer t(c, KIND_SHADE);
             if (guided && icMode) k_shade<true, true><<<c->shadeGridGuidedIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);
             else if (icMode) k_shade<false, true><<<c->shadeGridIC, 128, 0, st>>>(fp, c->dscene, c->wf, cur);

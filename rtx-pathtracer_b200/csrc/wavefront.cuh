@@ -23,7 +23,9 @@ struct FrameParams {
 // and reads its own element count from here, so a frame's iterations are issued back-to-back without host round trips.
 enum { CNT_PATH0 = 0, CNT_PATH1 = 1, CNT_PROBE = 2, CNT_SHADOW = 3, CNT_INLINE_SHADOW = 4, CNT_WORK_TRACE = 5, CNT_SHADE_N = 6,
        CNT_TICKET = 7,      // k_probe_resolve_prep: blocks that have finished (the last one does the iteration bookkeeping)
-       CNT_NUM = 8 };
+       CNT_ICQ_N = 8,       // IC frames: queue entries that need a cache lookup (length of the cell-sorted order, k_icq_*)
+       CNT_REGEN = 9,       // IC frames: pixels whose path ended in this shade pass (k_regen starts their next path)
+       CNT_NUM = 10 };
 // 64-bit statistics accumulated on the device by k_iter_prep
 enum { DST_EXTEND = 0, DST_SHADOW = 1, DST_VERTICES = 2, DST_ITERATIONS = 3, DST_NUM = 4 };
 
@@ -70,6 +72,7 @@ struct Wavefront {
     ICState ic;              // irradiance cache / ADRRS state (useIrradianceCache / useADRRS / splitOnFirst frames)
     float4 *aov;             // optional per-pixel layer: max depth, depth sum, path count, split count (b200pt_set_aovs)
     FrameBatch batch;        // b200pt_render_frames: the frames a pixel walks through without waiting for the other pixels
+    uint32_t *regenQ;        // IC / ADRRS frames: pixel ids handed from k_shade to k_regen (nullptr: next paths start inside k_shade)
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -236,6 +239,7 @@ __device__ __forceinline__ void iterPrep(const Wavefront &wf, int cur, volatile 
     if (nPath + nProbe + nShadow) wf.dstats[DST_ITERATIONS] += 1;
     c[CNT_SHADE_N] = nPath;
     c[CNT_PATH0 + (1 - cur)] = 0; c[CNT_PROBE] = 0; c[CNT_SHADOW] = 0; c[CNT_INLINE_SHADOW] = 0; c[CNT_WORK_TRACE] = 0;
+    c[CNT_REGEN] = 0;
 }
 __global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, uint32_t seq) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -302,25 +306,103 @@ __global__ void __launch_bounds__(256) k_probe_resolve_prep(FrameParams fp, Devi
 // chain of dependent loads over a cell list of some tens of entries; inside the 128-register shade kernel (4 CTAs per
 // SM) it was latency bound — issue slots 12 % busy, 60 % of the kernel's instructions (profiles/r01c_ncu_shade_ic.txt).
 // As a kernel of its own it runs at full occupancy and the shade kernel just reads the result.
+__device__ __forceinline__ void icQueryOne(const FrameParams &fp, const DeviceScene &sc, const Wavefront &wf, const int cur, const uint32_t qi) {
+    const b200pt_push_constants &pc = fp.pc;
+    const float4 hr = wf.pathHit[qi];
+    HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
+    if (h.prim == PT_MISS) return;
+    const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
+    const int pid = __float_as_int(ro.w);
+    const uint32_t depth = (wf.state[pid] & 0xffffu) + 1u;
+    if (!(pc.useIrradianceCache || (pc.useADRRS && depth > 1))) return;
+    HitInfo info;
+    computeHitInfo(sc, h, make_vec3(ro), make_vec3(rd), info);
+    const int type = sc.materials[info.matIndex].type;
+    if (hasDiscreteDirection(type) || !isICCapable(pc, type)) return;
+    vec3 irr = V3(0.0f);
+    const bool found = queryIrradianceCache(wf.ic.view, pc, info.worldPos, info.normal, irr);
+    wf.ic.queryResult[qi] = make_f4(irr, found ? 1.0f : 0.0f);
+}
 __global__ void __launch_bounds__(256) k_ic_query(FrameParams fp, DeviceScene sc, Wavefront wf, int cur) {
     const uint32_t n = wf.counters[CNT_SHADE_N];
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) icQueryOne(fp, sc, wf, cur, qi);
+}
+
+// Cell-sorted lookups.  In queue order the lanes of a warp look into different grid cells: lists of 0-150 entries inside one
+// warp, 10.5 of 32 lanes busy per instruction (profiles/r01c_ncu_ic_query.txt).  A counting sort of the queue entries that
+// need a lookup by (approximate) grid cell puts lanes with the same list next to each other: same trip count, the list
+// loads are broadcasts.  The order only says WHICH thread serves which queue entry; the result still goes to
+// queryResult[queue index], every lookup walks its list in index order, so nothing changes per pixel.
+struct ICQuerySort {
+    uint32_t *key;        // per queue entry: cell, or ICQ_SKIP
+    uint32_t *hist;       // per cell: entries (zero outside k_icq_count .. k_icq_scan)
+    uint32_t *cursor;     // per cell: exclusive scan, advanced by k_icq_scatter
+    uint32_t *order;      // queue indices, grouped by cell
+    int numCells;
+};
+#define ICQ_SKIP 0xffffffffu
+__global__ void __launch_bounds__(256) k_icq_count(FrameParams fp, Wavefront wf, ICQuerySort qs, int cur) {
+    const uint32_t n = wf.counters[CNT_SHADE_N];
     const b200pt_push_constants &pc = fp.pc;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
-        const float4 hr = wf.pathHit[qi];
-        HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
-        if (h.prim == PT_MISS) continue;
-        const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
-        const int pid = __float_as_int(ro.w);
-        const uint32_t depth = (wf.state[pid] & 0xffffu) + 1u;
-        if (!(pc.useIrradianceCache || (pc.useADRRS && depth > 1))) continue;
-        HitInfo info;
-        computeHitInfo(sc, h, make_vec3(ro), make_vec3(rd), info);
-        const int type = sc.materials[info.matIndex].type;
-        if (hasDiscreteDirection(type) || !isICCapable(pc, type)) continue;
-        vec3 irr = V3(0.0f);
-        const bool found = queryIrradianceCache(wf.ic.view, pc, info.worldPos, info.normal, irr);
-        wf.ic.queryResult[qi] = make_f4(irr, found ? 1.0f : 0.0f);
+    const ICView &ic = wf.ic.view;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t qi = base + lane;
+        uint32_t key = ICQ_SKIP;
+        if (qi < n) {
+            const float4 hr = wf.pathHit[qi];
+            if (__float_as_uint(hr.y) != PT_MISS) {
+                const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
+                const uint32_t depth = (wf.state[__float_as_int(ro.w)] & 0xffffu) + 1u;
+                if (pc.useIrradianceCache || (pc.useADRRS && depth > 1)) {
+                    // the hit point up to rounding (the lookup itself takes the interpolated vertex position): good enough for a sort key
+                    const int cx = icCellCoord(ic, 0, ro.x + hr.x * rd.x), cy = icCellCoord(ic, 1, ro.y + hr.x * rd.y), cz = icCellCoord(ic, 2, ro.z + hr.x * rd.z);
+                    key = uint32_t((cz * ic.dim[1] + cy) * ic.dim[0] + cx);
+                }
+            }
+            qs.key[qi] = key;
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (key != ICQ_SKIP && int(lane) == __ffs(m) - 1) atomicAdd(&qs.hist[key], uint32_t(__popc(m)));
     }
+}
+// exclusive scan of the cell histogram by one block -> cursor, histogram back to zero, total -> CNT_ICQ_N
+__global__ void __launch_bounds__(1024) k_icq_scan(ICQuerySort qs, uint32_t *counters) {
+    __shared__ uint32_t partial[1024];
+    const int n = qs.numCells;
+    const int per = (n + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(n, b0 + per);
+    uint32_t s = 0;
+    for (int i = b0; i < b1; i++) s += qs.hist[i];
+    partial[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? partial[threadIdx.x - off] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
+    for (int i = b0; i < b1; i++) { const uint32_t c = qs.hist[i]; qs.cursor[i] = run; run += c; qs.hist[i] = 0u; }
+    if (threadIdx.x == 1023) counters[CNT_ICQ_N] = partial[1023];
+}
+__global__ void __launch_bounds__(256) k_icq_scatter(Wavefront wf, ICQuerySort qs) {
+    const uint32_t n = wf.counters[CNT_SHADE_N];
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t qi = base + lane;
+        const uint32_t key = qi < n ? qs.key[qi] : ICQ_SKIP;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(m) - 1;
+        uint32_t pos = 0;
+        if (key != ICQ_SKIP && int(lane) == leader) pos = atomicAdd(&qs.cursor[key], uint32_t(__popc(m)));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (key != ICQ_SKIP) qs.order[pos + uint32_t(__popc(m & ((1u << lane) - 1u)))] = qi;
+    }
+}
+__global__ void __launch_bounds__(256) k_ic_query_sorted(FrameParams fp, DeviceScene sc, Wavefront wf, ICQuerySort qs, int cur) {
+    const uint32_t n = wf.counters[CNT_ICQ_N];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) icQueryOne(fp, sc, wf, cur, qs.order[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -433,7 +515,8 @@ __device__ __forceinline__ void accumulatePixel(const b200pt_push_constants &pc,
 #define PT_SHADE_MIN_BLOCKS 5        // 96 registers, ~200 B of spills: 5 CTAs per SM beat 4 without spills by 5 % (tools/tune_variants.sh)
 #endif
 // BATCH compiles in the frame walk of b200pt_render_frames (plain frames only)
-template <bool GUIDE, bool IC, bool BATCH = false>
+// DEFER (IC variants): a pixel whose path ended only goes to the regen queue; k_regen starts its next path (see there)
+template <bool GUIDE, bool IC, bool BATCH = false, bool DEFER = false>
 __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const __grid_constant__ DeviceScene sc,
                                                                     const __grid_constant__ Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
@@ -615,6 +698,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid
                 if (IC && wf.ic.splitState) a.w = float(wf.ic.splitState[pid] & 0xffffu);
                 wf.aov[pid] = a;
             }
+            if (DEFER) {
+                wf.regenQ[queuePush(&wf.counters[CNT_REGEN])] = uint32_t(pid);
+            } else {
             // next sample of this pixel (rgen:1668-1681): same RNG stream, fresh path state
             uint32_t s = wf.sampleIdx[pid] + 1;
             if (BATCH && int(s & 0xffffu) >= fp.samplesPerPixel) {
@@ -666,6 +752,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid
                     wf.ic.splitState[pid] = (wf.ic.splitState[pid] & 0xffffu) | (iSplit << 16);
                 }
             }
+            }
         } else {
             outO = origin; outD = direction;
             pushPath = true;
@@ -683,6 +770,75 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid
 #undef NEE_QUEUED
 #undef GET_NEW_DIRECTION
 #undef EVAL_BSDF
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// regen (IC / ADRRS frames): the tail of the megakernel's sample loop (rgen:1668-1708) for the pixels whose path ended in
+// this iteration's shade pass — the next sample's camera ray, or, when all samples are done, the next record of the pixel's
+// split list (its NEE, its new direction).  Inside k_shade<.,IC> this was a second copy of the heavy light-sampling /
+// direction-sampling code that a warp ran AFTER its surviving lanes had been through the first one (13 000 SASS
+// instructions, 61 % of the stall cycles "no instruction", profiles/r01e_shade_code_size.txt); as a kernel of its own each
+// half fits the instruction cache and the lanes of a warp do the same thing.  Per pixel nothing changes: seed, throughput
+// and state travel through the per-pixel arrays exactly as they do between two shade passes.
+#ifndef PT_REGEN_MIN_BLOCKS
+#define PT_REGEN_MIN_BLOCKS 5
+#endif
+template <bool GUIDE>
+__global__ void __launch_bounds__(128, PT_REGEN_MIN_BLOCKS) k_regen(const __grid_constant__ FrameParams fp, const __grid_constant__ DeviceScene sc,
+                                                                    const __grid_constant__ Wavefront wf, int cur) {
+    __shared__ uint2 stack[PT_STACK_SMEM * 128];
+    const uint32_t n = wf.counters[CNT_REGEN];
+    const b200pt_push_constants &pc = fp.pc;
+    const bool useNEE = pc.enableNEE != 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pid = int(wf.regenQ[i]);
+        uint32_t seed = wf.seed[pid];
+        const uint32_t s = wf.sampleIdx[pid] + 1;
+        wf.sampleIdx[pid] = s;
+        bool pushPath = false;
+        vec3 outO = V3(0.0f), outD = V3(0.0f), T = V3(1.0f);
+        uint32_t depth = 0;
+        bool addNext = true, follow = false;
+        if (int(s) < fp.samplesPerPixel) {
+            cameraRay(fp, seed, pid % fp.width, pid / fp.width, outO, outD);
+            pushPath = true;
+        } else if (wf.ic.splitState) {
+            // all samples done: drain the pixel's split list, one split per finished path (rgen:1684-1708)
+            const uint32_t ss = wf.ic.splitState[pid];
+            const uint32_t nextSlot = ss & 0xffffu;
+            uint32_t iSplit = ss >> 16;
+            if (iSplit < nextSlot) {
+                const float4 *sp = wf.ic.splitData + (size_t(pid) * IC_MAX_SPLITS + iSplit) * IC_SPLIT_F4;
+                const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3], s4 = sp[4];
+                iSplit++;
+                HitInfo sinfo;
+                sinfo.worldPos = make_vec3(s0); sinfo.normal = make_vec3(s1); sinfo.u = s0.w; sinfo.v = s1.w;
+                sinfo.matIndex = __float_as_int(s2.w); sinfo.t = 0.0f; sinfo.isFrontFace = s4.x != 0.0f; sinfo.isSphere = false; sinfo.instanceIndex = 0u;
+                const vec3 swi = make_vec3(s2), sT = make_vec3(s3);
+                const b200pt_material smat = sc.materials[sinfo.matIndex];
+                if (useNEE && neeSupported(smat.type))      // the split happened before NEE: do it for the split's origin
+                    neeQueued(fp, sc, wf, seed, smat, sinfo, sinfo.worldPos, sinfo.normal, swi, sT, pid, false, 0, stack + threadIdx.x);
+                vec3 newDirection = V3(0.0f);
+                const float pdf = getNewDirection<GUIDE>(pc, wf.guide, seed, smat, sinfo.worldPos, sinfo.normal, swi, sinfo.isFrontFace, newDirection);
+                if (pdf <= 0.0f) iSplit = nextSlot;      // `break`: the remaining splits are dropped
+                else {
+                    T = sT * evalBsdf(sc, smat, sinfo.u, sinfo.v, sinfo.normal, swi, newDirection, sinfo.isFrontFace) / pdf;
+                    outO = sinfo.worldPos; outD = newDirection;
+                    depth = uint32_t(__float_as_int(s3.w)); addNext = false; follow = true;
+                    pushPath = true;
+                }
+                wf.ic.splitState[pid] = (ss & 0xffffu) | (iSplit << 16);
+            }
+        }
+        wf.seed[pid] = seed;
+        if (pushPath) {
+            wf.thr[pid] = make_f4(T, 0.0f);
+            wf.state[pid] = (depth & 0xffffu) | (addNext ? ST_ADDNEXT : 0u) | (follow ? ST_FOLLOW : 0u);
+            const uint32_t slot = queuePush(&wf.counters[CNT_PATH0 + (1 - cur)]);
+            wf.pathRayO[1 - cur][slot] = make_f4(outO, __int_as_float(pid));
+            wf.pathRayD[1 - cur][slot] = make_f4(outD, 0.0f);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Summarise ncu outputs into small text files for profiles/.
-  python tools/ncu_summary.py launches gpurun_out/launches.csv            -> per-kernel launch list summary
+  python tools/ncu_summary.py launches gpurun_out/launches.csv [F]        -> per-kernel launch list summary (F: skip the first F frames,
+                                                                             a frame ends with its k_accumulate launch)
   python tools/ncu_summary.py rep gpurun_out/prof_extend.ncu-rep          -> key metrics of a --set full capture"""
 import collections
 import csv
@@ -16,10 +17,15 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
-def launches(path):
+def launches(path, skip_frames=0):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
+    frames = 0
     for row in csv.DictReader(lines):
+        if frames < skip_frames:
+            if row["Kernel Name"].startswith("k_accumulate") and row.get("Metric Name", "gpu__time_duration.sum") == "gpu__time_duration.sum":
+                frames += 1
+            continue
         try:
             v = float(row["Metric Value"].replace(",", ""))
         except Exception:
@@ -47,4 +53,7 @@ def rep(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    else:
+        rep(sys.argv[2])

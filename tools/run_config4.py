@@ -1,6 +1,7 @@
 """BASELINE config 4: sponzaXML 1920x1080, IC_SIZE=10000, ADRRS with splitting — driven through the frame driver exactly
 like RayTracingApp does (50 IC prepare frames at 1 spp, one estimate frame, then ADRRS frames); also an IC-only run and
-a plain NEE+MIS run for comparison.  Prints one JSON line per run.  Usage: python tools/run_config4.py [W H frames spp]"""
+a plain NEE+MIS run for comparison.  Prints one JSON line per run.  Usage: python tools/run_config4.py [W H frames spp]
+Environment: RUN4_RUNS=plain,ic,adrrs (default all), RUN4_STAGE=0 turns the per-kernel events off (they cost ~10 %)."""
 import json
 import os
 import sys
@@ -23,7 +24,7 @@ def run(name, **settings):
     r.set_scene(scene)
     r.set_camera(view, proj)
     t_scene = time.time() - t0
-    r.set_stage_timing(True)
+    r.set_stage_timing(os.environ.get("RUN4_STAGE", "1") != "0")
     app = P.App(r, accumulate=True, samplesPerPixel=SPP, enableNEE=1, enableMIS=1, **settings)
     phases = []
 
@@ -49,6 +50,10 @@ def run(name, **settings):
     r.close()
 
 
-run("plain NEE+MIS")
-run("IC", useIrradianceCache=1)
-run("ADRRS+split", useADRRS=1, adrrsSplit=1, adrrsS=5.0)
+RUNS = os.environ.get("RUN4_RUNS", "plain,ic,adrrs").split(",")
+if "plain" in RUNS:
+    run("plain NEE+MIS")
+if "ic" in RUNS:
+    run("IC", useIrradianceCache=1)
+if "adrrs" in RUNS:
+    run("ADRRS+split", useADRRS=1, adrrsSplit=1, adrrsS=5.0)

@@ -13,7 +13,8 @@ r = P.Renderer(W, H, 10000, 0)
 r.set_scene(scene)
 r.set_camera(view, proj)
 app = P.App(r, accumulate=True, samplesPerPixel=4, enableNEE=1, enableMIS=1, useADRRS=1, adrrsSplit=1)
-app.state.irradianceCachePrepareFrames = 6
-for f in range(6 + 1 + 2):
+PREP = int(os.environ.get("RUN4_PREPARE", "6"))
+app.state.irradianceCachePrepareFrames = PREP
+for f in range(PREP + 1 + 2):
     app.draw_frame(P.tea(f, 0xC0FFEE))
 print("cache entries", r.ic_get()[0].nextCacheSlot)
