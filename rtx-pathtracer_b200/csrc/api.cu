@@ -106,7 +106,7 @@ struct b200pt_ctx {
     DevBuf<uint32_t> batchCounter;
     int icBuildBlocksPerSM = 2;
     // IC / ADRRS frames: lookups in grid-cell order (k_icq_*), next paths of finished pixels in a kernel of their own (k_regen)
-    bool icqSort = true, regenSplit = true;
+    bool icqSort = true, regenSplit = true, shadeSorted = true;
     DevBuf<uint32_t> icqKey, icqHist, icqCursor, icqOrder, regenQ;
     int regenGrid = 0, regenGridGuided = 0, shadeGridICDefer = 0, shadeGridGuidedICDefer = 0;
     int numSMs = 0, traceGrid = 0, traceGridRec = 0, shadeGrid = 0, shadeGridGuided = 0, shadeGridIC = 0, shadeGridGuidedIC = 0, shadeGridBatch = 0, resolveGrid = 0, icQueryGrid = 0;
@@ -208,7 +208,7 @@ static int ensureIC(b200pt_ctx *c, bool needCache, bool splitMode) {
     CUDA_TRY(c->icList.alloc(N));
     if (c->regenSplit) CUDA_TRY(c->regenQ.alloc(N));
     if (needCache && c->icqSort) {
-        const size_t cells = size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + 1;
+        const size_t cells = size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + ICQ_EXTRA_BINS;
         CUDA_TRY(c->icqKey.alloc(N)); CUDA_TRY(c->icqOrder.alloc(N));
         if (!c->icqHist.p) {        // the histogram is zero between two sorts (k_icq_scan clears what k_icq_count added)
             CUDA_TRY(c->icqHist.alloc(cells));
@@ -338,6 +338,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
         if (const char *e = getenv("B200PT_FUSE_PREP")) c->fusePrep = atoi(e) != 0;
         if (const char *e = getenv("B200PT_ICQ_SORT")) c->icqSort = atoi(e) != 0;
         if (const char *e = getenv("B200PT_REGEN_SPLIT")) c->regenSplit = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_SHADE_SORTED")) c->shadeSorted = atoi(e) != 0;
     }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
@@ -697,6 +698,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         }
         if (splitMode) { w.ic.splitState = c->icSplitState.p; w.ic.splitData = c->icSplitData.p; }
         w.regenQ = (icMode && c->regenSplit) ? c->regenQ.p : nullptr;
+        w.shadeOrder = (useCache && c->icqSort && c->shadeSorted) ? c->icqOrder.p : nullptr;
     }
     FrameParams fp;
     fp.pc = *pc;
@@ -786,7 +788,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         }
         if (useCache && c->icqSort) {
             StageTimer t(c, KIND_SHADE);
-            const ICQuerySort qs{c->icqKey.p, c->icqHist.p, c->icqCursor.p, c->icqOrder.p, c->icNumCells};
+            const ICQuerySort qs{c->icqKey.p, c->icqHist.p, c->icqCursor.p, c->icqOrder.p, c->icNumCells, c->shadeSorted ? 1 : 0};
             k_icq_count<<<c->icQueryGrid, 256, 0, st>>>(fp, c->wf, qs, cur);
             k_icq_scan<<<1, 1024, 0, st>>>(qs, c->counters.p);
             k_icq_scatter<<<c->icQueryGrid, 256, 0, st>>>(c->wf, qs);

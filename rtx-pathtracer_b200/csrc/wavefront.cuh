@@ -73,6 +73,7 @@ struct Wavefront {
     float4 *aov;             // optional per-pixel layer: max depth, depth sum, path count, split count (b200pt_set_aovs)
     FrameBatch batch;        // b200pt_render_frames: the frames a pixel walks through without waiting for the other pixels
     uint32_t *regenQ;        // IC / ADRRS frames: pixel ids handed from k_shade to k_regen (nullptr: next paths start inside k_shade)
+    const uint32_t *shadeOrder;   // IC / ADRRS frames: the order in which k_shade<.,IC> walks the path queue (k_icq_*; nullptr: queue order)
 };
 
 #define ST_ADDNEXT (1u << 24)
@@ -335,12 +336,14 @@ __global__ void __launch_bounds__(256) k_ic_query(FrameParams fp, DeviceScene sc
 // queryResult[queue index], every lookup walks its list in index order, so nothing changes per pixel.
 struct ICQuerySort {
     uint32_t *key;        // per queue entry: cell, or ICQ_SKIP
-    uint32_t *hist;       // per cell: entries (zero outside k_icq_count .. k_icq_scan)
-    uint32_t *cursor;     // per cell: exclusive scan, advanced by k_icq_scatter
-    uint32_t *order;      // queue indices, grouped by cell
-    int numCells;
+    uint32_t *hist;       // per bin: entries (zero outside k_icq_count .. k_icq_scan)
+    uint32_t *cursor;     // per bin: exclusive scan, advanced by k_icq_scatter
+    uint32_t *order;      // queue indices, grouped by bin
+    int numCells;         // bins: one per grid cell (entries that need a lookup), then ICQ_EXTRA_BINS classes of entries that do not
+    int all;              // 1: the entries without a lookup are sorted behind the others (k_shade walks the whole order), 0: left out
 };
 #define ICQ_SKIP 0xffffffffu
+#define ICQ_EXTRA_BINS 2      // numCells + 0: surface hit without a lookup, numCells + 1: miss
 __global__ void __launch_bounds__(256) k_icq_count(FrameParams fp, Wavefront wf, ICQuerySort qs, int cur) {
     const uint32_t n = wf.counters[CNT_SHADE_N];
     const b200pt_push_constants &pc = fp.pc;
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(256) k_icq_count(FrameParams fp, Wavefront wf,
         uint32_t key = ICQ_SKIP;
         if (qi < n) {
             const float4 hr = wf.pathHit[qi];
+            if (qs.all) key = uint32_t(qs.numCells) + (__float_as_uint(hr.y) != PT_MISS ? 0u : 1u);
             if (__float_as_uint(hr.y) != PT_MISS) {
                 const float4 ro = wf.pathRayO[cur][qi], rd = wf.pathRayD[cur][qi];
                 const uint32_t depth = (wf.state[__float_as_int(ro.w)] & 0xffffu) + 1u;
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(256) k_icq_count(FrameParams fp, Wavefront wf,
 // exclusive scan of the cell histogram by one block -> cursor, histogram back to zero, total -> CNT_ICQ_N
 __global__ void __launch_bounds__(1024) k_icq_scan(ICQuerySort qs, uint32_t *counters) {
     __shared__ uint32_t partial[1024];
-    const int n = qs.numCells;
+    const int n = qs.numCells + ICQ_EXTRA_BINS;
     const int per = (n + 1023) / 1024;
     const int b0 = threadIdx.x * per, b1 = min(n, b0 + per);
     uint32_t s = 0;
@@ -383,8 +387,11 @@ __global__ void __launch_bounds__(1024) k_icq_scan(ICQuerySort qs, uint32_t *cou
         __syncthreads();
     }
     uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
-    for (int i = b0; i < b1; i++) { const uint32_t c = qs.hist[i]; qs.cursor[i] = run; run += c; qs.hist[i] = 0u; }
-    if (threadIdx.x == 1023) counters[CNT_ICQ_N] = partial[1023];
+    for (int i = b0; i < b1; i++) {
+        const uint32_t c = qs.hist[i]; qs.cursor[i] = run; qs.hist[i] = 0u;
+        if (i == qs.numCells) counters[CNT_ICQ_N] = run;        // everything in front of the first extra bin needs a lookup
+        run += c;
+    }
 }
 __global__ void __launch_bounds__(256) k_icq_scatter(Wavefront wf, ICQuerySort qs) {
     const uint32_t n = wf.counters[CNT_SHADE_N];
@@ -525,7 +532,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid
     #define GET_NEW_DIRECTION(...) (NI ? getNewDirectionNI<GUIDE>(__VA_ARGS__) : getNewDirection<GUIDE>(__VA_ARGS__))
     #define EVAL_BSDF(...) (NI ? evalBsdfNI(__VA_ARGS__) : evalBsdf(__VA_ARGS__))
     const uint32_t n = wf.counters[CNT_SHADE_N];
-  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+  for (uint32_t qiter = blockIdx.x * blockDim.x + threadIdx.x; qiter < n; qiter += gridDim.x * blockDim.x) {
+    const uint32_t qi = (IC && wf.shadeOrder) ? wf.shadeOrder[qiter] : qiter;
     bool pushPath = false;
     vec3 outO = V3(0.0f), outD = V3(0.0f);
     int pid = 0;
