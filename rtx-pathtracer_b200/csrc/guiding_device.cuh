@@ -46,8 +46,13 @@ __device__ __forceinline__ uint32_t guidingLeafRegion(const GuidingView &g, uint
     return best;
 }
 
-__device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 p) {
-    if (!aabbContains(g.levels[0], p)) return B200PT_INVALID_REGION;
+// the backtracking walk: only needed when the greedy descent below runs into a dead end (the point lies in the one-ulp gap
+// or overlap between two sibling boxes)
+// (scalar arguments: an out-of-line call that passes a struct by reference costs its caller even when it is never executed)
+__device__ __noinline__ uint32_t getGuidingRegionWalk(const b200pt_aabb *levels, const b200pt_aabb *aabbs, const int32_t *spawnFirst, const int32_t *spawnNext,
+                                                      int splits, float px, float py, float pz) {
+    GuidingView g; g.levels = levels; g.vmms = nullptr; g.splits = splits; g.aabbs = aabbs; g.spawnFirst = spawnFirst; g.spawnNext = spawnNext;
+    const vec3 p = V3(px, py, pz);
     int level = 0;
     uint32_t node = 0;
     uint32_t triedRight = 0;          // bit L: the right child of the node on the current path at level L was entered
@@ -75,6 +80,30 @@ __device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 
             }
         }
     }
+}
+
+// Greedy descent first: at every level take the left child if its box contains the point, else the right one — the same
+// choices the walk above makes until its first dead end, but with one trip per level for every lane of the warp and selects
+// instead of branches.  (As a per-lane walk with `continue` / `break` the lanes of a warp parted ways at the first level and
+// never met again: 3 of 32 lanes per instruction, half of the guided shade kernel's instructions — profiles/r02b_shade_training_by_line.txt.)
+// If some level offers no child, or the leaf has been split adaptively and rejects the point, the walk decides.
+__device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 p) {
+    if (!aabbContains(g.levels[0], p)) return B200PT_INVALID_REGION;
+    uint32_t node = 0;
+    bool ok = true;
+    for (int level = 0; level < g.splits; level++) {
+        const b200pt_aabb *next = g.levels + ((1u << (level + 1)) - 1u);
+        const bool inL = aabbContains(next[2u * node], p);
+        const bool inR = aabbContains(next[2u * node + 1u], p);
+        ok = ok && (inL || inR);
+        node = 2u * node + (inL ? 0u : 1u);
+    }
+    if (ok) {
+        if (!g.spawnFirst) return node;
+        const uint32_t r = guidingLeafRegion(g, node, p);
+        if (r != B200PT_INVALID_REGION) return r;
+    }
+    return getGuidingRegionWalk(g.levels, g.aabbs, g.spawnFirst, g.spawnNext, g.splits, p.x, p.y, p.z);
 }
 
 __device__ __forceinline__ float vmfPdf(vec3 wo, const b200pt_vmf_theta &th, vec3 worldPos, bool parallax) {   // guiding.glsl:32-44
