@@ -66,31 +66,42 @@ __device__ __forceinline__ vec3 approxDiffuse(const DeviceScene &sc, const b200p
     return V3(-1.0f, -1.0f, -1.0f);
 }
 
-// rgen:748-773: weighted sum over the cache spheres that contain `origin`
+// rgen:748-773: weighted sum over the cache spheres that contain `origin`.
+// Two passes per window of 32 list entries: (1) the containment test of every entry, four independent 128-bit loads in
+// flight, result = one bit per entry; (2) the weight / colour arithmetic for the set bits only, in list order (ascending cache
+// index, the oracle's summation order).  With one pass the ~100 instructions of (2) ran for every entry that ANY lane of the
+// warp contained (10 of 32 lanes busy, profiles/r02b_ic_query_by_line.txt); now a lane's trip count is its own number of hits.
 __device__ __forceinline__ bool queryIrradianceCache(const ICView &ic, const b200pt_push_constants &pc, vec3 origin, vec3 normal, vec3 &color) {
     const int cx = icCellCoord(ic, 0, origin.x), cy = icCellCoord(ic, 1, origin.y), cz = icCellCoord(ic, 2, origin.z);
     const int cell = (cz * ic.dim[1] + cy) * ic.dim[0] + cx;
     const uint32_t b = __ldg(&ic.cellStart[cell]), e = __ldg(&ic.cellStart[cell + 1]);
     vec3 cacheValueSum = V3(0.0f);
     float totalWeight = 0.0f;
-    for (uint32_t k0 = b; k0 < e; k0 += 4) {
-        // four independent 128-bit loads in flight per round (the list is walked in order: ascending cache index)
-        float4 s4[4];
+    for (uint32_t w0 = b; w0 < e; w0 += 32u) {
+        const uint32_t wn = min(32u, e - w0);
+        uint32_t inside = 0u;
+        for (uint32_t k0 = 0; k0 < wn; k0 += 4u) {
+            float4 s4[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) s4[j] = __ldg(&ic.cellSpheres[min(k0 + j, e - 1u)]);
+            for (int j = 0; j < 4; j++) s4[j] = __ldg(&ic.cellSpheres[w0 + min(k0 + j, wn - 1u)]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (k0 + j >= e) break;
-            const float4 s = s4[j];
+            for (int j = 0; j < 4; j++) {
+                const float dist = length(origin - make_vec3(s4[j]));
+                if (k0 + j < wn && dist <= s4[j].w) inside |= 1u << (k0 + j);                     // irradiance.rint:15-20
+            }
+        }
+        while (inside) {
+            const uint32_t k = w0 + uint32_t(__ffs(inside) - 1);
+            inside &= inside - 1u;
+            const float4 s = __ldg(&ic.cellSpheres[k]);
             const vec3 oc = origin - make_vec3(s);
             const float dist = length(oc);
-            if (!(dist <= s.w)) continue;                                               // irradiance.rint:15-20
-            const uint32_t i = __ldg(&ic.cellItems[k0 + j]);
+            const uint32_t i = __ldg(&ic.cellItems[k]);
             const float4 nr = __ldg(&ic.normalR[i]);
             const vec3 cn = make_vec3(nr);
             float weight = 1.0f / (dist / nr.w + sqrtf(1.0f - dot(normal, cn)));         // irradiance.rahit:18-21
             if (isnan(weight) || isinf(weight)) weight = 1000000.0f;
-            const bool vis = -0.001f <= dot(oc, (normal + cn) / 2.0f);
+            const bool vis = -0.001f <= dot(oc, (normal + cn) * 0.5f);                   // x / 2 == x * 0.5 for every float
             if (weight <= 1.0f / pc.irradianceA || (pc.irradianceCachePerformVisibilityCheck && !vis)) continue;
             const vec3 c = make_vec3(__ldg(&ic.color[i]));
             if (pc.useIrradianceGradients) {
