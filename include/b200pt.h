@@ -426,7 +426,8 @@ int b200pt_guiding_selftest_division(b200pt_ctx *ctx, float lo, float hi, uint64
  * last bit, which used to make 0.5-15 % of same-seed pixels differ between this library and its CPU checker).  Parity
  * hooks: `fn` over n inputs on the device / by the host compilation of the same header; b may be NULL for unary functions. */
 enum { B200PT_DM_SIN = 0, B200PT_DM_COS, B200PT_DM_TAN, B200PT_DM_ASIN, B200PT_DM_ACOS, B200PT_DM_ATAN, B200PT_DM_ATAN2, B200PT_DM_POW,
-       B200PT_DM_LOG, B200PT_DM_EXP };
+       B200PT_DM_LOG, B200PT_DM_EXP,
+       B200PT_DM_DIV3 /* component (i mod 3) of the kernels' vec3 / scalar: vec3(a) / b; on the host plain a / b */ };
 int b200pt_detmath_eval(b200pt_ctx *ctx, int fn, const float *a, const float *b, float *out, int n);
 int b200pt_detmath_eval_host(int fn, const float *a, const float *b, float *out, int n);
 

@@ -134,7 +134,7 @@ class Stats(C.Structure):
 
 
 GUIDING_ORDER_STRICT, GUIDING_ORDER_REORDERED = 0, 1      # b200pt_guiding_set_order
-DM_FUNCTIONS = ("sin", "cos", "tan", "asin", "acos", "atan", "atan2", "pow", "log", "exp")      # B200PT_DM_*
+DM_FUNCTIONS = ("sin", "cos", "tan", "asin", "acos", "atan", "atan2", "pow", "log", "exp", "div3")      # B200PT_DM_*
 
 
 def detmath_host(fn, a, b=None):

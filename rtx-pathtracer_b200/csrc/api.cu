@@ -1092,11 +1092,15 @@ __host__ __device__ static inline float detmathApply(int fn, float a, float b) {
 }
 __global__ void __launch_bounds__(256) k_detmath(int fn, const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = detmathApply(fn, a[i], b ? b[i] : 0.0f);
+    if (i >= n) return;
+    if (fn == B200PT_DM_DIV3) {            // the kernels' vec3 / scalar (device_math.cuh div3), one component per element
+        const vec3 q = V3(a[i], a[i], a[i]) / (b ? b[i] : 1.0f);
+        out[i] = i % 3 == 0 ? q.x : (i % 3 == 1 ? q.y : q.z);
+    } else out[i] = detmathApply(fn, a[i], b ? b[i] : 0.0f);
 }
 extern "C" {
 int b200pt_detmath_eval(b200pt_ctx *c, int fn, const float *a, const float *b, float *out, int n) {
-    if (!c || fn < 0 || fn > B200PT_DM_EXP || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval: bad argument");
+    if (!c || fn < 0 || fn > B200PT_DM_DIV3 || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval: bad argument");
     if (n == 0) return B200PT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     DevBuf<float> da, db, dout;
@@ -1112,8 +1116,8 @@ int b200pt_detmath_eval(b200pt_ctx *c, int fn, const float *a, const float *b, f
 }
 /* the same functions evaluated by the host compilation of the header (no device involved) */
 int b200pt_detmath_eval_host(int fn, const float *a, const float *b, float *out, int n) {
-    if (fn < 0 || fn > B200PT_DM_EXP || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval_host: bad argument");
-    for (int i = 0; i < n; i++) out[i] = detmathApply(fn, a[i], b ? b[i] : 0.0f);
+    if (fn < 0 || fn > B200PT_DM_DIV3 || n < 0 || (n > 0 && (!a || !out))) return setError(B200PT_E_INVALID, "b200pt_detmath_eval_host: bad argument");
+    for (int i = 0; i < n; i++) out[i] = fn == B200PT_DM_DIV3 ? a[i] / (b ? b[i] : 1.0f) : detmathApply(fn, a[i], b ? b[i] : 0.0f);
     return B200PT_OK;
 }
 int b200pt_guiding_selftest_division(b200pt_ctx *c, float lo, float hi, uint64_t *mismatches, uint64_t *tested) {
