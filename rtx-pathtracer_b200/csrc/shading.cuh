@@ -115,6 +115,14 @@ __device__ __forceinline__ void computeHitInfo(const DeviceScene &sc, const HitR
     info.instanceIndex = instIdx;
 }
 
+// material index of a hit without the rest of computeHitInfo (one index load + one vertex load instead of ten loads): for callers
+// that only go on when the surface is of a certain material (the MIS probe: lights only)
+__device__ __forceinline__ int hitMaterialIndex(const DeviceScene &sc, const HitRec &h) {
+    if (h.prim >= sc.trace.numTris) return sc.spheres[h.prim - sc.trace.numTris].materialIndex;
+    const int4 pv = __ldg(&sc.primVerts[h.prim]);
+    return __float_as_int(__ldg(reinterpret_cast<const float4 *>(&sc.vertices[pv.x]) + 2).z);     // materialIndex of v0 (quirk 4)
+}
+
 // --- BSDF kit ------------------------------------------------------------------------------------------------
 PT_NI_M3 float fresnelDielectric(float eta, float cosThetaI) {   // rgen:145-160
     float sinThetaSqr = eta * eta * (1 - cosThetaI * cosThetaI);

@@ -251,12 +251,14 @@ __global__ void k_iter_prep(Wavefront wf, int cur, volatile uint32_t *hostSlot, 
 // probe resolve: the BSDF-sampled direct-light check of MIS (rgen:684-727), run on the probe hits
 __device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const DeviceScene &sc, const Wavefront &wf, const uint32_t k) {
     const float4 hr = wf.probeHit[k];
+    HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
+    // most probes end on an ordinary surface: look at the material before anything else of the record is read
+    if (h.prim != PT_MISS && sc.materials[hitMaterialIndex(sc, h)].type != B200PT_MAT_LIGHT) return;
     const float4 A = wf.probeA[k], B = wf.probeB[k];
     const vec3 bsdf = make_vec3(A), T = make_vec3(B);
     const float pdfMat = A.w;
     const int pix = __float_as_int(B.w);
     const vec3 o = make_vec3(wf.probeRayO[k]), d = make_vec3(wf.probeRayD[k]);
-    HitRec h; h.t = hr.x; h.prim = __float_as_uint(hr.y); h.u = hr.z; h.v = hr.w;
     vec3 lightColor; float pdfLights;
     if (h.prim == PT_MISS) {
         lightColor = envColor(sc, d);
@@ -265,7 +267,6 @@ __device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const Dev
         HitInfo info;
         computeHitInfo(sc, h, o, d, info);
         const b200pt_material *m = &sc.materials[info.matIndex];
-        if (m->type != B200PT_MAT_LIGHT) return;
         int iLight = info.isSphere ? sc.spheres[info.instanceIndex].iLight : sc.instances[info.instanceIndex].iLight;
         if (iLight < 0) return;
         lightColor = V3(m->lightColor[0], m->lightColor[1], m->lightColor[2]);

@@ -189,3 +189,44 @@ def test_guiding_training_returns_early_while_splitting():
     r.render_frame(_pc(P, 1, updateGuiding=1, splitOnFirst=1, previousFrames=1))
     assert np.array_equal(before, r.read_image())
     assert (r.guiding_get_samples()["flags"] == P.INVALID_REGION).all()
+
+
+def test_lookup_order_and_regen_kernel_do_not_change_the_result(monkeypatch):
+    """IC / ADRRS frames sort the path queue by grid cell for the lookups (k_icq_*), let k_shade walk it in that order and start
+    the next paths of finished pixels in k_regen.  All three only decide WHICH thread serves which pixel: with the knobs off
+    (queue order, next paths inside k_shade — the round-1 kernels) the cache and the lookup frame must be bit-identical, the
+    frames of the split modes identical up to the order of a pixel's float atomics."""
+    P = helpers.pt()
+    scene = P.Scene(helpers.scene_path(SCENE))
+    view, proj = scene.camera_matrices(W / H)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = P.Renderer(W, H, IC_SIZE, 0)          # the knobs are read when the context is created
+        r.set_scene(scene)
+        r.set_camera(view, proj)
+        out = []
+        for f in range(3):
+            r.render_frame(_prepare_pc(P, f))
+        out.append(r.ic_get()[1].view(np.uint8).copy())
+        r.render_frame(_pc(P, 9, samplesPerPixel=2, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, irradianceCreateProb=0.0, irradianceUpdateProb=0.0))
+        out.append(r.read_image().copy())
+        est = np.full((H, W, 4), 0.5, np.float32)
+        r.write_image(P.IMAGE_ESTIMATE, est)
+        r.render_frame(_pc(P, 10, samplesPerPixel=2, useADRRS=1, adrrsSplit=1, adrrsS=5.0, irradianceCreateProb=0.0, irradianceUpdateProb=0.0, enableMIS=0))
+        out.append(r.read_image().copy())
+        r.render_frame(_pc(P, 11, samplesPerPixel=2, splitOnFirst=1, enableMIS=0))
+        out.append(r.read_image().copy())
+        r.close()
+        return out
+
+    new = run(dict(B200PT_ICQ_SORT="1", B200PT_REGEN_SPLIT="1", B200PT_SHADE_SORTED="1"))
+    for env in (dict(B200PT_ICQ_SORT="0", B200PT_REGEN_SPLIT="0"), dict(B200PT_ICQ_SORT="1", B200PT_REGEN_SPLIT="0", B200PT_SHADE_SORTED="0"),
+                dict(B200PT_ICQ_SORT="0", B200PT_REGEN_SPLIT="1")):
+        old = run(env)
+        for i, (a, b) in enumerate(zip(new, old)):
+            if i < 2:       # cache + lookup frame: one light sample per pixel and iteration, every sum has a fixed order
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (env, i)
+            else:           # split modes: a pixel can have two light samples in one trace pass, their float atomics commute only to the last bit
+                assert np.allclose(a, b, rtol=2e-6, atol=1e-7), (env, i, float(np.abs(a - b).max()))
