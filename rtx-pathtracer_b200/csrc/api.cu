@@ -105,6 +105,7 @@ struct b200pt_ctx {
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
     int icBuildBlocksPerSM = 2;
+    bool icBuildGroup = true;     // B200PT_IC_BUILD_GROUP=0: one lane per cache entry (the state before round 2b), for A/B
     // IC / ADRRS frames: lookups in grid-cell order (k_icq_*), next paths of finished pixels in a kernel of their own (k_regen)
     bool icqSort = true, regenSplit = true, shadeSorted = true;
     DevBuf<uint32_t> icqKey, icqHist, icqCursor, icqOrder, regenQ;
@@ -285,17 +286,18 @@ static int compactPixels(b200pt_ctx *c, Pred pred) {
     return B200PT_OK;
 }
 
-// launch shape of the cache-build kernels.  One entry = 200 sequential paths on one lane (the pixel's RNG stream is consumed in
-// order), and the kernels hold 255 registers: 2 blocks of 4 warps per SM are resident.  While the list fits that many warps every
-// entry gets a warp of its own (lane 0 active: no divergence); a longer list — the first prepare frames create thousands of
-// entries — is packed 2 / 4 / ... / 32 entries per warp, the sparsest packing that still runs in ONE wave: a second wave costs a
-// whole entry latency (~10 ms), sharing a warp between a few latency-bound entries costs far less.
-static void buildLaunchShape(const b200pt_ctx *c, uint32_t entries, int &grid, int &stride) {
+// launch shape of the cache-build kernels.  One entry = 200 sequential paths (the pixel's RNG stream is consumed in order), and the
+// kernels hold 255 registers: 2 blocks of 4 warps per SM are resident.  Group mode (lanes = 8, ic_kernels.cuh): eight lanes share
+// one entry and trace every ray together; an entry slot is 32, 16 or 8 threads wide — the sparsest packing that still runs in
+// ONE wave, because a second wave costs a whole entry latency.  Lists too long even for four groups per warp (the first prepare
+// frames create thousands of entries) fall back to one lane per entry, 8 / 16 / 32 entries per warp.
+static void buildLaunchShape(const b200pt_ctx *c, uint32_t entries, int &grid, int &stride, int &lanes) {
     const uint32_t residentWarps = uint32_t(c->numSMs) * uint32_t(std::max(1, c->icBuildBlocksPerSM)) * 4u;
-    uint32_t lanes = 1;
-    while (lanes < 32u && (entries + lanes - 1) / lanes > residentWarps) lanes *= 2;
-    if (getenv("B200PT_IC_BUILD_LANES")) lanes = uint32_t(std::max(1, std::min(32, atoi(getenv("B200PT_IC_BUILD_LANES")))));
-    stride = int(32u / lanes);
+    uint32_t perWarp = 1;
+    while (perWarp < 32u && (entries + perWarp - 1) / perWarp > residentWarps) perWarp *= 2;
+    if (getenv("B200PT_IC_BUILD_LANES")) perWarp = uint32_t(std::max(1, std::min(32, atoi(getenv("B200PT_IC_BUILD_LANES")))));
+    lanes = (c->icBuildGroup && perWarp <= 4u) ? 8 : 1;
+    stride = int(32u / perWarp);
     grid = int(gridFor(uint64_t(entries) * uint64_t(stride), 128));
 }
 
@@ -339,6 +341,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
         if (const char *e = getenv("B200PT_ICQ_SORT")) c->icqSort = atoi(e) != 0;
         if (const char *e = getenv("B200PT_REGEN_SPLIT")) c->regenSplit = atoi(e) != 0;
         if (const char *e = getenv("B200PT_SHADE_SORTED")) c->shadeSorted = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_IC_BUILD_GROUP")) c->icBuildGroup = atoi(e) != 0;
     }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
@@ -741,10 +744,10 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             StageTimer t(c, KIND_SHADE);
             CUDA_TRY(c->icUpdSlot.alloc(entries)); CUDA_TRY(c->icPending.alloc(size_t(entries) * 3));
             ICBuffers b = icBuffers(c);
-            int grid, stride;
-            buildLaunchShape(c, entries, grid, stride);
+            int grid, stride, lanes;
+            buildLaunchShape(c, entries, grid, stride, lanes);
             k_ic_update_assign<<<1, 32, 0, st>>>(b);
-            k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride);
+            k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride, lanes);
             k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
             c->stats.kernel_launches += 2;
         }
@@ -873,9 +876,9 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             const size_t slots = size_t(entries) * IC_MAX_NEW;
             CUDA_TRY(c->icPending.alloc(slots * 3)); CUDA_TRY(c->icValidFlags.alloc(slots)); CUDA_TRY(c->icValidOffsets.alloc(slots + 1));
             ICBuffers b = icBuffers(c);
-            int grid, stride;
-            buildLaunchShape(c, entries, grid, stride);
-            k_ic_create<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride);
+            int grid, stride, lanes;
+            buildLaunchShape(c, entries, grid, stride, lanes);
+            k_ic_create<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride, lanes);
             k_scan_single_block<<<1, 1024, 0, st>>>(c->icValidFlags.p, c->icValidOffsets.p, int(slots), nullptr);
             k_ic_create_commit<<<gridFor(slots, 256), 256, 0, st>>>(fp, c->wf, b);
             c->stats.kernel_launches += 2;

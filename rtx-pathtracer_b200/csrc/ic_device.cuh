@@ -133,12 +133,16 @@ __device__ __forceinline__ float applyWeightWindow(const b200pt_push_constants &
 }
 
 // rgen:883-902 — returns false when the pixel's split list is full
+// (`store` = false: an eight-lane group of the cache build runs this redundantly, one lane writes — the __syncwarp orders the other lanes' read in front of it)
 __device__ __forceinline__ bool splitPush(const ICState &ic, int pid, vec3 origin, vec3 normal, vec3 wi, vec3 throughput, float u, float v, int matIndex,
-                                          int currentDepth, bool isFrontFace) {
+                                          int currentDepth, bool isFrontFace, bool store = true, unsigned syncMask = 0u) {
     if (!ic.splitState) return false;
+    if (syncMask) __syncwarp(syncMask);
     const uint32_t ss = ic.splitState[pid];
+    if (syncMask) __syncwarp(syncMask);
     const uint32_t next = ss & 0xffffu;
     if (next >= IC_MAX_SPLITS) return false;
+    if (!store) return true;
     float4 *d = ic.splitData + (size_t(pid) * IC_MAX_SPLITS + next) * IC_SPLIT_F4;
     d[0] = make_f4(origin, u);
     d[1] = make_f4(normal, v);
@@ -185,10 +189,17 @@ struct InlineTracer {
     int pid;
     uint32_t seed;
     uint32_t extendRays, shadowRays, vertices;
+    bool group;        // eight lanes run this tracer in lockstep on the same entry and share every ray (traceRayGroup); lane 0 of the group stores
 
     __device__ __forceinline__ InlineTracer(const b200pt_push_constants &pc_, const DeviceScene &sc_, const ICState &ic_, const GuidingView &g_,
-                                            uint2 *stack_, int stride_, int pid_, uint32_t seed_)
-        : pc(pc_), sc(sc_), ic(ic_), guide(g_), stack(stack_), stride(stride_), pid(pid_), seed(seed_), extendRays(0), shadowRays(0), vertices(0) {}
+                                            uint2 *stack_, int stride_, int pid_, uint32_t seed_, bool group_ = false)
+        : pc(pc_), sc(sc_), ic(ic_), guide(g_), stack(stack_), stride(stride_), pid(pid_), seed(seed_), extendRays(0), shadowRays(0), vertices(0), group(group_) {}
+
+    template <bool ANY>
+    __device__ __forceinline__ void trace(vec3 o, vec3 d, float tmin, float tmax, HitRec &h) {
+        if (group) traceRayGroup<ANY>(sc.trace, o, d, tmin, tmax, h, stack, stride);
+        else traceRay<ANY>(sc.trace, o, d, tmin, tmax, h, stack, stride);
+    }
 
     // nextEventEstimation, rgen:601-731
     __device__ vec3 nee(const b200pt_material &mat, vec3 origin, vec3 wi, vec3 normal, float tu, float tv, bool isFrontFace) {
@@ -202,7 +213,7 @@ struct InlineTracer {
         if (cosThetaLight > 0.0f && pdfLights > 0.0f) {
             HitRec sh;
             shadowRays++;
-            traceRay<true>(sc.trace, origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh, stack, stride);
+            trace<true>(origin, lightDir, PT_TMIN, lightDistance * (1 - 0.0001f), sh);
             if (sh.prim == PT_MISS) isShadowed = false;
         }
         if (!isShadowed) {
@@ -219,7 +230,7 @@ struct InlineTracer {
             if (pdfMat > 0.0f) {
                 HitRec h;
                 extendRays++;
-                traceRay<false>(sc.trace, origin, bsdfDir, PT_TMIN, PT_TMAX, h, stack, stride);
+                trace<false>(origin, bsdfDir, PT_TMIN, PT_TMAX, h);
                 if (h.prim == PT_MISS) {
                     lightColor = envColor(sc, bsdfDir);
                     pdfLights = 1.0f / (2.0f * PT_PI) / float(sc.numLights);
@@ -264,7 +275,7 @@ struct InlineTracer {
             depth++;
             HitRec h;
             extendRays++;
-            traceRay<false>(sc.trace, origin, direction, PT_TMIN, PT_TMAX, h, stack, stride);
+            trace<false>(origin, direction, PT_TMIN, PT_TMAX, h);
             if (h.prim == PT_MISS) {
                 if (addNextDirectLights) result += throughput * envColor(sc, direction);
                 break;
@@ -295,7 +306,8 @@ struct InlineTracer {
                     }
                 }
                 if (pc.splitOnFirst && depth == 1) {
-                    if (splitPush(ic, pid, origin, normal, wi, throughput * 0.5f, info.u, info.v, info.matIndex, depth, info.isFrontFace)) throughput *= 0.5f;
+                    if (splitPush(ic, pid, origin, normal, wi, throughput * 0.5f, info.u, info.v, info.matIndex, depth, info.isFrontFace,
+                                  !group || (threadIdx.x & 7u) == 0u, group ? 0xffu << (threadIdx.x & 24u) : 0u)) throughput *= 0.5f;
                 }
                 const vec3 neeLight = multipleNEE(mat, origin, wi, normal, info.u, info.v, info.isFrontFace, numNEE);
                 result += throughput * neeLight;

@@ -146,31 +146,36 @@ __global__ void k_ic_update_assign(ICBuffers b) {
     b.header->nextUpdateSlot = slot;
 }
 
-// entryStride = 32: one entry per warp (lane 0 works — the paths of one entry are serial, and a warp of 32 unrelated
-// entries would serialise their divergent control flow anyway); entryStride = 1: one entry per thread (long lists)
-__global__ void __launch_bounds__(128) k_ic_update(FrameParams fp, DeviceScene sc, Wavefront wf, ICBuffers b, int entryStride) {
+// Launch shape of the two build kernels (buildLaunchShape, api.cu): `entryStride` threads per entry slot, of which the first
+// `lanes` work on the entry.  lanes = 1: the entry's 200 paths run on one lane (entryStride 32 = a warp of its own ... 1 = every
+// lane an entry, for the long lists of the first prepare frames).  lanes = 8 (entryStride 32 / 16 / 8): eight lanes run the SAME
+// entry in lockstep — same seed, same control flow, every ray traced by the group (traceRayGroup) — and lane 0 of the group stores.
+__global__ void __launch_bounds__(128) k_ic_update(FrameParams fp, DeviceScene sc, Wavefront wf, ICBuffers b, int entryStride, int lanes) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = b.snapHdr[ICH_LIST_COUNT];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid % uint32_t(entryStride)) return;
+    if (gtid % uint32_t(entryStride) >= uint32_t(lanes)) return;
+    const bool group = lanes == 8, leader = gtid % uint32_t(entryStride) == 0u;
     for (uint32_t e = gtid / uint32_t(entryStride); e < n; e += gridDim.x * blockDim.x / uint32_t(entryStride)) {
         const int pid = int(b.list[e]);
         uint32_t seed = tea(uint32_t(pid), fp.pc.randomUInt);
         rnd(seed);                                              // the draw that selected this pixel
         const int32_t cacheIndex = b.updSlot[e];
         if (cacheIndex >= 0) {
-            InlineTracer tr(fp.pc, sc, wf.ic, wf.guide, stack + threadIdx.x, blockDim.x, pid, seed);
+            InlineTracer tr(fp.pc, sc, wf.ic, wf.guide, stack + threadIdx.x, blockDim.x, pid, seed, group);
             vec3 color, rotGrad, transGrad;
             const float harmonicR = tr.calculateCacheData(make_vec3(b.snapSphere[cacheIndex]), make_vec3(b.snapNormalR[cacheIndex]), color, rotGrad, transGrad);
             seed = tr.seed;
-            b.pending[e * 3 + 0] = make_f4(color, harmonicR);
-            b.pending[e * 3 + 1] = make_f4(rotGrad, 0.0f);
-            b.pending[e * 3 + 2] = make_f4(transGrad, 0.0f);
-            atomicAdd(&wf.dstats[DST_EXTEND], (unsigned long long)tr.extendRays);
-            atomicAdd(&wf.dstats[DST_SHADOW], (unsigned long long)tr.shadowRays);
-            atomicAdd(&wf.dstats[DST_VERTICES], (unsigned long long)tr.vertices);
+            if (leader) {
+                b.pending[e * 3 + 0] = make_f4(color, harmonicR);
+                b.pending[e * 3 + 1] = make_f4(rotGrad, 0.0f);
+                b.pending[e * 3 + 2] = make_f4(transGrad, 0.0f);
+                atomicAdd(&wf.dstats[DST_EXTEND], (unsigned long long)tr.extendRays);
+                atomicAdd(&wf.dstats[DST_SHADOW], (unsigned long long)tr.shadowRays);
+                atomicAdd(&wf.dstats[DST_VERTICES], (unsigned long long)tr.vertices);
+            }
         }
-        wf.seed[pid] = seed;                                    // k_generate continues this pixel's stream from here
+        if (leader) wf.seed[pid] = seed;                        // k_generate continues this pixel's stream from here
     }
 }
 
@@ -203,27 +208,32 @@ __global__ void k_ic_update_commit(FrameParams fp, ICBuffers b) {
 }
 
 // ---- cache creation (after the frame's last path): rgen:1821-1827 + :1383-1421 ------------------------------------
-__global__ void __launch_bounds__(128) k_ic_create(FrameParams fp, DeviceScene sc, Wavefront wf, ICBuffers b, int entryStride) {
+__global__ void __launch_bounds__(128) k_ic_create(FrameParams fp, DeviceScene sc, Wavefront wf, ICBuffers b, int entryStride, int lanes) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
     const uint32_t n = b.snapHdr[ICH_LIST_COUNT];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid % uint32_t(entryStride)) return;
+    if (gtid % uint32_t(entryStride) >= uint32_t(lanes)) return;
+    const bool group = lanes == 8, leader = gtid % uint32_t(entryStride) == 0u;
     const bool full = b.header->nextCacheSlot > b.header->maxCaches;   // rgen:1384 (the live header only changes in k_ic_create_commit)
     for (uint32_t e = gtid / uint32_t(entryStride); e < n; e += gridDim.x * blockDim.x / uint32_t(entryStride)) {
         const int pid = int(b.list[e]);
         const uint32_t cnt = min(wf.ic.newCount[pid], uint32_t(IC_MAX_NEW));
-        InlineTracer tr(fp.pc, sc, wf.ic, wf.guide, stack + threadIdx.x, blockDim.x, pid, wf.seed[pid]);
+        const uint32_t seed0 = wf.seed[pid];
+        if (group) __syncwarp(0xffu << (threadIdx.x & 24u));    // every lane of the group has read the seed before the leader stores the new one
+        InlineTracer tr(fp.pc, sc, wf.ic, wf.guide, stack + threadIdx.x, blockDim.x, pid, seed0, group);
         for (uint32_t k = 0; k < IC_MAX_NEW; k++) {
             float4 *pe = b.pending + (size_t(e) * IC_MAX_NEW + k) * 3;
-            if (k >= cnt || full) { b.validFlags[size_t(e) * IC_MAX_NEW + k] = 0u; continue; }
+            if (k >= cnt || full) { if (leader) b.validFlags[size_t(e) * IC_MAX_NEW + k] = 0u; continue; }
             const float4 o = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 0], nn = wf.ic.newEntries[(size_t(pid) * IC_MAX_NEW + k) * 2 + 1];
             vec3 color, rotGrad, transGrad;
             const float harmonicR = tr.calculateCacheData(make_vec3(o), make_vec3(nn), color, rotGrad, transGrad);
+            if (!leader) continue;
             pe[0] = make_f4(color, harmonicR);
             pe[1] = make_f4(rotGrad, 0.0f);
             pe[2] = make_f4(transGrad, 0.0f);
             b.validFlags[size_t(e) * IC_MAX_NEW + k] = harmonicR < 0.0f ? 0u : 1u;      // rgen:1391-1393
         }
+        if (!leader) continue;
         wf.seed[pid] = tr.seed;
         atomicAdd(&wf.dstats[DST_EXTEND], (unsigned long long)tr.extendRays);
         atomicAdd(&wf.dstats[DST_SHADOW], (unsigned long long)tr.shadowRays);

@@ -138,6 +138,15 @@ __device__ __noinline__ bool alphaRejects(const TraceScene &sc, uint32_t prim, f
     return alphaRejectsInline(sc, prim, bu, bv, ox, t);
 }
 
+// order-preserving map float -> uint32 (and back); -0 is folded onto +0 first
+__device__ __forceinline__ uint32_t orderedBitsOf(float f) {
+    const uint32_t b = __float_as_uint(__fadd_rn(f, 0.0f));
+    return b ^ (uint32_t(int32_t(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float orderedBitsToFloat(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
 // Traversal is written as an explicit per-lane state machine (init / step) so that the persistent trace kernel can
 // hand a lane a NEW ray as soon as its current one is finished (dynamic ray fetch), instead of idling until the slowest
 // ray of the warp is done.  One step = pop one entry: visit a BVH8 node (5 x 128-bit loads, 8 slab tests) or test one
@@ -339,6 +348,135 @@ __device__ __forceinline__ void traceRayInline(const TraceScene &sc, const vec3 
                                                HitRec &hit, uint2 *smemStack, const int stride) {
     if (sc.alpha) traceRayT<ANY, 2>(sc, o, d, tmin, tmax, hit, smemStack, stride);
     else traceRayT<ANY, 0>(sc, o, d, tmin, tmax, hit, smemStack, stride);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One ray on EIGHT lanes (the serial cache build, ic_device.cuh InlineTracer): the eight lanes of a group hold the same ray
+// and the same traversal state; in a node step lane c slab-tests child c only and the hit masks are OR-reduced over the
+// group, in a leaf the set triangles are dealt round-robin and the candidates merged by the closest-hit rule (minimum of
+// (t, id), the same key the cooperative triangle phase uses).  Per child / per triangle the arithmetic is travNode's /
+// travStep's, so the result is the per-lane traversal's bit for bit; what shrinks is the dependent instruction chain of a
+// step (~230 -> ~60 instructions), and that chain IS the run time of a kernel whose parallelism is one entry per warp.
+// All eight lanes must call with identical arguments, converged; `gmask` = the group's lanes.
+__device__ __forceinline__ void travNodeGroup(Trav &s, const TraceScene &sc, uint2 &cur, uint2 &triGroup, uint2 *smemStack, uint2 *localStack, const int stride,
+                                              const unsigned sub, const unsigned gmask) {
+    const vec3 o = s.o, d = s.d;
+    const uint32_t hits = cur.y;
+    const int bit = 31 - __clz(hits);
+    cur.y &= ~(1u << bit);
+    if (cur.y & 0xff000000u) {   // push the rest of the group
+        if (s.sp < PT_STACK_SMEM) smemStack[s.sp * stride] = cur;
+        else localStack[s.sp - PT_STACK_SMEM] = cur;
+        s.sp++;
+    }
+    const uint32_t octInv = s.octInv;
+    const uint32_t octInv4 = octInv * 0x01010101u;
+    const uint32_t slot = (uint32_t(bit) - 24u) ^ octInv;
+    const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
+    const uint32_t nodeIdx = cur.x + rel;
+    const float4 n0 = __ldg(&sc.nodes[nodeIdx * 5 + 0]);
+    const float4 n1 = __ldg(&sc.nodes[nodeIdx * 5 + 1]);
+    const float4 n2 = __ldg(&sc.nodes[nodeIdx * 5 + 2]);
+    const float4 n3 = __ldg(&sc.nodes[nodeIdx * 5 + 3]);
+    const float4 n4 = __ldg(&sc.nodes[nodeIdx * 5 + 4]);
+    const uint32_t e = __float_as_uint(n0.w);
+    const float ax = __uint_as_float((e & 0xffu) << 23) * s.idx;
+    const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * s.idy;
+    const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
+    const float ox = (n0.x - o.x) * s.idx, oy = (n0.y - o.y) * s.idy, oz = (n0.z - o.z) * s.idz;
+    const bool half = (sub & 4u) != 0u;
+    const int j = int(sub & 3u);
+    const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+    const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
+    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+    const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+    const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+    const uint32_t xn = d.x < 0.0f ? qhix : qlox, xf = d.x < 0.0f ? qlox : qhix;
+    const uint32_t yn = d.y < 0.0f ? qhiy : qloy, yf = d.y < 0.0f ? qloy : qhiy;
+    const uint32_t zn = d.z < 0.0f ? qhiz : qloz, zf = d.z < 0.0f ? qloz : qhiz;
+    const float t0x = fmaf(float(byteOf(xn, j)), ax, ox), t1x = fmaf(float(byteOf(xf, j)), ax, ox);
+    const float t0y = fmaf(float(byteOf(yn, j)), ay, oy), t1y = fmaf(float(byteOf(yf, j)), ay, oy);
+    const float t0z = fmaf(float(byteOf(zn, j)), az, oz), t1z = fmaf(float(byteOf(zf, j)), az, oz);
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, s.best));
+    const uint32_t mine = tn <= tf ? byteOf(childBits4, j) << byteOf(bitIndex4, j) : 0u;
+    const uint32_t hitmask = __reduce_or_sync(gmask, mine);
+    cur.x = __float_as_uint(n1.x);
+    cur.y = (hitmask & 0xff000000u) | (e >> 24);
+    triGroup.x = __float_as_uint(n1.y);
+    triGroup.y = hitmask & 0x00ffffffu;
+}
+
+template <bool ANY, int ALPHA>
+__device__ __forceinline__ void traceRayGroupT(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                               HitRec &hit, uint2 *smemStack, const int stride) {
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 7u;
+    const unsigned gmask = 0xffu << (lane & 24u);
+    Trav s;
+    uint2 localStack[PT_STACK_LOCAL];
+    bool done = travInit(s, sc, o, d, tmin, tmax, ANY);
+    while (!done) {
+        uint2 cur = s.cur;
+        uint2 triGroup;
+        if (cur.y & 0xff000000u) travNodeGroup(s, sc, cur, triGroup, smemStack, localStack, stride, sub, gmask);
+        else { triGroup = cur; cur = make_uint2(0u, 0u); }
+        if (triGroup.y) {
+            // the k-th set triangle goes to lane k mod 8; every lane keeps the best candidate of its share
+            const unsigned long long curKey = ((unsigned long long)orderedBitsOf(s.best) << 32) | (s.hit.prim == PT_MISS ? 0xffffffffu : s.hit.prim);
+            unsigned long long key = curKey;
+            float bu = 0.0f, bv = 0.0f;
+            uint32_t m = triGroup.y, k = 0u;
+            while (m) {
+                const int ti = __ffs(m) - 1;
+                m &= m - 1u;
+                if ((k++ & 7u) != sub) continue;
+                const uint32_t base = (triGroup.x + uint32_t(ti)) * 3u;
+                const float4 a = __ldg(&sc.tris[base + 0]);
+                const float4 b = __ldg(&sc.tris[base + 1]);
+                const float4 c = __ldg(&sc.tris[base + 2]);
+                float t, u, v;
+                if (intersectTriExact(a, b, c, o, d, t, u, v) && t > s.tmin && t < s.tmax) {
+                    const uint32_t id = __float_as_uint(a.w);
+                    const unsigned long long cand = ((unsigned long long)orderedBitsOf(t) << 32) | id;
+                    // travStep's rule: t < best, or t == best with a lower id (a miss so far: nothing to tie with, tmax is exclusive)
+                    if (cand < key && (t < s.best || s.hit.prim != PT_MISS)) {
+                        if (!ALPHA || __float_as_uint(b.w) == 0u || !(ALPHA == 2 ? alphaRejectsInline(sc, id, u, v, o.x, t) : alphaRejects(sc, id, u, v, o.x, t))) { key = cand; bu = u; bv = v; }
+                    }
+                }
+            }
+            unsigned long long best = key;
+#pragma unroll
+            for (int dl = 1; dl < 8; dl <<= 1) {
+                const unsigned long long other = __shfl_xor_sync(gmask, best, dl);
+                best = other < best ? other : best;
+            }
+            if (best != curKey) {
+                const int src = __ffs(__ballot_sync(gmask, key == best) & gmask) - 1;
+                s.hit.u = __shfl_sync(gmask, bu, src);
+                s.hit.v = __shfl_sync(gmask, bv, src);
+                s.best = s.hit.t = orderedBitsToFloat(uint32_t(best >> 32));
+                s.hit.prim = uint32_t(best);
+                if (ANY) break;
+            }
+        }
+        if ((cur.y & 0xff000000u) == 0u) {
+            if (s.sp == 0) break;
+            s.sp--;
+            if (s.sp < PT_STACK_SMEM) cur = smemStack[s.sp * stride];
+            else cur = localStack[s.sp - PT_STACK_SMEM];
+        }
+        s.cur = cur;
+    }
+    hit = s.hit;
+}
+template <bool ANY>
+__device__ __noinline__ void traceRayGroup(const TraceScene &sc, const vec3 o, const vec3 d, const float tmin, const float tmax,
+                                           HitRec &hit, uint2 *smemStack, const int stride) {
+    if (sc.alpha) traceRayGroupT<ANY, 2>(sc, o, d, tmin, tmax, hit, smemStack, stride);
+    else traceRayGroupT<ANY, 0>(sc, o, d, tmin, tmax, hit, smemStack, stride);
 }
 
 // Persistent-warp ray loop with dynamic fetch.  `total` rays are numbered 0..total-1; warps take chunks of `chunk`
