@@ -439,7 +439,7 @@ def main():
         trace_only_bytes = (stats["extend_rays"] * 48.0 + stats["shadow_rays"] * 64.0) / ext_launches
         # DRAM traffic of one k_trace launch from the committed ncu --set full capture (profiles/), if present
         traffic, traffic_src = None, None
-        for name in ("r02_ncu_trace.txt", "r01e_ncu_trace.txt"):
+        for name in ("r02b_ncu_trace.txt", "r02_ncu_trace.txt", "r01e_ncu_trace.txt"):
             try:
                 rd = wr = None
                 for l in open(os.path.join(ROOT, "profiles", name)):
