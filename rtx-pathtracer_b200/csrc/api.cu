@@ -676,7 +676,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
 
     {   // guiding views: region tree + mixtures, and (training frames) the sample-recording state
         Wavefront &w = c->wf;
-        w.guide.levels = c->guiding.levelAabbs; w.guide.vmms = c->guiding.vmms; w.guide.splits = c->guiding.splits;
+        w.guide.levels = c->guiding.levelAabbs; w.guide.levelSplits = c->guiding.levelSplits; w.guide.vmms = c->guiding.vmms; w.guide.splits = c->guiding.splits;
         w.guide.aabbs = c->guiding.aabbs;
         w.guide.spawnFirst = c->guiding.hasSpawns ? c->guiding.spawnFirst : nullptr;
         w.guide.spawnNext = c->guiding.hasSpawns ? c->guiding.spawnNext : nullptr;

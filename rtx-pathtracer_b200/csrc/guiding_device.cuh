@@ -16,6 +16,7 @@ namespace b200pt {
 // oracle's linear scan defines; the reference leaves the choice among overlapping boxes to the driver).
 struct GuidingView {
     const b200pt_aabb *levels;        // all levels concatenated: level L starts at (2^L - 1)
+    const float4 *levelSplits;        // per inner node (same numbering): split axis (int bits), left child's max / right child's min on that axis
     const b200pt_vmm_theta *vmms;     // binding 16
     int splits;
     // adaptive refinement (PathGuiding::splitRegion, src/PathGuiding.cpp:328-348): a split region keeps its index and the
@@ -51,7 +52,7 @@ __device__ __forceinline__ uint32_t guidingLeafRegion(const GuidingView &g, uint
 // (scalar arguments: an out-of-line call that passes a struct by reference costs its caller even when it is never executed)
 __device__ __noinline__ uint32_t getGuidingRegionWalk(const b200pt_aabb *levels, const b200pt_aabb *aabbs, const int32_t *spawnFirst, const int32_t *spawnNext,
                                                       int splits, float px, float py, float pz) {
-    GuidingView g; g.levels = levels; g.vmms = nullptr; g.splits = splits; g.aabbs = aabbs; g.spawnFirst = spawnFirst; g.spawnNext = spawnNext;
+    GuidingView g; g.levels = levels; g.levelSplits = nullptr; g.vmms = nullptr; g.splits = splits; g.aabbs = aabbs; g.spawnFirst = spawnFirst; g.spawnNext = spawnNext;
     const vec3 p = V3(px, py, pz);
     int level = 0;
     uint32_t node = 0;
@@ -91,10 +92,26 @@ __device__ __forceinline__ uint32_t getGuidingRegion(const GuidingView &g, vec3 
     if (!aabbContains(g.levels[0], p)) return B200PT_INVALID_REGION;
     uint32_t node = 0;
     bool ok = true;
+    // The children of a box differ from it on the split axis only (splitAabb: l.max[axis] -= h, r.min[axis] += h), and p is inside
+    // the parent by induction, so "the child contains p" (raytrace.guiding.rint:15-17 on all six faces) is one comparison:
+    // fmax(l.max, p) == l.max <=> p <= l.max, fmin(r.min, p) == r.min <=> p >= r.min (p is finite here; +-0 compare equal both ways).
+    // PT_REGION_SPLITREC = 1 does exactly that with one 16-byte record per inner node instead of the two child boxes (twelve loads per
+    // level).  Same regions; measured on config 5 (gpurun_scratch/ab_rec.sh, two alternating repetitions): training render 4 169 ->
+    // 4 117 ms, but guided frames 578 -> 610 ms per 4 — a net loss for anything but the seven training frames, so it stays off.
+#ifndef PT_REGION_SPLITREC
+#define PT_REGION_SPLITREC 0
+#endif
     for (int level = 0; level < g.splits; level++) {
+#if PT_REGION_SPLITREC
+        const float4 sp = __ldg(&g.levelSplits[((1u << level) - 1u) + node]);
+        const int axis = __float_as_int(sp.x);
+        const float pa = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+        const bool inL = pa <= sp.y, inR = pa >= sp.z;
+#else
         const b200pt_aabb *next = g.levels + ((1u << (level + 1)) - 1u);
         const bool inL = aabbContains(next[2u * node], p);
         const bool inR = aabbContains(next[2u * node + 1u], p);
+#endif
         ok = ok && (inL || inR);
         node = 2u * node + (inL ? 0u : 1u);
     }

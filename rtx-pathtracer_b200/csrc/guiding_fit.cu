@@ -39,6 +39,7 @@ namespace b200pt {
 #define SORT_TILE 2048              // records per warp in the counting sort
 #define SORT_WARPS 8                // warps per block in the counting sort
 
+static inline float __int_as_float_host(int i) { float f; memcpy(&f, &i, sizeof(f)); return f; }
 static void splitAabb(const b200pt_aabb &b, b200pt_aabb &l, b200pt_aabb &r) {   // src/Shapes.h:32-46, axis = largest
     float size[3] = {b.max[0] - b.min[0], b.max[1] - b.min[1], b.max[2] - b.min[2]};
     int axis = size[0] > size[1] ? (size[0] > size[2] ? 0 : 2) : (size[1] > size[2] ? 1 : 2);
@@ -1398,6 +1399,20 @@ int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax
     this->splits = splits;
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&levelAabbs), allLevels.size() * sizeof(b200pt_aabb)));
     G_TRY(cudaMemcpyAsync(levelAabbs, allLevels.data(), allLevels.size() * sizeof(b200pt_aabb), cudaMemcpyHostToDevice, stream));
+    {   // what the tracer's greedy descent reads per level (guiding_device.cuh getGuidingRegion): the children differ from their parent
+        // on the split axis only (splitAabb), so "child contains p" is one comparison there once p is known to be inside the parent
+        const size_t inner = (size_t(1) << splits) - 1;
+        std::vector<float4> recs(std::max<size_t>(inner, 1), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        for (size_t i = 0; i < inner; i++) {
+            const b200pt_aabb &b = allLevels[i];
+            const float size[3] = {b.max[0] - b.min[0], b.max[1] - b.min[1], b.max[2] - b.min[2]};
+            const int axis = size[0] > size[1] ? (size[0] > size[2] ? 0 : 2) : (size[1] > size[2] ? 1 : 2);      // splitAabb's choice
+            const b200pt_aabb &l = allLevels[2 * i + 1], &r = allLevels[2 * i + 2];
+            recs[i] = make_float4(__int_as_float_host(axis), l.max[axis], r.min[axis], 0.0f);
+        }
+        G_TRY(cudaMalloc(reinterpret_cast<void **>(&levelSplits), recs.size() * sizeof(float4)));
+        G_TRY(cudaMemcpyAsync(levelSplits, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    }
     G_TRY(cudaStreamSynchronize(stream));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&aabbs), size_t(maxRegions) * sizeof(b200pt_aabb)));
     G_TRY(cudaMalloc(reinterpret_cast<void **>(&vmms), size_t(maxRegions) * sizeof(b200pt_vmm_theta)));
@@ -1928,6 +1943,8 @@ void GuidingState::release() {
     if (aabbs) cudaFree(aabbs);
     if (levelAabbs) cudaFree(levelAabbs);
     levelAabbs = nullptr;
+    if (levelSplits) cudaFree(levelSplits);
+    levelSplits = nullptr;
     if (spawnFirst) cudaFree(spawnFirst);
     if (spawnNext) cudaFree(spawnNext);
     if (splitPairs) cudaFree(splitPairs);

@@ -38,6 +38,7 @@ struct GuidingState {
     int splits = 0;
     b200pt_aabb *aabbs = nullptr;          // device, binding 15
     b200pt_aabb *levelAabbs = nullptr;     // device: all 2^(splits+1)-1 boxes of the halving tree, level by level
+    float4 *levelSplits = nullptr;         // device: per inner node of that tree {split axis (int bits), left child's max, right child's min on that axis, -}
     b200pt_vmm_theta *vmms = nullptr;      // device, binding 16
     GMix *mixes = nullptr;                 // device: lightpmm PMM + PMM_ExtraData per region
     // sort scratch

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """Join an `ncu --page source --csv --print-source sass` dump with `nvdisasm -g` line info of the same build and sum the
 executed warp instructions / stall samples per source line.
-usage: sass_by_line.py <sass.csv> <kernel mangled-name substring> [top N]   (run after `make`, same libb200pt.so)"""
+usage: sass_by_line.py <sass.csv> <kernel mangled-name substring> [top N] [smp]   (run after `make`, same libb200pt.so;
+"smp" sorts by stall samples instead of executed instructions)"""
 import csv, os, re, subprocess, sys, tempfile, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csvf, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+key = 2 if len(sys.argv) > 4 and sys.argv[4] == "smp" else 0
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rtx-pathtracer_b200", "libb200pt.so")], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 lines = {}
@@ -34,7 +36,7 @@ for r in data:
 tot = sum(a[0] for a in agg.values()); totS = sum(a[2] for a in agg.values())
 print("# %s: %d SASS instructions mapped, warp instructions %d" % (kern, len(lines), tot))
 src = {}
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
     if f not in src:
         p = os.path.join(ROOT, "rtx-pathtracer_b200", "csrc", f)
         src[f] = open(p).read().splitlines() if os.path.exists(p) else []
