@@ -528,7 +528,10 @@ template <bool GUIDE, bool IC, bool BATCH = false, bool DEFER = false>
 __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const __grid_constant__ DeviceScene sc,
                                                                     const __grid_constant__ Wavefront wf, int cur) {
     __shared__ uint2 stack[PT_STACK_SMEM * 128];
-    constexpr bool NI = PT_SHADE_NI && IC;      // heavy callees out of line (see neeQueuedNI); guided-only: one expansion each, nothing to share
+#ifndef PT_SHADE_NI_GUIDE
+#define PT_SHADE_NI_GUIDE 0       // the same for the guided-only variant: measured slower (config 5 training render 4 166 -> 4 895 ms, guided frames 578 -> 641)
+#endif
+    constexpr bool NI = PT_SHADE_NI && (IC || (PT_SHADE_NI_GUIDE && GUIDE));      // heavy callees out of line (see neeQueuedNI); guided-only: one expansion each, nothing to share
     #define NEE_QUEUED(...) do { if (NI) neeQueuedNI(__VA_ARGS__); else neeQueued(__VA_ARGS__); } while (0)
     #define GET_NEW_DIRECTION(...) (NI ? getNewDirectionNI<GUIDE>(__VA_ARGS__) : getNewDirection<GUIDE>(__VA_ARGS__))
     #define EVAL_BSDF(...) (NI ? evalBsdfNI(__VA_ARGS__) : evalBsdf(__VA_ARGS__))
