@@ -105,6 +105,9 @@ struct b200pt_ctx {
     DevBuf<unsigned long long> dstats;
     DevBuf<uint32_t> batchCounter;
     int icBuildBlocksPerSM = 2;
+    bool icOverlap = true;        // B200PT_IC_OVERLAP=0: the cache update runs in front of the frame's paths on the same stream
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool icBuildGroup = true;     // B200PT_IC_BUILD_GROUP=0: one lane per cache entry (the state before round 2b), for A/B
     // IC / ADRRS frames: lookups in grid-cell order (k_icq_*), next paths of finished pixels in a kernel of their own (k_regen)
     bool icqSort = true, regenSplit = true, shadeSorted = true;
@@ -342,6 +345,12 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
         if (const char *e = getenv("B200PT_REGEN_SPLIT")) c->regenSplit = atoi(e) != 0;
         if (const char *e = getenv("B200PT_SHADE_SORTED")) c->shadeSorted = atoi(e) != 0;
         if (const char *e = getenv("B200PT_IC_BUILD_GROUP")) c->icBuildGroup = atoi(e) != 0;
+        if (const char *e = getenv("B200PT_IC_OVERLAP")) c->icOverlap = atoi(e) != 0;
+        int prLo = 0, prHi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prHi));     // its few blocks should not queue behind a full wave
+        CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     }
     CUDA_TRY(c->batchCounter.alloc(1));
     // persistent launches: one full wave of resident CTAs (SM count x occupancy), sized once
@@ -442,6 +451,9 @@ int b200pt_destroy(b200pt_ctx *c) {
     if (c->evB) cudaEventDestroy(c->evB);
     if (c->evTimer0) cudaEventDestroy(c->evTimer0);
     if (c->evTimer1) cudaEventDestroy(c->evTimer1);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B200PT_OK;
@@ -734,6 +746,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         }
         if (c->hostIcHdr[ICH_GRID_TOTAL]) { k_ic_cells<true><<<gridFor(uint64_t(c->icNumCells), 256), 256, 0, st>>>(b, c->icGrid); c->stats.kernel_launches++; }
     }
+    bool overlapUpdate = false;
     if (pc->useIrradianceCache && pc->irradianceUpdateProb > 0.0f) {
         // updateIrradianceCache (rgen:1334-1381) for the pixels whose first random number selects them, before any path
         PredICUpdate pred{pc->randomUInt, pc->irradianceUpdateProb};
@@ -747,16 +760,32 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             int grid, stride, lanes;
             buildLaunchShape(c, entries, grid, stride, lanes);
             k_ic_update_assign<<<1, 32, 0, st>>>(b);
-            k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride, lanes);
-            k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
-            c->stats.kernel_launches += 2;
+            // One entry is ~10 ms of dependent work on a handful of warps, whatever the list length, and nothing in the frame waits
+            // for it except the selected pixels themselves (lookups read the frame-start snapshot; the blend is committed afterwards):
+            // it runs on a second stream BESIDE the wavefront loop, the selected pixels start their paths when it is done.
+            overlapUpdate = c->icOverlap && !earlyReturn && !batch;
+            if (overlapUpdate) {
+                CUDA_TRY(cudaEventRecord(c->evFork, st));
+                CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
+                k_ic_update<<<grid, 128, 0, c->stream2>>>(fp, c->dscene, c->wf, b, stride, lanes);
+                CUDA_TRY(cudaEventRecord(c->evJoin, c->stream2));
+                c->stats.kernel_launches += 1;
+            } else {
+                k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride, lanes);
+                k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
+                c->stats.kernel_launches += 2;
+            }
         }
     }
 
-    { StageTimer t(c, KIND_SHADE); k_generate<<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf); }
     c->stats.samples += uint64_t(N) * uint64_t(batch ? batchCount : 1);
-    uint32_t init[CNT_NUM] = {N, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t init[CNT_NUM] = {overlapUpdate ? 0u : N, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    {
+        StageTimer t(c, KIND_SHADE);
+        if (overlapUpdate) k_generate<true><<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf);
+        else k_generate<false><<<gridFor(N, 256), 256, 0, st>>>(fp, c->wf);
+    }
     // Wavefront loop.  Every kernel reads its queue sizes from device memory, so iterations are issued back-to-back;
     // the host only peeks at the counters of iteration i-LAG to learn when the queues have drained.
     int cur = 0;
@@ -764,8 +793,21 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
     const uint64_t maxIter = uint64_t(batch ? batchCount : 1) * pathsPerPixel * (uint64_t(pc->maxDepth) + uint64_t(std::max(0, pc->maxFollowDiscrete)) + 4) + 4 + b200pt_ctx::LAG;
     bool drained = earlyReturn;
     const uint32_t seqBase = c->ringSeq;          // sequence numbers never repeat across frames
-    for (uint64_t iter = 0; !drained; iter++) {
-        if (iter > maxIter) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
+    uint64_t iter = 0, passStart = 0;
+  for (int pass = 0; pass < (overlapUpdate ? 2 : 1); pass++) {
+    if (pass == 1) {
+        // the cache update has finished: blend its results in and start the paths of the pixels it selected
+        StageTimer t(c, KIND_SHADE);
+        CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
+        const ICBuffers b = icBuffers(c);
+        k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
+        k_generate_list<<<gridFor(uint64_t(c->hostIcHdr[ICH_LIST_COUNT]), 256), 256, 0, st>>>(fp, c->wf, c->icList.p, c->icSnapHdr.p + ICH_LIST_COUNT, cur);
+        c->stats.kernel_launches++;
+        drained = false;
+        passStart = iter;
+    }
+    for (; !drained; iter++) {
+        if (iter > maxIter + passStart) return setError(B200PT_E_STATE, "b200pt_render_frame: wavefront did not drain (internal error)");
         {
             StageTimer t(c, KIND_EXTEND);
             const bool alpha = c->dscene.trace.alpha != nullptr;     // some texture of the scene has a transparent texel
@@ -822,7 +864,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         if (c->counterCopy) {
             CUDA_TRY(cudaMemcpyAsync(c->hostCounters + slot * CNT_NUM, c->counters.p, CNT_NUM * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaEventRecord(c->ringEvent[slot], st));
-            if (iter >= b200pt_ctx::LAG) {
+            if (iter >= passStart + b200pt_ctx::LAG) {
                 const int old = int((iter - b200pt_ctx::LAG) % b200pt_ctx::RING);
                 CUDA_TRY(cudaEventSynchronize(c->ringEvent[old]));
                 const uint32_t *hc = c->hostCounters + old * CNT_NUM;
@@ -831,7 +873,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
                 qPath = hc[CNT_PATH0 + liveQ]; qProbe = hc[CNT_PROBE]; qShadow = hc[CNT_SHADOW];
                 have = true;
             }
-        } else if (iter >= b200pt_ctx::LAG) {
+        } else if (iter >= passStart + b200pt_ctx::LAG) {
             // queue sizes iteration j = iter - LAG STARTED with (= what the shade pass of j - 1 left), published by its k_iter_prep
             const uint64_t j = iter - b200pt_ctx::LAG;
             volatile uint32_t *hs = c->hostRing + (j % b200pt_ctx::RING) * 8;
@@ -856,7 +898,8 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
             if (c->dumpIters) fprintf(c->dumpIters, "%llu %u %u %u\n", (unsigned long long)(iter - b200pt_ctx::LAG), qPath, qProbe, qShadow);
         }
     }
-    c->ringSeq = seqBase + uint32_t(maxIter) + 8u;
+  }
+    c->ringSeq = seqBase + uint32_t(iter) + 8u;
     if (!earlyReturn) {
         StageTimer t(c, KIND_SHADE);
         if (batch) {      // the last frame of the batch (every earlier one was folded in by the pixels themselves)

@@ -106,21 +106,16 @@ __device__ __forceinline__ void cameraRay(const FrameParams &fp, uint32_t &seed,
 
 // ---------------------------------------------------------------------------------------------------------------
 // generate: rgen main() :1625 (seed) and the first getCameraRay of the spp loop (:1668-1670)
-__global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= fp.numPixels) return;
-    uint32_t seed = tea(uint32_t(p), fp.pc.randomUInt);
-    if (fp.pc.useIrradianceCache) {      // rgen:1639-1641: the update draw; k_ic_update has advanced the stream of the selected pixels
-        if (rnd(seed) < fp.pc.irradianceUpdateProb) seed = wf.seed[p];
-    }
+// slot: where the camera ray goes in path queue `q` (the pixel index for a full frame)
+__device__ __forceinline__ void generatePixel(const FrameParams &fp, const Wavefront &wf, const int p, uint32_t seed, const int q, const uint32_t slot) {
     if (wf.aov) wf.aov[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (wf.ic.newCount) wf.ic.newCount[p] = 0u;
     if (wf.ic.splitState) wf.ic.splitState[p] = 0u;
     const int px = p % fp.width, py = p / fp.width;
     vec3 o, d;
     cameraRay(fp, seed, px, py, o, d);
-    wf.pathRayO[0][p] = make_f4(o, __int_as_float(p));
-    wf.pathRayD[0][p] = make_f4(d, 0.0f);
+    wf.pathRayO[q][slot] = make_f4(o, __int_as_float(p));
+    wf.pathRayD[q][slot] = make_f4(d, 0.0f);
     wf.seed[p] = seed;
     wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     wf.state[p] = ST_ADDNEXT;     // depth 0, addNextDirectLights = addFirstHitLight = true (rgen:995,1676)
@@ -133,6 +128,28 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) 
         wf.rec.distanceFactor[p] = 1.0f;
         wf.rec.pathSum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+}
+// DEFER_UPDATED (irradiance-cache frames whose cache update runs on a second stream beside the wavefront loop, api.cu): the pixels
+// the update draw selects are left out — their RNG stream continues where k_ic_update leaves it, so they start with
+// k_generate_list once it has finished; the others are appended to the queue instead of sitting at their pixel index.
+template <bool DEFER_UPDATED>
+__global__ void __launch_bounds__(256) k_generate(FrameParams fp, Wavefront wf) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.numPixels) return;
+    uint32_t seed = tea(uint32_t(p), fp.pc.randomUInt);
+    if (fp.pc.useIrradianceCache) {      // rgen:1639-1641: the update draw; k_ic_update has advanced the stream of the selected pixels
+        if (rnd(seed) < fp.pc.irradianceUpdateProb) {
+            if (DEFER_UPDATED) return;
+            seed = wf.seed[p];
+        }
+    }
+    generatePixel(fp, wf, p, seed, 0, DEFER_UPDATED ? queuePush(&wf.counters[CNT_PATH0]) : uint32_t(p));
+}
+__global__ void __launch_bounds__(256) k_generate_list(FrameParams fp, Wavefront wf, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count, int q) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= *count) return;
+    const int p = int(list[e]);
+    generatePixel(fp, wf, p, wf.seed[p], q, queuePush(&wf.counters[CNT_PATH0 + q]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -234,10 +251,11 @@ __device__ __forceinline__ void iterPrep(const Wavefront &wf, int cur, volatile 
         __threadfence_system();
         hostSlot[7] = seq;
     }
-    wf.dstats[DST_EXTEND] += (unsigned long long)nPath + nProbe;
-    wf.dstats[DST_SHADOW] += (unsigned long long)nShadow + c[CNT_INLINE_SHADOW];
-    wf.dstats[DST_VERTICES] += nPath;
-    if (nPath + nProbe + nShadow) wf.dstats[DST_ITERATIONS] += 1;
+    // (atomic: the cache update may be adding its rays to the same words from a second stream)
+    atomicAdd(&wf.dstats[DST_EXTEND], (unsigned long long)nPath + nProbe);
+    atomicAdd(&wf.dstats[DST_SHADOW], (unsigned long long)nShadow + c[CNT_INLINE_SHADOW]);
+    atomicAdd(&wf.dstats[DST_VERTICES], (unsigned long long)nPath);
+    if (nPath + nProbe + nShadow) atomicAdd(&wf.dstats[DST_ITERATIONS], 1ull);
     c[CNT_SHADE_N] = nPath;
     c[CNT_PATH0 + (1 - cur)] = 0; c[CNT_PROBE] = 0; c[CNT_SHADOW] = 0; c[CNT_INLINE_SHADOW] = 0; c[CNT_WORK_TRACE] = 0;
     c[CNT_REGEN] = 0;

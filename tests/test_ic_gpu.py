@@ -221,11 +221,12 @@ def test_lookup_order_and_regen_kernel_do_not_change_the_result(monkeypatch):
         r.close()
         return out
 
-    on = dict(B200PT_ICQ_SORT="1", B200PT_REGEN_SPLIT="1", B200PT_SHADE_SORTED="1", B200PT_IC_BUILD_GROUP="1")
+    on = dict(B200PT_ICQ_SORT="1", B200PT_REGEN_SPLIT="1", B200PT_SHADE_SORTED="1", B200PT_IC_BUILD_GROUP="1", B200PT_IC_OVERLAP="1")
     new = run(on)
-    # (the last one: cache entries built by one lane each instead of an eight-lane group sharing every ray)
+    # (the last two: cache entries built by one lane each instead of an eight-lane group sharing every ray; the cache update in
+    # front of the frame's paths instead of beside them on a second stream)
     for env in (dict(on, B200PT_ICQ_SORT="0", B200PT_REGEN_SPLIT="0"), dict(on, B200PT_REGEN_SPLIT="0", B200PT_SHADE_SORTED="0"),
-                dict(on, B200PT_ICQ_SORT="0"), dict(on, B200PT_IC_BUILD_GROUP="0")):
+                dict(on, B200PT_ICQ_SORT="0"), dict(on, B200PT_IC_BUILD_GROUP="0"), dict(on, B200PT_IC_OVERLAP="0")):
         old = run(env)
         for i, (a, b) in enumerate(zip(new, old)):
             if i < 2:       # cache + lookup frame: one light sample per pixel and iteration, every sum has a fixed order
