@@ -548,7 +548,10 @@ __device__ __forceinline__ void tracePersistent(const TraceScene &sc, const IO &
 #define PT_COOP_STEPS 2       // node steps per pooled triangle phase, 1..4 (more: fewer phases, but `best` shrinks later)
 #endif
 #ifndef PT_COOP_LIST
-#define PT_COOP_LIST 0        // work-list construction: 0 = one merged loop over the groups, 1 = one loop per group
+#define PT_COOP_LIST 2        // pooled triangle work: 0 = list in shared memory built by one merged per-lane loop, 1 = one loop per group,
+                              // 2 = no list, every lane finds the (owner, triangle) of its slot itself (round 2b: the list loops ran as long as the
+                              // lane with the most triangles, 11 % of the kernel's instructions at 8 of 32 lanes on cornell-dielectric, 15 % at 4 lanes
+                              // on sponzaXML; trace-alone 4 562 -> 4 602 Mrays/s on config 2, sponzaXML plain frames 1 781 -> 1 857 Mrays/s)
 #endif
 struct CoopSmem {
     float4 rayO[PT_TRACE_BLOCK];                 // origin, tmin of the lane's current ray
@@ -586,6 +589,75 @@ __device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, con
         for (int g = 0; g < PT_COOP_STEPS; g++) sm.base[g][tid] = tg[g].x;
     }
     volatile unsigned long long *vkey = sm.key;
+#if PT_COOP_LIST == 2
+    // No list in memory: slot i of the pooled work belongs to the lane whose prefix-sum interval contains i (binary search over
+    // the lanes' inclusive sums by shuffles) and, inside that lane's bits, to the (i - first)-th set triangle (popcount search).
+    // Every lane does this for its own slot, so building the work costs ~50 instructions per 32 slots at full lanes instead of a
+    // loop that runs as long as the lane with the most triangles.
+    static_assert(PT_COOP_STEPS <= 2, "PT_COOP_LIST 2 is written for one or two triangle groups per lane");
+    {
+        const uint32_t b0own = bits[0], b1own = PT_COOP_STEPS > 1 ? bits[PT_COOP_STEPS - 1] : 0u;
+        const uint32_t cnt = uint32_t(__popc(b0own)) + (PT_COOP_STEPS > 1 ? uint32_t(__popc(b1own)) : 0u);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, dlt);
+            if (int(lane) >= dlt) incl += nb;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl = incl - cnt;
+        __syncwarp();            // sm.key / sm.base of the owners are visible
+        for (uint32_t i0 = 0; i0 < total; i0 += 32u) {
+            const uint32_t i = min(i0 + lane, total - 1u);
+            const bool live = i0 + lane < total;
+            uint32_t lo = 0u, hi = 31u;          // first lane whose inclusive sum exceeds i
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, int(mid));
+                if (v > i) hi = mid; else lo = mid + 1u;
+            }
+            const uint32_t owner = lo;
+            uint32_t r = i - __shfl_sync(0xffffffffu, excl, int(owner));
+            const uint32_t ob0 = __shfl_sync(0xffffffffu, b0own, int(owner));
+            const uint32_t ob1 = __shfl_sync(0xffffffffu, b1own, int(owner));
+            const uint32_t c0 = uint32_t(__popc(ob0));
+            const uint32_t g = (PT_COOP_STEPS > 1 && r >= c0) ? 1u : 0u;
+            uint32_t bb = g ? ob1 : ob0;
+            if (g) r -= c0;
+            // position of the r-th set bit of the 24-bit mask bb (it has more than r bits set)
+            uint32_t ti = 0u, c;
+            c = uint32_t(__popc(bb & 0xfffu)); if (r >= c) { r -= c; ti = 12u; }
+            c = uint32_t(__popc((bb >> ti) & 0x3fu)); if (r >= c) { r -= c; ti += 6u; }
+            c = uint32_t(__popc((bb >> ti) & 0x7u)); if (r >= c) { r -= c; ti += 3u; }
+            const uint32_t t3 = (bb >> ti) & 0x7u;
+            // r-th set bit of three: t3 = 1:0 2:1 3:0,1 4:2 5:0,2 6:1,2 7:0,1,2  (two bits per (t3, r), r = 0..2)
+            ti += uint32_t((0x909202101000ull >> ((t3 * 3u + r) * 2u)) & 3ull);
+            bool won = false;
+            unsigned long long cand = 0ull;
+            float u = 0.0f, v = 0.0f;
+            const uint32_t ol = wl + owner;
+            if (live) {
+                const uint32_t tb = (sm.base[g][ol] + ti) * 3u;
+                const float4 ro = sm.rayO[ol], rd = sm.rayD[ol];
+                const float4 a = __ldg(&sc.tris[tb + 0]);
+                const float4 b = __ldg(&sc.tris[tb + 1]);
+                const float4 c4 = __ldg(&sc.tris[tb + 2]);
+                float t;
+                if (intersectTriExact(a, b, c4, make_vec3(ro), make_vec3(rd), t, u, v) && t > ro.w) {
+                    const uint32_t id = __float_as_uint(a.w);
+                    cand = ((unsigned long long)orderedBits(t) << 32) | id;
+                    if (cand < vkey[ol]) {
+                        if (!ALPHA || __float_as_uint(b.w) == 0u || !(ALPHA == 2 ? alphaRejectsInline(sc, id, u, v, ro.x, t) : alphaRejects(sc, id, u, v, ro.x, t)))
+                            won = cand < atomicMin(&sm.key[ol], cand);
+                    }
+                }
+            }
+            __syncwarp();
+            if (won && vkey[ol] == cand) sm.uv[ol] = make_float2(u, v);
+        }
+    }
+#else
     for (;;) {
         uint32_t cnt = 0u;
 #pragma unroll
@@ -663,6 +735,7 @@ __device__ __forceinline__ void coopTriangles(Trav &s, const TraceScene &sc, con
         if (total <= uint32_t(PT_COOP_CAP)) break;
         __syncwarp();            // the next round rewrites the work list
     }
+#endif
     __syncwarp();
     if (mine) {
         const unsigned long long k = sm.key[tid];
