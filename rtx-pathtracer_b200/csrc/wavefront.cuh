@@ -292,7 +292,8 @@ __device__ __forceinline__ void probeResolveOne(const FrameParams &fp, const Dev
     }
     const float heuristic = fp.pc.usePowerHeuristic ? powerHeuristic(pdfMat, pdfLights) : balanceHeuristic(pdfMat, pdfLights);
     if (h.prim != PT_MISS && isnan(heuristic)) return;
-    const vec3 nee = (bsdf * lightColor * heuristic / pdfMat) / float(fp.pc.numNEE);
+    vec3 nee = bsdf * lightColor * heuristic / pdfMat;
+    if (fp.pc.numNEE != 1) nee = nee / float(fp.pc.numNEE);       // x / 1.0f == x: one out-of-line IEEE vec3 division less in the common case
     const vec3 c = T * nee;
     float *dst = reinterpret_cast<float *>(&wf.pixelSum[pix]);
     atomicAdd(dst + 0, c.x); atomicAdd(dst + 1, c.y); atomicAdd(dst + 2, c.z);
@@ -470,8 +471,9 @@ __device__ __forceinline__ void neeQueued(const FrameParams &fp, const DeviceSce
             const uint32_t slotS = queuePush(&wf.counters[CNT_SHADOW]);
             wf.shRayO[slotS] = make_f4(origin, __int_as_float(pid));
             wf.shRayD[slotS] = make_f4(lightDir, lightDistance * (1 - 0.0001f));
-            wf.shC[slotS] = make_f4(T * (C / float(pc.numNEE)), 0.0f);
-            if (saveSamples) wf.shG[slotS] = make_f4(C / float(pc.numNEE), __int_as_float(cso));
+            const vec3 Cn = pc.numNEE == 1 ? C : C / float(pc.numNEE);       // x / 1.0f == x
+            wf.shC[slotS] = make_f4(T * Cn, 0.0f);
+            if (saveSamples) wf.shG[slotS] = make_f4(Cn, __int_as_float(cso));
         }
         bool pushProbe = false;
         vec3 bsdfDir = V3(0.0f); float pdfMat = 0.0f;
