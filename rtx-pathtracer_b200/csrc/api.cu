@@ -747,6 +747,9 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         if (c->hostIcHdr[ICH_GRID_TOTAL]) { k_ic_cells<true><<<gridFor(uint64_t(c->icNumCells), 256), 256, 0, st>>>(b, c->icGrid); c->stats.kernel_launches++; }
     }
     bool overlapUpdate = false;
+    // an error return while the cache update is still running on the second stream must not leave it behind (the next call may
+    // release the buffers it works on)
+    struct JoinGuard { cudaStream_t s; bool armed; ~JoinGuard() { if (armed) cudaStreamSynchronize(s); } } joinGuard{c->stream2, false};
     if (pc->useIrradianceCache && pc->irradianceUpdateProb > 0.0f) {
         // updateIrradianceCache (rgen:1334-1381) for the pixels whose first random number selects them, before any path
         PredICUpdate pred{pc->randomUInt, pc->irradianceUpdateProb};
@@ -769,6 +772,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
                 CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
                 k_ic_update<<<grid, 128, 0, c->stream2>>>(fp, c->dscene, c->wf, b, stride, lanes);
                 CUDA_TRY(cudaEventRecord(c->evJoin, c->stream2));
+                joinGuard.armed = true;
                 c->stats.kernel_launches += 1;
             } else {
                 k_ic_update<<<grid, 128, 0, st>>>(fp, c->dscene, c->wf, b, stride, lanes);
@@ -799,6 +803,7 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
         // the cache update has finished: blend its results in and start the paths of the pixels it selected
         StageTimer t(c, KIND_SHADE);
         CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
+        joinGuard.armed = false;          // from here on the frame's own stream is ordered behind it
         const ICBuffers b = icBuffers(c);
         k_ic_update_commit<<<1, 32, 0, st>>>(fp, b);
         k_generate_list<<<gridFor(uint64_t(c->hostIcHdr[ICH_LIST_COUNT]), 256), 256, 0, st>>>(fp, c->wf, c->icList.p, c->icSnapHdr.p + ICH_LIST_COUNT, cur);
