@@ -727,6 +727,8 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
     CUDA_TRY(cudaEventRecord(c->evA, st));
     CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, DST_NUM * sizeof(unsigned long long), st));
 
+    if (useCache && c->icqSort)      // the sort histogram is zero between two sorts — unless an earlier frame was abandoned between them
+        CUDA_TRY(cudaMemsetAsync(c->icqHist.p, 0, (size_t(IC_GRID_MAX) * IC_GRID_MAX * IC_GRID_MAX + ICQ_EXTRA_BINS) * sizeof(uint32_t), st));
     if (useCache) {
         // frame-start snapshot of the cache + lookup grid (replaces IrradianceCache::updateSpheres, src/IrradianceCache.cpp:81-104)
         StageTimer t(c, KIND_SHADE);
