@@ -233,3 +233,26 @@ def test_lookup_order_and_regen_kernel_do_not_change_the_result(monkeypatch):
                 assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (env, i)
             else:           # split modes: a pixel can have two light samples in one trace pass, their float atomics commute only to the last bit
                 assert np.allclose(a, b, rtol=2e-6, atol=1e-7), (env, i, float(np.abs(a - b).max()))
+
+
+def test_guided_sampling_inside_ic_and_adrrs_frames_matches_oracle():
+    """useGuiding together with the irradiance cache / ADRRS + splitting: the guided variants of the IC kernels
+    (k_shade<GUIDE, IC> and k_regen<GUIDE>: region lookup + mixture sampling for the new direction of a path and of a drained
+    split) against the oracle's megakernel with the same mixtures."""
+    import test_guided_tracer_gpu as tg
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE, guiding_splits=3)
+    cache = _build_cache(P, o)
+    r.ic_put(*cache)
+    est = np.full((H, W, 4), 0.5, np.float32)
+    r.write_image(P.IMAGE_ESTIMATE, est)
+    o.set_image(P.IMAGE_ESTIMATE, est)
+    vm = tg._synthetic_vmms(P, r.guiding_aabbs(), 9)
+    r.guiding_put_vmms(vm)
+    o.set_guiding(r.guiding_aabbs(), vm)
+    frames = [dict(useADRRS=1, adrrsSplit=1, adrrsS=5.0), dict(useIrradianceCache=1, useIrradianceCacheOnGlossy=1), dict(splitOnFirst=1)]
+    for f, kw in enumerate(frames):
+        pc = _pc(P, 60 + f, samplesPerPixel=2, useGuiding=1, guidingProb=0.5, useParallaxCompensation=1, irradianceCreateProb=0.0, irradianceUpdateProb=0.0, **kw)
+        r.render_frame(pc)
+        o.render_region(pc, threads=NT)
+        _images_close(r.read_image(), o.image(), "guided %r" % (kw,), frac_needed=0.985, mean_tol=5e-3)
