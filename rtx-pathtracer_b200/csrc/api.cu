@@ -658,8 +658,6 @@ static int renderFrames(b200pt_ctx *c, const b200pt_push_constants *pc, const b2
     const bool splitMode = (pc->useADRRS && pc->adrrsSplit) || pc->splitOnFirst;
     const bool icMode = useCache || splitMode;
     if (useCache && c->icSize < 1) return setError(B200PT_E_STATE, "b200pt_render_frame: irradiance cache / ADRRS need a context created with ic_size > 0");
-    if (pc->updateGuiding && pc->useIrradianceCache)
-        return setError(B200PT_E_STATE, "b200pt_render_frame: guiding training on irradiance-cache frames is not supported");
     const bool guided = pc->useGuiding || pc->updateGuiding;
     if (guided && !c->guiding.ready) return setError(B200PT_E_STATE, "b200pt_render_frame: guiding needs a scene (region tree)");
     if (pc->numNEE < 1 || pc->samplesPerPixel < 1 || pc->maxDepth < 0 || pc->maxDepth > 60000)

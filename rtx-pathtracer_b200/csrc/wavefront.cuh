@@ -648,7 +648,9 @@ __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(const __grid
                             }
                         } else {
                             add += T * approxDiffuse(sc, mat, normal, wi, info.u, info.v) * irradianceColor;
-                            if (neeSupported(mat.type)) NEE_QUEUED(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.y, stack + threadIdx.x);
+                            // rgen:1119-1123 adds this NEE to `result` only — no updateSamples() on the way out: on a training frame the light
+                            // samples carry cso = sampleOffset, which makes the deferred update an empty loop while the path sum still counts them
+                            if (neeSupported(mat.type)) NEE_QUEUED(fp, sc, wf, seed, mat, info, origin, normal, wi, T, pid, saveSamples, gst.x, stack + threadIdx.x);
                             terminated = true;
                         }
                     } else if (rnd(seed) < pc.irradianceCreateProb) {                  // createIC is true on every path of main()

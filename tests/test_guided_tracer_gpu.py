@@ -22,17 +22,12 @@ def _pair(scene_name, splits):
     return P, scene, r, o
 
 
-@pytest.mark.parametrize("scene_name,spp", [("cornell-dielectric", 2), ("veachMIS", 2)])
-def test_recorded_samples_match_oracle(scene_name, spp):
-    """updateGuiding = 1 (training frame, unguided): every pixel's 16 DirectionalData slots against the oracle."""
-    P, scene, r, o = _pair(scene_name, 4)
-    pc = P.default_push_constants(randomUInt=P.tea(0, 0xC0FFEE), previousFrames=0, samplesPerPixel=spp, enableMIS=1, updateGuiding=1)
-    r.render_frame(pc)
-    o.render_region(pc, threads=NT)
+def compare_recorded_samples(P, r, o, min_valid=0.3):
+    """every pixel's 16 DirectionalData slots of the last training frame: device (C ABI) against the oracle"""
     g = r.guiding_get_samples().reshape(H * W, 16)
     c = o.samples(P.DIRECTIONAL_DATA_DTYPE).reshape(H * W, 16)
     gv, cv = g["flags"] != INVALID, c["flags"] != INVALID
-    assert cv.sum() > 0.3 * H * W                              # the scene does produce samples
+    assert cv.sum() > min_valid * H * W                        # the scene does produce samples
     same_slots = (gv == cv).all(axis=1)
     # pixels whose paths diverged at a stochastic branch (1-ulp libm differences) record different slots; the rest must agree
     assert same_slots.mean() >= 0.99, same_slots.mean()
@@ -58,6 +53,16 @@ def test_recorded_samples_match_oracle(scene_name, spp):
         dw = np.abs(g["weight"] - c["weight"]) / np.maximum(np.abs(c["weight"]), 1e-3)
     both = gv & cv & same_slots[:, None]
     assert np.mean(((dw <= 1e-3) | (g["weight"] == c["weight"]))[both]) >= 0.99
+
+
+@pytest.mark.parametrize("scene_name,spp", [("cornell-dielectric", 2), ("veachMIS", 2)])
+def test_recorded_samples_match_oracle(scene_name, spp):
+    """updateGuiding = 1 (training frame, unguided): every pixel's 16 DirectionalData slots against the oracle."""
+    P, scene, r, o = _pair(scene_name, 4)
+    pc = P.default_push_constants(randomUInt=P.tea(0, 0xC0FFEE), previousFrames=0, samplesPerPixel=spp, enableMIS=1, updateGuiding=1)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    compare_recorded_samples(P, r, o)
     # radiance of the training frame is the ordinary unguided frame
     gi, ci = r.read_image()[..., :3].astype(np.float64), o.image()[..., :3].astype(np.float64)
     rel = np.abs(gi - ci) / np.maximum(np.abs(ci), 1e-3)

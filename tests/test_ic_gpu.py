@@ -256,3 +256,31 @@ def test_guided_sampling_inside_ic_and_adrrs_frames_matches_oracle():
         r.render_frame(pc)
         o.render_region(pc, threads=NT)
         _images_close(r.read_image(), o.image(), "guided %r" % (kw,), frac_needed=0.985, mean_tol=5e-3)
+
+
+def test_guiding_training_on_cache_frames_matches_oracle():
+    """updateGuiding on frames that use the irradiance cache, or ADRRS without splitting (the reference allows both,
+    rgen:1642-1650 only returns early for the split modes): the recorded DirectionalData of every pixel against the oracle.
+    A path that ends on a cache record adds the record and its light samples to `result` without updateSamples()
+    (rgen:1117-1124), so its earlier samples keep the light they had collected until then; Russian roulette ends a path
+    the same way.  The third frame also creates and updates cache entries beside the training paths."""
+    import test_guided_tracer_gpu as tg
+    P = helpers.pt()
+    scene, r, o = helpers.make_pair(SCENE, W, H, ic_size=IC_SIZE, guiding_splits=3)
+    cache = _build_cache(P, o)
+    r.ic_put(*cache)
+    est = np.full((H, W, 4), 0.5, np.float32)
+    r.write_image(P.IMAGE_ESTIMATE, est)
+    o.set_image(P.IMAGE_ESTIMATE, est)
+    o.set_guiding(r.guiding_aabbs(), r.guiding_get_vmms())
+    off = dict(irradianceCreateProb=0.0, irradianceUpdateProb=0.0)
+    frames = [(dict(useIrradianceCache=1, useIrradianceCacheOnGlossy=1, **off), 0.02),
+              (dict(useADRRS=1, adrrsSplit=0, adrrsS=5.0, **off), 0.1),
+              (dict(useIrradianceCache=1, useIrradianceCacheOnGlossy=1, irradianceCreateProb=0.02, irradianceUpdateProb=0.005), 0.02)]
+    for f, (kw, min_valid) in enumerate(frames):
+        pc = _pc(P, 80 + f, samplesPerPixel=2, updateGuiding=1, **kw)
+        r.render_frame(pc)
+        o.render_region(pc, threads=NT)
+        tg.compare_recorded_samples(P, r, o, min_valid=min_valid)
+        _images_close(r.read_image(), o.image(), "training %r" % (kw,), frac_needed=0.985, mean_tol=5e-3)
+    _compare_caches(P, r.ic_get(), o.ic_get(P), "cache after a training frame that builds entries")
