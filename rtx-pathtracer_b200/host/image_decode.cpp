@@ -1,7 +1,7 @@
-// Bitmap texture decoding for the scene loader: baseline JPEG and PNG to RGBA8.
+// Bitmap texture decoding for the scene loader: JPEG (baseline, extended sequential and progressive Huffman) and PNG to RGBA8.
 // The reference decodes textures with the vendored stb_image (`stbi_load(path, &w, &h, &channels, 4)`,
 // src/SceneLoader.cpp:198-207).  This file is an independent implementation of the two published formats
-// (ITU-T T.81 baseline sequential DCT + JFIF colour; PNG / RFC 2083 with zlib's inflate).  So that texel bytes agree
+// (ITU-T T.81 sequential and progressive DCT + JFIF colour; PNG / RFC 2083 with zlib's inflate, Adam7 included).  So that texel bytes agree
 // with what the reference uploads, the JPEG path uses the same well-known arithmetic stb_image documents:
 //   - the 13-bit-constant "islow" integer inverse DCT of the IJG library (Loeffler–Ligtenberg–Moschytz), two extra
 //     bits kept between the passes;
@@ -198,14 +198,84 @@ void upsampleRow(uint8_t *out, const uint8_t *nearRow, const uint8_t *farRow, in
 
 inline int fixedColour(float x) { return int(x * 4096.0f + 0.5f) << 8; }
 
+// One scan of a progressive frame works on the stored coefficients of the blocks it covers (T.81 Annex G): DC scans
+// (first / refinement of the point transform Al) and AC band scans (first: run / size symbols with end-of-band runs;
+// refinement: one correction bit per already-nonzero coefficient, new +-1 << Al coefficients placed after `r` zeros).
+struct ScanParams { int ss = 0, se = 63, ah = 0, al = 0; };
+
+void progressiveDc(BitReader &br, const HuffTable &h, Component &c, short *blk, const ScanParams &sp) {
+    if (sp.ah == 0) {
+        memset(blk, 0, 64 * sizeof(short));
+        const int t = decodeHuff(br, h);
+        if (t > 15) throw std::runtime_error("JPEG: bad DC size");
+        c.dcPred += t ? extend(br.getBits(t), t) : 0;
+        blk[0] = short(c.dcPred << sp.al);
+    } else if (br.getBit()) blk[0] = short(blk[0] + short(1 << sp.al));
+}
+
+void progressiveAc(BitReader &br, const HuffTable &h, short *blk, const ScanParams &sp, int &eobRun) {
+    if (sp.ah == 0) {
+        if (eobRun) { eobRun--; return; }
+        for (int k = sp.ss; k <= sp.se;) {
+            const int rs = decodeHuff(br, h);
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+                if (r < 15) {                       // end of band for this block and the next (1 << r) + bits - 1 blocks
+                    eobRun = (1 << r) - 1;
+                    if (r) eobRun += br.getBits(r);
+                    break;
+                }
+                k += 16;
+            } else {
+                k += r;
+                if (k > 63) throw std::runtime_error("JPEG: coefficient index out of range");
+                blk[kZigZag[k++]] = short(extend(br.getBits(s), s) << sp.al);
+            }
+        }
+        return;
+    }
+    const short bit = short(1 << sp.al);
+    auto refine = [&](short &p) {                    // correction bit of a coefficient that is already nonzero
+        if (br.getBit() && (p & bit) == 0) p = short(p > 0 ? p + bit : p - bit);
+    };
+    if (eobRun) {
+        eobRun--;
+        for (int k = sp.ss; k <= sp.se; k++) { short &p = blk[kZigZag[k]]; if (p != 0) refine(p); }
+        return;
+    }
+    for (int k = sp.ss; k <= sp.se;) {
+        const int rs = decodeHuff(br, h);
+        int r = rs >> 4, s = rs & 15;
+        if (s == 0) {
+            if (r < 15) {
+                eobRun = (1 << r) - 1;
+                if (r) eobRun += br.getBits(r);
+                r = 64;                              // the rest of the band only gets correction bits
+            }                                        // r == 15: sixteen zeros (fifteen skipped + a zero "new coefficient")
+        } else {
+            if (s != 1) throw std::runtime_error("JPEG: bad refinement symbol");
+            s = br.getBit() ? bit : -bit;
+        }
+        while (k <= sp.se) {
+            short &p = blk[kZigZag[k++]];
+            if (p != 0) refine(p);
+            else {
+                if (r == 0) { p = short(s); break; }
+                r--;
+            }
+        }
+    }
+}
+
 void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vector<uint8_t> &rgba) {
     if (d.size() < 4 || d[0] != 0xff || d[1] != 0xd8) throw std::runtime_error("JPEG: no SOI marker");
     uint16_t quant[4][64];
     bool quantDefined[4] = {false, false, false, false};
     HuffTable dc[4], ac[4];
     std::vector<Component> comps;
-    int hmax = 1, vmax = 1, restartInterval = 0;
-    bool haveFrame = false, adobeTransformKnown = false;
+    std::vector<std::vector<short>> coeff;      // progressive frames: 64 coefficients per block, w2 / 8 blocks per row
+    int hmax = 1, vmax = 1, restartInterval = 0, mcux = 0, mcuy = 0, scans = 0;
+    bool haveFrame = false, progressive = false, adobeTransformKnown = false;
     int adobeTransform = -1;
     size_t pos = 2;
     width = height = 0;
@@ -213,10 +283,10 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
     for (;;) {
         while (pos < d.size() && d[pos] != 0xff) pos++;
         while (pos < d.size() && d[pos] == 0xff) pos++;
-        if (pos >= d.size()) throw std::runtime_error("JPEG: no image data");
+        if (pos >= d.size()) { if (scans) break; throw std::runtime_error("JPEG: no image data"); }      // like stb_image, a missing EOI after the last scan is tolerated
         const int marker = d[pos++];
-        if (marker == 0xd9) throw std::runtime_error("JPEG: no scan");
-        if (marker == 0x01 || (marker >= 0xd0 && marker <= 0xd7)) continue;
+        if (marker == 0xd9) { if (scans) break; throw std::runtime_error("JPEG: no scan"); }
+        if (marker == 0x00 || marker == 0x01 || (marker >= 0xd0 && marker <= 0xd7)) continue;          // stuffed byte of a scan's tail, TEM, RSTn
         const int len = u16(pos);
         const size_t seg = pos + 2, segEnd = pos + size_t(len);
         if (len < 2 || segEnd > d.size()) throw std::runtime_error("JPEG: bad segment length");
@@ -246,12 +316,17 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
                 (tc ? ac[th] : dc[th]).build(counts, &d[i], n);
                 i += size_t(n);
             }
-        } else if (marker == 0xc0 || marker == 0xc1) {           // SOF0 / SOF1: baseline / extended sequential, Huffman
+        } else if (marker == 0xc0 || marker == 0xc1 || marker == 0xc2) {      // SOF0 / SOF1 / SOF2: baseline / extended sequential / progressive, Huffman
+            if (haveFrame) throw std::runtime_error("JPEG: more than one frame header");
             segNeed(seg, 6);
             if (d[seg] != 8) throw std::runtime_error("JPEG: only 8-bit samples are supported");
             height = u16(seg + 1); width = u16(seg + 3);
             const int n = d[seg + 5];
             if (width <= 0 || height <= 0 || (n != 1 && n != 3)) throw std::runtime_error("JPEG: unsupported frame (size or component count)");
+            // a corrupt size must not turn into gigabytes of planes: every 8x8 block of every component costs the file at least one
+            // bit (its DC code), so a frame that claims more blocks than the file has bits is refused before anything is allocated
+            if (uint64_t(width) * uint64_t(height) > (1ull << 28) || (uint64_t(width + 7) / 8) * (uint64_t(height + 7) / 8) > 8ull * d.size() + 1024ull)
+                throw std::runtime_error("JPEG: the frame size does not fit the file");
             segNeed(seg + 6, 3 * size_t(n));
             comps.assign(size_t(n), Component());
             for (int k = 0; k < n; k++) {
@@ -263,86 +338,139 @@ void decodeJpeg(const std::vector<uint8_t> &d, int &width, int &height, std::vec
                 hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v);
             }
             haveFrame = true;
-        } else if (marker == 0xc2 || (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc)) {
-            throw std::runtime_error("JPEG: progressive / lossless / arithmetic-coded files are not supported");
+            progressive = marker == 0xc2;
+            if (comps.size() == 1) { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }      // a single-component scan is never interleaved
+            const int mcuW = 8 * hmax, mcuH = 8 * vmax;
+            mcux = (width + mcuW - 1) / mcuW; mcuy = (height + mcuH - 1) / mcuH;
+            if (progressive) coeff.resize(comps.size());
+            for (size_t k = 0; k < comps.size(); k++) {
+                Component &c = comps[k];
+                c.w2 = mcux * c.h * 8; c.h2 = mcuy * c.v * 8;
+                c.cols = (width * c.h + hmax - 1) / hmax; c.rows = (height * c.v + vmax - 1) / vmax;
+                c.plane.assign(size_t(c.w2) * size_t(c.h2), 0);
+                if (progressive) coeff[k].assign(size_t(c.w2 / 8) * size_t(c.h2 / 8) * 64, 0);
+            }
+        } else if (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc) {
+            throw std::runtime_error("JPEG: lossless / hierarchical / arithmetic-coded files are not supported");
         } else if (marker == 0xdd) {
             segNeed(seg, 2);
             restartInterval = u16(seg);
         } else if (marker == 0xee && len >= 14 && memcmp(&d[seg], "Adobe", 5) == 0) {
             adobeTransformKnown = true; adobeTransform = d[seg + 11];
-        } else if (marker == 0xda) {                             // SOS: the (single, interleaved) scan of a baseline file
+        } else if (marker == 0xda) {                             // SOS: one scan (a baseline file has one interleaved scan or one per component)
             if (!haveFrame) throw std::runtime_error("JPEG: scan before frame header");
             segNeed(seg, 1);
             const int ns = d[seg];
-            if (ns != int(comps.size())) throw std::runtime_error("JPEG: non-interleaved scans are not supported");
-            segNeed(seg + 1, 2 * size_t(ns));
+            if (ns < 1 || ns > int(comps.size())) throw std::runtime_error("JPEG: bad scan component count");
+            segNeed(seg + 1, 2 * size_t(ns) + 3);
+            std::vector<size_t> order;
             for (int k = 0; k < ns; k++) {
                 const int cid = d[seg + 1 + 2 * size_t(k)], tbl = d[seg + 2 + 2 * size_t(k)];
-                Component *c = nullptr;
-                for (auto &cc : comps) if (cc.id == cid) c = &cc;
-                if (!c) throw std::runtime_error("JPEG: bad scan component");
-                c->td = tbl >> 4; c->ta = tbl & 15;
-                if (c->td > 3 || c->ta > 3 || !dc[c->td].defined || !ac[c->ta].defined || !quantDefined[c->tq]) throw std::runtime_error("JPEG: missing table");
+                size_t which = comps.size();
+                for (size_t q = 0; q < comps.size(); q++) if (comps[q].id == cid) { which = q; break; }
+                if (which == comps.size()) throw std::runtime_error("JPEG: bad scan component");
+                Component &c = comps[which];
+                c.td = tbl >> 4; c.ta = tbl & 15;
+                if (c.td > 3 || c.ta > 3) throw std::runtime_error("JPEG: bad table index");
+                order.push_back(which);
             }
-            pos = segEnd;
-            break;
-        }
-        pos = segEnd;
-    }
-    // ---- entropy-coded data -> component planes
-    if (comps.size() == 1) { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }      // a single-component scan is never interleaved
-    const int mcuW = 8 * hmax, mcuH = 8 * vmax;
-    const int mcux = (width + mcuW - 1) / mcuW, mcuy = (height + mcuH - 1) / mcuH;
-    for (auto &c : comps) {
-        c.w2 = mcux * c.h * 8; c.h2 = mcuy * c.v * 8;
-        c.cols = (width * c.h + hmax - 1) / hmax; c.rows = (height * c.v + vmax - 1) / vmax;
-        c.plane.assign(size_t(c.w2) * size_t(c.h2), 0);
-        c.dcPred = 0;
-    }
-    BitReader br(d.data() + pos, d.data() + d.size());
-    int todo = restartInterval ? restartInterval : 0x7fffffff;
-    short block[64];
-    for (int my = 0; my < mcuy; my++) {
-        for (int mx = 0; mx < mcux; mx++) {
-            for (auto &c : comps) {
-                for (int by = 0; by < c.v; by++) {
-                    for (int bx = 0; bx < c.h; bx++) {
-                        memset(block, 0, sizeof(block));
-                        const int t = decodeHuff(br, dc[c.td]);
-                        if (t > 15) throw std::runtime_error("JPEG: bad DC size");
-                        const int diff = t ? extend(br.getBits(t), t) : 0;
-                        c.dcPred += diff;
-                        block[0] = short(c.dcPred * quant[c.tq][0]);
-                        for (int k = 1; k < 64;) {
-                            const int rs = decodeHuff(br, ac[c.ta]);
-                            const int r = rs >> 4, s = rs & 15;
-                            if (s == 0) {
-                                if (rs != 0xf0) break;      // end of block
-                                k += 16;
-                            } else {
-                                k += r;
-                                if (k > 63) throw std::runtime_error("JPEG: coefficient index out of range");
-                                const int zig = kZigZag[k];
-                                block[zig] = short(extend(br.getBits(s), s) * quant[c.tq][zig]);
-                                k++;
-                            }
-                        }
-                        const int x0 = (mx * c.h + bx) * 8, y0 = (my * c.v + by) * 8;
-                        idctBlock(&c.plane[size_t(y0) * size_t(c.w2) + size_t(x0)], c.w2, block);
-                    }
-                }
+            ScanParams sp;
+            sp.ss = d[seg + 1 + 2 * size_t(ns)]; sp.se = d[seg + 2 + 2 * size_t(ns)];
+            sp.ah = d[seg + 3 + 2 * size_t(ns)] >> 4; sp.al = d[seg + 3 + 2 * size_t(ns)] & 15;
+            if (progressive) {
+                if (sp.ss > 63 || sp.se > 63 || sp.ss > sp.se || sp.ah > 13 || sp.al > 13) throw std::runtime_error("JPEG: bad scan parameters");
+                if (sp.ss == 0 && sp.se != 0) throw std::runtime_error("JPEG: a progressive scan cannot mix DC and AC coefficients");
+                if (sp.ss != 0 && ns != 1) throw std::runtime_error("JPEG: progressive AC scans hold one component");
+            } else {
+                if (sp.ss != 0 || sp.ah != 0 || sp.al != 0) throw std::runtime_error("JPEG: bad scan parameters");
+                sp.se = 63;
             }
-            if (--todo <= 0) {       // restart interval: skip to the RSTn marker, reset predictors
+            for (size_t which : order) {
+                const Component &c = comps[which];
+                const bool needDc = !progressive || sp.ss == 0, needAc = !progressive || sp.ss != 0;
+                if ((needDc && !(progressive && sp.ah) && !dc[c.td].defined) || (needAc && !ac[c.ta].defined) || !quantDefined[c.tq]) throw std::runtime_error("JPEG: missing table");
+            }
+            // ---- entropy-coded data of this scan
+            BitReader br(d.data() + segEnd, d.data() + d.size());
+            int todo = restartInterval ? restartInterval : 0x7fffffff, eobRun = 0;
+            for (auto &c : comps) c.dcPred = 0;
+            bool stop = false;
+            auto mcuDone = [&]() {       // restart interval: skip to the RSTn marker, reset predictors; anything else there ends the scan
+                if (--todo > 0) return;
                 const uint8_t *p = br.p;
                 while (p + 1 < br.end && !(p[0] == 0xff && p[1] >= 0xd0 && p[1] <= 0xd7)) {
                     if (p[0] == 0xff && p[1] != 0 && p[1] != 0xff) break;
                     p++;
                 }
                 if (p + 1 < br.end && p[0] == 0xff && p[1] >= 0xd0 && p[1] <= 0xd7) p += 2;
+                else stop = true;
                 br.p = p; br.reset();
                 for (auto &c : comps) c.dcPred = 0;
-                todo = restartInterval;
+                todo = restartInterval; eobRun = 0;
+            };
+            short block[64];
+            auto codeBlock = [&](Component &c, size_t which, int bxAbs, int byAbs) {
+                if (progressive) {
+                    short *blk = &coeff[which][(size_t(byAbs) * size_t(c.w2 / 8) + size_t(bxAbs)) * 64];
+                    if (sp.ss == 0) progressiveDc(br, dc[c.td], c, blk, sp);
+                    else progressiveAc(br, ac[c.ta], blk, sp, eobRun);
+                    return;
+                }
+                memset(block, 0, sizeof(block));
+                const int t = decodeHuff(br, dc[c.td]);
+                if (t > 15) throw std::runtime_error("JPEG: bad DC size");
+                const int diff = t ? extend(br.getBits(t), t) : 0;
+                c.dcPred += diff;
+                block[0] = short(c.dcPred * quant[c.tq][0]);
+                for (int k = 1; k < 64;) {
+                    const int rs = decodeHuff(br, ac[c.ta]);
+                    const int r = rs >> 4, s = rs & 15;
+                    if (s == 0) {
+                        if (rs != 0xf0) break;      // end of block
+                        k += 16;
+                    } else {
+                        k += r;
+                        if (k > 63) throw std::runtime_error("JPEG: coefficient index out of range");
+                        const int zig = kZigZag[k];
+                        block[zig] = short(extend(br.getBits(s), s) * quant[c.tq][zig]);
+                        k++;
+                    }
+                }
+                idctBlock(&c.plane[size_t(byAbs) * 8 * size_t(c.w2) + size_t(bxAbs) * 8], c.w2, block);
+            };
+            if (ns == 1) {               // not interleaved: the blocks that carry image samples, row by row
+                Component &c = comps[order[0]];
+                const int bw = (c.cols + 7) >> 3, bh = (c.rows + 7) >> 3;
+                for (int by = 0; by < bh && !stop; by++)
+                    for (int bx = 0; bx < bw && !stop; bx++) { codeBlock(c, order[0], bx, by); mcuDone(); }
+            } else {
+                for (int my = 0; my < mcuy && !stop; my++)
+                    for (int mx = 0; mx < mcux && !stop; mx++) {
+                        for (size_t which : order) {
+                            Component &c = comps[which];
+                            for (int by = 0; by < c.v; by++)
+                                for (int bx = 0; bx < c.h; bx++) codeBlock(c, which, mx * c.h + bx, my * c.v + by);
+                        }
+                        mcuDone();
+                    }
             }
+            scans++;
+            pos = size_t(br.p - d.data());       // at the marker that ended the entropy-coded data (or where the reader stopped)
+            continue;
+        }
+        pos = segEnd;
+    }
+    if (progressive) {                           // dequantise (16-bit products, like the stored baseline coefficients) + inverse DCT
+        for (size_t k = 0; k < comps.size(); k++) {
+            Component &c = comps[k];
+            if (!quantDefined[c.tq]) throw std::runtime_error("JPEG: missing table");
+            const int bw = (c.cols + 7) >> 3, bh = (c.rows + 7) >> 3;
+            for (int by = 0; by < bh; by++)
+                for (int bx = 0; bx < bw; bx++) {
+                    short *blk = &coeff[k][(size_t(by) * size_t(c.w2 / 8) + size_t(bx)) * 64];
+                    for (int i = 0; i < 64; i++) blk[i] = short(blk[i] * quant[c.tq][i]);
+                    idctBlock(&c.plane[size_t(by) * 8 * size_t(c.w2) + size_t(bx) * 8], c.w2, blk);
+                }
         }
     }
     // ---- upsample + colour convert
@@ -408,21 +536,45 @@ void decodePng(const std::vector<uint8_t> &d, int &width, int &height, std::vect
         pos += 12 + size_t(len);
     }
     if (!haveHeader || width <= 0 || height <= 0) throw std::runtime_error("PNG: no header");
-    if (interlace) throw std::runtime_error("PNG: interlaced files are not supported");
+    if (interlace > 1) throw std::runtime_error("PNG: bad interlace method");
     if (!(depth == 8 || depth == 16 || (colour == 3 && (depth == 1 || depth == 2 || depth == 4)) || (colour == 0 && depth < 8)))
         throw std::runtime_error("PNG: unsupported bit depth");
     const int channels = colour == 0 ? 1 : colour == 2 ? 3 : colour == 3 ? 1 : colour == 4 ? 2 : colour == 6 ? 4 : 0;
     if (!channels) throw std::runtime_error("PNG: bad colour type");
     const size_t bpp = std::max<size_t>(1, size_t(channels) * size_t(depth) / 8);          // filter distance in bytes
-    const size_t stride = (size_t(width) * size_t(channels) * size_t(depth) + 7) / 8;
-    std::vector<uint8_t> raw((stride + 1) * size_t(height));
+    // the image is one pass, or the seven reduced images of Adam7 (RFC 2083 section 2.6): pixel (x, y) of a pass is pixel
+    // (x0 + x * dx, y0 + y * dy) of the image; every pass is filtered on its own, empty passes have no bytes
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const Pass whole = {0, 0, 1, 1};
+    const Pass *passes = interlace ? adam7 : &whole;
+    const int numPasses = interlace ? 7 : 1;
+    auto passWidth = [&](const Pass &ps) { return (width - ps.x0 + ps.dx - 1) / ps.dx; };
+    auto passHeight = [&](const Pass &ps) { return (height - ps.y0 + ps.dy - 1) / ps.dy; };
+    auto passStride = [&](int pw) { return (size_t(pw) * size_t(channels) * size_t(depth) + 7) / 8; };
+    size_t rawSize = 0;
+    for (int ip = 0; ip < numPasses; ip++) {
+        const int pw = passWidth(passes[ip]), ph = passHeight(passes[ip]);
+        if (pw > 0 && ph > 0) rawSize += (passStride(pw) + 1) * size_t(ph);
+    }
+    // deflate expands at most 1032 : 1: a header whose image cannot come out of the IDAT bytes present is refused before the
+    // (possibly gigabytes of) scanlines and pixels are allocated
+    if (uint64_t(width) * uint64_t(height) > (1ull << 28) || uint64_t(rawSize) > 1032ull * idat.size() + 1024ull)
+        throw std::runtime_error("PNG: the image size does not fit the file");
+    std::vector<uint8_t> raw(rawSize);
     uLongf rawLen = uLongf(raw.size());
     int zr = uncompress(raw.data(), &rawLen, idat.data(), uLong(idat.size()));
     if (zr != Z_OK || rawLen != raw.size()) throw std::runtime_error("PNG: inflate failed");
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
     rgba.assign(size_t(width) * size_t(height) * 4, 255);
-    for (int y = 0; y < height; y++) {
-        const uint8_t *line = &raw[(stride + 1) * size_t(y)];
+    size_t rawPos = 0;
+    for (int ip = 0; ip < numPasses; ip++) {
+    const Pass ps = passes[ip];
+    const int pw = passWidth(ps), ph = passHeight(ps);
+    if (pw <= 0 || ph <= 0) continue;
+    const size_t stride = passStride(pw);
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    for (int y = 0; y < ph; y++) {
+        const uint8_t *line = &raw[rawPos + (stride + 1) * size_t(y)];
         const int filter = line[0];
         for (size_t i = 0; i < stride; i++) {
             const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
@@ -437,8 +589,9 @@ void decodePng(const std::vector<uint8_t> &d, int &width, int &height, std::vect
             }
             cur[i] = uint8_t(v);
         }
-        uint8_t *out = &rgba[size_t(y) * size_t(width) * 4];
-        for (int x = 0; x < width; x++) {
+        uint8_t *outRow = &rgba[size_t(ps.y0 + y * ps.dy) * size_t(width) * 4];
+        for (int x = 0; x < pw; x++) {
+            uint8_t *out = outRow + size_t(ps.x0 + x * ps.dx) * 4;
             int s[4] = {0, 0, 0, 255};
             for (int ch = 0; ch < channels; ch++) {
                 if (depth == 8) s[ch] = cur[size_t(x) * size_t(channels) + size_t(ch)];
@@ -452,23 +605,25 @@ void decodePng(const std::vector<uint8_t> &d, int &width, int &height, std::vect
                 int g = s[0], a = 255;
                 if (depth < 8) g = g * (255 / ((1 << depth) - 1));
                 if (trns.size() >= 2 && depth <= 8 && cur.size() && s[0] == ((int(trns[0]) << 8 | trns[1]) & ((1 << depth) - 1))) a = 0;
-                out[4 * x] = out[4 * x + 1] = out[4 * x + 2] = uint8_t(g); out[4 * x + 3] = uint8_t(a);
+                out[0] = out[1] = out[2] = uint8_t(g); out[3] = uint8_t(a);
             } else if (colour == 2) {
                 int a = 255;
                 if (trns.size() >= 6 && depth == 8 && s[0] == trns[1] && s[1] == trns[3] && s[2] == trns[5]) a = 0;
-                out[4 * x] = uint8_t(s[0]); out[4 * x + 1] = uint8_t(s[1]); out[4 * x + 2] = uint8_t(s[2]); out[4 * x + 3] = uint8_t(a);
+                out[0] = uint8_t(s[0]); out[1] = uint8_t(s[1]); out[2] = uint8_t(s[2]); out[3] = uint8_t(a);
             } else if (colour == 3) {
                 const size_t idx = size_t(s[0]);
                 if (idx * 3 + 2 >= palette.size()) throw std::runtime_error("PNG: palette index out of range");
-                out[4 * x] = palette[idx * 3]; out[4 * x + 1] = palette[idx * 3 + 1]; out[4 * x + 2] = palette[idx * 3 + 2];
-                out[4 * x + 3] = idx < trns.size() ? trns[idx] : 255;
+                out[0] = palette[idx * 3]; out[1] = palette[idx * 3 + 1]; out[2] = palette[idx * 3 + 2];
+                out[3] = idx < trns.size() ? trns[idx] : 255;
             } else if (colour == 4) {
-                out[4 * x] = out[4 * x + 1] = out[4 * x + 2] = uint8_t(s[0]); out[4 * x + 3] = uint8_t(s[1]);
+                out[0] = out[1] = out[2] = uint8_t(s[0]); out[3] = uint8_t(s[1]);
             } else {
-                out[4 * x] = uint8_t(s[0]); out[4 * x + 1] = uint8_t(s[1]); out[4 * x + 2] = uint8_t(s[2]); out[4 * x + 3] = uint8_t(s[3]);
+                out[0] = uint8_t(s[0]); out[1] = uint8_t(s[1]); out[2] = uint8_t(s[2]); out[3] = uint8_t(s[3]);
             }
         }
         prev.swap(cur);
+    }
+    rawPos += (stride + 1) * size_t(ph);
     }
 }
 

@@ -48,13 +48,46 @@ def test_bad_files_fail_loudly(tmp_path):
     with pytest.raises(P.B200ptError):
         P.read_image_file(str(tmp_path / "missing.jpg"))
     bad = tmp_path / "bad.jpg"
-    bad.write_bytes(b"\xff\xd8\xff\xc2" + b"\x00" * 64)        # progressive frame header
+    bad.write_bytes(b"\xff\xd8\xff\xc2" + b"\x00" * 64)        # frame header without a body
     with pytest.raises(P.B200ptError):
         P.read_image_file(str(bad))
+    arith = tmp_path / "arith.jpg"
+    arith.write_bytes(b"\xff\xd8\xff\xc9\x00\x0b\x08\x00\x08\x00\x08\x01\x01\x11\x00" + b"\x00" * 32)   # SOF9: arithmetic coding
+    with pytest.raises(P.B200ptError):
+        P.read_image_file(str(arith))
     junk = tmp_path / "junk.png"
     junk.write_bytes(b"not an image at all")
     with pytest.raises(P.B200ptError):
         P.read_image_file(str(junk))
+
+
+def test_interlaced_png_equals_plain_png(tmp_path):
+    """Adam7 (RFC 2083 section 2.6) only reorders the pixels: the interlaced and the plain file of the same samples must decode to
+    the same RGBA bytes — every colour type and bit depth, sizes that leave some of the seven passes empty, all five filters."""
+    import sys
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests", "golden"))
+    import make_interlaced_png as M
+    P = helpers.pt()
+    for (w, h) in ((1, 1), (2, 3), (5, 2), (8, 8), (9, 17), (33, 20)):
+        for name, colour, depth in M.cases():
+            out = []
+            for interlace in (0, 1):
+                path = str(tmp_path / ("%s_%dx%d_%d.png" % (name, w, h, interlace)))
+                M.make(path, name, colour, depth, w, h, interlace, seed=w * 100 + h)
+                out.append(P.read_image_file(path))
+            assert out[0].shape == (h, w, 4) and np.array_equal(out[0], out[1]), (name, w, h)
+
+
+def test_progressive_jpeg_fixture_kinds():
+    """the committed fixtures do cover what their names say (SOF2 frames, restart markers, several scans)"""
+    img_dir = os.path.join(helpers.ROOT, "tests", "golden", "images")
+    for name, sof, rst in (("prog_444.jpg", 0xC2, False), ("prog_422.jpg", 0xC2, False), ("prog_420.jpg", 0xC2, False), ("prog_gray.jpg", 0xC2, False),
+                           ("prog_rst.jpg", 0xC2, True), ("base_rst.jpg", 0xC0, True)):
+        d = open(os.path.join(img_dir, name), "rb").read()
+        markers = [d[i + 1] for i in range(len(d) - 1) if d[i] == 0xFF and d[i + 1] not in (0x00, 0xFF)]
+        assert sof in markers and (0xD0 in markers) == rst, name
+        assert markers.count(0xDA) >= (2 if sof == 0xC2 else 1), name
+        assert "tests/golden/images/" + name in DIGESTS
 
 
 def test_sponza_scene_loads_with_textures():
@@ -160,3 +193,34 @@ def test_corrupt_jpeg_segments_raise(tmp_path):
         assert P.read_image_file(p).ndim == 3
     except P.B200ptError:
         pass
+
+
+def test_corrupted_bitmaps_raise_or_decode_but_never_hang(tmp_path):
+    """Seeded byte flips in the header region and truncations of every fixture (progressive / restart JPEGs, Adam7 PNGs): the
+    decoders either return an image or raise the loader's error; a corrupt size field is refused before it becomes an
+    allocation of gigabytes (the whole loop runs in a second or two)."""
+    import glob
+    import time
+    P = helpers.pt()
+    rng = np.random.default_rng(2)
+    files = sorted(glob.glob(os.path.join(helpers.ROOT, "tests", "golden", "images", "*")))
+    t0 = time.time()
+    outcomes = {"ok": 0, "raised": 0}
+    for it in range(600):
+        f = files[it % len(files)]
+        d = bytearray(open(f, "rb").read())
+        if rng.integers(0, 3) == 0:
+            d = d[:rng.integers(1, len(d))]
+        else:
+            for _ in range(rng.integers(1, 6)):
+                d[rng.integers(2, min(len(d), 400))] = rng.integers(0, 256)
+        p = str(tmp_path / ("fuzz" + os.path.splitext(f)[1]))
+        open(p, "wb").write(d)
+        try:
+            img = P.read_image_file(p)
+            assert img.ndim == 3 and img.shape[2] == 4
+            outcomes["ok"] += 1
+        except P.B200ptError:
+            outcomes["raised"] += 1
+    assert outcomes["ok"] > 20 and outcomes["raised"] > 200, outcomes
+    assert time.time() - t0 < 60
