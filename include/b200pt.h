@@ -286,7 +286,8 @@ typedef struct b200pt_stats {
     float ms_guiding_gather;                /* device time: all-gather of the fitted mixtures */
 } b200pt_stats;
 
-#define B200PT_MAX_GUIDING_SPLITS 9          /* 512 initial regions; adaptive refinement (splitRegions) may grow them to 1024 */
+#define B200PT_MAX_GUIDING_SPLITS 11         /* 2048 initial regions; adaptive refinement (splitRegions) may double the initial count
+                                              (per-region buffers: 1024 regions up to 9 splits, 4096 for 10 and 11) */
 typedef struct b200pt_ctx b200pt_ctx;       /* opaque, one per GPU */
 typedef struct b200pt_scene b200pt_scene;   /* opaque host-side scene (loader output) */
 

@@ -318,7 +318,7 @@ int b200pt_create(int device_ordinal, int width, int height, int ic_size, int gu
     if (!out || width <= 0 || height <= 0 || ic_size < 0 || guiding_splits < 0)
         return setError(B200PT_E_INVALID, "b200pt_create: bad arguments");
     if (guiding_splits > B200PT_MAX_GUIDING_SPLITS)
-        return setError(B200PT_E_INVALID, "b200pt_create: GUIDING_SPLITS > 9 is not supported (the device sort and plan handle at most 1024 regions, "
+        return setError(B200PT_E_INVALID, "b200pt_create: GUIDING_SPLITS > 11 is not supported (the device sort and plan handle at most 4096 regions, "
                                           "and adaptive region refinement needs head room above 2^splits)");
     int n = b200pt_device_count();
     if (n <= 0) return setError(B200PT_E_NODEVICE, "b200pt_create: no CUDA device visible (libb200pt has no CPU fallback)");

@@ -37,7 +37,8 @@ namespace b200pt {
 // accumulators to local memory instead.
 #define G_NO_HOIST() asm volatile("" ::: "memory")
 #define SORT_TILE 2048              // records per warp in the counting sort
-#define SORT_WARPS 8                // warps per block in the counting sort
+#define SORT_WARPS 8                // warps per block in the counting sort (at most; GuidingState::update uses fewer when R is large)
+#define G_PLAN_MAX_REGIONS 4096     // what k_plan's shared arrays hold = the largest maxRegions
 
 static inline float __int_as_float_host(int i) { float f; memcpy(&f, &i, sizeof(f)); return f; }
 static void splitAabb(const b200pt_aabb &b, b200pt_aabb &l, b200pt_aabb &r) {   // src/Shapes.h:32-46, axis = largest
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_count(const b200pt_dir
                                                                 uint32_t *__restrict__ tileCounts /* [tiles][R] */, uint32_t numTiles) {
     extern __shared__ uint32_t hist[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * SORT_WARPS + warp;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + warp;      // 8 warps per block, fewer when R histograms of 8 warps exceed 48 KB
     uint32_t *h = hist + warp * R;
     for (uint32_t i = lane; i < R; i += 32) h[i] = 0;
     __syncwarp();
@@ -129,20 +130,24 @@ struct GPlanSummary {
 __global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allCounts, int N, int me, uint32_t R, uint32_t stride, int peerMode,
                                                uint32_t *srcStart, uint32_t *regionBegin, uint32_t *regionCount, uint32_t *regionOffset,
                                                uint32_t *activeRegions, uint32_t *totalAll, uint8_t *ownerOut, uint32_t *regionSlot, GSegment *segments, GPlanSummary *summary) {
-    __shared__ uint32_t total[1024];
-    __shared__ uint16_t order[1024], binOf[1024], regionOfBin[1024];
-    __shared__ uint8_t own[1024];
+    __shared__ uint32_t total[G_PLAN_MAX_REGIONS];
+    __shared__ uint16_t order[G_PLAN_MAX_REGIONS], binOf[G_PLAN_MAX_REGIONS], regionOfBin[G_PLAN_MAX_REGIONS];
+    __shared__ uint8_t own[G_PLAN_MAX_REGIONS];
     __shared__ uint32_t firstBin[B200PT_MAX_RANKS + 1], sliceStart[B200PT_MAX_RANKS], stageStart[B200PT_MAX_RANKS], recvCount[B200PT_MAX_RANKS];
     const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    uint32_t v = 0;
-    if (t < R) for (int s = 0; s < N; s++) v += allCounts[size_t(s) * stride + t];
-    total[t] = v;
+    // (per-region work: thread t takes regions t, t + 1024, ...)
+    for (uint32_t g = t; g < R; g += 1024u) {
+        uint32_t v = 0;
+        for (int s = 0; s < N; s++) v += allCounts[size_t(s) * stride + g];
+        total[g] = v;
+    }
     __syncthreads();
-    if (t < R) {                                   // position in the order (total descending, region id ascending)
+    for (uint32_t g = t; g < R; g += 1024u) {     // position in the order (total descending, region id ascending)
+        const uint32_t v = total[g];
         uint32_t rk = 0;
-        for (uint32_t u = 0; u < R; u++) rk += (total[u] > v) || (total[u] == v && u < t);
-        order[rk] = uint16_t(t);
-        totalAll[t] = v;
+        for (uint32_t u = 0; u < R; u++) rk += (total[u] > v) || (total[u] == v && u < g);
+        order[rk] = uint16_t(g);
+        totalAll[g] = v;
     }
     __syncthreads();
     if (t == 0) {
@@ -161,16 +166,16 @@ __global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allC
         summary->numActive = numActive; summary->ownedSamples = loads[me]; summary->totalSamples = tot;
     }
     __syncthreads();
-    if (t < R) {                                   // bins: regions ordered by (owner, region id)
+    for (uint32_t g = t; g < R; g += 1024u) {     // bins: regions ordered by (owner, region id)
         uint32_t b = 0;
-        for (uint32_t u = 0; u < R; u++) b += (own[u] < own[t]) || (own[u] == own[t] && u < t);
-        binOf[t] = uint16_t(b); regionOfBin[b] = uint16_t(t);
-        ownerOut[t] = own[t];
-        regionCount[t] = own[t] == me ? total[t] : 0u;
+        for (uint32_t u = 0; u < R; u++) b += (own[u] < own[g]) || (own[u] == own[g] && u < g);
+        binOf[g] = uint16_t(b); regionOfBin[b] = uint16_t(g);
+        ownerOut[g] = own[g];
+        regionCount[g] = own[g] == me ? total[g] : 0u;
     }
     if (t <= unsigned(N)) { uint32_t c = 0; for (uint32_t u = 0; u < R; u++) c += own[u] < t; firstBin[t] = c; }
     __syncthreads();
-    if (t < R) regionSlot[t] = own[t] == me ? uint32_t(binOf[t]) - firstBin[me] : 0u;      // position among this rank's regions
+    for (uint32_t g = t; g < R; g += 1024u) regionSlot[g] = own[g] == me ? uint32_t(binOf[g]) - firstBin[me] : 0u;      // position among this rank's regions
     for (int s = int(warp); s < N; s += 32) {      // every rank's sorted layout: exclusive scan of its counts over the bins
         uint32_t run = 0;
         for (uint32_t base = 0; base < R; base += 32) {
@@ -217,19 +222,20 @@ __global__ void __launch_bounds__(1024) k_plan(const uint32_t *__restrict__ allC
         summary->numSegments = (firstBin[me + 1] - firstBin[me]) * uint32_t(N);
     }
     __syncthreads();
-    if (t < R && own[t] == me) {
-        const uint32_t idx = binOf[t] - firstBin[me];
-        uint32_t dst = regionBegin[t];
+    for (uint32_t g = t; g < R; g += 1024u) {
+        if (own[g] != me) continue;
+        const uint32_t idx = binOf[g] - firstBin[me];
+        uint32_t dst = regionBegin[g];
         for (int s = 0; s < N; s++) {
-            const uint32_t len = allCounts[size_t(s) * stride + t];
-            uint32_t off = srcStart[size_t(s) * stride + t];
+            const uint32_t len = allCounts[size_t(s) * stride + g];
+            uint32_t off = srcStart[size_t(s) * stride + g];
             if (!peerMode && s != me) off = stageStart[s] + (off - sliceStart[s]);
             segments[size_t(idx) * N + s] = GSegment{uint32_t(s), off, dst, len};
             dst += len;
         }
     }
     if (N == 1) {                                  // region-order offsets of the sorted buffer (parity hook b200pt_guiding_get_sorted)
-        if (t < R) regionOffset[t] = regionBegin[t];
+        for (uint32_t g = t; g < R; g += 1024u) regionOffset[g] = regionBegin[g];
         if (t == 0) regionOffset[R] = uint32_t(summary->totalSamples);
     }
 }
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_scatter(const b200pt_d
                                                                   uint32_t *__restrict__ srcIndex) {
     extern __shared__ uint32_t hist[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * SORT_WARPS + warp;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + warp;      // 8 warps per block, fewer when R histograms of 8 warps exceed 48 KB
     uint32_t *h = hist + warp * R;
     if (tile < numTiles) for (uint32_t i = lane; i < R; i += 32) h[i] = regionStart[i] + tileOffsets[uint64_t(tile) * R + i];
     __syncwarp();
@@ -1379,7 +1385,10 @@ __global__ void __launch_bounds__(128) k_guiding_split_regions(GMix *mixes, b200
 int GuidingState::init(int splits, const float sceneMin[3], const float sceneMax[3], cudaStream_t stream) {
     release();
     regionCount = 1 << splits;
-    maxRegions = 1024;                              // what the device sort / plan handle; b200pt_create limits splits to 9 so adaptive refinement has room
+    // capacity of the per-region buffers: 1024 up to GUIDING_SPLITS 9 (512 initial regions), G_PLAN_MAX_REGIONS beyond (b200pt_create limits
+    // splits to B200PT_MAX_GUIDING_SPLITS = 11, 2048 initial regions) — adaptive refinement always has room to double the initial count
+    maxRegions = regionCount <= 512 ? 1024 : G_PLAN_MAX_REGIONS;
+    if (2 * regionCount > maxRegions) { error = "too many guiding regions (GUIDING_SPLITS <= 11)"; return B200PT_E_INVALID; }
     b200pt_aabb scene;
     for (int a = 0; a < 3; a++) {   // Aabb::addEpsilon, src/Shapes.h:48-53
         float extent = sceneMax[a] - sceneMin[a];
@@ -1589,7 +1598,7 @@ void GuidingState::closePeers() {
 int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, const b200pt_guiding_params &params, cudaStream_t stream,
                          b200pt_stats *stats, RankComm *rc) {
     if (!ready) { error = "guiding state not initialised"; return B200PT_E_STATE; }
-    if (regionCount > 1024) { error = "the device sort supports at most 1024 guiding regions (GUIDING_SPLITS <= 10)"; return B200PT_E_INVALID; }
+    if (regionCount > G_PLAN_MAX_REGIONS) { error = "the device sort supports at most 4096 guiding regions"; return B200PT_E_INVALID; }
     if (numSamples < 0 || numSamples > int64_t(0xfffffff0u)) { error = "bad sample count"; return B200PT_E_INVALID; }
     if (params.numInitialComponents < 1 || params.numInitialComponents > G_MAXK || params.maxItr < 0 || params.minItr < 0) {
         error = "bad guiding parameters"; return B200PT_E_INVALID;
@@ -1612,15 +1621,18 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     const bool peerMode = N > 1 && rc->peerMode;
     const uint32_t R = uint32_t(regionCount), stride = uint32_t(maxRegions);
     const uint32_t numTiles = uint32_t((uint64_t(numSamples) + SORT_TILE - 1) / SORT_TILE);
-    const uint32_t sortBlocks = (numTiles + SORT_WARPS - 1) / SORT_WARPS;
-    const size_t sortSmem = size_t(SORT_WARPS) * R * sizeof(uint32_t);
+    // one histogram of R bins per warp in shared memory: 8 warps per block while that fits the 48 KB every kernel may use, fewer beyond
+    uint32_t sortWarps = SORT_WARPS;
+    while (sortWarps > 1u && size_t(sortWarps) * R * sizeof(uint32_t) > 48u * 1024u) sortWarps >>= 1;
+    const uint32_t sortBlocks = (numTiles + sortWarps - 1) / sortWarps;
+    const size_t sortSmem = size_t(sortWarps) * R * sizeof(uint32_t);
     unsigned launches = 0;
     G_TRY(cudaEventRecord(ev[0], stream));
     G_TRY(cudaMemsetAsync(devScalars, 0, 2 * sizeof(unsigned long long), stream));
     // ---- count (local), exchange the counts, plan
     uint32_t *myCounts = allCounts + size_t(me) * stride;
     if (numTiles) {
-        k_sort_count<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles);
+        k_sort_count<<<sortBlocks, sortWarps * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles);
         k_sort_scan_tiles<<<R, 256, 0, stream>>>(tileCounts, numTiles, R, myCounts);
         launches += 2;
     } else {
@@ -1635,7 +1647,7 @@ int GuidingState::update(b200pt_directional_data *samples, int64_t numSamples, c
     G_TRY(cudaEventRecord(ev[2], stream));
     // ---- scatter (sorted by (owner, region); preFit applied), while the host waits for the plan
     if (numTiles) {
-        k_sort_scatter<<<sortBlocks, SORT_WARPS * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles, srcStart + size_t(me) * stride, aabbs,
+        k_sort_scatter<<<sortBlocks, sortWarps * 32, sortSmem, stream>>>(samples, uint64_t(numSamples), R, tileCounts, numTiles, srcStart + size_t(me) * stride, aabbs,
                                                                           params.useParallaxCompensation, dirw, pdfDist, srcIndex);
         launches++;
     }
@@ -1806,7 +1818,7 @@ int GuidingState::splitRegions(const b200pt_guiding_params &params, cudaStream_t
     const int currentRegionCount = regionCount;
     for (int r = 0; r < currentRegionCount; r++) {
         if (!(numSamples[size_t(r)] > params.samplesForRegionSplit)) continue;
-        if (regionCount >= maxRegions) break;          // the device sort handles at most 1024 regions: refinement stops there
+        if (regionCount >= maxRegions) break;          // the per-region buffers are full: refinement stops there
         b200pt_aabb l, rr;
         splitAabb(hostAabbs[size_t(r)], l, rr);
         hostAabbs[size_t(r)] = l;

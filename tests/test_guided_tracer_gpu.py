@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 NT = os.cpu_count() or 1
 INVALID = 0xFFFFFFFF
 W, H = 96, 54
+P_MAX_SPLITS = 11          # B200PT_MAX_GUIDING_SPLITS (include/b200pt.h)
 
 
 def _pair(scene_name, splits):
@@ -67,6 +68,28 @@ def test_recorded_samples_match_oracle(scene_name, spp):
     gi, ci = r.read_image()[..., :3].astype(np.float64), o.image()[..., :3].astype(np.float64)
     rel = np.abs(gi - ci) / np.maximum(np.abs(ci), 1e-3)
     assert (rel <= 1e-4).all(axis=-1).mean() >= 0.99
+
+
+def test_recorded_regions_with_the_deepest_tree():
+    """GUIDING_SPLITS = 11 (B200PT_MAX_GUIDING_SPLITS, 2048 regions): the region every recorded sample lands in against the
+    oracle's point-in-box search, and one refit of those samples (sort by 2048 keys, plan, fit) leaves valid mixtures."""
+    P, scene, r, o = _pair("cornell-dielectric", P_MAX_SPLITS)
+    assert len(r.guiding_aabbs()) == 1 << P_MAX_SPLITS
+    pc = P.default_push_constants(randomUInt=P.tea(4, 0xC0FFEE), previousFrames=0, samplesPerPixel=2, enableMIS=1, updateGuiding=1)
+    r.render_frame(pc)
+    o.render_region(pc, threads=NT)
+    compare_recorded_samples(P, r, o)
+    g = r.guiding_get_samples()
+    valid = g["flags"] != INVALID
+    assert valid.any() and g["flags"][valid].max() < (1 << P_MAX_SPLITS) and len(np.unique(g["flags"][valid])) > 200
+    r.guiding_update(P.default_guiding_params())
+    vm = r.guiding_get_vmms()
+    K = vm["usedDistributions"]
+    assert (K >= 1).all() and (K <= 16).all()
+    for i in np.unique(g["flags"][valid])[:64]:
+        assert abs(float(vm[i]["pi"][:K[i]].sum()) - 1.0) < 1e-4 and np.isfinite(vm[i]["thetas"]["k"][:K[i]]).all()
+    with pytest.raises(P.B200ptError):
+        P.Renderer(16, 16, 0, P_MAX_SPLITS + 1)
 
 
 def _synthetic_vmms(P, aabbs, seed):

@@ -56,7 +56,7 @@ def reference_plan(counts, me, peer_mode):
     return dict(owner=owner, active=active, src_start=src_start, begin=begin, mine=mine, segs=np.array(segs, np.int64).reshape(-1, 4), loads=loads, total=total)
 
 
-@pytest.mark.parametrize("nranks,splits,seed", [(1, 3, 0), (2, 5, 1), (4, 8, 2), (8, 8, 3), (8, 2, 4), (3, 6, 5)])
+@pytest.mark.parametrize("nranks,splits,seed", [(1, 3, 0), (2, 5, 1), (4, 8, 2), (8, 8, 3), (8, 2, 4), (3, 6, 5), (2, 11, 6), (4, 10, 7)])
 def test_plan_matches_numpy_restatement(nranks, splits, seed):
     P = helpers.pt()
     scene = P.Scene(helpers.scene_path("cornell-dielectric"))
