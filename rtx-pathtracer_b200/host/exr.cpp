@@ -1,7 +1,8 @@
 // Minimal OpenEXR scanline IO for the headless host: replaces CommonOps::writeEXR / readEXR
 // (src/CommonOps.cpp:12-65), which link OpenEXR 2.5.  Writer: three FLOAT channels, no compression.
-// Reader: HALF/FLOAT channels, compression NONE / ZIPS / ZIP (what Mitsuba and the reference app write).
-// PIZ (used by the scenes' envmap.exr files) is not implemented yet — reported as an error, never silently skipped.
+// Reader: HALF / FLOAT channels, compression NONE / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A — everything OpenEXR's
+// RgbaInputFile reads from a scanline file except DWAA / DWAB, which (like tiled, multipart and deep files) are reported as
+// an error, never silently skipped.  Checked against OpenEXR's own decode (tests/golden/exr_digests.json).
 #include "scene.h"
 #include <algorithm>
 #include <cstring>
@@ -280,6 +281,122 @@ void pizDecompress(const unsigned char *src, size_t srcLen, unsigned char *dst, 
             o += n * 2;
         }
 }
+
+// ---- RLE (compression 1): runs of signed-count bytes, then the same predictor + byte de-interleave as ZIP
+void rleDecompress(const unsigned char *src, size_t srcLen, unsigned char *dst, size_t dstLen) {
+    size_t i = 0, o = 0;
+    while (i < srcLen) {
+        const int count = static_cast<signed char>(src[i++]);
+        if (count < 0) {                                   // -count literal bytes
+            const size_t n = size_t(-count);
+            if (n > srcLen - i || n > dstLen - o) throw std::runtime_error("EXR/RLE: run past the end of the chunk");
+            memcpy(dst + o, src + i, n);
+            i += n; o += n;
+        } else {                                           // the next byte count + 1 times
+            const size_t n = size_t(count) + 1;
+            if (i >= srcLen || n > dstLen - o) throw std::runtime_error("EXR/RLE: run past the end of the chunk");
+            memset(dst + o, src[i++], n);
+            o += n;
+        }
+    }
+    if (o != dstLen) throw std::runtime_error("EXR/RLE: chunk of the wrong size");
+}
+
+// ---- PXR24 (compression 5): zlib over byte planes; per scanline and channel the bytes of the pixel-to-pixel differences are
+// stored most significant plane first (HALF: 2 planes, FLOAT: 3 planes — the float's low byte is dropped)
+void pxr24Decompress(const unsigned char *src, size_t srcLen, unsigned char *dst, int width, int lines, const std::vector<int> &chanTypes) {
+    size_t planeBytes = 0;
+    for (int t : chanTypes) planeBytes += size_t(width) * (t == 1 ? 2 : 3);
+    std::vector<unsigned char> tmp(planeBytes * size_t(lines));
+    uLongf dl = uLongf(tmp.size());
+    if (uncompress(tmp.data(), &dl, src, uLong(srcLen)) != Z_OK || dl != tmp.size()) throw std::runtime_error("EXR/PXR24: zlib error");
+    const unsigned char *p = tmp.data();
+    unsigned char *o = dst;
+    const size_t n = size_t(width);
+    for (int y = 0; y < lines; y++)
+        for (int t : chanTypes) {
+            uint32_t pixel = 0;
+            if (t == 1) {
+                for (size_t x = 0; x < n; x++) {
+                    pixel += (uint32_t(p[x]) << 8) | uint32_t(p[n + x]);
+                    const uint16_t h = uint16_t(pixel);
+                    memcpy(o, &h, 2); o += 2;
+                }
+                p += 2 * n;
+            } else {
+                for (size_t x = 0; x < n; x++) {
+                    pixel += (uint32_t(p[x]) << 24) | (uint32_t(p[n + x]) << 16) | (uint32_t(p[2 * n + x]) << 8);
+                    memcpy(o, &pixel, 4); o += 4;
+                }
+                p += 3 * n;
+            }
+        }
+}
+
+// ---- B44 / B44A (compression 6 / 7): HALF channels in 4x4 blocks of 14 bytes (B44A: 3 bytes for a block of one value), stored
+// channel after channel; FLOAT channels uncompressed.  A block holds its first value and 6-bit running differences, on 16-bit
+// codes in which the ordering of the half values is monotonic (sign bit flipped for positives, all bits for negatives).
+inline uint16_t b44FromOrdered(uint16_t s) { return (s & 0x8000u) ? uint16_t(s & 0x7fffu) : uint16_t(~s); }
+void b44Unpack14(const unsigned char b[14], uint16_t s[16]) {
+    const uint32_t shift = b[2] >> 2, bias = 0x20u << shift;
+    auto d = [&](uint32_t six) { return (six & 0x3fu) << shift; };
+    s[0] = uint16_t((uint32_t(b[0]) << 8) | b[1]);
+    s[4] = uint16_t(s[0] + d((uint32_t(b[2]) << 4) | (b[3] >> 4)) - bias);
+    s[8] = uint16_t(s[4] + d((uint32_t(b[3]) << 2) | (b[4] >> 6)) - bias);
+    s[12] = uint16_t(s[8] + d(b[4]) - bias);
+    s[1] = uint16_t(s[0] + d(b[5] >> 2) - bias);
+    s[5] = uint16_t(s[4] + d((uint32_t(b[5]) << 4) | (b[6] >> 4)) - bias);
+    s[9] = uint16_t(s[8] + d((uint32_t(b[6]) << 2) | (b[7] >> 6)) - bias);
+    s[13] = uint16_t(s[12] + d(b[7]) - bias);
+    s[2] = uint16_t(s[1] + d(b[8] >> 2) - bias);
+    s[6] = uint16_t(s[5] + d((uint32_t(b[8]) << 4) | (b[9] >> 4)) - bias);
+    s[10] = uint16_t(s[9] + d((uint32_t(b[9]) << 2) | (b[10] >> 6)) - bias);
+    s[14] = uint16_t(s[13] + d(b[10]) - bias);
+    s[3] = uint16_t(s[2] + d(b[11] >> 2) - bias);
+    s[7] = uint16_t(s[6] + d((uint32_t(b[11]) << 4) | (b[12] >> 4)) - bias);
+    s[11] = uint16_t(s[10] + d((uint32_t(b[12]) << 2) | (b[13] >> 6)) - bias);
+    s[15] = uint16_t(s[14] + d(b[13]) - bias);
+    for (int i = 0; i < 16; i++) s[i] = b44FromOrdered(s[i]);
+}
+void b44Decompress(const unsigned char *src, size_t srcLen, unsigned char *dst, int width, int lines, const std::vector<int> &chanTypes) {
+    // planes channel after channel, then re-interleaved per scanline like the uncompressed layout
+    std::vector<std::vector<unsigned char>> planes(chanTypes.size());
+    size_t pos = 0;
+    for (size_t c = 0; c < chanTypes.size(); c++) {
+        const size_t bytes = chanTypes[c] == 1 ? 2 : 4;
+        planes[c].assign(size_t(width) * size_t(lines) * bytes, 0);
+        if (chanTypes[c] != 1) {                           // not HALF: raw
+            if (planes[c].size() > srcLen - pos) throw std::runtime_error("EXR/B44: truncated chunk");
+            memcpy(planes[c].data(), src + pos, planes[c].size());
+            pos += planes[c].size();
+            continue;
+        }
+        uint16_t *plane = reinterpret_cast<uint16_t *>(planes[c].data());
+        for (int y = 0; y < lines; y += 4)
+            for (int x = 0; x < width; x += 4) {
+                uint16_t s[16];
+                if (srcLen - pos < 3) throw std::runtime_error("EXR/B44: truncated chunk");
+                if (src[pos + 2] >= (13 << 2)) {           // one value for the whole block (3 bytes)
+                    const uint16_t v = b44FromOrdered(uint16_t((uint32_t(src[pos]) << 8) | src[pos + 1]));
+                    for (int k = 0; k < 16; k++) s[k] = v;
+                    pos += 3;
+                } else {
+                    if (srcLen - pos < 14) throw std::runtime_error("EXR/B44: truncated chunk");
+                    b44Unpack14(src + pos, s);
+                    pos += 14;
+                }
+                for (int j = 0; j < 4 && y + j < lines; j++)
+                    for (int k = 0; k < 4 && x + k < width; k++) plane[size_t(y + j) * size_t(width) + size_t(x + k)] = s[j * 4 + k];
+            }
+    }
+    unsigned char *o = dst;
+    for (int y = 0; y < lines; y++)
+        for (size_t c = 0; c < chanTypes.size(); c++) {
+            const size_t n = size_t(width) * (chanTypes[c] == 1 ? 2 : 4);
+            memcpy(o, planes[c].data() + size_t(y) * n, n);
+            o += n;
+        }
+}
 }  // namespace
 
 void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, int &height, bool viaHalf) {
@@ -335,10 +452,10 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
     if (w64 <= 0 || h64 <= 0 || w64 > 65536 || h64 > 65536 || chans.empty()) throw std::runtime_error("EXR: bad header " + path);
     width = int(w64); height = int(h64);
     int linesPerBlock;
-    if (comp == 0 || comp == 2) linesPerBlock = 1;
-    else if (comp == 3) linesPerBlock = 16;
-    else if (comp == 4) linesPerBlock = 32;
-    else throw std::runtime_error("EXR: compression type " + std::to_string(comp) + " not supported (only NONE/ZIPS/ZIP/PIZ): " + path);
+    if (comp == 0 || comp == 1 || comp == 2) linesPerBlock = 1;
+    else if (comp == 3 || comp == 5) linesPerBlock = 16;
+    else if (comp == 4 || comp == 6 || comp == 7) linesPerBlock = 32;
+    else throw std::runtime_error("EXR: compression type " + std::to_string(comp) + " not supported (NONE / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A are): " + path);
     size_t bytesPerLine = 0;
     for (auto &c : chans) {
         if (c.type != 1 && c.type != 2) throw std::runtime_error("EXR: only HALF/FLOAT channels supported");
@@ -367,10 +484,18 @@ void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, 
             std::vector<int> wordsPerPixel;
             for (auto &c : chans) wordsPerPixel.push_back(c.type == 1 ? 1 : 2);
             pizDecompress(src, size_t(sz), raw.data(), expect, width, lines, wordsPerPixel);
+        } else if (comp == 5 || comp == 6 || comp == 7) {
+            std::vector<int> chanTypes;
+            for (auto &c : chans) chanTypes.push_back(c.type);
+            if (comp == 5) pxr24Decompress(src, size_t(sz), raw.data(), width, lines, chanTypes);
+            else b44Decompress(src, size_t(sz), raw.data(), width, lines, chanTypes);
         } else {
             tmp.resize(expect);
-            uLongf dl = uLongf(expect);
-            if (uncompress(tmp.data(), &dl, src, uLong(sz)) != Z_OK || dl != expect) throw std::runtime_error("EXR: zlib error");
+            if (comp == 1) rleDecompress(src, size_t(sz), tmp.data(), expect);
+            else {
+                uLongf dl = uLongf(expect);
+                if (uncompress(tmp.data(), &dl, src, uLong(sz)) != Z_OK || dl != expect) throw std::runtime_error("EXR: zlib error");
+            }
             for (size_t k = 1; k < expect; k++) tmp[k] = (unsigned char)(int(tmp[k - 1]) + int(tmp[k]) - 128);
             size_t half = (expect + 1) / 2;
             for (size_t k = 0; k < expect; k++) raw[k] = (k & 1) ? tmp[half + k / 2] : tmp[k / 2];

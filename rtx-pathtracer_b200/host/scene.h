@@ -109,7 +109,7 @@ void mat4Mul(const float a[16], const float b[16], float out[16]);
 bool mat4Inverse(const float m[16], float out[16]);
 void mat4TransformPoint(const float m[16], const float p[3], float out[3]);
 
-// minimal EXR IO (scanline, NONE/ZIPS/ZIP compression, HALF/FLOAT channels)
+// EXR IO (scanline files; reader: NONE / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A, HALF / FLOAT channels; writer: NONE, FLOAT)
 void writeExrRGB(const std::string &path, const float *rgba, int width, int height);
 void readExrRGBA(const std::string &path, std::vector<float> &rgba, int &width, int &height, bool viaHalf);
 float halfToFloat(uint16_t h);

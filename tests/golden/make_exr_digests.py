@@ -1,6 +1,6 @@
 """Regenerates tests/golden/exr_digests.json: SHA-256 of the float32 RGB pixels that OpenEXR itself (through OpenCV's
 imread, build container only) decodes from the EXR files kept in this repository — the known answers for the host's own
-EXR reader (host/exr.cpp: NONE / ZIPS / ZIP / PIZ)."""
+EXR reader (host/exr.cpp: NONE / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A)."""
 import glob
 import hashlib
 import json
@@ -12,7 +12,7 @@ import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 out = {}
-for f in sorted(glob.glob(os.path.join(ROOT, "scenes", "**", "*.exr"), recursive=True)):
+for f in sorted(glob.glob(os.path.join(ROOT, "scenes", "**", "*.exr"), recursive=True) + glob.glob(os.path.join(ROOT, "tests", "golden", "exr", "*.exr"))):
     img = cv2.imread(f, cv2.IMREAD_UNCHANGED)
     # CommonOps::readEXR goes through Imf::RgbaInputFile: every value passes through half precision (a no-op for HALF files)
     rgb = np.ascontiguousarray(img[..., 2::-1].astype(np.float32).astype(np.float16).astype(np.float32))

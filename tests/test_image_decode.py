@@ -106,12 +106,13 @@ EXR_DIGESTS = json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "exr_
 @pytest.mark.parametrize("rel", sorted(EXR_DIGESTS))
 def test_exr_reader_matches_openexr_digest(rel):
     """host/exr.cpp against OpenEXR's own decode (digests made with tests/golden/make_exr_digests.py): the reference's
-    PIZ-compressed environment map and the uncompressed file our writer produces."""
+    PIZ-compressed environment map, the uncompressed file our writer produces, and one small HALF and FLOAT file per further
+    compression (tests/golden/exr, written by make_exr_fixtures.py)."""
     img = helpers.pt().read_exr(os.path.join(helpers.ROOT, rel))
     want = EXR_DIGESTS[rel]
     assert img.shape == (want["height"], want["width"], 4)
     assert hashlib.sha256(np.ascontiguousarray(img[..., :3]).tobytes()).hexdigest() == want["sha256"]
-    assert {EXR_DIGESTS[k]["compression"] for k in EXR_DIGESTS} >= {0, 4}
+    assert {EXR_DIGESTS[k]["compression"] for k in EXR_DIGESTS} >= {0, 1, 2, 3, 4, 5, 6, 7}        # every compression but DWAA / DWAB
 
 
 def _expect_loader_error(fn, path):
@@ -224,3 +225,29 @@ def test_corrupted_bitmaps_raise_or_decode_but_never_hang(tmp_path):
             outcomes["raised"] += 1
     assert outcomes["ok"] > 20 and outcomes["raised"] > 200, outcomes
     assert time.time() - t0 < 60
+
+
+def test_corrupted_exr_chunks_of_every_compression_raise_or_decode(tmp_path):
+    """Seeded byte flips and truncations of the RLE / ZIPS / ZIP / PXR24 / B44 / B44A fixtures: runs, byte planes and 4x4 blocks
+    that point past their chunk end in the loader's error, never in an out-of-bounds access."""
+    import glob
+    P = helpers.pt()
+    rng = np.random.default_rng(4)
+    files = sorted(glob.glob(os.path.join(helpers.ROOT, "tests", "golden", "exr", "*.exr")))
+    assert len(files) == 12
+    outcomes = {"ok": 0, "raised": 0}
+    for it in range(600):
+        d = bytearray(open(files[it % len(files)], "rb").read())
+        if rng.integers(0, 3) == 0:
+            d = d[:rng.integers(1, len(d))]
+        else:
+            for _ in range(rng.integers(1, 6)):
+                d[rng.integers(8, len(d))] = rng.integers(0, 256)
+        p = str(tmp_path / "fuzz.exr")
+        open(p, "wb").write(d)
+        try:
+            assert P.read_exr(p).shape[2] == 4
+            outcomes["ok"] += 1
+        except P.B200ptError:
+            outcomes["raised"] += 1
+    assert outcomes["ok"] > 50 and outcomes["raised"] > 200, outcomes
