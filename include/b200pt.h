@@ -307,6 +307,18 @@ int b200pt_destroy(b200pt_ctx *ctx);        /* RayTracingApp::cleanup, src/RayTr
  * the guiding region tree from the scene AABB (src/PathGuiding.cpp:11-24,81-104) and resets the IC. */
 int b200pt_set_scene(b200pt_ctx *ctx, const b200pt_scene_desc *scene);
 
+/* Host-only structural check of the acceleration structure b200pt_set_scene would build for `scene` (no context, no GPU, no
+ * traversal): flattens the instances to world-space triangles like set_scene, builds the BVH8 and verifies what the
+ * device traversal relies on — every primitive in exactly one leaf, every triangle inside the DEQUANTISED box of its slot
+ * and of all its ancestors' slots, consistent child / triangle indexing, the recorded depth.  The reference has no
+ * counterpart (its BLAS / TLAS come from the driver, src/SceneLoader.cpp:1101-1193); this is the CPU-side test hook of
+ * our builder.  The first six fields are violation counts (all 0 for a valid tree), the rest statistics. */
+typedef struct b200pt_bvh_report {
+    uint32_t missing_prims, duplicate_prims, outside_box, bad_meta, depth_mismatch, unreachable_nodes;
+    uint32_t num_nodes, num_tris, max_depth, inner_children, leaf_children;
+} b200pt_bvh_report;
+int b200pt_scene_bvh_check(const b200pt_scene_desc *scene, b200pt_bvh_report *report);
+
 /* replaces RayTracingApp::updateUniformBuffer (src/RayTracingApp.cpp:559-585); column-major mat4, inverses are
  * computed inside like :578-579 */
 int b200pt_set_camera(b200pt_ctx *ctx, const float view[16], const float proj[16]);

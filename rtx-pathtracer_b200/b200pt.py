@@ -100,6 +100,12 @@ _PC_FIELDS = [
     ("guidingPiPHighlightRegion", C.c_int32), ("guidingPiPShowSpheres", C.c_int32), ("guidingPiPSize", C.c_float)]
 
 
+class BvhReport(C.Structure):
+    """b200pt_bvh_report: the first six fields count violations (0 for a valid tree), the rest are statistics."""
+    _fields_ = [(n, C.c_uint32) for n in ("missing_prims", "duplicate_prims", "outside_box", "bad_meta", "depth_mismatch", "unreachable_nodes",
+                                          "num_nodes", "num_tris", "max_depth", "inner_children", "leaf_children")]
+
+
 class PushConstants(C.Structure):
     """RtPushConstant — src/RayTracingApp.h:116-165 (192 bytes)."""
     _fields_ = _PC_FIELDS
@@ -174,6 +180,7 @@ EXPORTS = [
     "b200pt_scene_free", "b200pt_scene_get_desc", "b200pt_scene_get_camera", "b200pt_camera_matrices", "b200pt_mat4_inverse", "b200pt_write_exr",
     "b200pt_read_exr", "b200pt_read_image_file", "b200pt_free",
     "b200pt_set_aovs", "b200pt_read_aovs", "b200pt_save_state", "b200pt_load_state", "b200pt_comm_unique_id", "b200pt_comm_init", "b200pt_comm_destroy", "b200pt_reduce_image", "b200pt_allgather_samples", "b200pt_guiding_update_all_ranks", "b200pt_guiding_update_all_ranks_device", "b200pt_guiding_plan_debug", "b200pt_comm_exchange_mode",
+    "b200pt_scene_bvh_check",
     "b200pt_app_init", "b200pt_app_scene_switched", "b200pt_app_begin_frame", "b200pt_app_end_frame", "b200pt_app_draw_frame"]
 
 _lib = None
@@ -196,6 +203,7 @@ def lib():
         L.b200pt_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.b200pt_destroy.argtypes = [C.c_void_p]
         L.b200pt_set_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+        L.b200pt_scene_bvh_check.argtypes = [C.POINTER(SceneDesc), C.POINTER(BvhReport)]
         L.b200pt_set_camera.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.b200pt_render_frame.argtypes = [C.c_void_p, C.POINTER(PushConstants)]
         L.b200pt_render_frames.argtypes = [C.c_void_p, C.POINTER(PushConstants), C.c_int]
@@ -330,6 +338,12 @@ class Scene:
     def camera_matrices(self, aspect):
         o, t, u, f = self.camera()
         return camera_matrices(o, t, u, f, aspect)
+
+    def bvh_check(self):
+        """Host-only structural check of the BVH8 that set_scene would build for this scene (b200pt_scene_bvh_check)."""
+        rep = BvhReport()
+        _check(lib().b200pt_scene_bvh_check(C.byref(self.desc), C.byref(rep)))
+        return rep
 
     @property
     def num_triangles(self):

@@ -464,44 +464,82 @@ static float srgbToLinear(uint8_t v) {
     return c <= 0.04045f ? c / 12.92f : b200pt_dm::powF((c + 0.055f) / 1.055f, 2.4f);
 }
 
+// Shared by b200pt_set_scene and b200pt_scene_bvh_check: per-model buffers concatenated, instances flattened to world-space
+// triangles (9 floats each); primVerts = global vertex ids + instance (| identity flag).  Returns what is wrong, or nullptr.
+static const char *flattenScene(const b200pt_scene_desc *s, std::vector<b200pt_vertex> &verts, std::vector<uint32_t> &inds, std::vector<int32_t> &vOff,
+                                std::vector<int32_t> &iOff, std::vector<float> &world, std::vector<int4> &primVerts) {
+    vOff.assign(size_t(std::max(1, s->num_models)), 0); iOff.assign(size_t(std::max(1, s->num_models)), 0);
+    for (int m = 0; m < s->num_models; m++) {
+        vOff[m] = int32_t(verts.size()); iOff[m] = int32_t(inds.size());
+        if (s->num_indices[m] % 3) return "index count not a multiple of 3";
+        verts.insert(verts.end(), s->vertices[m], s->vertices[m] + s->num_vertices[m]);
+        inds.insert(inds.end(), s->indices[m], s->indices[m] + s->num_indices[m]);
+        for (int k = 0; k < s->num_indices[m]; k++)
+            if (s->indices[m][k] >= uint32_t(s->num_vertices[m])) return "vertex index out of range";
+    }
+    for (int i = 0; i < s->num_instances; i++) {
+        const b200pt_instance &inst = s->instances[i];
+        int m = inst.modelIndex;
+        if (m < 0 || m >= s->num_models) return "instance model index out of range";
+        int nt = s->num_indices[m] / 3;
+        bool identity = true;
+        for (int k = 0; k < 16; k++) identity = identity && inst.transform[k] == (k % 5 == 0 ? 1.0f : 0.0f) && inst.normalTransform[k] == (k % 5 == 0 ? 1.0f : 0.0f);
+        for (int t = 0; t < nt; t++) {
+            int4 pv;
+            int *pvp = &pv.x;
+            for (int k = 0; k < 3; k++) {
+                uint32_t li = s->indices[m][3 * t + k];
+                float w[3];
+                mat4TransformPoint(inst.transform, s->vertices[m][li].pos, w);
+                world.insert(world.end(), w, w + 3);
+                pvp[k] = vOff[m] + int(li);
+            }
+            pv.w = int(uint32_t(i) | (identity ? PT_INSTANCE_IDENTITY : 0u));
+            primVerts.push_back(pv);
+        }
+    }
+    return nullptr;
+}
+
+int b200pt_scene_bvh_check(const b200pt_scene_desc *s, b200pt_bvh_report *report) {
+    if (!s || !report) return setError(B200PT_E_INVALID, "b200pt_scene_bvh_check: null argument");
+    try {
+        std::vector<b200pt_vertex> verts; std::vector<uint32_t> inds;
+        std::vector<int32_t> vOff, iOff;
+        std::vector<float> world; std::vector<int4> primVerts;
+        if (const char *bad = flattenScene(s, verts, inds, vOff, iOff, world, primVerts)) return setError(B200PT_E_INVALID, std::string("b200pt_scene_bvh_check: ") + bad);
+        Bvh8 bvh;
+        buildBvh8(world.data(), uint32_t(primVerts.size()), bvh);
+        // test knob: damage the tree before checking it, to show that the check notices (tests/test_scene.py)
+        if (const char *m = getenv("B200PT_BVH_CHECK_MUTATE")) {
+            const int kind = atoi(m);
+            Bvh8Node &n = bvh.nodes[bvh.nodes.size() / 2];
+            if (kind == 1) { for (int sl = 0; sl < 8; sl++) if (n.meta[sl]) { n.qhi[0][sl] = n.qlo[0][sl]; n.qhi[1][sl] = n.qlo[1][sl]; } }      // boxes collapsed to a line
+            else if (kind == 2 && bvh.tris.size() > 1) bvh.tris[1].prim = bvh.tris[0].prim;                    // one primitive twice, one lost
+            else if (kind == 3) { for (int sl = 0; sl < 8; sl++) if (n.meta[sl] && !((n.imask >> sl) & 1)) { n.meta[sl] = uint8_t((5u << 5) | (n.meta[sl] & 31u)); break; } }   // bad unary count
+            else if (kind == 4) bvh.maxDepth++;
+        }
+        Bvh8Report r;
+        validateBvh8(bvh, world.data(), uint32_t(primVerts.size()), r);
+        report->missing_prims = r.missingPrims; report->duplicate_prims = r.duplicatePrims; report->outside_box = r.outsideBox;
+        report->bad_meta = r.badMeta; report->depth_mismatch = r.depthMismatch; report->unreachable_nodes = r.unreachableNodes;
+        report->num_nodes = r.numNodes; report->num_tris = r.numTris; report->max_depth = r.maxDepth;
+        report->inner_children = r.innerChildren; report->leaf_children = r.leafChildren;
+    } catch (const std::exception &e) {
+        return setError(B200PT_E_INVALID, std::string("b200pt_scene_bvh_check: ") + e.what());
+    }
+    return B200PT_OK;
+}
+
 int b200pt_set_scene(b200pt_ctx *c, const b200pt_scene_desc *s) {
     if (!c || !s) return setError(B200PT_E_INVALID, "b200pt_set_scene: null argument");
     CUDA_TRY(cudaSetDevice(c->device));
     try {
-        // concatenate per-model buffers
-        std::vector<int32_t> vOff(std::max(1, s->num_models)), iOff(std::max(1, s->num_models));
+        // concatenate per-model buffers; flatten instances to world-space triangles (primitive ids follow instance order)
         std::vector<b200pt_vertex> verts; std::vector<uint32_t> inds;
-        for (int m = 0; m < s->num_models; m++) {
-            vOff[m] = int32_t(verts.size()); iOff[m] = int32_t(inds.size());
-            if (s->num_indices[m] % 3) return setError(B200PT_E_INVALID, "b200pt_set_scene: index count not a multiple of 3");
-            verts.insert(verts.end(), s->vertices[m], s->vertices[m] + s->num_vertices[m]);
-            inds.insert(inds.end(), s->indices[m], s->indices[m] + s->num_indices[m]);
-            for (int k = 0; k < s->num_indices[m]; k++)
-                if (s->indices[m][k] >= uint32_t(s->num_vertices[m])) return setError(B200PT_E_INVALID, "b200pt_set_scene: vertex index out of range");
-        }
-        // flatten instances to world-space triangles; primitive ids follow instance order
+        std::vector<int32_t> vOff, iOff;
         std::vector<float> world; std::vector<int4> primVerts;
-        for (int i = 0; i < s->num_instances; i++) {
-            const b200pt_instance &inst = s->instances[i];
-            int m = inst.modelIndex;
-            if (m < 0 || m >= s->num_models) return setError(B200PT_E_INVALID, "b200pt_set_scene: instance model index out of range");
-            int nt = s->num_indices[m] / 3;
-            bool identity = true;
-            for (int k = 0; k < 16; k++) identity = identity && inst.transform[k] == (k % 5 == 0 ? 1.0f : 0.0f) && inst.normalTransform[k] == (k % 5 == 0 ? 1.0f : 0.0f);
-            for (int t = 0; t < nt; t++) {
-                int4 pv;
-                int *pvp = &pv.x;
-                for (int k = 0; k < 3; k++) {
-                    uint32_t li = s->indices[m][3 * t + k];
-                    float w[3];
-                    mat4TransformPoint(inst.transform, s->vertices[m][li].pos, w);
-                    world.insert(world.end(), w, w + 3);
-                    pvp[k] = vOff[m] + int(li);
-                }
-                pv.w = int(uint32_t(i) | (identity ? PT_INSTANCE_IDENTITY : 0u));
-                primVerts.push_back(pv);
-            }
-        }
+        if (const char *bad = flattenScene(s, verts, inds, vOff, iOff, world, primVerts)) return setError(B200PT_E_INVALID, std::string("b200pt_set_scene: ") + bad);
         for (int i = 0; i < s->num_materials; i++)
             if ((s->materials[i].textureIdDiffuse >= s->num_textures) || (s->materials[i].textureIdSpecular >= s->num_textures))
                 return setError(B200PT_E_INVALID, "b200pt_set_scene: texture id out of range");

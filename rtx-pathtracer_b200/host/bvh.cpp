@@ -314,4 +314,66 @@ void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out) {
     }
 }
 
+void validateBvh8(const Bvh8 &bvh, const float *verts, uint32_t numTris, Bvh8Report &rep) {
+    rep = Bvh8Report();
+    rep.numNodes = uint32_t(bvh.nodes.size()); rep.numTris = uint32_t(bvh.tris.size()); rep.maxDepth = uint32_t(bvh.maxDepth);
+    if (bvh.nodes.empty()) { rep.badMeta = 1; return; }
+    std::vector<uint32_t> uses(numTris, 0);
+    std::vector<uint8_t> visited(bvh.nodes.size(), 0);
+    struct Item { uint32_t node; int depth; double lo[3], hi[3]; };        // lo / hi: intersection of the ancestors' slot boxes
+    std::vector<Item> stack;
+    Item root; root.node = 0; root.depth = 1;
+    for (int a = 0; a < 3; a++) { root.lo[a] = -std::numeric_limits<double>::infinity(); root.hi[a] = std::numeric_limits<double>::infinity(); }
+    stack.push_back(root);
+    int deepest = 0;
+    while (!stack.empty()) {
+        const Item it = stack.back(); stack.pop_back();
+        if (it.node >= bvh.nodes.size() || visited[it.node]) { rep.badMeta++; continue; }
+        visited[it.node] = 1;
+        deepest = std::max(deepest, it.depth);
+        const Bvh8Node &n = bvh.nodes[it.node];
+        uint32_t innerRank = 0, triOffset = 0;
+        for (int s = 0; s < 8; s++) {
+            const bool inner = (n.imask >> s) & 1;
+            if (n.meta[s] == 0) { if (inner) rep.badMeta++; continue; }
+            // the box the device's slab test sees: p + q * 2^(e - 127), exact in double
+            double lo[3], hi[3];
+            for (int a = 0; a < 3; a++) {
+                const double scale = std::ldexp(1.0, int(n.e[a]) - 127);
+                lo[a] = std::max(it.lo[a], double(n.p[a]) + double(n.qlo[a][s]) * scale);
+                hi[a] = std::min(it.hi[a], double(n.p[a]) + double(n.qhi[a][s]) * scale);
+            }
+            if (inner) {
+                if (n.meta[s] != uint8_t((1u << 5) | (24u + uint32_t(s)))) rep.badMeta++;
+                Item c; c.node = n.childBase + innerRank; c.depth = it.depth + 1;       // inner children are contiguous in slot order
+                for (int a = 0; a < 3; a++) { c.lo[a] = lo[a]; c.hi[a] = hi[a]; }
+                stack.push_back(c);
+                innerRank++; rep.innerChildren++;
+                continue;
+            }
+            rep.leafChildren++;
+            const uint32_t unary = n.meta[s] >> 5, offset = n.meta[s] & 31u;
+            const uint32_t count = unary == 1 ? 1u : unary == 3 ? 2u : unary == 7 ? 3u : 0u;
+            if (count == 0 || offset != triOffset || offset + count > 24u || size_t(n.triBase) + offset + count > bvh.tris.size()) { rep.badMeta++; continue; }
+            triOffset += count;
+            for (uint32_t k = 0; k < count; k++) {
+                const PackedTri &pt = bvh.tris[size_t(n.triBase) + offset + k];
+                if (pt.prim >= numTris) { rep.badMeta++; continue; }
+                if (uses[pt.prim]++) rep.duplicatePrims++;
+                const float *v = verts + size_t(pt.prim) * 9;
+                bool same = true, inside = true;
+                for (int a = 0; a < 3; a++) {
+                    same = same && pt.v0[a] == v[a] && pt.e1[a] == v[3 + a] - v[a] && pt.e2[a] == v[6 + a] - v[a];
+                    for (int c = 0; c < 3; c++) inside = inside && double(v[3 * c + a]) >= lo[a] && double(v[3 * c + a]) <= hi[a];
+                }
+                if (!same) rep.badMeta++;
+                if (!inside) rep.outsideBox++;
+            }
+        }
+    }
+    for (uint32_t t = 0; t < numTris; t++) if (!uses[t]) rep.missingPrims++;
+    for (uint8_t v : visited) if (!v) rep.unreachableNodes++;
+    if (numTris && deepest != bvh.maxDepth) rep.depthMismatch = 1;       // (no triangles: one empty node, depth 0)
+}
+
 }  // namespace b200pt

@@ -37,4 +37,17 @@ struct Bvh8 {
 // verts: numTris * 9 floats (world space), prim ids are 0..numTris-1
 void buildBvh8(const float *verts, uint32_t numTris, Bvh8 &out);
 
+// Structural check of a built tree against the triangles it was built from (host only, no traversal): what the device's
+// traversal relies on.  Every field counts violations and must be 0, except the statistics at the end.
+struct Bvh8Report {
+    uint32_t missingPrims = 0;        // primitives that appear in no leaf
+    uint32_t duplicatePrims = 0;      // primitives that appear in more than one leaf slot
+    uint32_t outsideBox = 0;          // leaf triangles with a vertex outside the dequantised box of their slot or of an ancestor's slot
+    uint32_t badMeta = 0;             // meta / imask / child index / triangle range inconsistencies, triangles that are not v0, v1 - v0, v2 - v0
+    uint32_t depthMismatch = 0;       // 1 when Bvh8::maxDepth is not the depth of the deepest node
+    uint32_t unreachableNodes = 0;    // nodes no parent points to
+    uint32_t numNodes = 0, numTris = 0, maxDepth = 0, innerChildren = 0, leafChildren = 0;
+};
+void validateBvh8(const Bvh8 &bvh, const float *verts, uint32_t numTris, Bvh8Report &report);
+
 }  // namespace b200pt

@@ -93,3 +93,75 @@ def test_camera_matrices():
     assert Pm[0, 0] == pytest.approx(1 / (16 / 9 * np.tan(np.radians(45) / 2)), rel=1e-6)
     inv = P.mat4_inverse(view).reshape(4, 4).T
     assert np.allclose(inv @ V, np.eye(4), atol=1e-5)
+
+
+VIOLATIONS = ("missing_prims", "duplicate_prims", "outside_box", "bad_meta", "depth_mismatch", "unreachable_nodes")
+
+
+@pytest.mark.parametrize("name", ["cornell-dielectric", "veachMIS", "sponzaXML", "test-scene", "irradianceCache", "alphaLeaf", "stackedCards", "envMap", "testSpheres"])
+def test_bvh8_structure_is_valid_for_every_scene(name):
+    """host/bvh.cpp on the CPU (b200pt_scene_bvh_check, no GPU): every primitive sits in exactly one leaf, every triangle lies
+    inside the dequantised 8-bit box of its slot and of all its ancestors' slots (what the slab test sees), child and
+    triangle indexing is consistent, and the recorded depth — which set_scene checks against the traversal stack — is exact."""
+    P = helpers.pt()
+    scene = P.Scene(helpers.scene_path(name))
+    rep = scene.bvh_check()
+    assert all(getattr(rep, f) == 0 for f in VIOLATIONS), {f: getattr(rep, f) for f in VIOLATIONS}
+    assert rep.num_tris == scene.num_triangles
+    if rep.num_tris > 24:
+        assert rep.inner_children == rep.num_nodes - 1 and rep.max_depth >= 2
+        assert (rep.inner_children + rep.leaf_children) / rep.num_nodes > 5.0        # the DP collapse fills the 8-wide nodes (greedy: ~4)
+    assert rep.max_depth <= 24                                                         # PT_STACK_LOCAL
+
+
+def test_bvh8_check_notices_damage(monkeypatch):
+    P = helpers.pt()
+    scene = P.Scene(helpers.scene_path("cornell-dielectric"))
+    for kind, field in ((1, "outside_box"), (2, "duplicate_prims"), (3, "bad_meta"), (4, "depth_mismatch")):
+        monkeypatch.setenv("B200PT_BVH_CHECK_MUTATE", str(kind))
+        rep = scene.bvh_check()
+        assert getattr(rep, field) > 0, (kind, field)
+        if kind == 2:
+            assert rep.missing_prims == 1
+    monkeypatch.delenv("B200PT_BVH_CHECK_MUTATE")
+    assert all(getattr(scene.bvh_check(), f) == 0 for f in VIOLATIONS)
+
+
+def test_bvh8_of_degenerate_and_coincident_triangles():
+    """zero-area triangles, all centroids equal, and one huge + many tiny triangles: the builder must still place every
+    primitive and keep it inside its boxes (the quantisation grid is 255 steps of the node's extent)."""
+    import ctypes as C
+    P = helpers.pt()
+    rng = np.random.default_rng(0)
+
+    def check(tri_pos):
+        n = len(tri_pos)
+        verts = (P.Vertex * (3 * n))()
+        for i, t in enumerate(tri_pos):
+            for k in range(3):
+                verts[3 * i + k].pos[0], verts[3 * i + k].pos[1], verts[3 * i + k].pos[2] = [float(x) for x in t[k]]
+        idx = (C.c_uint32 * (3 * n))(*range(3 * n))
+        d = P.SceneDesc()
+        vp = (C.POINTER(P.Vertex) * 1)(C.cast(verts, C.POINTER(P.Vertex)))
+        ip = (C.POINTER(C.c_uint32) * 1)(C.cast(idx, C.POINTER(C.c_uint32)))
+        nv, ni = (C.c_int32 * 1)(3 * n), (C.c_int32 * 1)(3 * n)
+        inst = (P.Instance * 1)()
+        for k in range(4):
+            inst[0].transform[5 * k] = 1.0
+            inst[0].normalTransform[5 * k] = 1.0
+        d.num_models, d.vertices, d.num_vertices, d.indices, d.num_indices = 1, vp, nv, ip, ni
+        d.num_instances, d.instances = 1, inst
+        rep = P.BvhReport()
+        assert P.lib().b200pt_scene_bvh_check(C.byref(d), C.byref(rep)) == 0
+        assert all(getattr(rep, f) == 0 for f in VIOLATIONS), {f: getattr(rep, f) for f in VIOLATIONS}
+        assert rep.num_tris == n
+        return rep
+
+    check(np.zeros((40, 3, 3)))                                                       # 40 points at the origin
+    same = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], float), (300, 1, 1))   # 300 coincident triangles (the tie test's stack)
+    check(same)
+    tiny = rng.random((500, 1, 3)) * 1e-3 + rng.random((500, 3, 3)) * 1e-6
+    huge = np.array([[[-1e4, -1e4, 0], [1e4, -1e4, 0], [0, 1e4, 0]]])
+    rep = check(np.concatenate([huge, tiny]))
+    assert rep.max_depth <= 24
+    check(rng.normal(size=(5000, 3, 3)) * np.array([1e3, 1.0, 1e-3]))                 # very anisotropic soup
