@@ -1,4 +1,6 @@
 """CPU: the headless scene front-end against facts about the reference's scenes recorded in SURVEY.md."""
+import os
+
 import numpy as np
 import pytest
 
@@ -165,3 +167,66 @@ def test_bvh8_of_degenerate_and_coincident_triangles():
     rep = check(np.concatenate([huge, tiny]))
     assert rep.max_depth <= 24
     check(rng.normal(size=(5000, 3, 3)) * np.array([1e3, 1.0, 1e-3]))                 # very anisotropic soup
+
+
+HOST_REF = os.path.join(helpers.ROOT, "oracle", "_ref", "libhost_ref.so")
+LIGHT_TABLE_DIGESTS = os.path.join(helpers.ROOT, "tests", "golden", "light_table_digests.json")
+
+
+def _light_tables(P, name):
+    """(random_light_index, lights, [face table per area light]) of a scene as our loader built them"""
+    import ctypes as C
+    s = P.Scene(helpers.scene_path(name))
+    d = s.desc
+    rl = np.ctypeslib.as_array(d.random_light_index, shape=(P.SIZE_LIGHT_RANDOM,)).copy()
+    lights = [d.lights[i] for i in range(d.num_lights)]
+    raw = np.ctypeslib.as_array(C.cast(d.random_tri_index, C.POINTER(C.c_uint32)), shape=(max(1, d.num_face_tables) * P.SIZE_TRI_RANDOM, 3)).copy()
+    tables = [raw[k * P.SIZE_TRI_RANDOM:(k + 1) * P.SIZE_TRI_RANDOM] for k in range(d.num_face_tables)]
+    keep = dict(rl=rl, tables=tables, probs=np.array([l.sampleProb for l in lights], np.float32), areas=np.array([l.area for l in lights], np.float32),
+                types=[l.type for l in lights])
+    return s, keep
+
+
+@pytest.mark.parametrize("name", ["cornell-dielectric", "test-scene", "veachMIS", "sponzaXML"])
+def test_light_and_face_tables_equal_the_reference_sampler(name):
+    """Binding 6 (LightSamplerBuffer): the 10 000-entry light table and the 10 000-entry face table of every area light against
+    the reference's OWN WeightedSampler (src/WeightedSampler.cpp compiled into oracle/_ref/libhost_ref.so) fed with the
+    weights SceneLoader::getLightSamplingVector / getFaceSamplingVector give it (src/SceneLoader.cpp:861-944): every light
+    weighs 1; an area light's faces weigh their areas, in face order.  Indices, probabilities, per-sample face areas and the
+    light's total area must be bit-equal.  Where the reference tree is absent the committed digests of the same tables are checked."""
+    import ctypes as C
+    import hashlib
+    import json
+    P = helpers.pt()
+    scene, t = _light_tables(P, name)
+    digest = hashlib.sha256(t["rl"].tobytes() + b"".join(x.tobytes() for x in t["tables"]) + t["probs"].tobytes() + t["areas"].tobytes()).hexdigest()
+    assert json.load(open(LIGHT_TABLE_DIGESTS))[name] == digest
+    if not os.path.exists(HOST_REF):
+        return
+    R = C.CDLL(HOST_REF)
+    R.host_ref_weighted_samples.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def reference(values, count):
+        v = np.ascontiguousarray(values, np.float32)
+        samples, probs, total = np.zeros(count, np.int32), np.zeros(len(v), np.float32), np.zeros(1, np.float32)
+        R.host_ref_weighted_samples(v.ctypes.data, len(v), count, samples.ctypes.data, probs.ctypes.data, total.ctypes.data)
+        return samples, probs, total[0]
+
+    n = len(t["types"])
+    samples, probs, _ = reference(np.ones(n, np.float32), P.SIZE_LIGHT_RANDOM)
+    assert np.array_equal(t["rl"], samples) and np.array_equal(t["probs"], probs)
+    area_lights = [i for i in range(n) if t["types"][i] == 0]             # B200PT_LIGHT_AREA
+    if not area_lights:                                                    # "Dummy data" (src/SceneLoader.cpp:909-918): one zeroed table
+        assert len(t["tables"]) == 1 and not t["tables"][0].any()
+        return
+    assert len(area_lights) == len(t["tables"])
+    for k, i in enumerate(area_lights):
+        tab = t["tables"][k]
+        idx, prob, area = tab[:, 0].view(np.int32), tab[:, 1].view(np.float32), tab[:, 2].view(np.float32)
+        faces = np.unique(idx)                                             # the emissive faces of the light's model, in face order
+        weights = np.array([area[idx == f][0] for f in faces], np.float32)
+        assert abs(float(np.unique(prob).astype(np.float64).sum()) - 1.0) < 1e-4 or len(np.unique(prob)) < len(faces)    # every face was drawn at least once
+        samples, probs, total = reference(weights, P.SIZE_TRI_RANDOM)
+        assert np.array_equal(idx, faces[samples]), (name, i)
+        assert np.array_equal(prob, probs[samples]) and np.array_equal(area, weights[samples])
+        assert t["areas"][i] == total
