@@ -1365,6 +1365,52 @@ int oracle_trace_rays(oracle_ctx *C, const b200pt_ray *rays, int64_t n, b200pt_h
 }
 
 uint32_t oracle_tea(uint32_t a, uint32_t b) { return tea(a, b); }
+// Unit access to the restated shader functions of random.glsl / transform.glsl / guiding.glsl, for the comparison with the
+// reference's own files compiled as C++ (oracle/glsl_ref.cpp: same function numbers and argument layout).
+//   0 randomOnUnitSphere()            1 randomInHemisphere(n)            2 randomInHemisphereCosine(n)
+//   3 randomInHemisphereCosinePower(reflected, p)                        4 randomOnSphere(center, radius) -> point, normal
+//   5 randomOnSphereVisible(center, radius, n) -> point, normal          6 randomBeckmannNormal(n, roughness)
+//   7 toWorld(v, n)                   9 sampleVMF(theta[10], worldPos, parallax)       10 vMF(theta[10], worldPos, parallax, wo)
+//  11 sampleVMM(vmm[180], worldPos, parallax)                           12 VMM(vmm[180], worldPos, parallax, wo)
+//  20 fresnel  21 fresnelConductor  22 evalBsdf  23 pdfBSDF  24 sampleBSDF -> pdf, direction  25 power / balance heuristic
+//  26 applyWeightWindow(throughput, adjoint, estimate, adrrsS) -> q, n   27 approxDiffuse  28 pdfLight  29 material predicates
+int oracle_unit_eval(int fn, uint32_t *seed_io, const float *in, float *out) {
+    static oracle_ctx dummy;
+    Pixel p(dummy);
+    p.seed = *seed_io;
+    auto put = [&](float *o, v3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; };
+    switch (fn) {
+        case 0: put(out, p.randomOnUnitSphere()); break;
+        case 1: put(out, p.randomInHemisphere(v3(in))); break;
+        case 2: put(out, p.randomInHemisphereCosine(v3(in))); break;
+        case 3: put(out, p.randomInHemisphereCosinePower(v3(in), in[3])); break;
+        case 4: { b200pt_sphere s; memset(&s, 0, sizeof(s)); memcpy(s.center, in, 12); s.radius = in[3]; v3 n; put(out, p.randomOnSphere(s, n)); put(out + 3, n); break; }
+        case 5: { b200pt_sphere s; memset(&s, 0, sizeof(s)); memcpy(s.center, in, 12); s.radius = in[3]; v3 n; put(out, p.randomOnSphereVisible(s, v3(in + 4), n)); put(out + 3, n); break; }
+        case 6: { b200pt_material m; memset(&m, 0, sizeof(m)); m.roughness = in[3]; put(out, p.randomBeckmannNormal(m, v3(in))); break; }
+        case 7: put(out, Pixel::toWorld(v3(in), v3(in + 3))); break;
+        case 9: { b200pt_vmf_theta t; memcpy(&t, in, sizeof(t)); put(out, p.sampleVMF(t, v3(in + 10), in[13] != 0.0f)); break; }
+        case 10: { b200pt_vmf_theta t; memcpy(&t, in, sizeof(t)); out[0] = Pixel::vMF(v3(in + 14), t, v3(in + 10), in[13] != 0.0f); break; }
+        case 11: { b200pt_vmm_theta t; memcpy(&t, in, sizeof(t)); put(out, p.sampleVMM(t, v3(in + 180), in[183] != 0.0f)); break; }
+        case 12: { b200pt_vmm_theta t; memcpy(&t, in, sizeof(t)); out[0] = Pixel::VMM(v3(in + 184), t, v3(in + 180), in[183] != 0.0f); break; }
+        // raytrace.rgen: material = b200pt_material (24 floats) at in[0], then normal, wi, wo, frontFace
+        case 20: out[0] = Pixel::fresnel(in[0], in[1]); break;
+        case 21: out[0] = Pixel::fresnelConductor(in[0], in[1], in[2]); break;
+        case 22: { b200pt_material m; memcpy(&m, in, sizeof(m)); put(out, p.evalBsdf(m, 0.0f, 0.0f, v3(in + 24), v3(in + 27), v3(in + 30), in[33] != 0.0f)); break; }
+        case 23: { b200pt_material m; memcpy(&m, in, sizeof(m)); out[0] = Pixel::pdfBSDF(m, v3(in + 24), v3(in + 27), v3(in + 30)); break; }
+        case 24: { b200pt_material m; memcpy(&m, in, sizeof(m)); v3 d(0.0f); out[0] = p.sampleBSDF(m, v3(in + 27), v3(in + 24), in[33] != 0.0f, d); put(out + 1, d); break; }
+        case 25: out[0] = Pixel::powerHeuristic(in[0], in[1]); out[1] = Pixel::balanceHeuristic(in[0], in[1]); break;
+        case 26: { p.estimate = v3(in + 6); dummy.pushC.adrrsS = in[9]; int n = 0; out[0] = p.applyWeightWindow(v3(in), v3(in + 3), n); out[1] = float(n); break; }
+        case 27: { b200pt_material m; memcpy(&m, in, sizeof(m)); put(out, p.approxDiffuse(m, v3(in + 24), v3(in + 27), 0.0f, 0.0f)); break; }
+        case 28: { b200pt_light l; memset(&l, 0, sizeof(l)); l.sampleProb = in[0]; l.area = in[1]; out[0] = Pixel::pdfLight(l, v3(in + 2), v3(in + 5), in[8]); break; }
+        case 29: { b200pt_material m; memcpy(&m, in, sizeof(m)); out[0] = float(p.hasDiscreteDirection(m)); out[1] = float(p.isMatAlmostDiscrete(m));
+                   dummy.pushC.useIrradianceCacheOnGlossy = 0; out[2] = float(p.isICCapable(m)); dummy.pushC.useIrradianceCacheOnGlossy = 1; out[3] = float(p.isICCapable(m)); break; }
+        default: return -1;
+    }
+    *seed_io = p.seed;
+    return 0;
+}
+uint32_t oracle_lcg(uint32_t *prev) { Pixel::rndS(*prev); return *prev & 0x00FFFFFFu; }
+float oracle_rnd(uint32_t *prev) { return Pixel::rndS(*prev); }
 
 float *oracle_image(oracle_ctx *C, int which) {
     return which == B200PT_IMAGE_OUTPUT ? C->image.data() : which == B200PT_IMAGE_ACCUM ? C->accumulateImage.data() : which == 3 ? C->aovImage.data() : C->estimateImage.data();
