@@ -6,6 +6,7 @@
 // deterministic elementary functions of include/b200pt_detmath.h, this build the C library's).
 #include "glsl_prelude.h"
 #include <string.h>
+#include "glsl_macros.h"
 namespace glsl {
 #include "_ref/glsl/limits.inc"
 #include "_ref/glsl/wavefront.inc"

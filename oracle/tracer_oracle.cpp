@@ -1364,6 +1364,21 @@ int oracle_trace_rays(oracle_ctx *C, const b200pt_ray *rays, int64_t n, b200pt_h
     return 0;
 }
 
+// One ray through the oracle's traversal, and one texture fetch, as plain C calls: oracle/shader_ref.cpp (the reference's shader
+// megakernel compiled as C++) gets its hits and texels from here — intersection order, tie rule and the sampler's filter are
+// defined by us (the reference leaves them to the driver), everything done WITH a hit or a texel is the reference's code.
+// out: t, u, v;  ids: global primitive, instance (or sphere index), primitive inside the instance, is-sphere.  Returns 1 on a hit.
+int oracle_trace_one(oracle_ctx *C, const float o[3], const float d[3], float tmin, float tmax, int any_hit, float out[3], uint32_t ids[4]) {
+    Pixel p(*C);
+    Pixel::Cand c = p.traverse(v3(o), v3(d), tmin, tmax, any_hit != 0);
+    if (c.prim == B200PT_MISS) return 0;
+    out[0] = c.t; out[1] = c.u; out[2] = c.v;
+    ids[0] = c.prim;
+    if (c.prim >= C->numTris) { ids[1] = c.prim - C->numTris; ids[2] = c.prim - C->numTris; ids[3] = 1u; }
+    else { ids[1] = C->primInstance[c.prim]; ids[2] = C->primLocal[c.prim]; ids[3] = 0u; }
+    return 1;
+}
+void oracle_texture(oracle_ctx *C, int id, float u, float v, float out[4]) { Pixel p(*C); p.textureRGBA(id, u, v, out); }
 uint32_t oracle_tea(uint32_t a, uint32_t b) { return tea(a, b); }
 // Unit access to the restated shader functions of random.glsl / transform.glsl / guiding.glsl, for the comparison with the
 // reference's own files compiled as C++ (oracle/glsl_ref.cpp: same function numbers and argument layout).
