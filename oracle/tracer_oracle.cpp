@@ -6,9 +6,14 @@
 // random.glsl, transform.glsl, guiding.glsl, raycommon.glsl.  Every function cites the shader lines it follows
 // (paths relative to /root/reference/shaders).  One pixel = one sequential program, exactly like a raygen invocation.
 //
-// PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for this path and its GLSL cannot run
-// here (no Vulkan, no glslc, no RT hardware) — see SURVEY.md §8(c).  What *is* pinned: the RNG (TEA/LCG constants of
-// random.glsl), the buffer layouts, and the converged images (scenes/*/**.exr, Mitsuba renders) at the relMSE level.
+// PARITY PINNED (round 2c) against the reference's own shader source: the reference ships no golden vectors and its GLSL cannot
+// run here as GLSL (no Vulkan, no glslc, no RT hardware — SURVEY.md §8(c)), but its shader files are C-like enough to be COMPILED
+// AS C++ where they lie (oracle/Makefile, oracle/glsl_prelude*.h, oracle/shader_ref.cpp -> oracle/_ref/libshader_ref.so).  Fed with
+// this file's hits, texels and elementary functions — the three things the reference leaves to the driver — that build renders
+// frames that are BIT-EQUAL to this restatement's in every mode (tests/test_shader_ref.py: path tracing on seven scenes, irradiance
+// cache lookups, ADRRS / splitting, guided sampling, every recorded DirectionalData record); function by function, with the C
+// library's elementary functions instead, tests/test_oracle_cpu.py.  Also pinned: the light / face tables (the reference's
+// WeightedSampler compiled into oracle/_ref/libhost_ref.so) and the converged images (scenes/*/**.exr) at the relMSE level.
 //
 // Ray traversal has no reference algorithm (driver / RT cores).  The oracle defines it as brute force over all
 // primitives with individually rounded IEEE operations (compile with -ffp-contract=off):
