@@ -2,8 +2,8 @@
 // guiding.glsl, raycommon.glsl, wavefront.glsl, limits.glsl) is C-like enough to be compiled as C++ once the vector types and
 // built-ins exist: this header supplies them (float semantics: every built-in on float calls the float libm function).
 // oracle/Makefile pipes the shader files through sed (parameter qualifiers `in` / `out` / `inout` -> C++ references, #include
-// lines dropped) into oracle/_ref/glsl/*.inc — build outputs, git-ignored, never copied into this repository — and
-// oracle/glsl_ref.cpp includes them where they are generated.
+// lines dropped) into oracle/_ref/glsl/*.inc — build intermediates, deleted after the compile, never copied into this repository —
+// and oracle/glsl_ref.cpp includes them where they are generated.
 #pragma once
 #include <math.h>
 #include <stdint.h>

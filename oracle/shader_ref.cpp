@@ -2,8 +2,8 @@
 //   raytrace.rgen (the megakernel: camera ray, bounce loop, NEE + MIS, light sampling, irradiance-cache lookup, ADRRS window and
 //   splits, guided sampling, sample recording, saveResult / saveEstimate), raytrace.rchit, raytrace.sphere.rchit, raytrace.rmiss,
 //   raytrace.shadow.rmiss, raytrace.irradiance.rint / .rahit, raytrace.guiding.rint / .rchit
-// — every line from /root/reference/shaders, piped through sed by oracle/Makefile into oracle/_ref/glsl/*.inc (build outputs,
-// git-ignored; see glsl_prelude.h for what the rewriting does).  Left out: the debug views (visualizeIC, the guiding
+// — every line from /root/reference/shaders, piped through sed by oracle/Makefile into oracle/_ref/glsl/*.inc (build intermediates,
+// deleted after the compile; see glsl_prelude.h for what the rewriting does).  Left out: the debug views (visualizeIC, the guiding
 // visualisations and the visualizeMode switch cases other than VISU_RAYTRACE).
 // What is NOT the reference's: traceRayEXT itself.  The reference hands rays to the driver's acceleration structure; here the
 // closest / any hit comes from oracle/tracer_oracle.cpp's traversal through a callback (hit distance, barycentrics, instance and
