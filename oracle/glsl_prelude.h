@@ -21,7 +21,13 @@
 namespace glsl {      // the built-ins below must hide the C library's overloads of the same names, not compete with them
 typedef uint32_t uint;
 struct uxy_t { uint x, y; };            // gl_LaunchIDEXT.xy
-struct vec2 { float x, y; vec2() = default; vec2(float a) : x(a), y(a) {} vec2(float a, float b) : x(a), y(b) {} vec2(uxy_t u) : x(float(u.x)), y(float(u.y)) {} };
+struct vec2 {
+    float x, y;
+    vec2() = default; vec2(float a) : x(a), y(a) {} vec2(float a, float b) : x(a), y(b) {} vec2(uxy_t u) : x(float(u.x)), y(float(u.y)) {}
+    // uint(vec2) takes the first component (raytrace.rahit:39).  Out-of-range float -> uint is undefined in GLSL; like the oracle and the
+    // kernels it saturates here (negative and NaN -> 0)
+    explicit operator uint() const { return x >= 4294967296.0f ? 0xFFFFFFFFu : (x > 0.0f ? uint(x) : 0u); }
+};
 struct vec3;
 struct xyz_t { float x, y, z; inline operator vec3() const; };          // `.xyz` of a vec3 / vec4 / texel
 struct vec3 {

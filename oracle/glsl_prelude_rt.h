@@ -12,6 +12,8 @@ static inline vec2 operator/(vec2 a, vec2 b) { return vec2(a.x / b.x, a.y / b.y)
 static inline vec2 operator*(vec2 a, float s) { return vec2(a.x * s, a.y * s); }
 static inline vec2 operator*(float s, vec2 a) { return vec2(a.x * s, a.y * s); }
 static inline vec2 operator/(vec2 a, float s) { return vec2(a.x / s, a.y / s); }
+static inline vec2 operator*(vec2 a, int s) { return vec2(a.x * float(s), a.y * float(s)); }
+static inline vec2 operator+(vec2 a, float s) { return vec2(a.x + s, a.y + s); }
 template <class T, class = typename std::enable_if<std::is_arithmetic<T>::value>::type> static inline vec3 operator/(vec3 a, T s) { return a / float(s); }
 template <class T, class = typename std::enable_if<std::is_integral<T>::value>::type> static inline vec3 operator*(T s, vec3 a) { return a * float(s); }
 static inline vec3 &operator/=(vec3 &a, float s) { a = a / s; return a; }

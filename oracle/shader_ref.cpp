@@ -18,7 +18,7 @@
 #include "../include/b200pt.h"
 
 namespace glsl {
-struct texel4rt { union { struct { float x, y, z, w; }; xyz_t xyz; }; };
+struct texel4rt { union { struct { float x, y, z, w; }; struct { float r, g, b, a; }; xyz_t xyz; }; };
 static sampler2D textureSamplers[256];
 typedef void (*texture_fn)(void *ctx, int id, float u, float v, float out[4]);
 typedef int (*trace_fn)(void *ctx, const float o[3], const float d[3], float tmin, float tmax, int any_hit, float out[3], uint32_t ids[4]);
@@ -77,6 +77,11 @@ namespace irradiance_rint { static sphere *&spheres = glsl::cacheSpheres;
 }
 namespace irradiance_rahit {
 #include "_ref/glsl/stage_irradiance_rahit.inc"
+}
+static bool g_ignored;
+static inline void ignoreIntersectionEXT() { g_ignored = true; }
+namespace rahit {
+#include "_ref/glsl/stage_rahit.inc"
 }
 namespace guiding_rint {
 #include "_ref/glsl/stage_guiding_rint.inc"
@@ -218,6 +223,16 @@ void shader_ref_ic_put(const b200pt_cache_header *h, const b200pt_cache_data *da
         s_cache[i] = c;
         s_cacheSpheres[i].center = v3(sp[i].center); s_cacheSpheres[i].radius = sp[i].radius; s_cacheSpheres[i].materialIndex = sp[i].materialIndex; s_cacheSpheres[i].iLight = sp[i].iLight;
     }
+}
+
+// the any-hit shader of the triangle geometry (raytrace.rahit: the stochastic alpha test) on one candidate hit; returns 1 when it
+// calls ignoreIntersectionEXT.  In a frame this decision is taken inside the traversal, i.e. on the oracle's side of the callback.
+int shader_ref_alpha_rejects(int instance, int prim, float u, float v, float origin_x, float t, uint32_t random_uint) {
+    gl_InstanceID = instance; gl_PrimitiveID = prim; attribs = vec3{u, v, 0.0f};
+    gl_WorldRayOriginEXT = vec3{origin_x, 0.0f, 0.0f}; gl_HitTEXT = t; pushC.randomUInt = random_uint;
+    g_ignored = false;
+    rahit::main();
+    return g_ignored ? 1 : 0;
 }
 
 float *shader_ref_image(int which) { return which == 0 ? s_image.data() : which == 1 ? s_accum.data() : s_estimate.data(); }

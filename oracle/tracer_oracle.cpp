@@ -1383,6 +1383,12 @@ int oracle_trace_one(oracle_ctx *C, const float o[3], const float d[3], float tm
     else { ids[1] = C->primInstance[c.prim]; ids[2] = C->primLocal[c.prim]; ids[3] = 0u; }
     return 1;
 }
+// the oracle's any-hit decision (raytrace.rahit) for one candidate hit on global primitive `prim`
+int oracle_alpha_rejects(oracle_ctx *C, uint32_t prim, float u, float v, float origin_x, float t, uint32_t random_uint) {
+    C->pushC.randomUInt = random_uint;
+    Pixel p(*C);
+    return p.alphaRejects(prim, u, v, v3(origin_x, 0.0f, 0.0f), t) ? 1 : 0;
+}
 void oracle_texture(oracle_ctx *C, int id, float u, float v, float out[4]) { Pixel p(*C); p.textureRGBA(id, u, v, out); }
 uint32_t oracle_tea(uint32_t a, uint32_t b) { return tea(a, b); }
 // Unit access to the restated shader functions of random.glsl / transform.glsl / guiding.glsl, for the comparison with the

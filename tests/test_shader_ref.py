@@ -93,7 +93,7 @@ PLAIN = [("cornell-dielectric", dict(enableMIS=1)), ("cornell-dielectric", dict(
          ("miPhong", dict(enableMIS=1)), ("miPhong", dict(enableNEE=0)),
          ("test-scene", dict(enableMIS=1)), ("test-scene", dict(enableNEE=0, maxDepth=3, maxFollowDiscrete=1)),
          ("envMap", dict(enableMIS=1)), ("envSynthetic", dict(enableMIS=1)), ("testSpheres", dict(enableMIS=1, useVisibleSphereSampling=1)),
-         ("sponzaXML", dict(enableMIS=1, samplesPerPixel=1, maxDepth=4)), ("stackedCards", dict(enableMIS=1))]
+         ("sponzaXML", dict(enableMIS=1, samplesPerPixel=1, maxDepth=4)), ("stackedCards", dict(enableMIS=1)), ("alphaLeaf", dict(enableMIS=1))]
 
 
 def frame_key(scene_name, kw):
@@ -201,3 +201,33 @@ def test_guided_sampling_and_sample_recording_are_bit_equal():
             ours = o.samples(P.DIRECTIONAL_DATA_DTYPE)
             assert (ours["flags"] != 0xFFFFFFFF).sum() > 0.3 * W * H
             _check("guiding_%d:samples" % i, ours.view(np.uint8), ref.samples(P.DIRECTIONAL_DATA_DTYPE).view(np.uint8) if ref else None)
+
+
+def test_alpha_test_decisions_equal_the_reference_any_hit_shader():
+    """raytrace.rahit (the stochastic alpha test of textured triangles) runs inside the traversal, i.e. on the oracle's side of the
+    callback in the frames above — so it is compared on its own: 40 000 candidate hits on the alpha-textured leaf of scenes/alphaLeaf
+    (random barycentrics, distances, origins, frame seeds; the texture has transparent, opaque and in-between texels), the oracle's
+    accept / reject decision against the compiled shader's ignoreIntersectionEXT."""
+    P, scene, o, ref = _setup("alphaLeaf")
+    O = helpers.oracle().lib()
+    O.oracle_alpha_rejects.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
+    rng = np.random.default_rng(21)
+    n = 40000
+    d = scene.desc
+    prims = []                                    # (global primitive, instance, primitive inside the instance), instance order like set_scene
+    for i in range(d.num_instances):
+        for t in range(d.num_indices[d.instances[i].modelIndex] // 3):
+            prims.append((len(prims), i, t))
+    pick = rng.integers(0, len(prims), n)
+    u = rng.random(n).astype(np.float32)
+    v = (rng.random(n) * (1 - u)).astype(np.float32)
+    ox = rng.normal(0, 3, n).astype(np.float32)
+    t = (10 ** rng.uniform(-2, 2, n)).astype(np.float32)
+    seeds = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    ours = np.array([O.oracle_alpha_rejects(o._h, prims[pick[k]][0], u[k], v[k], ox[k], t[k], int(seeds[k])) for k in range(n)], np.uint8)
+    assert 0.05 < ours.mean() < 0.95              # both outcomes occur
+    ref_value = None
+    if ref:
+        ref.S.shader_ref_alpha_rejects.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
+        ref_value = np.array([ref.S.shader_ref_alpha_rejects(prims[pick[k]][1], prims[pick[k]][2], u[k], v[k], ox[k], t[k], int(seeds[k])) for k in range(n)], np.uint8)
+    _check("alpha_test", ours, ref_value)
