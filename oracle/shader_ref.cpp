@@ -91,6 +91,7 @@ namespace guiding_rchit { static guidingInfo &info = glsl::guidingInfos;
 }
 
 static int g_numGuidingRegions = 0;
+static uint g_icEntriesAtFrameStart = 0;
 static void traceRayEXT(accelerationStructureEXT as, uint flags, uint, uint, uint, uint missIndex, vec3 origin, float tmin, vec3 direction, float tmax, int) {
     gl_WorldRayOriginEXT = origin; gl_WorldRayDirectionEXT = direction; gl_RayTmaxEXT = tmax;
     if (as.id == 0) {                                   // topLevelAS: triangles + analytic spheres
@@ -105,7 +106,9 @@ static void traceRayEXT(accelerationStructureEXT as, uint flags, uint, uint, uin
         } else if (missIndex == 0u) rmiss::main();
         else shadow_rmiss::main();
     } else if (as.id == 1) {                            // irradianceAS: one box per cache entry, intersection + any-hit shader per candidate
-        const uint n = header.nextCacheSlot < header.maxCaches ? header.nextCacheSlot : header.maxCaches;
+        // the lookup structure is the one the host built before the frame (IrradianceCache::updateSpheres runs between frames,
+        // src/IrradianceCache.cpp:81-104): entries created during this frame are not in it yet
+        const uint n = g_icEntriesAtFrameStart;
         for (uint i = 0; i < n; i++) {
             gl_PrimitiveID = int(i); g_reported = false; g_numReported = 0;
             irradiance_rint::main();
@@ -235,6 +238,17 @@ int shader_ref_alpha_rejects(int instance, int prim, float u, float v, float ori
     return g_ignored ? 1 : 0;
 }
 
+void shader_ref_ic_get(b200pt_cache_header *h, b200pt_cache_data *data, b200pt_sphere *sp, int n) {
+    h->nextCacheSlot = header.nextCacheSlot; h->maxCaches = header.maxCaches; h->nextUpdateSlot = header.nextUpdateSlot;
+    for (int i = 0; i < n && size_t(i) < s_cache.size(); i++) {
+        const cacheData &c = s_cache[i];
+        memset(&data[i], 0, sizeof(data[i])); memset(&sp[i], 0, sizeof(sp[i]));
+        for (int a = 0; a < 3; a++) { data[i].color[a] = (&c.color.x)[a]; data[i].normal[a] = (&c.normal.x)[a]; data[i].rotGrad[a] = (&c.rotGrad.x)[a]; data[i].transGrad[a] = (&c.transGrad.x)[a]; sp[i].center[a] = (&s_cacheSpheres[i].center.x)[a]; }
+        data[i].harmonicR = c.harmonicR; data[i].numUpdates = c.numUpdates;
+        sp[i].radius = s_cacheSpheres[i].radius; sp[i].materialIndex = s_cacheSpheres[i].materialIndex; sp[i].iLight = s_cacheSpheres[i].iLight;
+    }
+}
+
 float *shader_ref_image(int which) { return which == 0 ? s_image.data() : which == 1 ? s_accum.data() : s_estimate.data(); }
 void *shader_ref_samples(void) { return s_samples.data(); }
 
@@ -253,6 +267,7 @@ int shader_ref_render(const b200pt_push_constants *pc, int x0, int y0, int x1, i
     PCF(guidingPiPHighlightRegion); PCF(guidingPiPShowSpheres); PCF(guidingPiPSize);
 #undef PCF
     if (!g_trace || !g_texture) return -1;
+    g_icEntriesAtFrameStart = header.nextCacheSlot < header.maxCaches ? header.nextCacheSlot : header.maxCaches;
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             gl_LaunchIDEXT.x = uint(x); gl_LaunchIDEXT.y = uint(y); gl_LaunchIDEXT.z = 0u;

@@ -231,3 +231,43 @@ def test_alpha_test_decisions_equal_the_reference_any_hit_shader():
         ref.S.shader_ref_alpha_rejects.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
         ref_value = np.array([ref.S.shader_ref_alpha_rejects(prims[pick[k]][1], prims[pick[k]][2], u[k], v[k], ox[k], t[k], int(seeds[k])) for k in range(n)], np.uint8)
     _check("alpha_test", ours, ref_value)
+
+
+def _ref_ic_get(P, ref, n=512):
+    hdr, data, sp = P.CacheHeader(), np.zeros(n, dtype=P.CACHE_DATA_DTYPE), np.zeros(n, dtype=P.SPHERE_DTYPE)
+    ref.S.shader_ref_ic_get(C.byref(hdr), data.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p), n)
+    return hdr, data, sp
+
+
+def _cache_bytes(c):
+    hdr, data, sp = c
+    n = min(int(hdr.nextCacheSlot), len(data))
+    return np.concatenate([np.array([hdr.nextCacheSlot, hdr.maxCaches, hdr.nextUpdateSlot], np.uint32).view(np.uint8),
+                           np.ascontiguousarray(data[:n]).view(np.uint8).reshape(-1), np.ascontiguousarray(sp[:n]).view(np.uint8).reshape(-1)])
+
+
+def test_irradiance_cache_creation_and_update_are_bit_equal():
+    """createIrradianceCache / calculateCacheData (20 x 10 stratified paths per entry, rotational and translational gradients, radius
+    clamps) on whole prepare frames: slots are handed out in pixel order on both sides and new entries are not in the lookup structure
+    before the next frame, so the caches — header, every entry, every sphere — and the images must be bit-equal.  updateIrradianceCache
+    rewrites entries that lookups of the same frame can observe (the reference races there; the oracle reads the frame-start snapshot),
+    so updates are compared on one-pixel frames, where the two semantics coincide: ten updates, the cache bit-equal after each."""
+    P, scene, o, ref = _setup("irradianceCache", ic_size=512)
+    prep = dict(previousFrames=0xFFFFFFFF, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, isIrradiancePrepareFrame=1, samplesPerPixel=1)
+    for f in range(3):
+        pc = _pc(P, f, irradianceCreateProb=0.02, irradianceUpdateProb=0.0, **prep)
+        o.render_region(pc, threads=NT)
+        if ref:
+            ref.render(pc)
+        _check("ic_create_%d:cache" % f, _cache_bytes(o.ic_get(P)), _cache_bytes(_ref_ic_get(P, ref)) if ref else None)
+        _check("ic_create_%d" % f, o.image(), ref.image() if ref else None)
+    assert o.ic_get(P)[0].nextCacheSlot > 60
+    rng = np.random.default_rng(5)
+    for k in range(10):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        pc = _pc(P, 100 + k, irradianceCreateProb=0.0, irradianceUpdateProb=1.0, **prep)
+        o.render_region(pc, x0=x, y0=y, x1=x + 1, y1=y + 1, threads=1)
+        if ref:
+            assert ref.S.shader_ref_render(C.byref(pc), x, y, x + 1, y + 1) == 0
+        _check("ic_update_%d:cache" % k, _cache_bytes(o.ic_get(P)), _cache_bytes(_ref_ic_get(P, ref)) if ref else None)
+    assert o.ic_get(P)[0].nextUpdateSlot == 10
