@@ -89,6 +89,11 @@ CPU_SAMPLE = "same scene, camera, 1280x720 view and %d spp per step; rows %s of 
     SPP, ", ".join("%d-%d" % (a, b - 1) for a, b in CPU_SAMPLE_ROWS))
 
 
+# what "port" means here: the reference has no CPU renderer (its path tracer is GLSL on RT cores); the port is oracle/tracer_oracle.cpp,
+# whose frames are bit-equal to the reference's own shader source compiled as C++ and run on the CPU (tests/test_shader_ref.py)
+PORT_PIN = "frames bit-equal to the reference's shader source compiled as C++ (oracle/shader_ref.cpp, tests/test_shader_ref.py)"
+
+
 def cpu_oracle_run(P, frames, threads):
     """The oracle (CPU port of the reference's shader megakernel, oracle/tracer_oracle.cpp, own BVH) on a bounded sample
     of the workload: the configuration is the bench's (view, 1280x720, SPP spp per step, same push constants), the
@@ -179,7 +184,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "spp_per_step": SPP},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if world == 1 and not args.no_em:
         # second headline: the reference's CPU guiding fit (its own lightpmm code), all host threads
@@ -525,7 +530,7 @@ def main():
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             times, crays = cpu_oracle_run(P, 3, threads)       # 1 warm-up + 2 timed steps of the bounded sample
-            line["cpu_baseline"] = {"value": sum(crays[1:]) / sum(times[1:]) / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE}
+            line["cpu_baseline"] = {"value": sum(crays[1:]) / sum(times[1:]) / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
