@@ -122,6 +122,16 @@ def _pc(P, frame, **kw):
     return P.default_push_constants(**base)
 
 
+IC_CASES = (dict(useIrradianceCacheOnGlossy=1), dict(useIrradianceGradients=0), dict(irradianceCachePerformVisibilityCheck=1, irradianceA=0.5),
+            dict(useIrradianceCacheOnGlossy=1, irradianceNumNEE=3, numNEE=2))
+# RayTracingApp::setEstimateRTSettings (src/RayTracingApp.cpp:1206-1217), at 4 spp
+ESTIMATE_FRAME = dict(storeEstimate=1, samplesPerPixel=4, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, enableNEE=1, maxDepth=1, maxFollowDiscrete=10, numNEE=5, useADRRS=0)
+ADRRS_CASES = (dict(useADRRS=1, adrrsSplit=1, adrrsS=5.0), dict(useADRRS=1, adrrsSplit=0, adrrsS=2.0), dict(splitOnFirst=1, enableMIS=0),
+               dict(useADRRS=1, adrrsSplit=1, adrrsS=5.0, useIrradianceCache=1, useIrradianceCacheOnGlossy=1))
+GUIDING_CASES = (dict(useGuiding=1, guidingProb=0.5, useParallaxCompensation=1), dict(useGuiding=1, guidingProb=1.0, useParallaxCompensation=0),
+                 dict(updateGuiding=1), dict(updateGuiding=1, useGuiding=1, guidingProb=0.5, enableMIS=0))
+
+
 def _cache_from_oracle(P, o, frames=4):
     for f in range(frames):       # RayTracingApp::raytrace during the prepare frames (src/RayTracingApp.cpp:1130-1143)
         o.render_region(_pc(P, f, previousFrames=0xFFFFFFFF, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, isIrradiancePrepareFrame=1,
@@ -139,8 +149,7 @@ def test_irradiance_cache_lookup_frames_are_bit_equal():
     if ref:
         ref.ic_put(*cache)
     off = dict(irradianceCreateProb=0.0, irradianceUpdateProb=0.0, useIrradianceCache=1)
-    for i, kw in enumerate((dict(useIrradianceCacheOnGlossy=1), dict(useIrradianceGradients=0), dict(irradianceCachePerformVisibilityCheck=1, irradianceA=0.5),
-                            dict(useIrradianceCacheOnGlossy=1, irradianceNumNEE=3, numNEE=2))):
+    for i, kw in enumerate(IC_CASES):
         pc = _pc(P, 20 + i, **off, **kw)
         o.render_region(pc, threads=NT)
         if ref:
@@ -156,14 +165,12 @@ def test_adrrs_and_split_frames_are_bit_equal():
     if ref:
         ref.ic_put(*cache)
     off = dict(irradianceCreateProb=0.0, irradianceUpdateProb=0.0)
-    est_pc = _pc(P, 30, storeEstimate=1, samplesPerPixel=4, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, enableNEE=1, maxDepth=1, maxFollowDiscrete=10,
-                 numNEE=5, useADRRS=0, **off)
+    est_pc = _pc(P, 30, **ESTIMATE_FRAME, **off)
     o.render_region(est_pc, threads=NT)
     if ref:
         ref.render(est_pc)
     _check("estimate_frame", o.image(P.IMAGE_ESTIMATE), ref.image(2) if ref else None)
-    for i, kw in enumerate((dict(useADRRS=1, adrrsSplit=1, adrrsS=5.0), dict(useADRRS=1, adrrsSplit=0, adrrsS=2.0), dict(splitOnFirst=1, enableMIS=0),
-                            dict(useADRRS=1, adrrsSplit=1, adrrsS=5.0, useIrradianceCache=1, useIrradianceCacheOnGlossy=1))):
+    for i, kw in enumerate(ADRRS_CASES):
         pc = _pc(P, 40 + i, **off, **kw)
         o.render_region(pc, threads=NT)
         if ref:
@@ -190,8 +197,7 @@ def test_guided_sampling_and_sample_recording_are_bit_equal():
     o.set_guiding(aabbs, vmms)
     if ref:
         ref.set_guiding(aabbs, vmms)
-    for i, kw in enumerate((dict(useGuiding=1, guidingProb=0.5, useParallaxCompensation=1), dict(useGuiding=1, guidingProb=1.0, useParallaxCompensation=0),
-                            dict(updateGuiding=1), dict(updateGuiding=1, useGuiding=1, guidingProb=0.5, enableMIS=0))):
+    for i, kw in enumerate(GUIDING_CASES):
         pc = _pc(P, 50 + i, numGuidingRegions=len(aabbs), **kw)
         o.render_region(pc, threads=NT)
         if ref:
