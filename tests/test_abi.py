@@ -74,3 +74,17 @@ def test_exr_round_trip(tmp_path):
     cvimg = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if cvimg is not None:
         assert np.array_equal(cvimg[..., ::-1], img[..., :3])
+
+
+def test_cli_usage_and_no_cpu_fallback():
+    """the headless command line (src/main.cpp:8-35): usage without arguments; without a CUDA device it fails loudly instead of rendering
+    on the CPU"""
+    import os
+    import subprocess
+    cli = os.path.join(helpers.PKG_DIR, "b200pt")
+    p = subprocess.run([cli], capture_output=True, text=True)
+    assert p.returncode != 0 and "WIDTH HEIGHT IC_SIZE GUIDING_SPLITS" in p.stdout
+    if helpers.has_gpu():
+        return
+    p = subprocess.run([cli, "64", "36", "0", "0", helpers.scene_path("cornell-dielectric"), "--frames=1"], capture_output=True, text=True)
+    assert p.returncode != 0 and "no CUDA device" in (p.stdout + p.stderr)
