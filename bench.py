@@ -15,8 +15,9 @@ kernels and the collective run on, max over ranks.  torch.distributed only carri
 max / sum of the per-rank numbers.  Extra objects of the JSON line: `strong` (1024 spp split over the N GPUs, time to the
 reduced image), `config5` (BASELINE configs[4]: 4K guiding training with the region-sharded refit, per-phase times),
 `em` (BASELINE configs[0], N = 1 only).
---impl reference times the CPU restatement of the reference's tracer (oracle/, all host threads) on the SAME view,
-resolution and spp, restricted to a bounded sample of the image rows (every 8th block of 10 rows).
+--impl reference times the reference's own shader source compiled as C++ (oracle/_ref/libshader_ref.so, one process per host
+core; without that library the CPU restatement oracle/tracer_oracle.cpp) on the SAME view, resolution and spp, restricted to a
+bounded sample of the image rows (every 8th block of 10 rows).
 """
 import argparse
 import importlib.util
@@ -117,6 +118,61 @@ def cpu_oracle_run(P, frames, threads):
     return times, rays
 
 
+SHADER_REF = os.path.join(ROOT, "oracle", "_ref", "libshader_ref.so")
+REFERENCE_KIND = ("the reference's own shader source (raytrace.rgen + hit / miss / intersection shaders) compiled as C++ and run on the CPU, one process per "
+                  "host core (oracle/shader_ref.cpp); ray / primitive intersection, texture filtering and the elementary functions — what the reference "
+                  "leaves to the driver — come from oracle/tracer_oracle.cpp")
+_ref_worker = {}
+
+
+def _ref_worker_init():
+    """one per process: the compiled reference shaders keep their descriptor sets in globals, like a shader invocation does"""
+    import ctypes as C
+    import numpy as np
+    P = _load("b200pt_binding", os.path.join(ROOT, "rtx-pathtracer_b200", "b200pt.py"))
+    O = _load("b200pt_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    scene = P.Scene(SCENE)
+    view, proj = scene.camera_matrices(WIDTH / HEIGHT)
+    o = O.TracerOracle(8, 8, 0, accel=True)        # only its traversal and its sampler are used (callbacks): no frame-sized buffers needed
+    o.set_scene(scene.desc)
+    S = C.CDLL(SHADER_REF)
+    S.shader_ref_rays_traced.restype = C.c_uint64
+    S.shader_ref_init(WIDTH, HEIGHT, 0)
+    S.shader_ref_set_scene(C.byref(scene.desc))
+    f = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+    S.shader_ref_set_camera(f(view), f(proj), f(P.mat4_inverse(view)), f(P.mat4_inverse(proj)))
+    L = O.lib()
+    S.shader_ref_set_callbacks(o._h, C.cast(L.oracle_trace_one, C.c_void_p), C.cast(L.oracle_texture, C.c_void_p))
+    _ref_worker.update(P=P, S=S, scene=scene, oracle=o, C=C)
+
+
+def _ref_worker_rows(job):
+    frame, rows = job
+    P, S, C = _ref_worker["P"], _ref_worker["S"], _ref_worker["C"]
+    pc = push_constants(P, P.tea(frame, SEED), 0, SPP)
+    before = S.shader_ref_rays_traced()
+    for y in rows:
+        assert S.shader_ref_render(C.byref(pc), 0, y, WIDTH, y + 1) == 0
+    return S.shader_ref_rays_traced() - before
+
+
+def cpu_reference_shaders_run(frames, procs):
+    """The reference's shader pipeline compiled as C++ (oracle/_ref/libshader_ref.so) on the bench's bounded sample: the rows of
+    CPU_SAMPLE_ROWS dealt round-robin to `procs` processes; wall time per frame around the whole pool."""
+    import multiprocessing as mp
+    rows = [y for y0, y1 in CPU_SAMPLE_ROWS for y in range(y0, y1)]
+    shares = [rows[k::procs] for k in range(procs)]
+    times, rays = [], []
+    with mp.get_context("fork").Pool(procs, initializer=_ref_worker_init) as pool:
+        pool.map(_ref_worker_rows, [(0, [])] * procs)          # every worker is up before the clock starts
+        for f in range(frames):
+            t0 = time.perf_counter()
+            counts = pool.map(_ref_worker_rows, [(f, sh) for sh in shares], chunksize=1)
+            times.append(time.perf_counter() - t0)
+            rays.append(sum(counts))
+    return times, rays
+
+
 EM_SPLITS, EM_PER_REGION = 8, 57600     # BASELINE configs[0]: 2^8 regions x (1280*720*16 / 256) records = the full sample buffer
 EM_BYTES_PER_SAMPLE_ITER = 16           # SURVEY.md §8(d): direction + weight per sample per EM iteration
 
@@ -171,20 +227,28 @@ def em_gpu(P, r, batches, torch, device):
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's tracer has no CPU implementation (GLSL + RT cores), so this times the CPU port
-    (oracle/) with every host thread, each step a bounded sample of the workload."""
+    """Reference arm: the reference's tracer has no CPU implementation (GLSL + RT cores).  What can run on the host is its shader source
+    compiled as C++ (oracle/_ref/libshader_ref.so, built from /root/reference in the build container): that is what is timed here, one
+    process per host core, each step a bounded sample of the workload.  Without that library: the CPU port (oracle/tracer_oracle.cpp)."""
     if rank != 0:
         return
     P = _load("b200pt_binding", os.path.join(ROOT, "rtx-pathtracer_b200", "b200pt.py"))
     threads = os.cpu_count() or 1
-    times, rays = cpu_oracle_run(P, args.warmup + args.steps, threads)
+    # the reference's own code when it compiled here (oracle/_ref travels with the repository), else the port
+    use_shaders = os.path.exists(SHADER_REF)
+    if use_shaders:
+        times, rays = cpu_reference_shaders_run(args.warmup + args.steps, threads)
+    else:
+        times, rays = cpu_oracle_run(P, args.warmup + args.steps, threads)
     t = sum(times[args.warmup:])
     r = sum(rays[args.warmup:])
     value = r / t / 1e6
+    baseline = ({"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": CPU_SAMPLE, "what": REFERENCE_KIND} if use_shaders else
+                {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN})
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "spp_per_step": SPP},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN},
+            "cpu_baseline": baseline,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if world == 1 and not args.no_em:
         # second headline: the reference's CPU guiding fit (its own lightpmm code), all host threads

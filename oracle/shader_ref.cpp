@@ -92,9 +92,11 @@ namespace guiding_rchit { static guidingInfo &info = glsl::guidingInfos;
 
 static int g_numGuidingRegions = 0;
 static uint g_icEntriesAtFrameStart = 0;
+static unsigned long long g_raysTraced = 0;
 static void traceRayEXT(accelerationStructureEXT as, uint flags, uint, uint, uint, uint missIndex, vec3 origin, float tmin, vec3 direction, float tmax, int) {
     gl_WorldRayOriginEXT = origin; gl_WorldRayDirectionEXT = direction; gl_RayTmaxEXT = tmax;
     if (as.id == 0) {                                   // topLevelAS: triangles + analytic spheres
+        g_raysTraced++;
         const float o[3] = {origin.x, origin.y, origin.z}, d[3] = {direction.x, direction.y, direction.z};
         float out[3]; uint32_t ids[4];
         const bool any = (flags & gl_RayFlagsTerminateOnFirstHitEXT) != 0u;
@@ -146,9 +148,7 @@ int shader_ref_init(int width, int height, int ic_size) {
     const size_t n = size_t(width) * height * 4;
     s_image.assign(n, 0.0f); s_accum.assign(n, 0.0f); s_estimate.assign(n, 0.0f);
     image = image2D{s_image.data(), width}; accumulateImage = image2D{s_accum.data(), width}; estimateImage = image2D{s_estimate.data(), width};
-    s_samples.assign(size_t(width) * height * MAX_DIRECTIONAL_DATA_PER_PIXEL, DirectionalData());
-    for (auto &d : s_samples) d.flags = INVALID;
-    directionalData = s_samples.data();
+    s_samples.clear(); directionalData = nullptr;          // binding 18 (W * H * 16 records) is allocated by the first training frame
     const size_t ic = size_t(ic_size > 0 ? ic_size : 1);
     s_cacheSpheres.assign(ic, sphere()); s_cache.assign(ic, cacheData()); s_cacheAabbs.assign(ic, aabb());
     cacheSpheres = s_cacheSpheres.data(); cache = s_cache.data(); cacheAabbs = s_cacheAabbs.data();
@@ -249,6 +249,8 @@ void shader_ref_ic_get(b200pt_cache_header *h, b200pt_cache_data *data, b200pt_s
     }
 }
 
+unsigned long long shader_ref_rays_traced(void) { return g_raysTraced; }     // extend + shadow rays handed to the callback so far
+
 float *shader_ref_image(int which) { return which == 0 ? s_image.data() : which == 1 ? s_accum.data() : s_estimate.data(); }
 void *shader_ref_samples(void) { return s_samples.data(); }
 
@@ -267,6 +269,11 @@ int shader_ref_render(const b200pt_push_constants *pc, int x0, int y0, int x1, i
     PCF(guidingPiPHighlightRegion); PCF(guidingPiPShowSpheres); PCF(guidingPiPSize);
 #undef PCF
     if (!g_trace || !g_texture) return -1;
+    if (pc->updateGuiding && s_samples.empty()) {
+        s_samples.assign(size_t(s_width) * s_height * MAX_DIRECTIONAL_DATA_PER_PIXEL, DirectionalData());
+        for (auto &d : s_samples) d.flags = INVALID;
+        directionalData = s_samples.data();
+    }
     g_icEntriesAtFrameStart = header.nextCacheSlot < header.maxCaches ? header.nextCacheSlot : header.maxCaches;
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
