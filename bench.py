@@ -173,6 +173,21 @@ def cpu_reference_shaders_run(frames, procs):
     return times, rays
 
 
+def cpu_baseline_reference_shaders():
+    """cpu_baseline of the GPU arm's line: the reference arm (1 warm-up + 2 timed steps of the bounded sample) in a process of its own —
+    its workers are forked, and nothing is forked from a process that holds a CUDA context.  None when the library is absent or the run fails."""
+    if not os.path.exists(SHADER_REF):
+        return None
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--no-em"],
+                             capture_output=True, text=True, timeout=600, env=env)
+        cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        return cpu if cpu.get("kind") == "reference" and cpu.get("value", 0) > 0 else None
+    except Exception:
+        return None
+
+
 EM_SPLITS, EM_PER_REGION = 8, 57600     # BASELINE configs[0]: 2^8 regions x (1280*720*16 / 256) records = the full sample buffer
 EM_BYTES_PER_SAMPLE_ITER = 16           # SURVEY.md §8(d): direction + weight per sample per EM iteration
 
@@ -592,9 +607,12 @@ def main():
                     em["strict_speedup_vs_cpu_all_cores"] = per_order["strict"]["value"] / cpu["value"]
             line["em"] = em
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            times, crays = cpu_oracle_run(P, 3, threads)       # 1 warm-up + 2 timed steps of the bounded sample
-            line["cpu_baseline"] = {"value": sum(crays[1:]) / sum(times[1:]) / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN}
+            cpu = cpu_baseline_reference_shaders() if world == 1 else None
+            if cpu is None:      # the compiled reference shaders did not travel (or N > 1): the port, threads inside this process
+                threads = os.cpu_count() or 1
+                times, crays = cpu_oracle_run(P, 3, threads)       # 1 warm-up + 2 timed steps of the bounded sample
+                cpu = {"value": sum(crays[1:]) / sum(times[1:]) / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE, "port_checked_against": PORT_PIN}
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
