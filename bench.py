@@ -181,7 +181,7 @@ def cpu_baseline_reference_shaders():
     try:
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--no-em"],
-                             capture_output=True, text=True, timeout=600, env=env)
+                             capture_output=True, text=True, timeout=240, env=env)
         cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         return cpu if cpu.get("kind") == "reference" and cpu.get("value", 0) > 0 else None
     except Exception:
