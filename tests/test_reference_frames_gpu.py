@@ -25,7 +25,10 @@ def _close(img, ref, what):
     assert (rel <= 1e-4).all(), (what, float(rel.max()), float((rel > 1e-4).any(-1).mean()))
 
 
-@pytest.mark.parametrize("scene_name,kw", T.PLAIN, ids=[T.frame_key(s, k) for s, k in T.PLAIN])
+GPU_CASES = T.PLAIN[:17]      # the cases that have run on a B200 (profiles/r02c_gpu_calls.txt); later additions of T.PLAIN are oracle-vs-reference only so far
+
+
+@pytest.mark.parametrize("scene_name,kw", GPU_CASES, ids=[T.frame_key(s, k) for s, k in GPU_CASES])
 def test_device_frames_match_the_reference_shaders(scene_name, kw):
     P = helpers.pt()
     scene, r, _ = helpers.make_pair(scene_name, W, H)

@@ -93,7 +93,8 @@ PLAIN = [("cornell-dielectric", dict(enableMIS=1)), ("cornell-dielectric", dict(
          ("miPhong", dict(enableMIS=1)), ("miPhong", dict(enableNEE=0)),
          ("test-scene", dict(enableMIS=1)), ("test-scene", dict(enableNEE=0, maxDepth=3, maxFollowDiscrete=1)),
          ("envMap", dict(enableMIS=1)), ("envSynthetic", dict(enableMIS=1)), ("testSpheres", dict(enableMIS=1, useVisibleSphereSampling=1)),
-         ("sponzaXML", dict(enableMIS=1, samplesPerPixel=1, maxDepth=4)), ("stackedCards", dict(enableMIS=1)), ("alphaLeaf", dict(enableMIS=1))]
+         ("sponzaXML", dict(enableMIS=1, samplesPerPixel=1, maxDepth=4)), ("stackedCards", dict(enableMIS=1)), ("alphaLeaf", dict(enableMIS=1)),
+         ("veachMIS", dict(enableMIS=1, enableAverageInsteadOfMix=0)), ("miPhong", dict(enableMIS=1, maxDepth=0, maxFollowDiscrete=0))]
 
 
 def frame_key(scene_name, kw):
@@ -260,8 +261,8 @@ def test_irradiance_cache_creation_and_update_are_bit_equal():
     so updates are compared on one-pixel frames, where the two semantics coincide: ten updates, the cache bit-equal after each."""
     P, scene, o, ref = _setup("irradianceCache", ic_size=512)
     prep = dict(previousFrames=0xFFFFFFFF, useIrradianceCache=1, useIrradianceCacheOnGlossy=1, isIrradiancePrepareFrame=1, samplesPerPixel=1)
-    for f in range(3):
-        pc = _pc(P, f, irradianceCreateProb=0.02, irradianceUpdateProb=0.0, **prep)
+    for f in range(3):      # (the third frame with tighter gradient / radius clamps)
+        pc = _pc(P, f, irradianceCreateProb=0.02, irradianceUpdateProb=0.0, **prep, **(dict(irradianceGradientsMaxLength=0.05, irradianceCacheMinRadius=0.3) if f == 2 else {}))
         o.render_region(pc, threads=NT)
         if ref:
             ref.render(pc)
