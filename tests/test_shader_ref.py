@@ -278,3 +278,28 @@ def test_irradiance_cache_creation_and_update_are_bit_equal():
             assert ref.S.shader_ref_render(C.byref(pc), x, y, x + 1, y + 1) == 0
         _check("ic_update_%d:cache" % k, _cache_bytes(o.ic_get(P)), _cache_bytes(_ref_ic_get(P, ref)) if ref else None)
     assert o.ic_get(P)[0].nextUpdateSlot == 10
+
+
+def test_config2_rows_at_full_resolution_are_bit_equal():
+    """BASELINE config 2 as the bench renders it (cornell-dielectric 1280x720, NEE + MIS, power heuristic, maxDepth 30, 16 spp): four rows
+    spread over the frame — the launch size enters the per-pixel seed and the camera ray."""
+    global W, H
+    P = helpers.pt()
+    old = (W, H)
+    try:
+        W, H = 1280, 720
+        scene, _, o = helpers.make_pair("cornell-dielectric", W, H, gpu=False)
+        view, proj = scene.camera_matrices(W / H)
+        ref = ShaderRef(scene, view, proj, o) if os.path.exists(SHADER_REF) else None
+        pc = P.default_push_constants(randomUInt=P.tea(0, 0xC0FFEE), previousFrames=0, samplesPerPixel=16, enableNEE=1, enableMIS=1, usePowerHeuristic=1, numNEE=1,
+                                      maxDepth=30, maxFollowDiscrete=3)
+        rows = (0, 241, 478, 719)
+        for y in rows:
+            o.render_region(pc, 0, y, W, y + 1, threads=NT)
+            if ref:
+                assert ref.S.shader_ref_render(C.byref(pc), 0, y, W, y + 1) == 0
+        ours = np.stack([o.image()[y] for y in rows])
+        assert np.abs(ours[..., :3]).sum() > 0
+        _check("config2_rows", ours, np.stack([ref.image()[y] for y in rows]) if ref else None)
+    finally:
+        W, H = old
