@@ -15,7 +15,8 @@
 //                                                      std::sort(par_unseq) leaves the order within a region unspecified)
 //       update / updateRegion / preFit / postFit       PathGuiding.cpp:276-312, 350-451
 //       computeEigenValuesVectors                      PathGuiding.cpp:454-484     (Eigen::EigenSolver restated for 2x2,
-//                                                      see eigen2x2 below — Eigen is absent: this piece is UNPINNED)
+//                                                      see eigen2x2 below — Eigen is absent: this piece is pinned to the
+//                                                      DEFINITION only, M v = lambda v against numpy in float64, tests/test_guiding_cpu.py)
 //       splitComponentUsingPCA / splitAll              PathGuiding.cpp:494-633
 //       mergeAll / computePearsonChiSquaredMergeMetric / mergeComponents   PathGuiding.cpp:635-788
 //       pmmToVMM_Theta / syncPMMsToVMM_Thetas / VMF_Theta::setK            PathGuiding.cpp:53-69,106-132, PathGuiding.h:36-56
@@ -486,6 +487,13 @@ void *refguiding_create(int splits, const float scene_min[3], const float scene_
     return g;
 }
 void refguiding_destroy(void *h) { delete static_cast<RefGuiding *>(h); }
+// the restated 2x2 eigen decomposition on its own (row-major m, eigenvectors as columns of V), for tests/test_guiding_cpu.py
+void refguiding_eigen2x2(const float m[4], float eval[2], float V[4]) {
+    const float mm[2][2] = {{m[0], m[1]}, {m[2], m[3]}};
+    float vv[2][2];
+    eigen2x2(mm, eval, vv);
+    V[0] = vv[0][0]; V[1] = vv[0][1]; V[2] = vv[1][0]; V[3] = vv[1][1];
+}
 int refguiding_region_count(void *h) { return int(static_cast<RefGuiding *>(h)->regionCount); }
 void refguiding_get_aabbs(void *h, b200pt_aabb *out) { auto *g = static_cast<RefGuiding *>(h); memcpy(out, g->aabbs.data(), g->aabbs.size() * sizeof(b200pt_aabb)); }
 void refguiding_update(void *h, const b200pt_directional_data *samples, int64_t n, int threads) { static_cast<RefGuiding *>(h)->update(samples, n, threads); }
