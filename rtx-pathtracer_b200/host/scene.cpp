@@ -140,6 +140,21 @@ static bool parseFloats(const char *s, float *out, int n) {
     return true;
 }
 
+// one line of an OBJ / MTL file: terminated by "\n", "\r\n" or a lone "\r" (old Mac exports — test-scene's sphere.obj is one), like
+// tinyobjloader's safeGetline; std::getline would hand such a file over as a single line and every statement after the first be lost
+static bool getLineAnyEol(std::istream &in, std::string &line) {
+    line.clear();
+    std::streambuf *sb = in.rdbuf();
+    if (!in.good()) return false;
+    for (;;) {
+        const int c = sb->sbumpc();
+        if (c == '\n') return true;
+        if (c == '\r') { if (sb->sgetc() == '\n') sb->sbumpc(); return true; }
+        if (c == std::streambuf::traits_type::eof()) { in.setstate(std::ios::eofbit); return !line.empty(); }
+        line.push_back(char(c));
+    }
+}
+
 static void readMtl(const std::string &path, std::vector<ObjMaterial> &mats, std::map<std::string, int> &byName) {
     std::ifstream in(path);
     if (!in) return;   // tinyobj only warns when a material file is missing
@@ -147,7 +162,7 @@ static void readMtl(const std::string &path, std::vector<ObjMaterial> &mats, std
     ObjMaterial cur;
     bool have = false;
     auto flush = [&]() { if (have) { byName[cur.name] = int(mats.size()); mats.push_back(cur); } };
-    while (std::getline(in, line)) {
+    while (getLineAnyEol(in, line)) {
         size_t p = line.find_first_not_of(" \t\r");
         if (p == std::string::npos || line[p] == '#') continue;
         while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
@@ -227,7 +242,7 @@ void readObj(const std::string &path, const std::string &mtlBaseDir, ObjData &ou
     int curMat = -1;
     std::string line;
     std::vector<ObjIndex> poly, tris;
-    while (std::getline(in, line)) {
+    while (getLineAnyEol(in, line)) {
         const char *s = line.c_str();
         while (*s == ' ' || *s == '\t') s++;
         if (s[0] == 'v' && (s[1] == ' ' || s[1] == '\t')) {
