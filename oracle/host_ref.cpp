@@ -22,6 +22,7 @@ extern "C" int host_ref_weighted_samples(const float *values, int n, int count, 
 #define TINYOBJLOADER_IMPLEMENTATION
 #include "tiny_obj_loader.h"
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -43,7 +44,7 @@ struct RefVertexHash {
         return h * 31 + size_t(v.mat);
     }
 };
-struct RefObj { std::vector<RefVertex> vertices; std::vector<uint32_t> indices; int numMaterials = 0; std::string error; };
+struct RefObj { std::vector<RefVertex> vertices; std::vector<uint32_t> indices; int numMaterials = 0; std::string error; std::vector<tinyobj::material_t> materials; };
 }
 
 extern "C" void *host_ref_obj_load(const char *path, const char *mtl_dir, int material_override) {
@@ -52,6 +53,7 @@ extern "C" void *host_ref_obj_load(const char *path, const char *mtl_dir, int ma
     std::string warn, err;
     if (!tinyobj::LoadObj(&attrib, &shapes, &materials, &warn, &err, path, mtl_dir)) { r->error = warn + err; return r; }
     r->numMaterials = int(materials.size());
+    r->materials = materials;
     const bool hasNormals = !attrib.normals.empty(), hasTexCoords = !attrib.texcoords.empty();
     std::unordered_map<RefVertex, uint32_t, RefVertexHash> unique;
     for (const auto &shape : shapes) {
@@ -95,3 +97,12 @@ extern "C" void host_ref_obj_copy(void *h, float *verts8 /* pos, normal, uv */, 
     memcpy(indices, r->indices.data(), r->indices.size() * 4);
 }
 extern "C" void host_ref_obj_free(void *h) { delete static_cast<RefObj *>(h); }
+
+// material i of the file's .mtl as the reference's parser read it: emission, diffuse, specular (3 each), shininess, ior, then illum and
+// the two texture names SceneLoader::addMaterials looks at (src/SceneLoader.cpp:139-182)
+extern "C" void host_ref_obj_material(void *h, int i, float out11[11], int *illum, char *diffuse_tex, char *specular_tex, int cap) {
+    const tinyobj::material_t &m = static_cast<RefObj *>(h)->materials[size_t(i)];
+    for (int a = 0; a < 3; a++) { out11[a] = m.emission[a]; out11[3 + a] = m.diffuse[a]; out11[6 + a] = m.specular[a]; }
+    out11[9] = m.shininess; out11[10] = m.ior; *illum = m.illum;
+    snprintf(diffuse_tex, size_t(cap), "%s", m.diffuse_texname.c_str()); snprintf(specular_tex, size_t(cap), "%s", m.specular_texname.c_str());
+}

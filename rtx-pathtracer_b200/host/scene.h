@@ -85,7 +85,7 @@ private:
 struct ObjIndex { int v, vt, vn; };
 struct ObjMaterial {
     std::string name;
-    float emission[3] = {0, 0, 0}, diffuse[3] = {0.6f, 0.6f, 0.6f}, specular[3] = {0, 0, 0};
+    float emission[3] = {0, 0, 0}, diffuse[3] = {0, 0, 0}, specular[3] = {0, 0, 0};      // InitMaterial of the reference's vendored tiny_obj_loader.h:1276-1310 (newer tinyobj versions default Kd to 0.6)
     float shininess = 1.0f, ior = 1.0f;
     int illum = 0;
     std::string diffuseTex, specularTex;

@@ -321,3 +321,41 @@ def test_obj_line_endings_lf_crlf_and_cr_only(tmp_path):
     scene = P.Scene(helpers.scene_path("test-scene"))
     assert all(scene.desc.num_indices[m] > 0 for m in range(scene.desc.num_models))
     assert scene.num_triangles == 19046 + 3 * 320                             # 3 instances of the two 320-triangle spheres were empty before
+
+
+def test_mtl_materials_equal_the_reference_parser():
+    """The JSON scenes take their materials from .mtl files: every material of scenes/test-scene against what the reference's parser
+    (tinyobjloader, compiled into oracle/_ref/libhost_ref.so) reads from the same files, mapped like SceneLoader::addMaterials
+    (src/SceneLoader.cpp:139-182): Ke / Kd / Ks / Ns / Ni, 1 / Ni, illum -> material type, materials accumulated file after file."""
+    import ctypes as C
+    if not os.path.exists(HOST_REF):
+        pytest.skip("oracle/_ref/libhost_ref.so needs the reference tree")
+    P = helpers.pt()
+    scene_file = helpers.scene_path("test-scene")
+    scene = P.Scene(scene_file)
+    R = C.CDLL(HOST_REF)
+    R.host_ref_obj_load.restype = C.c_void_p
+    R.host_ref_obj_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    R.host_ref_obj_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.host_ref_obj_material.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    R.host_ref_obj_free.argtypes = [C.c_void_p]
+    illum_to_type = {0: 0, 1: 0, 2: 4, 3: 1, 4: 2, 7: 2, 11: 3}          # eDiffuse, ePhong, eSpecular, eDielectric, eLight
+    k = 0
+    for path, mtl_dir, _ in _obj_files_of(scene_file):
+        h = R.host_ref_obj_load(path.encode(), mtl_dir.encode(), -1)
+        nv, ni, nm = C.c_int(), C.c_int(), C.c_int()
+        R.host_ref_obj_counts(h, C.byref(nv), C.byref(ni), C.byref(nm))
+        assert nm.value >= 1, path
+        for i in range(nm.value):
+            vals, illum = np.zeros(11, np.float32), C.c_int()
+            dtex, stex = C.create_string_buffer(512), C.create_string_buffer(512)
+            R.host_ref_obj_material(h, i, vals.ctypes.data, C.byref(illum), dtex, stex, 512)
+            m = scene.desc.materials[k]
+            assert np.array_equal(np.array(m.lightColor[:], np.float32), vals[0:3]) and np.array_equal(np.array(m.diffuse[:], np.float32), vals[3:6]), (path, i)
+            assert np.array_equal(np.array(m.specular[:], np.float32), vals[6:9]) and np.float32(m.specularHighlight) == vals[9], (path, i)
+            assert np.float32(m.refractionIndex) == vals[10] and np.float32(m.refractionIndexInv) == np.float32(1.0) / vals[10], (path, i)
+            assert m.type == illum_to_type[illum.value], (path, i, illum.value)
+            assert (m.textureIdDiffuse != -1) == bool(dtex.value or stex.value), (path, i)       # (sic: a specular map lands in textureIdDiffuse too, :175-177)
+            k += 1
+        R.host_ref_obj_free(h)
+    assert k == scene.desc.num_materials
