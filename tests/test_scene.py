@@ -359,3 +359,45 @@ def test_mtl_materials_equal_the_reference_parser():
             k += 1
         R.host_ref_obj_free(h)
     assert k == scene.desc.num_materials
+
+
+def test_json_instance_transforms_follow_parse_instances():
+    """SceneLoader::parseInstances (src/SceneLoader.cpp:706-758): transform = T * Rx * Ry * Rz * S with GLM's post-multiplying
+    translate / rotate (degrees -> radians, axes x, y, z in that order) / scale, normalTransform = Rx * Ry * Rz * S^-1; area lights get an
+    instance index, point lights follow.  Recomputed here in float64 from the JSON file and compared with the loader's column-major matrices."""
+    import json
+    P = helpers.pt()
+    path = helpers.scene_path("test-scene")
+    scene = P.Scene(path)
+    j = json.load(open(path))
+    names = [list(m.keys())[0] for m in j["models"]]
+
+    def rot(deg, axis):
+        c, s = np.cos(np.radians(deg)), np.sin(np.radians(deg))
+        m = np.eye(4)
+        a, b = [(1, 2), (2, 0), (0, 1)][axis]
+        m[a, a], m[a, b], m[b, a], m[b, b] = c, -s, s, c
+        return m
+
+    assert scene.desc.num_instances == len(j["instances"])
+    for i, inst in enumerate(j["instances"]):
+        name, props = list(inst.items())[0]
+        T, N = np.eye(4), np.eye(4)
+        if "translate" in props:
+            t = np.eye(4); t[:3, 3] = props["translate"]; T = T @ t
+        if "rotate" in props:
+            for axis in range(3):
+                T = T @ rot(props["rotate"][axis], axis); N = N @ rot(props["rotate"][axis], axis)
+        if "scale" in props:
+            T = T @ np.diag(list(props["scale"]) + [1.0]); N = N @ np.diag([1.0 / x for x in props["scale"]] + [1.0])
+        got = scene.desc.instances[i]
+        assert got.modelIndex == names.index(name)
+        assert np.allclose(np.array(got.transform[:]).reshape(4, 4).T, T, rtol=1e-6, atol=1e-6), (i, name)
+        assert np.allclose(np.array(got.normalTransform[:]).reshape(4, 4).T, N, rtol=1e-6, atol=1e-6), (i, name)
+    lights = [scene.desc.lights[k] for k in range(scene.desc.num_lights)]
+    area = [l for l in lights if l.type == 0]
+    assert [l.instanceIndex for l in area] == [i for i, inst in enumerate(j["instances"]) if list(inst.keys())[0] == "lightBox"]
+    points = [l for l in lights if l.type == 1]
+    assert len(points) == len(j["lights"]) and lights[-len(points):] == points or all(l.type == 1 for l in lights[len(area):])
+    for l, jl in zip(points, j["lights"]):
+        assert np.allclose(l.color[:], jl["color"]) and np.allclose(l.pos[:], jl["position"])
