@@ -401,3 +401,107 @@ def test_json_instance_transforms_follow_parse_instances():
     assert len(points) == len(j["lights"]) and lights[-len(points):] == points or all(l.type == 1 for l in lights[len(area):])
     for l, jl in zip(points, j["lights"]):
         assert np.allclose(l.color[:], jl["color"]) and np.allclose(l.pos[:], jl["position"])
+
+
+def _expected_xml_scene(scene_file):
+    """SceneLoader::parseMitsubaSceneFile recomputed with ElementTree (src/SceneLoader.cpp:329-648, src/MitsubaXML.h): the material list —
+    top-level <bsdf> in document order, then per shape an inline <bsdf> and, for a shape with an <emitter>, a light copy of its
+    material — and the material index of every obj model and sphere."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(scene_file).getroot()
+
+    def named(el, tag, name):
+        for c in el.findall(tag):
+            if c.get("name") == name:
+                return c
+        raise KeyError(name)
+
+    def rgb(el, name):
+        vals = [float(x) for x in named(el, "rgb", name).get("value").replace(",", " ").split()]
+        return vals * 3 if len(vals) == 1 else vals
+
+    textures = {}
+    for i, t in enumerate(root.findall("texture")):
+        textures[t.get("id")] = 1 + i                      # slot 0 is the environment map; scenes here do not repeat a file
+
+    def bsdf(el):
+        m = dict(type=None, diffuse=None, specular=None, exponent=None, ior=None, eta=None, k=None, alpha=None, tex=-1, light=None)
+        t = el.get("type")
+        if t == "phong":
+            m.update(type=4, specular=rgb(el, "specularReflectance"), diffuse=rgb(el, "diffuseReflectance"), exponent=float(named(el, "float", "exponent").get("value")))
+        elif t == "diffuse":
+            m.update(type=0, specular=[0, 0, 0], exponent=0.0)
+            ref = el.find("ref")
+            if ref is not None and ref.get("name") == "reflectance":
+                m.update(diffuse=[1, 1, 1], tex=textures[ref.get("id")])
+            else:
+                m.update(diffuse=rgb(el, "reflectance"))
+        elif t == "dielectric":
+            m.update(type=2, specular=[1, 1, 1], ior=np.float32(named(el, "float", "intIOR").get("value")) / np.float32(named(el, "float", "extIOR").get("value")))
+        elif t == "conductor":
+            mat = [s for s in el.findall("string") if s.get("name") == "material"]
+            if mat and mat[0].get("value") == "none":
+                m.update(type=1, specular=[1, 1, 1])
+            else:
+                m.update(type=5, eta=float(named(el, "spectrum", "eta").get("value")), k=float(named(el, "spectrum", "k").get("value")))
+        elif t == "roughconductor":
+            m.update(type=6, alpha=float(named(el, "float", "alpha").get("value")), eta=float(named(el, "spectrum", "eta").get("value")), k=float(named(el, "spectrum", "k").get("value")))
+        return m
+
+    mats, by_id = [], {}
+    for el in root.findall("bsdf"):
+        by_id[el.get("id")] = len(mats)
+        mats.append(bsdf(el))
+    models, spheres = [], []
+    for sh in root.findall("shape"):
+        idx = -1
+        inline = sh.find("bsdf")
+        if inline is not None:
+            idx = len(mats); mats.append(bsdf(inline))
+        if idx < 0 and sh.find("ref") is not None:
+            idx = by_id[sh.find("ref").get("id")]
+        em = sh.find("emitter")
+        if em is not None:
+            light = dict(mats[idx]); light.update(type=3, light=rgb(em, "radiance"))
+            mats.append(light); idx = len(mats) - 1
+        if sh.get("type") == "obj":
+            models.append(idx)
+        elif sh.get("type") == "sphere":
+            p = named(sh, "point", "center")
+            spheres.append((idx, float(named(sh, "float", "radius").get("value")), [float(p.get(a)) for a in "xyz"]))
+    return mats, models, spheres
+
+
+@pytest.mark.parametrize("name", ["cornell-dielectric", "veachMIS", "miPhong", "irradianceCache", "envMap", "sponzaXML", "alphaLeaf", "stackedCards", "testSpheres", "envSynthetic"])
+def test_xml_materials_shapes_and_spheres_follow_the_reference_loader(name):
+    P = helpers.pt()
+    scene_file = helpers.scene_path(name)
+    scene = P.Scene(scene_file)
+    d = scene.desc
+    mats, models, spheres = _expected_xml_scene(scene_file)
+    assert d.num_materials == len(mats) and d.num_models == len(models) and d.num_spheres == len(spheres)
+    f32 = lambda x: np.array(x, np.float32)
+    for i, e in enumerate(mats):
+        m = d.materials[i]
+        assert m.type == e["type"], (i, m.type, e)
+        if e["diffuse"] is not None:
+            assert np.array_equal(f32(m.diffuse[:]), f32(e["diffuse"])), i
+        if e["specular"] is not None:
+            assert np.array_equal(f32(m.specular[:]), f32(e["specular"])), i
+        if e["exponent"] is not None:
+            assert np.float32(m.specularHighlight) == np.float32(e["exponent"]), i
+        if e["ior"] is not None:
+            assert np.float32(m.refractionIndex) == e["ior"] and np.float32(m.refractionIndexInv) == np.float32(1.0) / e["ior"], i
+        if e["eta"] is not None:
+            assert np.float32(m.eta) == np.float32(e["eta"]) and np.float32(m.k) == np.float32(e["k"]), i
+        if e["alpha"] is not None:
+            assert np.float32(m.roughness) == np.float32(e["alpha"]), i
+        if e["light"] is not None:
+            assert np.array_equal(f32(m.lightColor[:]), f32(e["light"])), i
+        assert m.textureIdDiffuse == e["tex"], (i, m.textureIdDiffuse, e["tex"])
+    for mi, want in enumerate(models):
+        _, vm, _ = _model_arrays(P, d, mi)
+        assert (vm == want).all(), (mi, want, np.unique(vm))
+    for si, (want, radius, center) in enumerate(spheres):
+        s = d.spheres[si]
+        assert s.materialIndex == want and np.float32(s.radius) == np.float32(radius) and np.array_equal(f32(s.center[:]), f32(center)), si
