@@ -491,6 +491,8 @@ static const char *flattenScene(const b200pt_scene_desc *s, std::vector<b200pt_v
                 uint32_t li = s->indices[m][3 * t + k];
                 float w[3];
                 mat4TransformPoint(inst.transform, s->vertices[m][li].pos, w);
+                // an overflowed coordinate or transform (1e40 in a file) would send the builder's binning out of its arrays
+                if (!(std::isfinite(w[0]) && std::isfinite(w[1]) && std::isfinite(w[2]))) return "a vertex position is not finite (after the instance transform)";
                 world.insert(world.end(), w, w + 3);
                 pvp[k] = vOff[m] + int(li);
             }

@@ -266,14 +266,22 @@ void readObj(const std::string &path, const std::string &mtlBaseDir, ObjData &ou
                 if (!*p) break;
                 ObjIndex idx{-1, -1, -1};
                 char *e;
+                // 1-based, or negative = relative to what has been read so far.  The reference's parser resolves an index without
+                // looking at it and the loader then reads out of bounds; a file is untrusted input here: anything outside the
+                // arrays (0, a forward reference, an overflowing number) is an error of the loader, not a wild read.
+                auto resolve = [&](long a, int count, const char *what) -> int {
+                    const long r = a > 0 ? a - 1 : long(count) + a;
+                    if (r < 0 || r >= long(count)) throw std::runtime_error(std::string("OBJ: ") + what + " index out of range in " + path);
+                    return int(r);
+                };
                 long a = strtol(p, &e, 10);
                 if (e == p) break;
-                idx.v = a > 0 ? int(a) - 1 : nv + int(a);
+                idx.v = resolve(a, nv, "vertex");
                 p = e;
                 if (*p == '/') {
                     p++;
-                    if (*p != '/') { long b = strtol(p, &e, 10); if (e != p) idx.vt = b > 0 ? int(b) - 1 : nt + int(b); p = e; }
-                    if (*p == '/') { p++; long c = strtol(p, &e, 10); if (e != p) idx.vn = c > 0 ? int(c) - 1 : nn + int(c); p = e; }
+                    if (*p != '/') { long b = strtol(p, &e, 10); if (e != p) idx.vt = resolve(b, nt, "texture coordinate"); p = e; }
+                    if (*p == '/') { p++; long c = strtol(p, &e, 10); if (e != p) idx.vn = resolve(c, nn, "normal"); p = e; }
                 }
                 poly.push_back(idx);
             }
@@ -400,7 +408,9 @@ struct XmlParser {
         }
         return r;
     }
+    int depth = 0;
     std::unique_ptr<XmlNode> parseElement() {
+        struct Depth { int &d; explicit Depth(int &x) : d(x) { if (++d > 256) throw std::runtime_error("XML: elements nested too deeply"); } ~Depth() { --d; } } guard(depth);
         skipMisc();
         if (i >= s.size() || s[i] != '<') throw std::runtime_error("XML: expected element");
         i++;
@@ -431,7 +441,12 @@ struct XmlParser {
             size_t lt = s.find('<', i);
             if (lt == std::string::npos) throw std::runtime_error("XML: missing close tag for " + node->name);
             i = lt;
-            if (starts("</")) { size_t e = s.find('>', i); i = e + 1; return node; }
+            if (starts("</")) {
+                size_t e = s.find('>', i);
+                if (e == std::string::npos) throw std::runtime_error("XML: unterminated close tag of " + node->name);     // (a truncated file; i = npos + 1 = 0 would parse it again, for ever)
+                i = e + 1;
+                return node;
+            }
             if (starts("<!--") || starts("<?") || starts("<!")) { skipMisc(); continue; }
             node->children.push_back(parseElement());
         }

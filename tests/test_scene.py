@@ -505,3 +505,51 @@ def test_xml_materials_shapes_and_spheres_follow_the_reference_loader(name):
     for si, (want, radius, center) in enumerate(spheres):
         s = d.spheres[si]
         assert s.materialIndex == want and np.float32(s.radius) == np.float32(radius) and np.array_equal(f32(s.center[:]), f32(center)), si
+
+
+def test_malformed_scene_files_raise_instead_of_crashing(tmp_path):
+    """Scene files are untrusted input.  Found by fuzzing in round 2c: a face index of 0 / out of range / overflowing long made the OBJ
+    reader index outside its arrays (the reference's parser does not look either); a truncated close tag sent the XML parser into endless
+    recursion; a coordinate that overflows float (1e40) sent the BVH builder's binning out of bounds.  All are loader errors now."""
+    import shutil
+    P = helpers.pt()
+    src = os.path.join(helpers.SCENES, "alphaLeaf")
+
+    def variant(name, rel, mutate):
+        dst = tmp_path / name
+        shutil.copytree(src, dst)
+        p = dst / rel
+        p.write_bytes(mutate(p.read_bytes()))
+        with pytest.raises(P.B200ptError):
+            P.Scene(str(dst / "alphaLeaf.xml")).bvh_check()
+
+    face = b"f 1/1/1 3/3/1 2/2/1"
+    assert face in open(os.path.join(src, "floor.obj"), "rb").read()
+    for k, bad in enumerate((b"f 1/1/1 -999999/3/1 2/2/1", b"f 1/2147483647/1 3/3/1 2/2/1", b"f 1/1/1 3/3/99999999999 2/2/1", b"f 0/1/1 3/3/1 2/2/1", b"f 1/1/1 3/3/1 77/2/1")):
+        variant("idx%d" % k, "floor.obj", lambda d, bad=bad: d.replace(face, bad))
+    variant("inf", "floor.obj", lambda d: d.replace(b"v ", b"v 1e40 ", 1))
+    xml = open(os.path.join(src, "alphaLeaf.xml"), "rb").read()
+    for k, cut in enumerate((len(xml) - 3, len(xml) - 12, len(xml) // 2, xml.rindex(b"</shape>") + 5)):
+        variant("cut%d" % k, "alphaLeaf.xml", lambda d, cut=cut: d[:cut])
+    variant("deep", "alphaLeaf.xml", lambda d: d.replace(b"<scene", b"<a>" * 400 + b"<scene", 1))
+    # and a seeded sweep of byte flips / truncations over the three files: the loader returns or raises
+    rng = np.random.default_rng(3)
+    outcomes = {"ok": 0, "raised": 0}
+    for it in range(120):
+        dst = tmp_path / ("fz%d" % it)
+        shutil.copytree(src, dst)
+        p = dst / ["floor.obj", "leafquad.obj", "alphaLeaf.xml"][it % 3]
+        d = bytearray(p.read_bytes())
+        if it % 2:
+            d = d[:rng.integers(1, len(d))]
+        else:
+            for _ in range(rng.integers(1, 8)):
+                d[rng.integers(0, len(d))] = rng.integers(32, 127)
+        p.write_bytes(bytes(d))
+        try:
+            P.Scene(str(dst / "alphaLeaf.xml")).bvh_check()
+            outcomes["ok"] += 1
+        except P.B200ptError:
+            outcomes["raised"] += 1
+        shutil.rmtree(dst)
+    assert outcomes["ok"] > 5 and outcomes["raised"] > 20, outcomes
