@@ -719,6 +719,8 @@ void Scene::parseMitsubaSceneFile(const std::string &filepath) {
             const XmlNode *c = namedChild(xShape, "center", "point");
             if (!c) throw std::runtime_error("Name not found: center");
             sphere.center[0] = attrFloat(c, "x"); sphere.center[1] = attrFloat(c, "y"); sphere.center[2] = attrFloat(c, "z");
+            if (!(std::isfinite(sphere.radius) && std::isfinite(sphere.center[0]) && std::isfinite(sphere.center[1]) && std::isfinite(sphere.center[2])))
+                throw std::runtime_error("sphere with a non-finite radius or centre");      // (would make the scene box, hence every guiding region, infinite)
             sphere.materialIndex = matIndex;
             sphere.iLight = -1;
             if (materials[matIndex].type == B200PT_MAT_LIGHT) {
